@@ -1,0 +1,536 @@
+// mor_b200.cu — handle, launch sequence and C ABI (include/mor_b200.h) of the B200-native MOR hot path.
+//
+// One handle = one CUDA device + one stream + device-resident SoA frame state that persists across
+// frames (previous frame's clusters, mo_vec, the corrs_vec / res_vec ring buffers). A frame is
+// pushRawCloudAndPose (reference cpp:516-611) = one H2D copy + ~14 kernel launches with no host
+// synchronisation, then filterCloud (cpp:613-696) = 2 launches + the D2H copy of the output cloud.
+// There is no CPU fallback: every entry point that computes needs the device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mor_kernels.cuh"
+
+using namespace mor;
+
+#define MOR_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            h->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+            return MOR_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+namespace {
+
+// ---- host-side pose delta (double, tf semantics A11) and the Eigen float affine (A12) -------------
+struct Tf { double m[3][3]; double o[3]; };
+
+// tf::Transform(tf::Quaternion(x,y,z,w), tf::Vector3) via Matrix3x3::setRotation; q is NOT normalised
+// (tf::poseMsgToTF, reference cpp:524).
+Tf tf_from_pose(const double p[7]) {
+    Tf t;
+    const double qx = p[3], qy = p[4], qz = p[5], qw = p[6];
+    const double s = 2.0 / (qx * qx + qy * qy + qz * qz + qw * qw);
+    const double xs = qx * s, ys = qy * s, zs = qz * s;
+    const double wx = qw * xs, wy = qw * ys, wz = qw * zs, xx = qx * xs, xy = qx * ys, xz = qx * zs, yy = qy * ys, yz = qy * zs, zz = qz * zs;
+    t.m[0][0] = 1.0 - (yy + zz); t.m[0][1] = xy - wz; t.m[0][2] = xz + wy;
+    t.m[1][0] = xy + wz; t.m[1][1] = 1.0 - (xx + zz); t.m[1][2] = yz - wx;
+    t.m[2][0] = xz - wy; t.m[2][1] = yz + wx; t.m[2][2] = 1.0 - (xx + yy);
+    t.o[0] = p[0]; t.o[1] = p[1]; t.o[2] = p[2];
+    return t;
+}
+
+// cb.ps.inverseTimes(ca.ps) (cpp:536): basis cur^T * prev, origin cur^T * (prev.o - cur.o).
+// Then tf getRotation (double) -> Eigen::Quaternionf -> Translation3f * q (pcl_ros::transformPointCloud).
+void pose_delta_affine(const double prev7[7], const double cur7[7], float M[12]) {
+    const Tf a = tf_from_pose(cur7), b = tf_from_pose(prev7);
+    double R[3][3], o[3];
+    const double v[3] = {b.o[0] - a.o[0], b.o[1] - a.o[1], b.o[2] - a.o[2]};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) R[i][j] = a.m[0][i] * b.m[0][j] + a.m[1][i] * b.m[1][j] + a.m[2][i] * b.m[2][j];
+        o[i] = a.m[0][i] * v[0] + a.m[1][i] * v[1] + a.m[2][i] * v[2];
+    }
+    double q[4];
+    const double trace = R[0][0] + R[1][1] + R[2][2];
+    if (trace > 0.0) {
+        double s = std::sqrt(trace + 1.0);
+        q[3] = s * 0.5;
+        s = 0.5 / s;
+        q[0] = (R[2][1] - R[1][2]) * s; q[1] = (R[0][2] - R[2][0]) * s; q[2] = (R[1][0] - R[0][1]) * s;
+    } else {
+        const int i = R[0][0] < R[1][1] ? (R[1][1] < R[2][2] ? 2 : 1) : (R[0][0] < R[2][2] ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
+        q[i] = s * 0.5;
+        s = 0.5 / s;
+        q[3] = (R[k][j] - R[j][k]) * s; q[j] = (R[j][i] + R[i][j]) * s; q[k] = (R[k][i] + R[i][k]) * s;
+    }
+    const float x = (float)q[0], y = (float)q[1], z = (float)q[2], w = (float)q[3];
+    const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+    const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    M[0] = 1.0f - (tyy + tzz); M[1] = txy - twz; M[2] = txz + twy; M[3] = (float)o[0];
+    M[4] = txy + twz; M[5] = 1.0f - (txx + tzz); M[6] = tyz - twx; M[7] = (float)o[1];
+    M[8] = txz - twy; M[9] = tyz + twx; M[10] = 1.0f - (txx + tyy); M[11] = (float)o[2];
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct mor_handle {
+    mor_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t nmax = 0, kmax = 0, momax = 0;
+    int ring_depth = 0, pde_ring = 0;
+    size_t select_smem = 0;
+    GridDesc grid;
+    std::string last_error;
+
+    // one big device arena + carved pointers
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    uint8_t* d_in = nullptr;
+    size_t d_in_bytes = 0;
+    uint8_t* zero_region = nullptr;  // Scratch + scan status + cell_count: one memset per frame
+    size_t zero_bytes = 0;
+    size_t lattice_cap = 0;
+    FramePtrs base;  // pointers that do not change from frame to frame
+    // ping-pong
+    float4* pts[2]; float4* spts[2]; int* cid[2]; int* cl_root[2]; int* cl_size[2]; float* cl_centroid[2]; uint8_t* cl_flags[2]; float* cl_bbox[2]; int* counts[2];
+    int cur = 0;
+    bool have_cur = false, have_prev = false, filtered = false;
+    double cur_pose[7], prev_pose[7];
+    float M[12];
+    bool two_frames = false;
+    uint32_t n_input = 0, n_prev_input = 0;
+    uint64_t launches = 0;
+    FramePtrs frame;  // arguments of the current frame
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t* h_counts = nullptr;  // pinned
+};
+
+namespace {
+
+template <typename T>
+T* carve(uint8_t*& p, size_t count) {
+    T* r = reinterpret_cast<T*>(p);
+    p += align_up(count * sizeof(T), 256);
+    return r;
+}
+
+int build_grid(mor_handle* h) {
+    const mor_config& c = h->cfg;
+    // A7: r2 = (float)((double)tol * (double)tol); effective radius = sqrt(r2); cell edge slightly larger so
+    // that float-rounded coordinates of two points with d2 < r2 never land two cells apart.
+    const float r2 = (float)((double)c.ec_distance_threshold * (double)c.ec_distance_threshold);
+    if (!(r2 > 0.f) || !(c.trim_x > 0.f) || !(c.trim_y > 0.f)) return MOR_ERR_CONFIG_VALUE;
+    const double hcell = std::sqrt((double)r2) * (1.0 + 1.0 / 1024.0);
+    GridDesc g;
+    g.ox = -(double)c.trim_x; g.oy = -(double)c.trim_y;
+    double zlo, zhi;
+    if (c.ground_mode == MOR_GROUND_CROP) { zlo = (double)c.gp_limit; zhi = (double)c.trim_z; }
+    else { zlo = -64.0; zhi = 64.0; }  // voxel modes: z is not cropped; generous fixed slab
+    if (!(zhi >= zlo)) zhi = zlo;
+    g.oz = zlo; g.inv_h = 1.0 / hcell;
+    const double fx = std::floor(2.0 * (double)c.trim_x / hcell) + 1, fy = std::floor(2.0 * (double)c.trim_y / hcell) + 1, fz = std::floor((zhi - zlo) / hcell) + 1;
+    if (fx * fy * fz > 268435456.0) return MOR_ERR_CAPACITY;  // 2^28 cells = 2 GB of cell tables
+    g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
+    h->grid = g;
+    h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / hcell);
+    if (h->pde_ring < 1) h->pde_ring = 1;
+    return MOR_OK;
+}
+
+int allocate(mor_handle* h) {
+    const size_t N = h->nmax, K = h->kmax, MO = h->momax, D = (size_t)h->ring_depth;
+    const size_t ncells = (size_t)h->grid.ncells;
+    const size_t tiles_pts = N / kBlock + 2, tiles_cells = ncells / kTile + 2;
+    size_t lat = 1;
+    while (lat < 2 * N) lat <<= 1;
+    h->lattice_cap = lat;
+    h->d_in_bytes = N * 32;
+    // ---- size pass (mirror of the carve pass below)
+    auto plan = [&](uint8_t* p0) -> uint8_t* {
+        uint8_t* p = p0;
+        FramePtrs& b = h->base;
+        h->d_in = carve<uint8_t>(p, h->d_in_bytes);
+        h->zero_region = p;
+        b.scratch = carve<Scratch>(p, 1);
+        b.st_ingest = carve<unsigned long long>(p, tiles_pts);
+        b.st_cells = carve<unsigned long long>(p, tiles_cells);
+        b.st_out = carve<unsigned long long>(p, tiles_pts);
+        b.cell_count = carve<int>(p, ncells + 1);
+        h->zero_bytes = (size_t)(p - h->zero_region);
+        b.cell_start = carve<int>(p, ncells + 1);
+        b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
+        b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
+        b.cell_key = carve<int>(p, N); b.cell_rank = carve<int>(p, N); b.skey = carve<int>(p, N);
+        b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
+        b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
+        b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
+        b.recip_q = carve<int>(p, K); b.recip_m = carve<int>(p, K); b.match_q = carve<int>(p, K); b.match_m = carve<int>(p, K);
+        b.match_dist = carve<float>(p, K); b.match_score = carve<double>(p, K);
+        b.match_of_prev = carve<int>(p, K); b.mid_of_prev = carve<int>(p, K); b.mid_of_cur = carve<int>(p, K);
+        b.anchor = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
+        b.lattice = carve<unsigned long long>(p, lat);
+        b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
+        b.out = carve<float4>(p, N * 2);
+        for (int f = 0; f < 2; f++) {
+            h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
+            h->cl_root[f] = carve<int>(p, K); h->cl_size[f] = carve<int>(p, K); h->cl_centroid[f] = carve<float>(p, K * 3);
+            h->cl_flags[f] = carve<uint8_t>(p, K); h->cl_bbox[f] = carve<float>(p, K * 6); h->counts[f] = carve<int>(p, MOR_NCOUNTS);
+        }
+        b.track = carve<TrackState>(p, 1); b.mo_centroid = carve<float>(p, MO * 3); b.mo_conf = carve<int>(p, MO);
+        b.res_ring = carve<uint8_t>(p, D * K); b.res_len = carve<int>(p, D); b.corr_ring = carve<int>(p, D * K); b.corr_len = carve<int>(p, D);
+        return p;
+    };
+    h->arena_bytes = (size_t)(plan(nullptr) - (uint8_t*)nullptr) + 256;
+    MOR_CUDA(cudaMalloc(&h->arena, h->arena_bytes));
+    plan(h->arena);
+    MOR_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+    MOR_CUDA(cudaMallocHost(&h->h_counts, sizeof(int32_t) * MOR_NCOUNTS));
+    for (int i = 0; i < 4; i++) MOR_CUDA(cudaEventCreate(&h->ev[i]));
+    int P = 1;
+    while (P < (int)K) P <<= 1;
+    h->select_smem = (size_t)P * sizeof(unsigned long long);
+    MOR_CUDA(cudaFuncSetAttribute(k_select_clusters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    return MOR_OK;
+}
+
+void fill_static(mor_handle* h) {
+    FramePtrs& b = h->base;
+    const mor_config& c = h->cfg;
+    b.trim_x = c.trim_x; b.trim_y = c.trim_y; b.trim_z = c.trim_z; b.gp_limit = c.gp_limit;
+    b.r2 = (float)((double)c.ec_distance_threshold * (double)c.ec_distance_threshold);
+    b.volume_constraint = c.volume_constraint; b.pde_lb = c.pde_lb; b.pde_ub = c.pde_ub; b.pde_thr = c.pde_distance_threshold;
+    b.leave_off = c.leave_off_distance; b.catch_up = c.catch_up_distance;
+    b.min_cluster = c.min_cluster_size; b.max_cluster = c.max_cluster_size;
+    b.method = c.method_choice; b.opc_factor = c.opc_normalization_factor;
+    b.moving_confidence = c.n_bad; b.static_confidence = c.n_good;
+    b.kmax = (int)h->kmax; b.momax = (int)h->momax; b.ring_depth = h->ring_depth;
+    b.grid = h->grid;
+    b.lattice_mask = (unsigned)(h->lattice_cap - 1);
+}
+
+inline unsigned blocks_for(uint32_t n) { return n ? (n + kBlock - 1) / kBlock : 1; }
+
+int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
+    cudaStream_t st = h->stream;
+    FramePtrs& a = h->frame;
+    a = h->base;
+    const int cur = h->cur, prev = cur ^ 1;
+    a.in = d_points; a.n = n; a.step = step; a.off_x = ox; a.off_y = oy; a.off_z = oz; a.off_i = oi;
+    a.vec16 = (step == 16 && ox == 0 && oy == 4 && oz == 8 && oi == 12 && ((uintptr_t)d_points % 16) == 0) ? 1 : 0;
+    a.pts = h->pts[cur]; a.spts = h->spts[cur]; a.cid = h->cid[cur]; a.cl_root = h->cl_root[cur]; a.cl_size = h->cl_size[cur];
+    a.cl_centroid = h->cl_centroid[cur]; a.cl_flags = h->cl_flags[cur]; a.cl_bbox = h->cl_bbox[cur]; a.counts = h->counts[cur];
+    a.p_pts = h->pts[prev]; a.p_spts = h->spts[prev]; a.p_cid = h->cid[prev]; a.p_cl_root = h->cl_root[prev]; a.p_cl_size = h->cl_size[prev];
+    a.p_cl_centroid = h->cl_centroid[prev]; a.p_cl_flags = h->cl_flags[prev]; a.p_counts = h->counts[prev];
+    a.two_frames = h->two_frames ? 1 : 0;
+    std::memcpy(a.M.m, h->M, sizeof(h->M));
+
+    const unsigned gb = blocks_for(n);
+    MOR_CUDA(cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, st));
+    k_ingest<<<gb, kBlock, 0, st>>>(a);
+    k_scan_cells<<<(h->grid.ncells + kTile - 1) / kTile, kBlock, 0, st>>>(a);
+    k_scatter<<<gb, kBlock, 0, st>>>(a);
+    k_neighbors<<<gb, kBlock, 0, st>>>(a);
+    k_flatten<<<gb, kBlock, 0, st>>>(a);
+    k_select_clusters<<<1, kSingle, h->select_smem, st>>>(a);
+    k_cluster_stats<<<gb, kBlock, 0, st>>>(a);
+    k_finalize_clusters<<<8, kSingle, 0, st>>>(a);
+    h->launches += 8;
+    if (h->two_frames) {
+        const unsigned gp = blocks_for(h->n_prev_input);
+        k_init_prev_boxes<<<(h->kmax + kBlock - 1) / kBlock, kBlock, 0, st>>>(a);
+        k_transform_prev<<<gp, kBlock, 0, st>>>(a);
+        k_match<<<1, kSingle, 0, st>>>(a);
+        h->launches += 3;
+        if (h->cfg.method_choice == 2) {
+            MOR_CUDA(cudaMemsetAsync(a.lattice, 0xFF, h->lattice_cap * sizeof(unsigned long long), st));
+            k_lattice_insert<<<gp, kBlock, 0, st>>>(a);
+            k_lattice_count<<<gb, kBlock, 0, st>>>(a);
+            h->launches += 2;
+        } else {
+            k_pde_count<<<gp, kBlock, 0, st>>>(a, h->pde_ring);
+            h->launches += 1;
+        }
+        k_flags_and_chain<<<1, kSingle, 0, st>>>(a);
+        h->launches += 1;
+    }
+    MOR_CUDA(cudaGetLastError());
+    return MOR_OK;
+}
+
+int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi, const double pose7[7]) {
+    if (!h || (!data && n) || !pose7) return MOR_ERR_ARG;
+    if (step < 12 || step % 4 || ox % 4 || oy % 4 || oz % 4 || (oi != 0xFFFFFFFFu && oi % 4)) return MOR_ERR_ARG;
+    if (ox + 4 > step || oy + 4 > step || oz + 4 > step || (oi != 0xFFFFFFFFu && oi + 4 > step)) return MOR_ERR_ARG;
+    if (n > h->nmax) { h->last_error = "frame larger than mor_limits.max_points"; return MOR_ERR_CAPACITY; }
+    MOR_CUDA(cudaSetDevice(h->device));
+    if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    const uint8_t* d_points = (const uint8_t*)data;
+    if (!on_device) {
+        const size_t bytes = (size_t)n * step;
+        if (bytes > h->d_in_bytes) { h->last_error = "n * point_step exceeds the staging buffer (32 B/point)"; return MOR_ERR_CAPACITY; }
+        if (bytes) MOR_CUDA(cudaMemcpyAsync(h->d_in, data, bytes, cudaMemcpyHostToDevice, h->stream));
+        d_points = h->d_in;
+    }
+    // ca = cb; cb = new frame (cpp:520-521)
+    if (h->have_cur) { h->cur ^= 1; std::memcpy(h->prev_pose, h->cur_pose, sizeof(h->cur_pose)); h->have_prev = true; h->n_prev_input = h->n_input; }
+    std::memcpy(h->cur_pose, pose7, sizeof(h->cur_pose));
+    h->n_input = n;
+    h->two_frames = h->have_prev;  // ca->init && cb->init (cpp:534)
+    std::memset(h->M, 0, sizeof(h->M));
+    if (h->two_frames) pose_delta_affine(h->prev_pose, h->cur_pose, h->M);
+    h->have_cur = true;
+    h->filtered = false;
+    int st = enqueue_push(h, d_points, n, step, ox, oy, oz, oi);
+    if (st != MOR_OK) return st;
+    if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    return MOR_OK;
+}
+
+int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uint32_t* n_out) {
+    if (!h) return MOR_ERR_ARG;
+    if (!h->have_cur) return MOR_ERR_STATE;
+    MOR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[2], st));
+    FramePtrs& a = h->frame;
+    if (on_device && out) a.out = (float4*)out;  // write the records straight into the caller's device buffer
+    else a.out = h->base.out;
+    if (on_device && out && cap_points < h->n_input) { h->last_error = "device output buffer must hold n_input points"; return MOR_ERR_CAPACITY; }
+    k_track<<<1, kSingle, 0, st>>>(a);
+    k_output<<<blocks_for(h->n_input), kBlock, 0, st>>>(a);
+    h->launches += 2;
+    MOR_CUDA(cudaGetLastError());
+    h->filtered = true;
+    if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[3], st));
+    if (on_device && !n_out) return MOR_OK;  // fully asynchronous device-resident mode
+    MOR_CUDA(cudaMemcpyAsync(h->h_counts, a.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, st));
+    MOR_CUDA(cudaStreamSynchronize(st));
+    const uint32_t no = (uint32_t)h->h_counts[MOR_CNT_NOUT];
+    if (n_out) *n_out = no;
+    if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
+        char msg[96];
+        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice)", h->h_counts[MOR_CNT_ERRFLAGS]);
+        h->last_error = msg;
+        return MOR_ERR_CAPACITY;
+    }
+    if (!on_device) {
+        if (no > cap_points) return MOR_ERR_CAPACITY;
+        if (no) {
+            MOR_CUDA(cudaMemcpyAsync(out, a.out, (size_t)no * 32, cudaMemcpyDeviceToHost, st));
+            MOR_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return MOR_OK;
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, const mor_limits* limits, mor_handle** out) {
+    if (!out || !config_path) return MOR_ERR_ARG;
+    *out = nullptr;
+    mor_config cfg;
+    int st = mor_parse_config(config_path, &cfg);
+    if (st != MOR_OK) return st;
+    cfg.n_bad = n_bad; cfg.n_good = n_good;
+    if (cfg.ground_mode != MOR_GROUND_CROP) return MOR_ERR_CONFIG_VALUE;  // voxel-covariance modes: see mor_ground.cuh (next milestone)
+    mor_handle* h = new mor_handle();
+    h->cfg = cfg; h->device = device;
+    h->nmax = limits && limits->max_points ? limits->max_points : 300000u;
+    h->kmax = limits && limits->max_clusters ? limits->max_clusters : 8192u;
+    h->momax = limits && limits->max_moving ? limits->max_moving : 1024u;
+    if (h->kmax > 32768u) h->kmax = 32768u;  // 15 bits of match id in the lattice key
+    h->ring_depth = (n_bad > 1 ? n_bad : 1) + 2;
+    st = build_grid(h);
+    if (st != MOR_OK) { delete h; return st; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return MOR_ERR_CUDA; }
+    st = allocate(h);
+    if (st != MOR_OK) { if (h->arena) cudaFree(h->arena); cudaStreamDestroy(h->stream); delete h; return st; }
+    fill_static(h);
+    *out = h;
+    return MOR_OK;
+}
+
+int mor_create(const char* config_path, int n_bad, int n_good, int device, mor_handle** out) {
+    return mor_create_ex(config_path, n_bad, n_good, device, nullptr, out);
+}
+
+int mor_destroy(mor_handle* h) {
+    if (!h) return MOR_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->arena) cudaFree(h->arena);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MOR_OK;
+}
+
+int mor_get_config(const mor_handle* h, mor_config* out) {
+    if (!h || !out) return MOR_ERR_ARG;
+    *out = h->cfg;
+    return MOR_OK;
+}
+
+const char* mor_last_error(const mor_handle* h) { return h ? h->last_error.c_str() : ""; }
+
+int mor_push_raw_cloud_and_pose(mor_handle* h, const void* data, uint32_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                                uint32_t off_i, const double pose7[7]) {
+    return do_push(h, data, false, n, point_step, off_x, off_y, off_z, off_i, pose7);
+}
+int mor_push_raw_cloud_and_pose_device(mor_handle* h, const void* d_data, uint32_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y,
+                                       uint32_t off_z, uint32_t off_i, const double pose7[7]) {
+    return do_push(h, d_data, true, n, point_step, off_x, off_y, off_z, off_i, pose7);
+}
+int mor_filter_cloud(mor_handle* h, void* out, uint32_t cap_points, uint32_t* n_out) {
+    if (!out && cap_points) return MOR_ERR_ARG;
+    return do_filter(h, out, false, cap_points, n_out);
+}
+int mor_filter_cloud_device(mor_handle* h, void* d_out, uint32_t cap_points, uint32_t* n_out) { return do_filter(h, d_out, true, cap_points, n_out); }
+
+int mor_sync(mor_handle* h) {
+    if (!h) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    return MOR_OK;
+}
+
+int mor_alloc_pinned(size_t bytes, void** out) { return cudaMallocHost(out, bytes) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA; }
+int mor_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA; }
+int mor_device_alloc(int device, size_t bytes, void** out) {
+    if (cudaSetDevice(device) != cudaSuccess) return MOR_ERR_CUDA;
+    return cudaMalloc(out, bytes) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA;
+}
+int mor_device_free(int device, void* p) {
+    if (cudaSetDevice(device) != cudaSuccess) return MOR_ERR_CUDA;
+    return cudaFree(p) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA;
+}
+int mor_device_upload(int device, void* d_dst, const void* src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return MOR_ERR_CUDA;
+    return cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA;
+}
+int mor_device_download(int device, void* dst, const void* d_src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return MOR_ERR_CUDA;
+    return cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA;
+}
+
+int mor_get_launch_count(const mor_handle* h, uint64_t* out) {
+    if (!h || !out) return MOR_ERR_ARG;
+    *out = h->launches;
+    return MOR_OK;
+}
+int mor_set_timing(mor_handle* h, int enabled) {
+    if (!h) return MOR_ERR_ARG;
+    h->timing = enabled != 0;
+    return MOR_OK;
+}
+int mor_get_last_device_ms(mor_handle* h, float* push_ms, float* filter_ms) {
+    if (!h || !h->timing) return MOR_ERR_STATE;
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    if (push_ms) MOR_CUDA(cudaEventElapsedTime(push_ms, h->ev[0], h->ev[1]));
+    if (filter_ms) MOR_CUDA(cudaEventElapsedTime(filter_ms, h->ev[2], h->ev[3]));
+    return MOR_OK;
+}
+
+// ---- parity taps ----------------------------------------------------------------------------------
+int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes) {
+    if (!h) return MOR_ERR_ARG;
+    if (!h->have_cur) return MOR_ERR_STATE;
+    MOR_CUDA(cudaSetDevice(h->device));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    const FramePtrs& a = h->frame;
+    int32_t c[MOR_NCOUNTS];
+    MOR_CUDA(cudaMemcpy(c, a.counts, sizeof(c), cudaMemcpyDeviceToHost));
+    const void* src = nullptr;
+    size_t bytes = 0;
+    std::vector<uint8_t> host;  // for taps assembled on the host
+    const size_t N = c[MOR_CNT_N], NC = c[MOR_CNT_NC], K = c[MOR_CNT_K], KP = c[MOR_CNT_KPREV], M = c[MOR_CNT_M], MU = c[MOR_CNT_MU], NMO = c[MOR_CNT_NMO],
+                 NCP = c[MOR_CNT_NCPREV];
+    switch (tap) {
+        case MOR_TAP_COUNTS: host.assign((uint8_t*)c, (uint8_t*)c + sizeof(c)); break;
+        case MOR_TAP_POINT_CLASS: src = a.point_class; bytes = N; break;
+        case MOR_TAP_LABELS: src = a.label; bytes = NC * 4; break;
+        case MOR_TAP_CLUSTER_ID: src = a.cid; bytes = NC * 4; break;
+        case MOR_TAP_CLUSTER_ROOT: src = a.cl_root; bytes = K * 4; break;
+        case MOR_TAP_CLUSTER_SIZE: src = a.cl_size; bytes = K * 4; break;
+        case MOR_TAP_CENTROIDS: src = a.cl_centroid; bytes = K * 12; break;
+        case MOR_TAP_TRANSFORM: host.assign((uint8_t*)h->M, (uint8_t*)h->M + sizeof(h->M)); break;
+        case MOR_TAP_PREV_CENTROIDS_T: src = a.pct; bytes = KP * 12; break;
+        case MOR_TAP_PREV_POINTS_T: {
+            std::vector<float4> t(NCP);
+            if (NCP) MOR_CUDA(cudaMemcpy(t.data(), a.tpts, NCP * sizeof(float4), cudaMemcpyDeviceToHost));
+            host.resize(NCP * 12);
+            float* o = (float*)host.data();
+            for (size_t i = 0; i < NCP; i++) {
+                int k; std::memcpy(&k, &t[i].w, 4);
+                const float nan = std::nanf("");
+                o[i * 3] = k >= 0 ? t[i].x : nan; o[i * 3 + 1] = k >= 0 ? t[i].y : nan; o[i * 3 + 2] = k >= 0 ? t[i].z : nan;
+            }
+        } break;
+        case MOR_TAP_MATCH_QUERY: src = a.match_q; bytes = M * 4; break;
+        case MOR_TAP_MATCH_MATCH: src = a.match_m; bytes = M * 4; break;
+        case MOR_TAP_MATCH_DIST: src = a.match_dist; bytes = M * 4; break;
+        case MOR_TAP_MATCH_SCORE: src = a.match_score; bytes = M * 8; break;
+        case MOR_TAP_FLAGS: src = a.cl_flags; bytes = K; break;
+        case MOR_TAP_MO_CENTROIDS: src = a.mo_centroid; bytes = NMO * 12; break;
+        case MOR_TAP_MO_CONF: src = a.mo_conf; bytes = NMO * 4; break;
+        case MOR_TAP_REMOVED_MASK: if (!h->filtered) return MOR_ERR_STATE; src = a.removed_mask; bytes = N; break;
+        case MOR_TAP_CLUSTER_REMOVED: if (!h->filtered) return MOR_ERR_STATE; src = a.cluster_removed; bytes = K; break;
+        case MOR_TAP_RECIP_QUERY: src = a.recip_q; bytes = MU * 4; break;
+        case MOR_TAP_RECIP_MATCH: src = a.recip_m; bytes = MU * 4; break;
+        case MOR_TAP_GROUND_VOXELS: bytes = 0; break;
+        case MOR_TAP_CLUSTER_BBOX: src = a.cl_bbox; bytes = K * 24; break;
+        case MOR_TAP_PREV_BBOX_T: src = a.pbbox; bytes = KP * 24; break;
+        default: return MOR_ERR_ARG;
+    }
+    if (!host.empty() || tap == MOR_TAP_PREV_POINTS_T) bytes = host.size();
+    if (n_bytes) *n_bytes = bytes;
+    if (bytes > cap_bytes) return MOR_ERR_CAPACITY;
+    if (!bytes) return MOR_OK;
+    if (!host.empty()) std::memcpy(dst, host.data(), bytes);
+    else MOR_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return MOR_OK;
+}
+
+#define MOR_NAMED_TAP(name, tapid, type)                                           \
+    int name(mor_handle* h, type* dst, size_t n) { size_t nb = 0; return mor_tap(h, tapid, dst, n * sizeof(type), &nb); }
+MOR_NAMED_TAP(mor_get_counts, MOR_TAP_COUNTS, int32_t)
+MOR_NAMED_TAP(mor_get_trim_mask, MOR_TAP_POINT_CLASS, uint8_t)
+MOR_NAMED_TAP(mor_get_ground_mask, MOR_TAP_POINT_CLASS, uint8_t)
+MOR_NAMED_TAP(mor_get_labels, MOR_TAP_LABELS, int32_t)
+MOR_NAMED_TAP(mor_get_cluster_order, MOR_TAP_CLUSTER_ROOT, int32_t)
+MOR_NAMED_TAP(mor_get_centroids, MOR_TAP_CENTROIDS, float)
+MOR_NAMED_TAP(mor_get_transform, MOR_TAP_TRANSFORM, float)
+MOR_NAMED_TAP(mor_get_transformed_xyz, MOR_TAP_PREV_POINTS_T, float)
+MOR_NAMED_TAP(mor_get_scores, MOR_TAP_MATCH_SCORE, double)
+MOR_NAMED_TAP(mor_get_flags, MOR_TAP_FLAGS, uint8_t)
+MOR_NAMED_TAP(mor_get_removed_mask, MOR_TAP_REMOVED_MASK, uint8_t)
+int mor_get_matches(mor_handle* h, int32_t* query, int32_t* match, size_t n) {
+    size_t nb = 0;
+    int st = mor_tap(h, MOR_TAP_MATCH_QUERY, query, n * 4, &nb);
+    return st != MOR_OK ? st : mor_tap(h, MOR_TAP_MATCH_MATCH, match, n * 4, &nb);
+}
+int mor_get_mo_vec(mor_handle* h, float* xyz, int32_t* conf, size_t n) {
+    size_t nb = 0;
+    int st = mor_tap(h, MOR_TAP_MO_CENTROIDS, xyz, n * 12, &nb);
+    return st != MOR_OK ? st : mor_tap(h, MOR_TAP_MO_CONF, conf, n * 4, &nb);
+}
+
+}  // extern "C"

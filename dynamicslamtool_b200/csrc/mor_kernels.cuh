@@ -1,0 +1,820 @@
+// mor_kernels.cuh — the per-frame MOR kernels (sm_100a), crop ground mode + clustering + matching +
+// moving tests + tracking + output. Launched by mor_b200.cu. Every kernel cites the reference lines
+// (src/MovingObjectRemoval.cpp unless noted) whose behaviour it reproduces; DESIGN.md has the data
+// layout and the roofline of each.
+#pragma once
+#include "mor_device.cuh"
+#include "../../include/mor_b200.h"
+
+namespace mor {
+
+constexpr int kSingle = 1024;  // threads of the single-block bookkeeping kernels
+
+enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8 };
+
+struct GridDesc {  // uniform grid over `cloud`; cell edge h = r*(1+2^-10) so d<r => |dcell| <= 1 per axis
+    double ox, oy, oz, inv_h;
+    int nx, ny, nz, ncells;
+};
+
+struct Scratch {  // zeroed at the start of every frame (one memset, together with cell_count)
+    int ticket_ingest, ticket_cells, ticket_out, n_roots;
+    int moving_total, pad0, pad1, pad2;
+};
+
+struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:109-128)
+    int n_mo;         // mo_vec.size()
+    int res_count, res_head;    // res_vec deque
+    int corr_count, corr_head;  // corrs_vec deque
+    int frames;
+    int extract_overflow;
+    int pad;
+};
+
+// Everything a kernel needs, passed by value (fits the 4 KB parameter space comfortably).
+struct FramePtrs {
+    // ---- input
+    const uint8_t* in; uint32_t n, step, off_x, off_y, off_z, off_i; int vec16;
+    // ---- config
+    float trim_x, trim_y, trim_z, gp_limit, r2, volume_constraint, pde_lb, pde_ub, pde_thr, leave_off, catch_up;
+    long long min_cluster, max_cluster;
+    int method, opc_factor, moving_confidence, static_confidence;
+    int kmax, momax, ring_depth;
+    GridDesc grid;
+    // ---- per-frame scratch
+    Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cells; unsigned long long* st_out;
+    int* cell_count; int* cell_start;
+    uint8_t* point_class; uint8_t* removed_mask;
+    int* cloud_src; float4* gpts; int* gsrc;
+    int* cell_key; int* cell_rank; int* skey;
+    int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
+    unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
+    unsigned* acc_box;            // [kmax*6] min xyz, max xyz keys
+    unsigned* pacc_box;           // [kmax*6] transformed prev clusters
+    float4* tpts;                 // transformed prev cloud points (w = prev cluster id bits, -1 if none)
+    float* pct;                   // [kmax*3] transformed prev centroids
+    float* pbbox;                 // [kmax*6] decoded
+    int* recip_q; int* recip_m; int* match_q; int* match_m; float* match_dist; double* match_score;
+    int* match_of_prev; int* mid_of_prev; int* mid_of_cur; double* anchor; int* newcount;
+    unsigned long long* lattice; unsigned lattice_mask;
+    uint8_t* cluster_removed; int* found;
+    float4* out;
+    // ---- ping-pong frame state: cur / prev
+    float4* pts; float4* spts; int* cid; int* cl_root; int* cl_size; float* cl_centroid; uint8_t* cl_flags; float* cl_bbox; int* counts;
+    const float4* p_pts; const float4* p_spts; const int* p_cid; const int* p_cl_root; const int* p_cl_size; const float* p_cl_centroid;
+    const uint8_t* p_cl_flags; const int* p_counts;
+    // ---- persistent tracking state
+    TrackState* track; float* mo_centroid; int* mo_conf;
+    uint8_t* res_ring; int* res_len; int* corr_ring; int* corr_len;
+    Affine12 M; int two_frames;
+};
+
+// ===================================================================================== K1
+// pcl::fromPCLPointCloud2 (cpp:523) + PassThrough x, y (cpp:66-74, A1) + CropBox with removed indices
+// (cpp:78-86, A2), fused with the stable two-way partition into `cloud` / gp_indices order, the grid
+// cell key of every cloud point and the per-cell histogram. One point per thread, coalesced AoS read.
+__global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const uint32_t i = (uint32_t)tile * kBlock + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
+    int cls = 0;
+    if (i < a.n) {
+        const uint8_t* p = a.in + (size_t)i * a.step;
+        if (a.vec16) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(p));
+            x = v.x; y = v.y; z = v.z; w = v.w;
+        } else {
+            x = __ldg(reinterpret_cast<const float*>(p + a.off_x));
+            y = __ldg(reinterpret_cast<const float*>(p + a.off_y));
+            z = __ldg(reinterpret_cast<const float*>(p + a.off_z));
+            w = a.off_i != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float*>(p + a.off_i)) : 0.f;
+        }
+        const bool fin = isfinite(x) && isfinite(y) && isfinite(z);
+        const bool in_xy = fin && !(x < -a.trim_x || x > a.trim_x) && !(y < -a.trim_y || y > a.trim_y);
+        if (in_xy) cls = (z < a.gp_limit || z > a.trim_z) ? 2 : 1;  // x,y box tests of CropBox are implied by the trim
+        a.point_class[i] = (uint8_t)cls;
+        a.removed_mask[i] = cls ? 1 : 0;
+    }
+    unsigned long long packed = (cls == 1 ? 1ull : 0ull) | (cls == 2 ? (1ull << 31) : 0ull);
+    unsigned long long total;
+    const unsigned long long in_block = block_exclusive_scan<unsigned long long>(packed, &total);
+    const unsigned long long before = tile_exclusive_prefix(a.st_ingest, tile, total);
+    const unsigned long long mine = before + in_block;
+    if (cls == 1) {
+        const int c = (int)(mine & 0x7FFFFFFFull);
+        a.pts[c] = make_float4(x, y, z, w);
+        a.cloud_src[c] = (int)i;
+        const GridDesc& g = a.grid;
+        int cx = (int)floor(((double)x - g.ox) * g.inv_h);
+        int cy = (int)floor(((double)y - g.oy) * g.inv_h);
+        int cz = (int)floor(((double)z - g.oz) * g.inv_h);
+        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+        const int key = (cz * g.ny + cy) * g.nx + cx;
+        a.cell_key[c] = key;
+        a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+        a.parent[c] = c;
+        a.comp_size[c] = 0;
+    } else if (cls == 2) {
+        const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
+        a.gpts[gi] = make_float4(x, y, z, w);
+        a.gsrc[gi] = (int)i;
+    }
+    const int last_tile = a.n ? (int)((a.n - 1) / kBlock) : 0;
+    if (tile == last_tile && threadIdx.x == 0) {
+        const unsigned long long all = before + total;
+        const int nc = (int)(all & 0x7FFFFFFFull), ng = (int)((all >> 31) & 0x7FFFFFFFull);
+        int* c = a.counts;
+        for (int k = 0; k < MOR_NCOUNTS; k++) c[k] = 0;
+        c[MOR_CNT_N] = (int)a.n; c[MOR_CNT_NT] = nc + ng; c[MOR_CNT_NC] = nc; c[MOR_CNT_NG] = ng;
+        c[MOR_CNT_TWO_FRAMES] = a.two_frames;
+        if (a.two_frames) { c[MOR_CNT_KPREV] = a.p_counts[MOR_CNT_K]; c[MOR_CNT_NCPREV] = a.p_counts[MOR_CNT_NC]; }
+        c[MOR_CNT_FRAME] = a.track->frames + 1;
+        a.track->frames += 1;
+    }
+}
+
+// ===================================================================================== K2
+// Exclusive scan of the per-cell histogram -> cell_start[0..ncells] (counting sort of the cell keys).
+__global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_cells, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int ncells = a.grid.ncells;
+    const int base = tile * kTile + threadIdx.x * kItems;
+    int v[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++) sum += v[k];
+    int total;
+    const int in_block = block_exclusive_scan<int>(sum, &total);
+    const int before = (int)tile_exclusive_prefix(a.st_cells, tile, (unsigned long long)total);
+    int run = before + in_block;
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        if (base + k < ncells) a.cell_start[base + k] = run;
+        run += v[k];
+    }
+    const int last_tile = (ncells - 1) / kTile;
+    if (tile == last_tile && threadIdx.x == 0) a.cell_start[ncells] = before + total;
+}
+
+// ===================================================================================== K3
+// Scatter cloud points into cell-sorted order (float4 xyz + cloud index) for the neighbour search.
+__global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) {
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= a.counts[MOR_CNT_NC]) return;
+    const int key = a.cell_key[c];
+    const int pos = a.cell_start[key] + a.cell_rank[c];
+    float4 p = a.pts[c];
+    p.w = __int_as_float(c);
+    a.spts[pos] = p;
+    a.skey[pos] = key;
+}
+
+// ===================================================================================== K4
+// pcl::EuclideanClusterExtraction radius graph (cpp:213-218; A5-A7): for every point, the 27-cell
+// neighbourhood is 9 x-rows, each a contiguous run of the sorted array. Pairs are visited once
+// (j > s) and every pair with L2_Simple distance < r2 (strict) is merged in the union-find.
+__global__ void __launch_bounds__(kBlock) k_neighbors(FramePtrs a) {
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int nc = a.counts[MOR_CNT_NC];
+    if (s >= nc) return;
+    const float4 p = a.spts[s];
+    const int c = __float_as_int(p.w);
+    const int key = a.skey[s];
+    const GridDesc& g = a.grid;
+    const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    int my_root = c;
+    bool rooted = false;
+    for (int dz = 0; dz <= 1; dz++) {  // rows with dz < 0 lie entirely before s in sorted order
+        const int zz = cz + dz;
+        if (zz >= g.nz) continue;
+        for (int dy = (dz == 0 ? 0 : -1); dy <= 1; dy++) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy >= g.ny) continue;
+            const int base = (zz * g.ny + yy) * g.nx;
+            int b = a.cell_start[base + x0];
+            const int e = a.cell_start[base + x1 + 1];
+            b = max(b, s + 1);
+            for (int j = b; j < e; j++) {
+                const float4 q = a.spts[j];
+                if (sqdist3(p.x, p.y, p.z, q.x, q.y, q.z) < a.r2) {
+                    const int jc = __float_as_int(q.w);
+                    if (!rooted) { my_root = uf_find(a.parent, c); rooted = true; }
+                    if (ld_parent(a.parent + jc) != my_root) my_root = uf_union(a.parent, c, jc);
+                }
+            }
+        }
+    }
+}
+
+// ===================================================================================== K5
+// Pointer-jump every point to its root (= min cloud index of its component), count component sizes
+// with warp-aggregated atomics (sorted order keeps a warp inside one component most of the time) and
+// collect the roots.
+__global__ void __launch_bounds__(kBlock) k_flatten(FramePtrs a) {
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int nc = a.counts[MOR_CNT_NC];
+    if (s >= nc) return;
+    const int c = __float_as_int(a.spts[s].w);
+    const int r = uf_find(a.parent, c);
+    a.label[c] = r;
+    if (r == c) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = c;
+    const unsigned active = __activemask();
+    const unsigned same = __match_any_sync(active, r);
+    if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.comp_size[r], __popc(same));
+}
+
+// ===================================================================================== K6
+// Size filter min <= size <= max (cpp:215-216), cluster order = size descending then min index
+// ascending (A9 canonical rule) by a shared-memory bitonic sort of (~size, root) keys.
+__global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ int s_k;
+    if (threadIdx.x == 0) s_k = 0;
+    __syncthreads();
+    const int n_roots = a.scratch->n_roots;
+    for (int t = threadIdx.x; t < n_roots; t += kSingle) {
+        const int root = a.root_list[t];
+        const int sz = a.comp_size[root];
+        if ((long long)sz >= a.min_cluster && (long long)sz <= a.max_cluster) {
+            const int slot = atomicAdd(&s_k, 1);
+            if (slot < a.kmax) keys[slot] = ((unsigned long long)(0xFFFFFFFFu - (unsigned)sz) << 32) | (unsigned)root;
+        } else {
+            a.cid_of_root[root] = -1;
+        }
+    }
+    __syncthreads();
+    int K = s_k;
+    if (K > a.kmax) {  // capacity exceeded: keep the first kmax found, flag the frame
+        if (threadIdx.x == 0) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_CLUSTER_CAP);
+        // the dropped roots must not keep a stale cluster id
+        for (int t = threadIdx.x; t < n_roots; t += kSingle) a.cid_of_root[a.root_list[t]] = -1;
+        K = a.kmax;
+    }
+    int P = 1;
+    while (P < K) P <<= 1;
+    for (int t = K + threadIdx.x; t < P; t += kSingle) keys[t] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += kSingle) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long A = keys[lo], B = keys[hi];
+                if ((A > B) == up) { keys[lo] = B; keys[hi] = A; }
+            }
+            __syncthreads();
+        }
+    }
+    int nk = 0;
+    for (int k = threadIdx.x; k < K; k += kSingle) {
+        const unsigned long long kk = keys[k];
+        const int root = (int)(unsigned)(kk & 0xFFFFFFFFull);
+        const int sz = (int)(0xFFFFFFFFu - (unsigned)(kk >> 32));
+        a.cl_root[k] = root; a.cl_size[k] = sz; a.cid_of_root[root] = k; a.cl_flags[k] = 0;
+        nk += sz;
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.acc_sum[k * 6 + q] = 0ull;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { a.acc_box[k * 6 + q] = 0xFFFFFFFFu; a.acc_box[k * 6 + 3 + q] = 0u; }
+    }
+    atomicAdd(&a.counts[MOR_CNT_NK], nk);
+    if (threadIdx.x == 0) a.counts[MOR_CNT_K] = K;
+}
+
+// ===================================================================================== K7
+// Per-cluster statistics (cpp:221-244): cluster id of every point, exact coordinate sums for
+// compute3DCentroid<double> (A10) and getMinMax3D bounding boxes (cpp:272-275), warp-aggregated.
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned warp_min_u(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned warp_max_u(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// Accumulate the bounding box of (x,y,z) into box[k*6..] for valid lanes; whole warp must call.
+__device__ __forceinline__ void warp_box_accumulate(unsigned* box, int k, bool valid, float x, float y, float z) {
+    const unsigned vmask = __ballot_sync(kFull, valid);
+    if (!vmask) return;
+    const int k0 = __shfl_sync(kFull, k, __ffs(vmask) - 1);
+    const bool uniform = __all_sync(kFull, !valid || k == k0);
+    unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
+    if (uniform) {
+        unsigned mnx = warp_min_u(valid ? kx : 0xFFFFFFFFu), mny = warp_min_u(valid ? ky : 0xFFFFFFFFu), mnz = warp_min_u(valid ? kz : 0xFFFFFFFFu);
+        unsigned mxx = warp_max_u(valid ? kx : 0u), mxy = warp_max_u(valid ? ky : 0u), mxz = warp_max_u(valid ? kz : 0u);
+        if ((threadIdx.x & 31) == 0) {
+            unsigned* b = box + k0 * 6;
+            atomicMin(b + 0, mnx); atomicMin(b + 1, mny); atomicMin(b + 2, mnz);
+            atomicMax(b + 3, mxx); atomicMax(b + 4, mxy); atomicMax(b + 5, mxz);
+        }
+    } else if (valid) {
+        unsigned* b = box + k * 6;
+        atomicMin(b + 0, kx); atomicMin(b + 1, ky); atomicMin(b + 2, kz);
+        atomicMax(b + 3, kx); atomicMax(b + 4, ky); atomicMax(b + 5, kz);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_cluster_stats(FramePtrs a) {
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int nc = a.counts[MOR_CNT_NC];
+    // whole warps stay alive for the shuffles
+    if ((s & ~31) >= nc) return;
+    const bool in = s < nc;
+    float4 p = make_float4(0, 0, 0, 0);
+    int k = -1;
+    if (in) {
+        p = a.spts[s];
+        const int c = __float_as_int(p.w);
+        k = a.cid_of_root[a.label[c]];
+        a.cid[c] = k;
+    }
+    const bool valid = k >= 0;
+    const unsigned vmask = __ballot_sync(kFull, valid);
+    if (!vmask) return;
+    long long h[3], l[3];
+    split_fixed(p.x, h[0], l[0]); split_fixed(p.y, h[1], l[1]); split_fixed(p.z, h[2], l[2]);
+    const int k0 = __shfl_sync(kFull, k, __ffs(vmask) - 1);
+    const bool uniform = __all_sync(kFull, !valid || k == k0);
+    if (uniform) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const long long sh = warp_sum_ll(valid ? h[q] : 0ll), sl = warp_sum_ll(valid ? l[q] : 0ll);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&a.acc_sum[k0 * 6 + q * 2], (unsigned long long)sh);
+                atomicAdd(&a.acc_sum[k0 * 6 + q * 2 + 1], (unsigned long long)sl);
+            }
+        }
+    } else if (valid) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            atomicAdd(&a.acc_sum[k * 6 + q * 2], (unsigned long long)h[q]);
+            atomicAdd(&a.acc_sum[k * 6 + q * 2 + 1], (unsigned long long)l[q]);
+        }
+    }
+    warp_box_accumulate(a.acc_box, k, valid, p.x, p.y, p.z);
+}
+
+// ===================================================================================== K8
+// pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12) and the bounding box
+// of the transformed points (getMinMax3D runs after the transform, cpp:272).
+__global__ void __launch_bounds__(kBlock) k_transform_prev(FramePtrs a) {
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int ncp = a.p_counts[MOR_CNT_NC];
+    if ((s & ~31) >= ncp) return;
+    int k = -1;
+    float3 t = make_float3(0, 0, 0);
+    if (s < ncp) {
+        const float4 p = a.p_spts[s];
+        const int c = __float_as_int(p.w);
+        k = a.p_cid[c];
+        if (k >= 0) {
+            t = xform(a.M, p.x, p.y, p.z);
+            a.tpts[c] = make_float4(t.x, t.y, t.z, __int_as_float(k));
+        } else {
+            a.tpts[c] = make_float4(0, 0, 0, __int_as_float(-1));
+        }
+    }
+    warp_box_accumulate(a.pacc_box, k, k >= 0, t.x, t.y, t.z);
+}
+
+__global__ void __launch_bounds__(kBlock) k_init_prev_boxes(FramePtrs a) {
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= a.p_counts[MOR_CNT_K]) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++) { a.pacc_box[k * 6 + q] = 0xFFFFFFFFu; a.pacc_box[k * 6 + 3 + q] = 0u; }
+}
+
+// Block-wide ordered compaction helper for the single-block kernels: returns the exclusive rank of
+// `flag` among all threads, *total = number of set flags. kSingle threads.
+__device__ __forceinline__ int single_block_rank(bool flag, int* total) {
+    __shared__ int s_w[kSingle / 32];
+    __shared__ int s_tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(kFull, flag);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_w[lane], inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_w[lane] = inc - v;
+        if (lane == 31) s_tot = inc;
+    }
+    __syncthreads();
+    const int r = s_w[warp] + __popc(m & ((1u << lane) - 1u));
+    *total = s_tot;
+    __syncthreads();
+    return r;
+}
+
+// ===================================================================================== K9
+// Finalise centroids/boxes, transform the previous centroids (cpp:540-541), reciprocal 1-NN between
+// centroid sets (cpp:291-294, A16), volume constraint (cpp:264-283, A17), per-match octree anchors.
+__global__ void __launch_bounds__(kSingle) k_finalize_clusters(FramePtrs a) {
+    const int K = a.counts[MOR_CNT_K];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        const double n = (double)a.cl_size[k];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            a.cl_centroid[k * 3 + q] = (float)join_fixed_mean((long long)a.acc_sum[k * 6 + q * 2], (long long)a.acc_sum[k * 6 + q * 2 + 1], n);
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.cl_bbox[k * 6 + q] = fkey_inv(a.acc_box[k * 6 + q]);
+    }
+}
+
+__device__ __forceinline__ int nn_brute(const float* pts, int n, float qx, float qy, float qz, float* out_d) {
+    int best = -1;
+    float bd = 3.402823466e+38f;
+    for (int i = 0; i < n; i++) {
+        const float d = sqdist3(qx, qy, qz, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]);
+        if (d < bd) { bd = d; best = i; }  // ties -> lowest index
+    }
+    *out_d = bd;
+    return best;
+}
+
+__global__ void __launch_bounds__(kSingle) k_match(FramePtrs a) {
+    const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K];
+    // previous centroids and boxes into the current frame
+    for (int i = threadIdx.x; i < Kp; i += kSingle) {
+        const float3 t = xform(a.M, a.p_cl_centroid[i * 3], a.p_cl_centroid[i * 3 + 1], a.p_cl_centroid[i * 3 + 2]);
+        a.pct[i * 3] = t.x; a.pct[i * 3 + 1] = t.y; a.pct[i * 3 + 2] = t.z;
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.pbbox[i * 6 + q] = fkey_inv(a.pacc_box[i * 6 + q]);
+        a.match_of_prev[i] = -1; a.mid_of_prev[i] = -1;
+    }
+    for (int j = threadIdx.x; j < K; j += kSingle) a.mid_of_cur[j] = -1;
+    __syncthreads();
+    // reciprocal correspondences, ascending query index
+    int n_recip = 0;
+    for (int base = 0; base < Kp; base += kSingle) {
+        const int i = base + threadIdx.x;
+        bool ok = false; int j = -1; float d = 0.f;
+        if (i < Kp && K > 0) {
+            j = nn_brute(a.cl_centroid, K, a.pct[i * 3], a.pct[i * 3 + 1], a.pct[i * 3 + 2], &d);
+            float dr;
+            const int ir = nn_brute(a.pct, Kp, a.cl_centroid[j * 3], a.cl_centroid[j * 3 + 1], a.cl_centroid[j * 3 + 2], &dr);
+            ok = (ir == i);
+        }
+        int tot;
+        const int r = single_block_rank(ok, &tot);
+        if (ok) { a.recip_q[n_recip + r] = i; a.recip_m[n_recip + r] = j; a.match_dist[n_recip + r] = d; }
+        n_recip += tot;
+    }
+    __syncthreads();
+    // volume constraint; match_dist is rewritten in place (rank <= index, chunked with barriers)
+    int n_match = 0, p1 = 0, p2 = 0;
+    for (int base = 0; base < n_recip; base += kSingle) {
+        const int u = base + threadIdx.x;
+        bool ok = false; int i = -1, j = -1; float d = 0.f;
+        if (u < n_recip) {
+            i = a.recip_q[u]; j = a.recip_m[u]; d = a.match_dist[u];
+            const float* bp = a.pbbox + i * 6; const float* bc = a.cl_bbox + j * 6;
+            const double volp = (double)__fmul_rn(__fmul_rn(__fsub_rn(bp[3], bp[0]), __fsub_rn(bp[4], bp[1])), __fsub_rn(bp[5], bp[2]));
+            const double volc = (double)__fmul_rn(__fmul_rn(__fsub_rn(bc[3], bc[0]), __fsub_rn(bc[4], bc[1])), __fsub_rn(bc[5], bc[2]));
+            ok = (fabs(volp - volc) / (volp + volc)) < (double)a.volume_constraint;  // NaN -> false
+        }
+        int tot;
+        const int r = single_block_rank(ok, &tot);
+        if (ok) {
+            const int m = n_match + r;
+            a.match_q[m] = i; a.match_m[m] = j; a.match_dist[m] = d;
+            a.match_of_prev[i] = j; a.mid_of_prev[i] = m; a.mid_of_cur[j] = m;
+            a.newcount[m] = 0; a.match_score[m] = 0.0;
+            // OctreePointCloudChangeDetector lattice anchor from the first point of the previous cluster
+            // (its min-index point) - PCL 1.8 adoptBoundingBoxToPoint + getKeyBitSize (A13)
+            const float4 f = a.tpts[a.p_cl_root[i]];
+            const double res = (double)0.1f, eps = (double)1.1920928955078125e-07f;
+            const double fv[3] = {(double)f.x, (double)f.y, (double)f.z};
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const double lo = fv[q] - res / 2, hi = fv[q] + res / 2;
+                const double side = 2.0 * res - eps;
+                const double over = (side - (hi - lo)) / 2.0;
+                a.anchor[m * 3 + q] = lo - over;
+            }
+            atomicAdd(&a.counts[MOR_CNT_P1], a.p_cl_size[i]);
+            atomicAdd(&a.counts[MOR_CNT_P2], a.cl_size[j]);
+        }
+        n_match += tot;
+    }
+    (void)p1; (void)p2;
+    if (threadIdx.x == 0) {
+        a.counts[MOR_CNT_MU] = n_recip; a.counts[MOR_CNT_M] = n_match;
+        a.counts[MOR_CNT_NKPREV] = a.p_counts[MOR_CNT_NK];
+    }
+}
+
+// ===================================================================================== K10 / K11 (method 2)
+// pcl::octree::OctreePointCloudChangeDetector (cpp:319-330, A13): the leaf lattice of every matched
+// pair is floor((p - anchor)/res) in double; the occupied leaves of the transformed previous cluster
+// go into one global hash set keyed (match, ix, iy, iz); the score is the number of points of the
+// current cluster whose leaf is absent.
+__device__ __forceinline__ bool lattice_key(const FramePtrs& a, int m, float x, float y, float z, unsigned long long* key) {
+    const double res = (double)0.1f;
+    const long long ix = (long long)floor(((double)x - a.anchor[m * 3]) / res);
+    const long long iy = (long long)floor(((double)y - a.anchor[m * 3 + 1]) / res);
+    const long long iz = (long long)floor(((double)z - a.anchor[m * 3 + 2]) / res);
+    const bool ok = ix >= -32768 && ix < 32768 && iy >= -32768 && iy < 32768 && iz >= -32768 && iz < 32768;
+    *key = ((unsigned long long)(unsigned)m << 48) | ((unsigned long long)(ix + 32768) << 32) | ((unsigned long long)(iy + 32768) << 16) |
+           (unsigned long long)(iz + 32768);
+    return ok;
+}
+
+__global__ void __launch_bounds__(kBlock) k_lattice_insert(FramePtrs a) {
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= a.p_counts[MOR_CNT_NC]) return;
+    const float4 t = a.tpts[c];
+    const int k = __float_as_int(t.w);
+    if (k < 0) return;
+    const int m = a.mid_of_prev[k];
+    if (m < 0) return;
+    unsigned long long key;
+    if (!lattice_key(a, m, t.x, t.y, t.z, &key)) { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); return; }
+    hset_insert(a.lattice, a.lattice_mask, key);
+}
+
+__global__ void __launch_bounds__(kBlock) k_lattice_count(FramePtrs a) {
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= a.counts[MOR_CNT_NC]) return;
+    const float4 p = a.spts[s];
+    const int c = __float_as_int(p.w);
+    const int k = a.cid[c];
+    const int m = k >= 0 ? a.mid_of_cur[k] : -1;
+    bool is_new = false;
+    if (m >= 0) {
+        unsigned long long key;
+        if (lattice_key(a, m, p.x, p.y, p.z, &key)) is_new = !hset_contains(a.lattice, a.lattice_mask, key);
+        else { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); is_new = true; }
+    }
+    if (is_new) {
+        const unsigned same = __match_any_sync(__activemask(), m);
+        if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.newcount[m], __popc(same));
+    }
+}
+
+// ===================================================================================== K10' (method 1)
+// CorrespondenceEstimation::determineCorrespondences (cpp:343-361): for every point of the transformed
+// previous cluster the nearest point of the matched current cluster; only squared distances inside
+// (pde_lb, pde_ub) count, so the search is bounded by sqrt(pde_ub) on the clustering grid.
+__global__ void __launch_bounds__(kBlock) k_pde_count(FramePtrs a, int ring) {
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= a.p_counts[MOR_CNT_NC]) return;
+    const float4 t = a.tpts[c];
+    const int kp = __float_as_int(t.w);
+    if (kp < 0) return;
+    const int m = a.mid_of_prev[kp];
+    if (m < 0) return;
+    const int target = a.match_m[m];
+    const GridDesc& g = a.grid;
+    const int cx = (int)floor(((double)t.x - g.ox) * g.inv_h), cy = (int)floor(((double)t.y - g.oy) * g.inv_h), cz = (int)floor(((double)t.z - g.oz) * g.inv_h);
+    float best = 3.402823466e+38f;
+    const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.nx - 1);
+    if (x0 <= x1) {
+        for (int zz = max(cz - ring, 0); zz <= min(cz + ring, g.nz - 1); zz++)
+            for (int yy = max(cy - ring, 0); yy <= min(cy + ring, g.ny - 1); yy++) {
+                const int base = (zz * g.ny + yy) * g.nx;
+                const int b = a.cell_start[base + x0], e = a.cell_start[base + x1 + 1];
+                for (int j = b; j < e; j++) {
+                    const float4 q = a.spts[j];
+                    if (a.cid[__float_as_int(q.w)] != target) continue;
+                    const float d = sqdist3(t.x, t.y, t.z, q.x, q.y, q.z);
+                    best = fminf(best, d);
+                }
+            }
+    }
+    if (best > a.pde_lb && best < a.pde_ub) atomicAdd(&a.newcount[m], 1);
+}
+
+// ===================================================================================== K12
+// Detection flags (cpp:580-606) and the N-frame consistency chain: checkMovingClusterChain
+// (cpp:478-514), recurseFindClusterChain (cpp:415-453), pushCentroid (cpp:455-476). corrs_vec /
+// res_vec are device-resident ring buffers; a correspondence map is stored as match_of_prev[].
+__global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
+    const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K], M = a.counts[MOR_CNT_M];
+    const int D = a.ring_depth, kmax = a.kmax;
+    TrackState* ts = a.track;
+    __shared__ int s_flag_any;
+    for (int m = threadIdx.x; m < M; m += kSingle) {
+        const unsigned long long n1 = (unsigned long long)a.p_cl_size[a.match_q[m]], n2 = (unsigned long long)a.cl_size[a.match_m[m]];
+        double score, thr;
+        if (a.method == 1) {
+            score = (double)a.newcount[m] / (double)((n1 + n2) / 2ull);  // cpp:361
+            thr = (double)a.pde_thr;                                       // cpp:586
+        } else {
+            score = (double)a.newcount[m];                                                 // cpp:330
+            thr = (double)((n1 + n2) / (unsigned long long)(long long)a.opc_factor);      // cpp:590, unsigned division
+        }
+        a.match_score[m] = score;
+        a.cl_flags[a.match_m[m]] = score > thr ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- checkMovingClusterChain: push buffers
+    const int corr_slot = (ts->corr_head + ts->corr_count) % D;
+    for (int i = threadIdx.x; i < Kp; i += kSingle) a.corr_ring[corr_slot * kmax + i] = a.match_of_prev[i];
+    int res_count = ts->res_count;
+    const int res_head = ts->res_head;
+    if (res_count == 0) {
+        const int slot = res_head % D;
+        for (int i = threadIdx.x; i < Kp; i += kSingle) a.res_ring[slot * kmax + i] = a.p_cl_flags[i];
+        if (threadIdx.x == 0) a.res_len[slot] = Kp;
+        res_count = 1;
+    }
+    {
+        const int slot = (res_head + res_count) % D;
+        for (int j = threadIdx.x; j < K; j += kSingle) a.res_ring[slot * kmax + j] = a.cl_flags[j];
+        if (threadIdx.x == 0) a.res_len[slot] = K;
+        res_count += 1;
+    }
+    if (threadIdx.x == 0) a.corr_len[corr_slot] = Kp;
+    const int corr_count = ts->corr_count + 1;
+    const int corr_head = ts->corr_head;
+    __syncthreads();
+    int n_mo = ts->n_mo;
+    if (res_count >= a.moving_confidence) {
+        const int r0 = res_head % D;
+        const int len0 = a.res_len[r0];
+        // every flagged cluster of the oldest frame is followed through all buffered maps
+        for (int i = threadIdx.x; i < len0; i += kSingle) {
+            int track = -1;
+            if (a.res_ring[r0 * kmax + i]) {
+                track = i;
+                for (int col = 0; col < corr_count && track >= 0; col++) {
+                    const int cs = (corr_head + col) % D;
+                    const int j = track < a.corr_len[cs] ? a.corr_ring[cs * kmax + track] : -1;
+                    const int rs = (res_head + col + 1) % D;
+                    track = (j >= 0 && a.res_ring[rs * kmax + j]) ? j : -1;
+                }
+            }
+            a.found[i] = track;
+        }
+        __syncthreads();
+        // keep the surviving chain ends, in ascending i (in place: write index <= read index)
+        int n_found = 0;
+        for (int base = 0; base < len0; base += kSingle) {
+            const int i = base + threadIdx.x;
+            const int f = i < len0 ? a.found[i] : -1;
+            int tot;
+            const int r = single_block_rank(f >= 0, &tot);
+            if (f >= 0) a.found[n_found + r] = f;
+            n_found += tot;
+            __syncthreads();
+        }
+        // pushCentroid in that order; the scan over mo_vec is parallel, the append is serial
+        for (int i = 0; i < n_found; i++) {
+            const int f = a.found[i];
+            const float px = a.cl_centroid[f * 3], py = a.cl_centroid[f * 3 + 1], pz = a.cl_centroid[f * 3 + 2];
+            if (threadIdx.x == 0) s_flag_any = 0;
+            __syncthreads();
+            bool close = false;
+            for (int t = threadIdx.x; t < n_mo; t += kSingle) {
+                const double dx = (double)__fsub_rn(px, a.mo_centroid[t * 3]), dy = (double)__fsub_rn(py, a.mo_centroid[t * 3 + 1]),
+                             dz = (double)__fsub_rn(pz, a.mo_centroid[t * 3 + 2]);
+                const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+                close |= dist < (double)a.catch_up;
+            }
+            if (close) s_flag_any = 1;
+            __syncthreads();
+            const bool any = s_flag_any != 0;
+            if (!any) {
+                if (n_mo < a.momax) {
+                    if (threadIdx.x == 0) {
+                        a.mo_centroid[n_mo * 3] = px; a.mo_centroid[n_mo * 3 + 1] = py; a.mo_centroid[n_mo * 3 + 2] = pz;
+                        a.mo_conf[n_mo] = a.static_confidence + 1;  // MovingObjectCentroid ctor, .h:91
+                    }
+                    n_mo++;
+                } else if (threadIdx.x == 0) {
+                    atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_MOVING_CAP);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (res_count >= a.moving_confidence) {  // pop_front both deques, cpp:511-512
+            ts->corr_head = (corr_head + 1) % D; ts->corr_count = corr_count - 1;
+            ts->res_head = (res_head + 1) % D; ts->res_count = res_count - 1;
+        } else {
+            ts->corr_count = corr_count; ts->res_count = res_count; ts->res_head = res_head % D;
+        }
+        ts->n_mo = n_mo;
+        a.counts[MOR_CNT_NMO] = n_mo;
+    }
+}
+
+// ===================================================================================== K13
+// filterCloud tracking part (cpp:630-671): 1-NN of every confirmed mover among the current centroids,
+// unconditional selection of that cluster (cpp:644-648), confidence update and erase.
+__global__ void __launch_bounds__(kSingle) k_track(FramePtrs a) {
+    const int K = a.counts[MOR_CNT_K];
+    TrackState* ts = a.track;
+    const int n_mo = ts->n_mo;
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    for (int k = threadIdx.x; k < K; k += kSingle) a.cluster_removed[k] = 0;
+    __syncthreads();
+    int kept_total = 0;
+    if (K > 0) {  // K == 0: un-built kd-tree in the reference (UB); defined here: entries untouched
+        for (int base = 0; base < n_mo; base += kSingle) {
+            const int t = base + threadIdx.x;
+            bool keep = false;
+            float cx = 0, cy = 0, cz = 0; int conf = 0;
+            if (t < n_mo) {
+                cx = a.mo_centroid[t * 3]; cy = a.mo_centroid[t * 3 + 1]; cz = a.mo_centroid[t * 3 + 2];
+                conf = a.mo_conf[t];
+                float d;
+                const int k = nn_brute(a.cl_centroid, K, cx, cy, cz, &d);
+                a.cluster_removed[k] = 1;
+                atomicAdd(&s_total, a.cl_size[k]);
+                if (!a.cl_flags[k] || d > a.leave_off) {  // cpp:650
+                    conf--;
+                    keep = conf != 0;
+                } else {
+                    cx = a.cl_centroid[k * 3]; cy = a.cl_centroid[k * 3 + 1]; cz = a.cl_centroid[k * 3 + 2];
+                    if (conf < a.static_confidence + 1) conf++;
+                    keep = true;
+                }
+            }
+            int tot;
+            const int r = single_block_rank(keep, &tot);  // barriers inside: all reads of this chunk precede the writes
+            if (keep) {
+                const int o = kept_total + r;
+                a.mo_centroid[o * 3] = cx; a.mo_centroid[o * 3 + 1] = cy; a.mo_centroid[o * 3 + 2] = cz;
+                a.mo_conf[o] = conf;
+            }
+            kept_total += tot;
+            __syncthreads();
+        }
+    } else {
+        kept_total = n_mo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ts->n_mo = kept_total;
+        a.counts[MOR_CNT_NMO] = kept_total;
+        // ExtractIndices: more indices than points => error, empty output (A18)
+        const int ov = s_total > a.counts[MOR_CNT_NC] ? 1 : 0;
+        ts->extract_overflow = ov;
+        a.counts[MOR_CNT_EXTRACT_OVERFLOW] = ov;
+    }
+}
+
+// ===================================================================================== K14
+// ExtractIndices(negative) of the moving points + append of the ground points (cpp:673-684), written
+// as pcl::PointXYZI wire records (cpp:690). Stable single-pass compaction over [cloud | ground].
+__global__ void __launch_bounds__(kBlock) k_output(FramePtrs a) {
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_out, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int nc = a.counts[MOR_CNT_NC], ng = a.counts[MOR_CNT_NG];
+    const int total_items = nc + ng;
+    const int last_tile = total_items ? (total_items - 1) / kBlock : 0;
+    if (tile > last_tile) return;
+    const int t = tile * kBlock + threadIdx.x;
+    const int overflow = a.track->extract_overflow;
+    bool keep = false;
+    float4 p = make_float4(0, 0, 0, 0);
+    if (t < nc) {
+        p = a.pts[t];
+        const int k = a.cid[t];
+        const bool removed = overflow || (k >= 0 && a.cluster_removed[k]);
+        keep = !removed;
+        if (removed) a.removed_mask[a.cloud_src[t]] = 2;
+    } else if (t < total_items) {
+        p = a.gpts[t - nc];
+        keep = true;
+    }
+    int tot;
+    const int in_block = block_exclusive_scan<int>(keep ? 1 : 0, &tot);
+    const int before = (int)tile_exclusive_prefix(a.st_out, tile, (unsigned long long)tot);
+    if (keep) {
+        const int o = before + in_block;
+        a.out[2 * o] = make_float4(p.x, p.y, p.z, 1.0f);
+        a.out[2 * o + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+    }
+    if (tile == last_tile && threadIdx.x == 0) a.counts[MOR_CNT_NOUT] = before + tot;
+}
+
+}  // namespace mor
