@@ -114,6 +114,10 @@ class MorBinding:
         self.get_last_device_ms = f("get_last_device_ms", [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)], True)
         self.set_timing = f("set_timing", [vp, C.c_int], True)
         self.last_error = f("last_error", [vp], True, C.c_char_p)
+        self.event_record = f("event_record", [vp, C.c_int], True)
+        self.event_elapsed_ms = f("event_elapsed_ms", [vp, C.c_int, C.c_int, C.POINTER(C.c_float)], True)
+        self.set_kernel_profiling = f("set_kernel_profiling", [vp, C.c_int], True)
+        self.get_kernel_profile = f("get_kernel_profile", [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], True)
 
     def _fn(self, name, argtypes, optional=False, restype=C.c_int):
         try:
@@ -247,6 +251,37 @@ class MovingObjectRemoval:
         n_out = C.c_uint32(0)
         self._check(self.b.filter_device(self.h, C.c_void_p(d_out), cap, C.byref(n_out) if want_count else None), "filter_device")
         return n_out.value
+
+    def event_record(self, slot: int):
+        self._check(self.b.event_record(self.h, slot), "event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._check(self.b.event_elapsed_ms(self.h, a, b, C.byref(ms)), "event_elapsed_ms")
+        return ms.value
+
+    def set_kernel_profiling(self, enabled: bool):
+        self._check(self.b.set_kernel_profiling(self.h, 1 if enabled else 0), "set_kernel_profiling")
+
+    def kernel_profile(self) -> dict:
+        """{kernel name: (total_ms, launches)} accumulated since profiling was enabled."""
+        out, i = {}, 0
+        while True:
+            name = C.create_string_buffer(32)
+            ms, n = C.c_double(0), C.c_uint64(0)
+            if self.b.get_kernel_profile(self.h, i, name, C.byref(ms), C.byref(n)):
+                break
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
+        return out
+
+    def set_timing(self, enabled: bool):
+        self._check(self.b.set_timing(self.h, 1 if enabled else 0), "set_timing")
+
+    def last_device_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(self.b.get_last_device_ms(self.h, C.byref(a), C.byref(b)), "get_last_device_ms")
+        return a.value, b.value
 
     def launch_count(self) -> int:
         v = C.c_uint64(0)

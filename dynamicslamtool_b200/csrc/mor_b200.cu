@@ -114,9 +114,47 @@ struct mor_handle {
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* h_counts = nullptr;  // pinned
+    // generic event slots (bench.py brackets its timed regions with these, on the handle's stream)
+    cudaEvent_t slot_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // per-kernel profiling (off by default: two extra event records per launch)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<int> prof_ids;  // kernel id of every recorded pair of the current frame
+    double prof_ms[32] = {0};
+    uint64_t prof_n[32] = {0};
 };
 
 namespace {
+
+enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
+                KID_INIT_PREV, KID_TRANSFORM_PREV, KID_MATCH, KID_CLEAR_LATTICE, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE, KID_CHAIN,
+                KID_TRACK, KID_OUTPUT, KID__COUNT };
+const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_scan_cells", "k_scatter", "k_link_cells", "k_flatten", "k_select_clusters",
+                                              "k_cluster_stats", "k_finalize_clusters", "k_init_prev_boxes", "k_transform_prev", "k_match",
+                                              "memset_lattice", "k_lattice_insert", "k_lattice_count", "k_pde_count", "k_flags_and_chain", "k_track",
+                                              "k_output"};
+
+inline void prof_begin(mor_handle* h, int id) {
+    if (!h->profiling) return;
+    const size_t i = h->prof_ids.size() * 2;
+    while (h->prof_pool.size() < i + 2) { cudaEvent_t e; cudaEventCreate(&e); h->prof_pool.push_back(e); }
+    cudaEventRecord(h->prof_pool[i], h->stream);
+    h->prof_ids.push_back(id);
+}
+inline void prof_end(mor_handle* h) {
+    if (!h->profiling) return;
+    cudaEventRecord(h->prof_pool[h->prof_ids.size() * 2 - 1], h->stream);
+}
+void prof_harvest(mor_handle* h) {  // stream must be idle
+    for (size_t i = 0; i < h->prof_ids.size(); i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_pool[2 * i], h->prof_pool[2 * i + 1]) == cudaSuccess) { h->prof_ms[h->prof_ids[i]] += ms; h->prof_n[h->prof_ids[i]]++; }
+    }
+    h->prof_ids.clear();
+}
+// Every device operation of the hot path goes through this: counted (mor_get_launch_count) and, when
+// profiling is on, bracketed by events on the handle's stream.
+#define MOR_LAUNCH(id, ...) do { prof_begin(h, id); __VA_ARGS__; prof_end(h); h->launches++; } while (0)
 
 template <typename T>
 T* carve(uint8_t*& p, size_t count) {
@@ -127,11 +165,12 @@ T* carve(uint8_t*& p, size_t count) {
 
 int build_grid(mor_handle* h) {
     const mor_config& c = h->cfg;
-    // A7: r2 = (float)((double)tol * (double)tol); effective radius = sqrt(r2); cell edge slightly larger so
-    // that float-rounded coordinates of two points with d2 < r2 never land two cells apart.
+    // A7: r2 = (float)((double)tol * (double)tol); effective radius = sqrt(r2). Cell edge h = r/sqrt(3) shrunk by
+    // 2^-10: the diagonal of a cell stays below r even after float rounding of the distance (every two points of
+    // a cell are neighbours), and d < r implies a cell offset of at most 2 per axis (r/h = 1.734).
     const float r2 = (float)((double)c.ec_distance_threshold * (double)c.ec_distance_threshold);
     if (!(r2 > 0.f) || !(c.trim_x > 0.f) || !(c.trim_y > 0.f)) return MOR_ERR_CONFIG_VALUE;
-    const double hcell = std::sqrt((double)r2) * (1.0 + 1.0 / 1024.0);
+    const double hcell = std::sqrt((double)r2) / std::sqrt(3.0) * (1.0 - 1.0 / 1024.0);
     GridDesc g;
     g.ox = -(double)c.trim_x; g.oy = -(double)c.trim_y;
     double zlo, zhi;
@@ -141,6 +180,7 @@ int build_grid(mor_handle* h) {
     g.oz = zlo; g.inv_h = 1.0 / hcell;
     const double fx = std::floor(2.0 * (double)c.trim_x / hcell) + 1, fy = std::floor(2.0 * (double)c.trim_y / hcell) + 1, fz = std::floor((zhi - zlo) / hcell) + 1;
     if (fx * fy * fz > 268435456.0) return MOR_ERR_CAPACITY;  // 2^28 cells = 2 GB of cell tables
+    if (fx < 1 || fy < 1 || fz < 1) return MOR_ERR_CONFIG_VALUE;
     g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
     h->grid = g;
     h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / hcell);
@@ -173,6 +213,7 @@ int allocate(mor_handle* h) {
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
         b.cell_key = carve<int>(p, N); b.cell_rank = carve<int>(p, N); b.skey = carve<int>(p, N);
         b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
+        b.comp = carve<int>(p, N); b.minidx = carve<int>(p, N); b.done = carve<unsigned long long>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
         b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
         b.recip_q = carve<int>(p, K); b.recip_m = carve<int>(p, K); b.match_q = carve<int>(p, K); b.match_m = carve<int>(p, K);
@@ -237,33 +278,28 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     std::memcpy(a.M.m, h->M, sizeof(h->M));
 
     const unsigned gb = blocks_for(n);
-    MOR_CUDA(cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, st));
-    k_ingest<<<gb, kBlock, 0, st>>>(a);
-    k_scan_cells<<<(h->grid.ncells + kTile - 1) / kTile, kBlock, 0, st>>>(a);
-    k_scatter<<<gb, kBlock, 0, st>>>(a);
-    k_neighbors<<<gb, kBlock, 0, st>>>(a);
-    k_flatten<<<gb, kBlock, 0, st>>>(a);
-    k_select_clusters<<<1, kSingle, h->select_smem, st>>>(a);
-    k_cluster_stats<<<gb, kBlock, 0, st>>>(a);
-    k_finalize_clusters<<<8, kSingle, 0, st>>>(a);
-    h->launches += 8;
+    MOR_LAUNCH(KID_CLEAR, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, st));
+    MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<(h->grid.ncells + kTile - 1) / kTile, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<<<gb, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<gb, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_SELECT, (k_select_clusters<<<1, kSingle, h->select_smem, st>>>(a)));
+    MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<gb, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_FINALIZE, (k_finalize_clusters<<<8, kSingle, 0, st>>>(a)));
     if (h->two_frames) {
         const unsigned gp = blocks_for(h->n_prev_input);
-        k_init_prev_boxes<<<(h->kmax + kBlock - 1) / kBlock, kBlock, 0, st>>>(a);
-        k_transform_prev<<<gp, kBlock, 0, st>>>(a);
-        k_match<<<1, kSingle, 0, st>>>(a);
-        h->launches += 3;
+        MOR_LAUNCH(KID_INIT_PREV, (k_init_prev_boxes<<<(h->kmax + kBlock - 1) / kBlock, kBlock, 0, st>>>(a)));
+        MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<gp, kBlock, 0, st>>>(a)));
+        MOR_LAUNCH(KID_MATCH, (k_match<<<1, kSingle, 0, st>>>(a)));
         if (h->cfg.method_choice == 2) {
-            MOR_CUDA(cudaMemsetAsync(a.lattice, 0xFF, h->lattice_cap * sizeof(unsigned long long), st));
-            k_lattice_insert<<<gp, kBlock, 0, st>>>(a);
-            k_lattice_count<<<gb, kBlock, 0, st>>>(a);
-            h->launches += 2;
+            MOR_LAUNCH(KID_CLEAR_LATTICE, cudaMemsetAsync(a.lattice, 0xFF, h->lattice_cap * sizeof(unsigned long long), st));
+            MOR_LAUNCH(KID_LATTICE_INSERT, (k_lattice_insert<<<gp, kBlock, 0, st>>>(a)));
+            MOR_LAUNCH(KID_LATTICE_COUNT, (k_lattice_count<<<gb, kBlock, 0, st>>>(a)));
         } else {
-            k_pde_count<<<gp, kBlock, 0, st>>>(a, h->pde_ring);
-            h->launches += 1;
+            MOR_LAUNCH(KID_PDE, (k_pde_count<<<gp, kBlock, 0, st>>>(a, h->pde_ring)));
         }
-        k_flags_and_chain<<<1, kSingle, 0, st>>>(a);
-        h->launches += 1;
+        MOR_LAUNCH(KID_CHAIN, (k_flags_and_chain<<<1, kSingle, 0, st>>>(a)));
     }
     MOR_CUDA(cudaGetLastError());
     return MOR_OK;
@@ -276,6 +312,7 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
     if (n > h->nmax) { h->last_error = "frame larger than mor_limits.max_points"; return MOR_ERR_CAPACITY; }
     MOR_CUDA(cudaSetDevice(h->device));
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    if (h->profiling && !h->prof_ids.empty()) { MOR_CUDA(cudaStreamSynchronize(h->stream)); prof_harvest(h); }
     const uint8_t* d_points = (const uint8_t*)data;
     if (!on_device) {
         const size_t bytes = (size_t)n * step;
@@ -308,15 +345,15 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     if (on_device && out) a.out = (float4*)out;  // write the records straight into the caller's device buffer
     else a.out = h->base.out;
     if (on_device && out && cap_points < h->n_input) { h->last_error = "device output buffer must hold n_input points"; return MOR_ERR_CAPACITY; }
-    k_track<<<1, kSingle, 0, st>>>(a);
-    k_output<<<blocks_for(h->n_input), kBlock, 0, st>>>(a);
-    h->launches += 2;
+    MOR_LAUNCH(KID_TRACK, (k_track<<<1, kSingle, 0, st>>>(a)));
+    MOR_LAUNCH(KID_OUTPUT, (k_output<<<blocks_for(h->n_input), kBlock, 0, st>>>(a)));
     MOR_CUDA(cudaGetLastError());
     h->filtered = true;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[3], st));
-    if (on_device && !n_out) return MOR_OK;  // fully asynchronous device-resident mode
+    if (on_device && !n_out && !h->profiling) return MOR_OK;  // fully asynchronous device-resident mode
     MOR_CUDA(cudaMemcpyAsync(h->h_counts, a.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, st));
     MOR_CUDA(cudaStreamSynchronize(st));
+    if (h->profiling) prof_harvest(h);
     const uint32_t no = (uint32_t)h->h_counts[MOR_CNT_NOUT];
     if (n_out) *n_out = no;
     if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
@@ -376,6 +413,8 @@ int mor_destroy(mor_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->slot_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->prof_pool) cudaEventDestroy(e);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->arena) cudaFree(h->arena);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -446,6 +485,37 @@ int mor_get_last_device_ms(mor_handle* h, float* push_ms, float* filter_ms) {
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     if (push_ms) MOR_CUDA(cudaEventElapsedTime(push_ms, h->ev[0], h->ev[1]));
     if (filter_ms) MOR_CUDA(cudaEventElapsedTime(filter_ms, h->ev[2], h->ev[3]));
+    return MOR_OK;
+}
+
+int mor_event_record(mor_handle* h, int slot) {
+    if (!h || slot < 0 || slot >= 8) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    if (!h->slot_ev[slot]) MOR_CUDA(cudaEventCreate(&h->slot_ev[slot]));
+    MOR_CUDA(cudaEventRecord(h->slot_ev[slot], h->stream));
+    return MOR_OK;
+}
+int mor_event_elapsed_ms(mor_handle* h, int slot_a, int slot_b, float* ms) {
+    if (!h || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !h->slot_ev[slot_a] || !h->slot_ev[slot_b]) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    MOR_CUDA(cudaEventSynchronize(h->slot_ev[slot_b]));
+    MOR_CUDA(cudaEventElapsedTime(ms, h->slot_ev[slot_a], h->slot_ev[slot_b]));
+    return MOR_OK;
+}
+int mor_set_kernel_profiling(mor_handle* h, int enabled) {
+    if (!h) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    if (!h->prof_ids.empty()) prof_harvest(h);
+    h->profiling = enabled != 0;
+    if (enabled) { std::memset(h->prof_ms, 0, sizeof(h->prof_ms)); std::memset(h->prof_n, 0, sizeof(h->prof_n)); }
+    return MOR_OK;
+}
+int mor_get_kernel_profile(mor_handle* h, int index, char name[32], double* total_ms, uint64_t* launches) {
+    if (!h || index < 0 || index >= KID__COUNT || !name || !total_ms || !launches) return MOR_ERR_ARG;
+    std::snprintf(name, 32, "%s", kKernelNames[index]);
+    *total_ms = h->prof_ms[index];
+    *launches = h->prof_n[index];
     return MOR_OK;
 }
 

@@ -9,10 +9,12 @@
 namespace mor {
 
 constexpr int kSingle = 1024;  // threads of the single-block bookkeeping kernels
+constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8 };
 
-struct GridDesc {  // uniform grid over `cloud`; cell edge h = r*(1+2^-10) so d<r => |dcell| <= 1 per axis
+struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-10): two points of one cell are always
+                   // within r (one union-find node per cell) and d<r => |dcell| <= 2 per axis
     double ox, oy, oz, inv_h;
     int nx, ny, nz, ncells;
 };
@@ -48,6 +50,8 @@ struct FramePtrs {
     int* cloud_src; float4* gpts; int* gsrc;
     int* cell_key; int* cell_rank; int* skey;
     int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
+    int* comp; int* minidx; unsigned long long* done;  // indexed by sorted position (cell leaders)
+    uint4* cell_box;  // [2*N] per leader position: {min x,y,z keys, count}, {max x,y,z keys, 0}
     unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
     unsigned* acc_box;            // [kmax*6] min xyz, max xyz keys
     unsigned* pacc_box;           // [kmax*6] transformed prev clusters
@@ -115,8 +119,8 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
         const int key = (cz * g.ny + cy) * g.nx + cx;
         a.cell_key[c] = key;
         a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
-        a.parent[c] = c;
-        a.comp_size[c] = 0;
+        a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // slot c doubles as a sorted position
+        a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
     } else if (cls == 2) {
         const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
         a.gpts[gi] = make_float4(x, y, z, w);
@@ -165,7 +169,9 @@ __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
 }
 
 // ===================================================================================== K3
-// Scatter cloud points into cell-sorted order (float4 xyz + cloud index) for the neighbour search.
+// Scatter cloud points into cell-sorted order (float4 xyz + cloud index) for the neighbour search and
+// reset the per-position union-find state. The first point of a cell (its "leader" position
+// cell_start[key]) is the union-find node of the whole cell.
 __global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) {
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.counts[MOR_CNT_NC]) return;
@@ -175,61 +181,117 @@ __global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) {
     p.w = __int_as_float(c);
     a.spts[pos] = p;
     a.skey[pos] = key;
+    a.parent[c] = c;  // c doubles as a sorted position here: both index spaces are [0, N_c)
+    a.comp_size[c] = 0;
+    a.minidx[c] = 0x7FFFFFFF;
+    a.done[c] = 0ull;
+    // tight bounding box of every crowded cell (prunes the point-vs-cell scans of k_link_cells);
+    // lanes of a warp that fall into the same cell are combined with redux before the atomics
+    const int cnt = a.cell_start[key + 1] - a.cell_start[key];
+    if (cnt > kBoxMinCount) {
+        const unsigned grp = __match_any_sync(__activemask(), key);
+        const unsigned kx = fkey(p.x), ky = fkey(p.y), kz = fkey(p.z);
+        const unsigned mnx = __reduce_min_sync(grp, kx), mny = __reduce_min_sync(grp, ky), mnz = __reduce_min_sync(grp, kz);
+        const unsigned mxx = __reduce_max_sync(grp, kx), mxy = __reduce_max_sync(grp, ky), mxz = __reduce_max_sync(grp, kz);
+        if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
+            unsigned* b = reinterpret_cast<unsigned*>(a.cell_box + 2 * a.cell_start[key]);
+            atomicMin(b + 0, mnx); atomicMin(b + 1, mny); atomicMin(b + 2, mnz);
+            atomicMax(b + 4, mxx); atomicMax(b + 5, mxy); atomicMax(b + 6, mxz);
+        }
+    }
 }
 
 // ===================================================================================== K4
-// pcl::EuclideanClusterExtraction radius graph (cpp:213-218; A5-A7): for every point, the 27-cell
-// neighbourhood is 9 x-rows, each a contiguous run of the sorted array. Pairs are visited once
-// (j > s) and every pair with L2_Simple distance < r2 (strict) is merged in the union-find.
-__global__ void __launch_bounds__(kBlock) k_neighbors(FramePtrs a) {
+// pcl::EuclideanClusterExtraction radius graph (cpp:213-218; A5-A7) on cell granularity. Every point q
+// looks at the 62 "backward" cells of its 5x5x5 neighbourhood (13 x-rows, each a contiguous run of the
+// sorted array); the first point of such a cell with L2_Simple distance < r2 (strict) connects the two
+// cells. A 62-bit mask per cell records the pairs already united, so each connected cell pair costs
+// one atomicOr + one union, however many point pairs realise it.
+__device__ __forceinline__ unsigned long long ld_done(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
     const int s = blockIdx.x * kBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
-    const float4 p = a.spts[s];
-    const int c = __float_as_int(p.w);
+    const float4 q = a.spts[s];
     const int key = a.skey[s];
     const GridDesc& g = a.grid;
     const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    int my_root = c;
-    bool rooted = false;
-    for (int dz = 0; dz <= 1; dz++) {  // rows with dz < 0 lie entirely before s in sorted order
-        const int zz = cz + dz;
-        if (zz >= g.nz) continue;
-        for (int dy = (dz == 0 ? 0 : -1); dy <= 1; dy++) {
-            const int yy = cy + dy;
-            if (yy < 0 || yy >= g.ny) continue;
+    const int lead = a.cell_start[key];
+    unsigned long long dmask = ld_done(a.done + lead);
+    const float r2_prune = a.r2 * 1.00001f;
+    const int x0 = max(cx - 2, 0);
+    int row = 0;
+    for (int dz = -2; dz <= 0; dz++) {
+        for (int dy = -2; dy <= (dz == 0 ? 0 : 2); dy++, row++) {
+            const int zz = cz + dz, yy = cy + dy;
+            if (zz < 0 || yy < 0 || yy >= g.ny) continue;
+            const int x1 = (dz == 0 && dy == 0) ? cx - 1 : min(cx + 2, g.nx - 1);
+            if (x1 < x0) continue;
             const int base = (zz * g.ny + yy) * g.nx;
-            int b = a.cell_start[base + x0];
+            int j = a.cell_start[base + x0];
             const int e = a.cell_start[base + x1 + 1];
-            b = max(b, s + 1);
-            for (int j = b; j < e; j++) {
-                const float4 q = a.spts[j];
-                if (sqdist3(p.x, p.y, p.z, q.x, q.y, q.z) < a.r2) {
-                    const int jc = __float_as_int(q.w);
-                    if (!rooted) { my_root = uf_find(a.parent, c); rooted = true; }
-                    if (ld_parent(a.parent + jc) != my_root) my_root = uf_union(a.parent, c, jc);
+            while (j < e) {
+                const int kj = a.skey[j];
+                const int cell_end = a.cell_start[kj + 1];
+                const int bit = row * 5 + (kj - base - cx + 2);
+                bool skip = (dmask >> bit) & 1ull;
+                if (!skip && cell_end - j > kBoxMinCount) {
+                    // conservative point-to-box distance: no point of the cell can be closer than this
+                    const uint4 lo = a.cell_box[2 * j], hi = a.cell_box[2 * j + 1];
+                    const float ex = fmaxf(fmaxf(fkey_inv(lo.x) - q.x, q.x - fkey_inv(hi.x)), 0.f);
+                    const float ey = fmaxf(fmaxf(fkey_inv(lo.y) - q.y, q.y - fkey_inv(hi.y)), 0.f);
+                    const float ez = fmaxf(fmaxf(fkey_inv(lo.z) - q.z, q.z - fkey_inv(hi.z)), 0.f);
+                    skip = ex * ex + ey * ey + ez * ez > r2_prune;
                 }
+                if (!skip) {
+                    bool hit = false;
+                    for (int it = 0; j < cell_end; j++, it++) {
+                        const float4 p = a.spts[j];
+                        if (sqdist3(q.x, q.y, q.z, p.x, p.y, p.z) < a.r2) { hit = true; break; }
+                        if ((it & 63) == 63) {  // somebody else of my cell may have connected this pair meanwhile
+                            dmask |= ld_done(a.done + lead);
+                            if ((dmask >> bit) & 1ull) break;
+                        }
+                    }
+                    if (hit) {
+                        dmask |= ld_done(a.done + lead);
+                        if (!((dmask >> bit) & 1ull)) {
+                            const unsigned long long old = atomicOr(a.done + lead, 1ull << bit);
+                            dmask |= old | (1ull << bit);
+                            if (!((old >> bit) & 1ull)) uf_union(a.parent, lead, a.cell_start[kj]);
+                        }
+                    }
+                }
+                j = cell_end;
             }
         }
     }
 }
 
 // ===================================================================================== K5
-// Pointer-jump every point to its root (= min cloud index of its component), count component sizes
-// with warp-aggregated atomics (sorted order keeps a warp inside one component most of the time) and
-// collect the roots.
+// Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud
+// index of every component (the canonical label) with warp-aggregated atomics, collect the roots.
 __global__ void __launch_bounds__(kBlock) k_flatten(FramePtrs a) {
     const int s = blockIdx.x * kBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
     const int c = __float_as_int(a.spts[s].w);
-    const int r = uf_find(a.parent, c);
-    a.label[c] = r;
-    if (r == c) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = c;
+    const int lead = a.cell_start[a.skey[s]];
+    const int r = uf_find(a.parent, lead);
+    a.comp[s] = r;
+    if (r == s) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s;
     const unsigned active = __activemask();
     const unsigned same = __match_any_sync(active, r);
-    if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.comp_size[r], __popc(same));
+    const int mn = __reduce_min_sync(same, c);
+    if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
+        atomicAdd(&a.comp_size[r], __popc(same));
+        atomicMin(&a.minidx[r], mn);
+    }
 }
 
 // ===================================================================================== K6
@@ -242,8 +304,9 @@ __global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
     __syncthreads();
     const int n_roots = a.scratch->n_roots;
     for (int t = threadIdx.x; t < n_roots; t += kSingle) {
-        const int root = a.root_list[t];
-        const int sz = a.comp_size[root];
+        const int rpos = a.root_list[t];
+        const int sz = a.comp_size[rpos];
+        const int root = a.minidx[rpos];  // min cloud index of the component = canonical label
         if ((long long)sz >= a.min_cluster && (long long)sz <= a.max_cluster) {
             const int slot = atomicAdd(&s_k, 1);
             if (slot < a.kmax) keys[slot] = ((unsigned long long)(0xFFFFFFFFu - (unsigned)sz) << 32) | (unsigned)root;
@@ -256,7 +319,7 @@ __global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
     if (K > a.kmax) {  // capacity exceeded: keep the first kmax found, flag the frame
         if (threadIdx.x == 0) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_CLUSTER_CAP);
         // the dropped roots must not keep a stale cluster id
-        for (int t = threadIdx.x; t < n_roots; t += kSingle) a.cid_of_root[a.root_list[t]] = -1;
+        for (int t = threadIdx.x; t < n_roots; t += kSingle) a.cid_of_root[a.minidx[a.root_list[t]]] = -1;
         K = a.kmax;
     }
     int P = 1;
@@ -343,7 +406,9 @@ __global__ void __launch_bounds__(kBlock) k_cluster_stats(FramePtrs a) {
     if (in) {
         p = a.spts[s];
         const int c = __float_as_int(p.w);
-        k = a.cid_of_root[a.label[c]];
+        const int lab = a.minidx[a.comp[s]];
+        a.label[c] = lab;
+        k = a.cid_of_root[lab];
         a.cid[c] = k;
     }
     const bool valid = k >= 0;

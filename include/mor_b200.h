@@ -131,6 +131,16 @@ int mor_get_last_device_ms(mor_handle* h, float* push_ms, float* filter_ms);
 /* Enable per-call CUDA-event timing (adds two event records per call). */
 int mor_set_timing(mor_handle* h, int enabled);
 
+/* Event slots (0..7) recorded on the handle's stream, so callers can time a region of calls on the
+ * device: mor_event_record(h, 0); ...calls...; mor_event_record(h, 1); mor_event_elapsed_ms(h, 0, 1, &ms). */
+int mor_event_record(mor_handle* h, int slot);
+int mor_event_elapsed_ms(mor_handle* h, int slot_a, int slot_b, float* ms);
+/* Per-kernel profiling: every launch of the hot path is bracketed by CUDA events; totals are read
+ * back with mor_get_kernel_profile(h, index, ...) for index = 0.. until it returns MOR_ERR_ARG.
+ * Forces a stream synchronisation per frame; never enable it inside a throughput measurement. */
+int mor_set_kernel_profiling(mor_handle* h, int enabled);
+int mor_get_kernel_profile(mor_handle* h, int index, char name[32], double* total_ms, uint64_t* launches);
+
 /* ---- parity taps ------------------------------------------------------------------------ */
 typedef enum mor_tap_id {
     MOR_TAP_COUNTS = 0,          /* int32[MOR_NCOUNTS], see below */
