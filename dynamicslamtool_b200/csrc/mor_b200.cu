@@ -7,6 +7,7 @@
 // There is no CPU fallback: every entry point that computes needs the device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -259,6 +260,10 @@ void fill_static(mor_handle* h) {
     b.kmax = (int)h->kmax; b.momax = (int)h->momax; b.ring_depth = h->ring_depth;
     b.grid = h->grid;
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
+    b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
+    b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((size_t)h->grid.ncells / kTile + 2);
+    const char* dbg = std::getenv("MOR_DEBUG");
+    b.debug = dbg ? std::atoi(dbg) : 0;
 }
 
 inline unsigned blocks_for(uint32_t n) { return n ? (n + kBlock - 1) / kBlock : 1; }
@@ -278,22 +283,18 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     std::memcpy(a.M.m, h->M, sizeof(h->M));
 
     const unsigned gb = blocks_for(n);
-    MOR_LAUNCH(KID_CLEAR, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, st));
     MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<(h->grid.ncells + kTile - 1) / kTile, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<<<gb, kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<<<dim3(gb, 13), kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<gb, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_SELECT, (k_select_clusters<<<1, kSingle, h->select_smem, st>>>(a)));
-    MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_FINALIZE, (k_finalize_clusters<<<8, kSingle, 0, st>>>(a)));
+    MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<(n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, st>>>(a)));
     if (h->two_frames) {
         const unsigned gp = blocks_for(h->n_prev_input);
-        MOR_LAUNCH(KID_INIT_PREV, (k_init_prev_boxes<<<(h->kmax + kBlock - 1) / kBlock, kBlock, 0, st>>>(a)));
-        MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<gp, kBlock, 0, st>>>(a)));
+        MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
         MOR_LAUNCH(KID_MATCH, (k_match<<<1, kSingle, 0, st>>>(a)));
         if (h->cfg.method_choice == 2) {
-            MOR_LAUNCH(KID_CLEAR_LATTICE, cudaMemsetAsync(a.lattice, 0xFF, h->lattice_cap * sizeof(unsigned long long), st));
             MOR_LAUNCH(KID_LATTICE_INSERT, (k_lattice_insert<<<gp, kBlock, 0, st>>>(a)));
             MOR_LAUNCH(KID_LATTICE_COUNT, (k_lattice_count<<<gb, kBlock, 0, st>>>(a)));
         } else {
@@ -568,6 +569,7 @@ int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes
         case MOR_TAP_GROUND_VOXELS: bytes = 0; break;
         case MOR_TAP_CLUSTER_BBOX: src = a.cl_bbox; bytes = K * 24; break;
         case MOR_TAP_PREV_BBOX_T: src = a.pbbox; bytes = KP * 24; break;
+        case 99: src = a.scratch; bytes = sizeof(Scratch); break;  // debug instrumentation (MOR_DEBUG)
         default: return MOR_ERR_ARG;
     }
     if (!host.empty() || tap == MOR_TAP_PREV_POINTS_T) bytes = host.size();

@@ -21,7 +21,8 @@ struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-1
 
 struct Scratch {  // zeroed at the start of every frame (one memset, together with cell_count)
     int ticket_ingest, ticket_cells, ticket_out, n_roots;
-    int moving_total, pad0, pad1, pad2;
+    int moving_total, stats_blocks_done, pad1, pad2;
+    unsigned long long dbg[8];  // MOR_DEBUG&4 instrumentation of k_link_cells
 };
 
 struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:109-128)
@@ -71,6 +72,9 @@ struct FramePtrs {
     TrackState* track; float* mo_centroid; int* mo_conf;
     uint8_t* res_ring; int* res_len; int* corr_ring; int* corr_len;
     Affine12 M; int two_frames;
+    int tiles_pts, tiles_cells;  // sizes of the scan status arrays
+    unsigned lattice_words16;    // lattice size in 16-byte units (cleared by k_ingest)
+    int debug;  // MOR_DEBUG env (profiling experiments only; 0 in production)
 };
 
 // ===================================================================================== K1
@@ -83,6 +87,17 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
     __syncthreads();
     const int tile = s_tile;
     const uint32_t i = (uint32_t)tile * kBlock + threadIdx.x;
+    if (a.two_frames) {
+        // housekeeping for the two-frame stages, spread over the grid: empty octree-lattice hash set,
+        // neutral bounding boxes for the transformed previous clusters
+        const uint32_t stride = gridDim.x * kBlock;
+        if (a.method == 2) {
+            uint4* lat = reinterpret_cast<uint4*>(a.lattice);
+            for (uint32_t t = i; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        }
+        const uint32_t kp6 = (uint32_t)a.p_counts[MOR_CNT_K] * 6u;
+        for (uint32_t t = i; t < kp6; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
+    }
     float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
     int cls = 0;
     if (i < a.n) {
@@ -152,6 +167,9 @@ __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
     int v[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++)
+        if (base + k < ncells && v[k]) a.cell_count[base + k] = 0;  // histogram consumed: ready for the next frame
     int sum = 0;
 #pragma unroll
     for (int k = 0; k < kItems; k++) sum += v[k];
@@ -214,62 +232,85 @@ __device__ __forceinline__ unsigned long long ld_done(const unsigned long long* 
 }
 
 __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
+    // grid = (point tiles, 13 rows): one thread per (point q, x-row of the backward neighbourhood), so the
+    // serial chain of a thread is at most 5 cells and a warp walks the same cells for neighbouring q.
     const int s = blockIdx.x * kBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
-    const float4 q = a.spts[s];
+    const int row = blockIdx.y;  // rows 0-4: dz=-2, 5-9: dz=-1, 10-12: dz=0 (dy=-2,-1,0)
+    const int dz = row < 5 ? -2 : (row < 10 ? -1 : 0);
+    const int dy = row < 10 ? (row % 5) - 2 : row - 12;
     const int key = a.skey[s];
     const GridDesc& g = a.grid;
     const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
-    const int lead = a.cell_start[key];
-    unsigned long long dmask = ld_done(a.done + lead);
-    const float r2_prune = a.r2 * 1.00001f;
+    const int zz = cz + dz, yy = cy + dy;
+    if (zz < 0 || yy < 0 || yy >= g.ny) return;
     const int x0 = max(cx - 2, 0);
-    int row = 0;
-    for (int dz = -2; dz <= 0; dz++) {
-        for (int dy = -2; dy <= (dz == 0 ? 0 : 2); dy++, row++) {
-            const int zz = cz + dz, yy = cy + dy;
-            if (zz < 0 || yy < 0 || yy >= g.ny) continue;
-            const int x1 = (dz == 0 && dy == 0) ? cx - 1 : min(cx + 2, g.nx - 1);
-            if (x1 < x0) continue;
-            const int base = (zz * g.ny + yy) * g.nx;
-            int j = a.cell_start[base + x0];
-            const int e = a.cell_start[base + x1 + 1];
-            while (j < e) {
-                const int kj = a.skey[j];
-                const int cell_end = a.cell_start[kj + 1];
-                const int bit = row * 5 + (kj - base - cx + 2);
-                bool skip = (dmask >> bit) & 1ull;
-                if (!skip && cell_end - j > kBoxMinCount) {
-                    // conservative point-to-box distance: no point of the cell can be closer than this
-                    const uint4 lo = a.cell_box[2 * j], hi = a.cell_box[2 * j + 1];
-                    const float ex = fmaxf(fmaxf(fkey_inv(lo.x) - q.x, q.x - fkey_inv(hi.x)), 0.f);
-                    const float ey = fmaxf(fmaxf(fkey_inv(lo.y) - q.y, q.y - fkey_inv(hi.y)), 0.f);
-                    const float ez = fmaxf(fmaxf(fkey_inv(lo.z) - q.z, q.z - fkey_inv(hi.z)), 0.f);
-                    skip = ex * ex + ey * ey + ez * ez > r2_prune;
+    const int x1 = row == 12 ? cx - 1 : min(cx + 2, g.nx - 1);
+    if (x1 < x0) return;
+    const int base = (zz * g.ny + yy) * g.nx;
+    int j = a.cell_start[base + x0];
+    const int e = a.cell_start[base + x1 + 1];
+    if (j >= e) return;
+    const float4 q = a.spts[s];
+    const int lead = a.cell_start[key];
+    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
+    unsigned long long dmask = ld_done(a.done + lead);
+    while (j < e) {
+        const int kj = a.skey[j];
+        const int cell_end = a.cell_start[kj + 1];
+        const int bit = row * 5 + (kj - base - cx + 2);
+        bool skip = (dmask >> bit) & 1ull;
+        if (!skip && cell_end - j > kBoxMinCount) {
+            // conservative point-to-box distance: no point of the cell can be closer than this
+            const uint4 lo = a.cell_box[2 * j], hi = a.cell_box[2 * j + 1];
+            const float ex = fmaxf(fmaxf(fkey_inv(lo.x) - q.x, q.x - fkey_inv(hi.x)), 0.f);
+            const float ey = fmaxf(fmaxf(fkey_inv(lo.y) - q.y, q.y - fkey_inv(hi.y)), 0.f);
+            const float ez = fmaxf(fmaxf(fkey_inv(lo.z) - q.z, q.z - fkey_inv(hi.z)), 0.f);
+            skip = ex * ex + ey * ey + ez * ez > r2_prune;
+            if ((a.debug & 4) && skip) atomicAdd(&a.scratch->dbg[6], 1ull);  // pruned by the box
+        }
+        if (!skip) {
+            bool hit = false;
+            int it = 0;
+            const int j_begin = j;
+            for (; j + 4 <= cell_end && !hit; j += 4) {  // 4 independent loads in flight
+                const float4 p0 = a.spts[j], p1 = a.spts[j + 1], p2 = a.spts[j + 2], p3 = a.spts[j + 3];
+                const float d0 = sqdist3(q.x, q.y, q.z, p0.x, p0.y, p0.z), d1 = sqdist3(q.x, q.y, q.z, p1.x, p1.y, p1.z);
+                const float d2 = sqdist3(q.x, q.y, q.z, p2.x, p2.y, p2.z), d3 = sqdist3(q.x, q.y, q.z, p3.x, p3.y, p3.z);
+                hit = fminf(fminf(d0, d1), fminf(d2, d3)) < r2;
+                if (((++it) & 63) == 63 && !hit) {  // somebody else of my cell may have connected this pair meanwhile
+                    dmask |= ld_done(a.done + lead);
+                    if ((dmask >> bit) & 1ull) break;
                 }
-                if (!skip) {
-                    bool hit = false;
-                    for (int it = 0; j < cell_end; j++, it++) {
-                        const float4 p = a.spts[j];
-                        if (sqdist3(q.x, q.y, q.z, p.x, p.y, p.z) < a.r2) { hit = true; break; }
-                        if ((it & 63) == 63) {  // somebody else of my cell may have connected this pair meanwhile
-                            dmask |= ld_done(a.done + lead);
-                            if ((dmask >> bit) & 1ull) break;
-                        }
-                    }
-                    if (hit) {
-                        dmask |= ld_done(a.done + lead);
-                        if (!((dmask >> bit) & 1ull)) {
-                            const unsigned long long old = atomicOr(a.done + lead, 1ull << bit);
-                            dmask |= old | (1ull << bit);
-                            if (!((old >> bit) & 1ull)) uf_union(a.parent, lead, a.cell_start[kj]);
-                        }
+            }
+            for (; j < cell_end && !hit; j++) {
+                const float4 p = a.spts[j];
+                hit = sqdist3(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+            }
+            if (a.debug & 4) {
+                const unsigned long long tested = (unsigned long long)(j - j_begin);
+                atomicAdd(&a.scratch->dbg[0], tested);                       // points tested
+                atomicAdd(&a.scratch->dbg[1], 1ull);                         // cells scanned
+                atomicMax(&a.scratch->dbg[2], tested);                       // longest single scan
+                if (!hit && j >= cell_end) { atomicAdd(&a.scratch->dbg[3], 1ull); atomicAdd(&a.scratch->dbg[4], tested); }  // full scans without hit
+                if (hit) atomicAdd(&a.scratch->dbg[5], 1ull);
+            }
+            if (hit) {
+                // lanes of the warp that found the same cell pair at the same time elect one publisher: the
+                // done word of a crowded cell would otherwise take thousands of same-address atomics
+                const unsigned grp = __match_any_sync(__activemask(), (lead << 6) | bit);
+                if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
+                    dmask |= ld_done(a.done + lead);
+                    if (!((dmask >> bit) & 1ull)) {
+                        const unsigned long long old = atomicOr(a.done + lead, 1ull << bit);
+                        if (!((old >> bit) & 1ull)) uf_union(a.parent, lead, a.cell_start[kj]);
                     }
                 }
-                j = cell_end;
+                dmask |= 1ull << bit;
             }
         }
+        j = cell_end;
     }
 }
 
@@ -352,6 +393,10 @@ __global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
     }
     atomicAdd(&a.counts[MOR_CNT_NK], nk);
     if (threadIdx.x == 0) a.counts[MOR_CNT_K] = K;
+    // the ingest / cell scans of this frame are complete: reset their look-back state for the next frame
+    for (int t = threadIdx.x; t < a.tiles_pts; t += kSingle) a.st_ingest[t] = 0ull;
+    for (int t = threadIdx.x; t < a.tiles_cells; t += kSingle) a.st_cells[t] = 0ull;
+    if (threadIdx.x == 0) { a.scratch->ticket_ingest = 0; a.scratch->ticket_cells = 0; a.scratch->n_roots = 0; a.scratch->stats_blocks_done = 0; }
 }
 
 // ===================================================================================== K7
@@ -373,37 +418,92 @@ __device__ __forceinline__ unsigned warp_max_u(unsigned v) {
     return v;
 }
 
-// Accumulate the bounding box of (x,y,z) into box[k*6..] for valid lanes; whole warp must call.
-__device__ __forceinline__ void warp_box_accumulate(unsigned* box, int k, bool valid, float x, float y, float z) {
+// Per-cluster accumulation of coordinate sums (optional) and bounding boxes with two levels of
+// aggregation before the global atomics: warp (shuffles) and block (shared memory). In sorted order a
+// block of kStatBlock consecutive points lies inside one cluster most of the time, so a 30k-point
+// cluster costs ~30 sets of atomics instead of 30k. Every thread of the block must call.
+constexpr int kStatBlock = 1024;
+
+template <bool WITH_SUMS>
+__device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc_sum, unsigned* acc_box, int k, bool valid, float x, float y, float z) {
+    __shared__ int s_k[kStatBlock / 32];                       // cluster of the warp, -1 = no valid lane, -2 = mixed
+    __shared__ unsigned long long s_sum[kStatBlock / 32][6];
+    __shared__ unsigned s_box[kStatBlock / 32][6];
+    __shared__ int s_mode;                                     // >= 0: the whole block is cluster s_mode; -1: per-warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp level: lanes are grouped by cluster (match.any) and every group is reduced with redux
     const unsigned vmask = __ballot_sync(kFull, valid);
-    if (!vmask) return;
-    const int k0 = __shfl_sync(kFull, k, __ffs(vmask) - 1);
-    const bool uniform = __all_sync(kFull, !valid || k == k0);
-    unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
-    if (uniform) {
-        unsigned mnx = warp_min_u(valid ? kx : 0xFFFFFFFFu), mny = warp_min_u(valid ? ky : 0xFFFFFFFFu), mnz = warp_min_u(valid ? kz : 0xFFFFFFFFu);
-        unsigned mxx = warp_max_u(valid ? kx : 0u), mxy = warp_max_u(valid ? ky : 0u), mxz = warp_max_u(valid ? kz : 0u);
-        if ((threadIdx.x & 31) == 0) {
-            unsigned* b = box + k0 * 6;
-            atomicMin(b + 0, mnx); atomicMin(b + 1, mny); atomicMin(b + 2, mnz);
-            atomicMax(b + 3, mxx); atomicMax(b + 4, mxy); atomicMax(b + 5, mxz);
+    const unsigned grp = __match_any_sync(kFull, valid ? k : -1);
+    const bool leader = valid && (int)(__ffs(grp) - 1) == lane;
+    const bool uniform = vmask != 0 && (grp & vmask) == vmask && valid;  // true in the valid lanes of a one-cluster warp
+    const bool warp_uniform = __any_sync(kFull, uniform);
+    unsigned bx[6];
+    {
+        const unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
+        bx[0] = __reduce_min_sync(grp, kx); bx[1] = __reduce_min_sync(grp, ky); bx[2] = __reduce_min_sync(grp, kz);
+        bx[3] = __reduce_max_sync(grp, kx); bx[4] = __reduce_max_sync(grp, ky); bx[5] = __reduce_max_sync(grp, kz);
+    }
+    unsigned long long sm[6] = {0, 0, 0, 0, 0, 0};
+    if (WITH_SUMS) {
+        const float v[3] = {x, y, z};
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            long long h, l;
+            split_fixed(v[q], h, l);  // h in [-2^31, 2^31), l in [0, 2^30): summed in 16/15-bit pieces so redux.add (32-bit) cannot overflow
+            const long long sh = ((long long)__reduce_add_sync(grp, (int)(h >> 16)) << 16) + (long long)__reduce_add_sync(grp, (int)(h & 0xFFFF));
+            const long long sl = ((long long)__reduce_add_sync(grp, (int)(l >> 15)) << 15) + (long long)__reduce_add_sync(grp, (int)(l & 0x7FFF));
+            sm[q * 2] = (unsigned long long)sh; sm[q * 2 + 1] = (unsigned long long)sl;
         }
-    } else if (valid) {
-        unsigned* b = box + k * 6;
-        atomicMin(b + 0, kx); atomicMin(b + 1, ky); atomicMin(b + 2, kz);
-        atomicMax(b + 3, kx); atomicMax(b + 4, ky); atomicMax(b + 5, kz);
+    }
+    if (warp_uniform && leader) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) { s_box[warp][q] = bx[q]; if (WITH_SUMS) s_sum[warp][q] = sm[q]; }
+    }
+    const int k_first = __shfl_sync(kFull, k, vmask ? __ffs(vmask) - 1 : 0);
+    if (lane == 0) s_k[warp] = !vmask ? -1 : (warp_uniform ? k_first : -2);
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        const int wk = lane < nw ? s_k[lane] : -1;
+        const unsigned has = __ballot_sync(kFull, wk != -1);
+        const int first = has ? __shfl_sync(kFull, wk, __ffs(has) - 1) : -1;
+        const bool same = __all_sync(kFull, wk == -1 || (wk == first && wk >= 0));
+        if (lane == 0) s_mode = (has && same) ? first : -1;
+    }
+    __syncthreads();
+    const int mode = s_mode;
+    if (mode >= 0) {  // the whole block is one cluster: one set of atomics
+        const int nw = blockDim.x >> 5;
+        if (threadIdx.x < 6) {
+            unsigned v = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+            for (int w = 0; w < nw; w++)
+                if (s_k[w] >= 0) v = threadIdx.x < 3 ? min(v, s_box[w][threadIdx.x]) : max(v, s_box[w][threadIdx.x]);
+            if (threadIdx.x < 3) atomicMin(acc_box + mode * 6 + threadIdx.x, v); else atomicMax(acc_box + mode * 6 + threadIdx.x, v);
+        } else if (WITH_SUMS && threadIdx.x >= 32 && threadIdx.x < 38) {
+            const int q = threadIdx.x - 32;
+            unsigned long long v = 0;
+            for (int w = 0; w < nw; w++)
+                if (s_k[w] >= 0) v += s_sum[w][q];
+            atomicAdd(acc_sum + mode * 6 + q, v);
+        }
+    } else if (leader) {  // one set of atomics per (warp, cluster) group
+        unsigned* b = acc_box + k * 6;
+        atomicMin(b + 0, bx[0]); atomicMin(b + 1, bx[1]); atomicMin(b + 2, bx[2]);
+        atomicMax(b + 3, bx[3]); atomicMax(b + 4, bx[4]); atomicMax(b + 5, bx[5]);
+        if (WITH_SUMS) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) atomicAdd(acc_sum + k * 6 + q, sm[q]);
+        }
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_cluster_stats(FramePtrs a) {
-    const int s = blockIdx.x * kBlock + threadIdx.x;
+__global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) {
+    const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
-    // whole warps stay alive for the shuffles
-    if ((s & ~31) >= nc) return;
-    const bool in = s < nc;
+    if (blockIdx.x * kStatBlock >= nc) return;  // whole blocks stay alive for the barriers
     float4 p = make_float4(0, 0, 0, 0);
     int k = -1;
-    if (in) {
+    if (s < nc) {
         p = a.spts[s];
         const int c = __float_as_int(p.w);
         const int lab = a.minidx[a.comp[s]];
@@ -411,39 +511,36 @@ __global__ void __launch_bounds__(kBlock) k_cluster_stats(FramePtrs a) {
         k = a.cid_of_root[lab];
         a.cid[c] = k;
     }
-    const bool valid = k >= 0;
-    const unsigned vmask = __ballot_sync(kFull, valid);
-    if (!vmask) return;
-    long long h[3], l[3];
-    split_fixed(p.x, h[0], l[0]); split_fixed(p.y, h[1], l[1]); split_fixed(p.z, h[2], l[2]);
-    const int k0 = __shfl_sync(kFull, k, __ffs(vmask) - 1);
-    const bool uniform = __all_sync(kFull, !valid || k == k0);
-    if (uniform) {
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const long long sh = warp_sum_ll(valid ? h[q] : 0ll), sl = warp_sum_ll(valid ? l[q] : 0ll);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&a.acc_sum[k0 * 6 + q * 2], (unsigned long long)sh);
-                atomicAdd(&a.acc_sum[k0 * 6 + q * 2 + 1], (unsigned long long)sl);
-            }
-        }
-    } else if (valid) {
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            atomicAdd(&a.acc_sum[k * 6 + q * 2], (unsigned long long)h[q]);
-            atomicAdd(&a.acc_sum[k * 6 + q * 2 + 1], (unsigned long long)l[q]);
-        }
+    block_cluster_accumulate<true>(a.acc_sum, a.acc_box, k, k >= 0, p.x, p.y, p.z);
+    // the last block to finish turns the accumulators into centroids (compute3DCentroid<double>, A10)
+    // and bounding boxes
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // the block's accumulator atomics are ordered before the ticket
+        s_last = atomicAdd(&a.scratch->stats_blocks_done, 1) == (nc + kStatBlock - 1) / kStatBlock - 1;
+        __threadfence();
     }
-    warp_box_accumulate(a.acc_box, k, valid, p.x, p.y, p.z);
+    __syncthreads();
+    if (!s_last) return;
+    const int K = a.counts[MOR_CNT_K];
+    for (int c = threadIdx.x; c < K; c += kStatBlock) {
+        const double n = (double)a.cl_size[c];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
+    }
 }
 
 // ===================================================================================== K8
 // pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12) and the bounding box
 // of the transformed points (getMinMax3D runs after the transform, cpp:272).
-__global__ void __launch_bounds__(kBlock) k_transform_prev(FramePtrs a) {
-    const int s = blockIdx.x * kBlock + threadIdx.x;
+__global__ void __launch_bounds__(kStatBlock) k_transform_prev(FramePtrs a) {
+    const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int ncp = a.p_counts[MOR_CNT_NC];
-    if ((s & ~31) >= ncp) return;
+    if (blockIdx.x * kStatBlock >= ncp) return;
     int k = -1;
     float3 t = make_float3(0, 0, 0);
     if (s < ncp) {
@@ -457,14 +554,7 @@ __global__ void __launch_bounds__(kBlock) k_transform_prev(FramePtrs a) {
             a.tpts[c] = make_float4(0, 0, 0, __int_as_float(-1));
         }
     }
-    warp_box_accumulate(a.pacc_box, k, k >= 0, t.x, t.y, t.z);
-}
-
-__global__ void __launch_bounds__(kBlock) k_init_prev_boxes(FramePtrs a) {
-    const int k = blockIdx.x * kBlock + threadIdx.x;
-    if (k >= a.p_counts[MOR_CNT_K]) return;
-#pragma unroll
-    for (int q = 0; q < 3; q++) { a.pacc_box[k * 6 + q] = 0xFFFFFFFFu; a.pacc_box[k * 6 + 3 + q] = 0u; }
+    block_cluster_accumulate<false>(nullptr, a.pacc_box, k, k >= 0, t.x, t.y, t.z);
 }
 
 // Block-wide ordered compaction helper for the single-block kernels: returns the exclusive rank of
@@ -496,18 +586,6 @@ __device__ __forceinline__ int single_block_rank(bool flag, int* total) {
 // ===================================================================================== K9
 // Finalise centroids/boxes, transform the previous centroids (cpp:540-541), reciprocal 1-NN between
 // centroid sets (cpp:291-294, A16), volume constraint (cpp:264-283, A17), per-match octree anchors.
-__global__ void __launch_bounds__(kSingle) k_finalize_clusters(FramePtrs a) {
-    const int K = a.counts[MOR_CNT_K];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
-        const double n = (double)a.cl_size[k];
-#pragma unroll
-        for (int q = 0; q < 3; q++)
-            a.cl_centroid[k * 3 + q] = (float)join_fixed_mean((long long)a.acc_sum[k * 6 + q * 2], (long long)a.acc_sum[k * 6 + q * 2 + 1], n);
-#pragma unroll
-        for (int q = 0; q < 6; q++) a.cl_bbox[k * 6 + q] = fkey_inv(a.acc_box[k * 6 + q]);
-    }
-}
-
 __device__ __forceinline__ int nn_brute(const float* pts, int n, float qx, float qy, float qz, float* out_d) {
     int best = -1;
     float bd = 3.402823466e+38f;
@@ -796,7 +874,8 @@ __global__ void __launch_bounds__(kSingle) k_track(FramePtrs a) {
     TrackState* ts = a.track;
     const int n_mo = ts->n_mo;
     __shared__ int s_total;
-    if (threadIdx.x == 0) s_total = 0;
+    if (threadIdx.x == 0) { s_total = 0; a.scratch->ticket_out = 0; }
+    for (int t = threadIdx.x; t < a.tiles_pts; t += kSingle) a.st_out[t] = 0ull;  // look-back state of k_output
     for (int k = threadIdx.x; k < K; k += kSingle) a.cluster_removed[k] = 0;
     __syncthreads();
     int kept_total = 0;
