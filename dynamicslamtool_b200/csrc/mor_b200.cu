@@ -127,10 +127,10 @@ struct mor_handle {
 
 namespace {
 
-enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
+enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
                 KID_INIT_PREV, KID_TRANSFORM_PREV, KID_MATCH, KID_CLEAR_LATTICE, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE, KID_CHAIN,
                 KID_TRACK, KID_OUTPUT, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_scan_cells", "k_scatter", "k_link_cells", "k_flatten", "k_select_clusters",
+const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten", "k_select_clusters",
                                               "k_cluster_stats", "k_finalize_clusters", "k_init_prev_boxes", "k_transform_prev", "k_match",
                                               "memset_lattice", "k_lattice_insert", "k_lattice_count", "k_pde_count", "k_flags_and_chain", "k_track",
                                               "k_output"};
@@ -286,7 +286,8 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<(h->grid.ncells + kTile - 1) / kTile, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<<<dim3(gb, 13), kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<1><<<dim3(gb, 5), kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_LINK_FAR, (k_link_cells<2><<<dim3(gb, 13), kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<gb, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_SELECT, (k_select_clusters<<<1, kSingle, h->select_smem, st>>>(a)));
     MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<(n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, st>>>(a)));

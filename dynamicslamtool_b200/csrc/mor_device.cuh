@@ -1,7 +1,7 @@
 // mor_device.cuh — device-side building blocks shared by the MOR kernels (sm_100a).
 //
 //  * decoupled look-back tile prefix (single-pass stable scans / partitions)
-//  * lock-free union-find (hook larger root under smaller => root == min index == canonical label)
+//  * lock-free union-find (roots ordered by a hashed priority => shallow forests)
 //  * order-preserving float<->uint keys for atomic min/max
 //  * exact, order-independent fixed-point accumulation of float coordinates (centroids)
 //  * the bit-exact distance / transform arithmetic shared with the CPU oracle
@@ -89,16 +89,23 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
     }
     return x;
 }
-// Returns the root of the merged set. Larger root is hooked under the smaller one, so the final
-// root of a component is its minimum index (the canonical label).
+// Roots are ordered by a hashed priority (ties by index) and the lower root is hooked under the higher
+// one. Any strict total order keeps the forest acyclic; a pseudo-random one keeps it shallow (sorted
+// positions would chain hundreds of cells of a wall along an x-row). The canonical label of a
+// component (its minimum cloud index) is reduced separately in k_flatten, so root identity is free.
+__device__ __forceinline__ bool uf_before(int a, int b) {
+    const unsigned ha = (unsigned)a * 0x9E3779B1u, hb = (unsigned)b * 0x9E3779B1u;
+    return ha < hb || (ha == hb && a < b);
+}
+// Returns the root of the merged set.
 __device__ __forceinline__ int uf_union(int* parent, int a, int b) {
     while (true) {
         a = uf_find(parent, a);
         b = uf_find(parent, b);
         if (a == b) return a;
-        if (a > b) { int t = a; a = b; b = t; }
-        int old = atomicCAS(&parent[b], b, a);
-        if (old == b) return a;
+        if (uf_before(b, a)) { int t = a; a = b; b = t; }  // a is the lower root
+        int old = atomicCAS(&parent[a], a, b);
+        if (old == a) return b;
     }
 }
 

@@ -10,6 +10,7 @@ namespace mor {
 
 constexpr int kSingle = 1024;  // threads of the single-block bookkeeping kernels
 constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
+constexpr int kRootCheckCount = 48;  // far pass: cells above this size are first checked for a common root
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8 };
 
@@ -231,31 +232,13 @@ __device__ __forceinline__ unsigned long long ld_done(const unsigned long long* 
     return v;
 }
 
-__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
-    // grid = (point tiles, 13 rows): one thread per (point q, x-row of the backward neighbourhood), so the
-    // serial chain of a thread is at most 5 cells and a warp walks the same cells for neighbouring q.
-    const int s = blockIdx.x * kBlock + threadIdx.x;
-    const int nc = a.counts[MOR_CNT_NC];
-    if (s >= nc) return;
-    const int row = blockIdx.y;  // rows 0-4: dz=-2, 5-9: dz=-1, 10-12: dz=0 (dy=-2,-1,0)
-    const int dz = row < 5 ? -2 : (row < 10 ? -1 : 0);
-    const int dy = row < 10 ? (row % 5) - 2 : row - 12;
-    const int key = a.skey[s];
-    const GridDesc& g = a.grid;
-    const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
-    const int zz = cz + dz, yy = cy + dy;
-    if (zz < 0 || yy < 0 || yy >= g.ny) return;
-    const int x0 = max(cx - 2, 0);
-    const int x1 = row == 12 ? cx - 1 : min(cx + 2, g.nx - 1);
-    if (x1 < x0) return;
-    const int base = (zz * g.ny + yy) * g.nx;
-    int j = a.cell_start[base + x0];
-    const int e = a.cell_start[base + x1 + 1];
-    if (j >= e) return;
-    const float4 q = a.spts[s];
-    const int lead = a.cell_start[key];
+// Examines the cells of one x-range of one row for point q; see k_link_cells.
+template <int PHASE>
+__device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4 q, int lead, int row, int base, int cx, int xa, int xb,
+                                                unsigned long long& dmask) {
+    int j = a.cell_start[base + xa];
+    const int e = a.cell_start[base + xb + 1];
     const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
-    unsigned long long dmask = ld_done(a.done + lead);
     while (j < e) {
         const int kj = a.skey[j];
         const int cell_end = a.cell_start[kj + 1];
@@ -268,14 +251,22 @@ __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
             const float ey = fmaxf(fmaxf(fkey_inv(lo.y) - q.y, q.y - fkey_inv(hi.y)), 0.f);
             const float ez = fmaxf(fmaxf(fkey_inv(lo.z) - q.z, q.z - fkey_inv(hi.z)), 0.f);
             skip = ex * ex + ey * ey + ez * ez > r2_prune;
-            if ((a.debug & 4) && skip) atomicAdd(&a.scratch->dbg[6], 1ull);  // pruned by the box
+            if (PHASE == 2 && !skip && cell_end - j > kRootCheckCount) {
+                // far pass: the near pass has already merged most of a dense surface; two cells of one
+                // component need no point tests (the pair is marked done, which is all the mask means)
+                if (uf_find(a.parent, lead) == uf_find(a.parent, j)) {
+                    const unsigned grp = __match_any_sync(__activemask(), (lead << 6) | bit);
+                    if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicOr(a.done + lead, 1ull << bit);
+                    dmask |= 1ull << bit;
+                    skip = true;
+                }
+            }
         }
         if (!skip) {
             bool hit = false;
-            int it = 0;
-            const int j_begin = j;
-            for (; j + 4 <= cell_end && !hit; j += 4) {  // 4 independent loads in flight
-                const float4 p0 = a.spts[j], p1 = a.spts[j + 1], p2 = a.spts[j + 2], p3 = a.spts[j + 3];
+            const int last = cell_end - 1;
+            for (int it = 0; j < cell_end && !hit; j += 4) {  // always 4 independent loads in flight (indices clamped)
+                const float4 p0 = a.spts[j], p1 = a.spts[min(j + 1, last)], p2 = a.spts[min(j + 2, last)], p3 = a.spts[min(j + 3, last)];
                 const float d0 = sqdist3(q.x, q.y, q.z, p0.x, p0.y, p0.z), d1 = sqdist3(q.x, q.y, q.z, p1.x, p1.y, p1.z);
                 const float d2 = sqdist3(q.x, q.y, q.z, p2.x, p2.y, p2.z), d3 = sqdist3(q.x, q.y, q.z, p3.x, p3.y, p3.z);
                 hit = fminf(fminf(d0, d1), fminf(d2, d3)) < r2;
@@ -283,18 +274,6 @@ __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
                     dmask |= ld_done(a.done + lead);
                     if ((dmask >> bit) & 1ull) break;
                 }
-            }
-            for (; j < cell_end && !hit; j++) {
-                const float4 p = a.spts[j];
-                hit = sqdist3(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
-            }
-            if (a.debug & 4) {
-                const unsigned long long tested = (unsigned long long)(j - j_begin);
-                atomicAdd(&a.scratch->dbg[0], tested);                       // points tested
-                atomicAdd(&a.scratch->dbg[1], 1ull);                         // cells scanned
-                atomicMax(&a.scratch->dbg[2], tested);                       // longest single scan
-                if (!hit && j >= cell_end) { atomicAdd(&a.scratch->dbg[3], 1ull); atomicAdd(&a.scratch->dbg[4], tested); }  // full scans without hit
-                if (hit) atomicAdd(&a.scratch->dbg[5], 1ull);
             }
             if (hit) {
                 // lanes of the warp that found the same cell pair at the same time elect one publisher: the
@@ -311,6 +290,40 @@ __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
             }
         }
         j = cell_end;
+    }
+}
+
+// grid = (point tiles, rows): one thread per (point q, x-row of the backward neighbourhood), so the serial
+// chain of a thread is a handful of cells and a warp walks the same cells for neighbouring q.
+// PHASE 1 = the 13 backward cells of the 3x3x3 block (5 rows); PHASE 2 = the 49 cells at offset 2 (13 rows).
+template <int PHASE>
+__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int nc = a.counts[MOR_CNT_NC];
+    if (s >= nc) return;
+    // canonical row ids (they fix the bit layout): 0-4: dz=-2, 5-9: dz=-1, 10-12: dz=0 with dy=-2,-1,0
+    int row = blockIdx.y;
+    if (PHASE == 1) row = blockIdx.y == 0 ? 12 : (blockIdx.y == 1 ? 11 : 4 + blockIdx.y);  // near rows: 12, 11, 6, 7, 8
+    const int dz = row < 5 ? -2 : (row < 10 ? -1 : 0);
+    const int dy = row < 10 ? (row % 5) - 2 : row - 12;
+    const bool near_row = dz >= -1 && dy >= -1 && dy <= 1;
+    const int key = a.skey[s];
+    const GridDesc& g = a.grid;
+    const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
+    const int zz = cz + dz, yy = cy + dy;
+    if (zz < 0 || yy < 0 || yy >= g.ny) return;
+    const int base = (zz * g.ny + yy) * g.nx;
+    const float4 q = a.spts[s];
+    const int lead = a.cell_start[key];
+    unsigned long long dmask = ld_done(a.done + lead);
+    if (PHASE == 1) {
+        const int xa = max(cx - 1, 0), xb = row == 12 ? cx - 1 : min(cx + 1, g.nx - 1);
+        if (xb >= xa) link_scan_range<1>(a, q, lead, row, base, cx, xa, xb, dmask);
+    } else if (!near_row) {
+        link_scan_range<2>(a, q, lead, row, base, cx, max(cx - 2, 0), min(cx + 2, g.nx - 1), dmask);
+    } else {
+        if (cx - 2 >= 0) link_scan_range<2>(a, q, lead, row, base, cx, cx - 2, cx - 2, dmask);
+        if (row != 12 && cx + 2 < g.nx) link_scan_range<2>(a, q, lead, row, base, cx, cx + 2, cx + 2, dmask);
     }
 }
 
