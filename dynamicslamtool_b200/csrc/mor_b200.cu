@@ -88,6 +88,8 @@ struct mor_handle {
     cudaStream_t stream = nullptr;
     uint32_t nmax = 0, kmax = 0, momax = 0;
     int ring_depth = 0, pde_ring = 0;
+    bool dynamic_grid = false; int max_cells = 0; double cell_h = 0;
+    int num_sms = 148;
     size_t select_smem = 0;
     GridDesc grid;
     std::string last_error;
@@ -127,10 +129,10 @@ struct mor_handle {
 
 namespace {
 
-enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
+enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
                 KID_INIT_PREV, KID_TRANSFORM_PREV, KID_MATCH, KID_CLEAR_LATTICE, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE, KID_CHAIN,
                 KID_TRACK, KID_OUTPUT, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten", "k_select_clusters",
+const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten", "k_select_clusters",
                                               "k_cluster_stats", "k_finalize_clusters", "k_init_prev_boxes", "k_transform_prev", "k_match",
                                               "memset_lattice", "k_lattice_insert", "k_lattice_count", "k_pde_count", "k_flags_and_chain", "k_track",
                                               "k_output"};
@@ -180,9 +182,19 @@ int build_grid(mor_handle* h) {
     if (!(zhi >= zlo)) zhi = zlo;
     g.oz = zlo; g.inv_h = 1.0 / hcell;
     const double fx = std::floor(2.0 * (double)c.trim_x / hcell) + 1, fy = std::floor(2.0 * (double)c.trim_y / hcell) + 1, fz = std::floor((zhi - zlo) / hcell) + 1;
-    if (fx * fy * fz > 268435456.0) return MOR_ERR_CAPACITY;  // 2^28 cells = 2 GB of cell tables
     if (fx < 1 || fy < 1 || fz < 1) return MOR_ERR_CONFIG_VALUE;
-    g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
+    h->cell_h = hcell;
+    h->max_cells = 1 << 24;  // 16.7 M cells: 2 x 64 MB of cell tables, ~15 us to scan
+    if (fx * fy * fz > (double)h->max_cells) {
+        // the crop box itself is too large for a dense table (e.g. trimming "disabled" with huge values):
+        // lay the grid over the bounding box of each frame's cloud instead (k_keys); a frame whose box
+        // still needs more than max_cells cells is rejected with MOR_ERR_CAPACITY
+        h->dynamic_grid = true;
+        g.nx = g.ny = g.nz = 1; g.ncells = h->max_cells;
+    } else {
+        h->dynamic_grid = false;
+        g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
+    }
     h->grid = g;
     h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / hcell);
     if (h->pde_ring < 1) h->pde_ring = 1;
@@ -210,6 +222,7 @@ int allocate(mor_handle* h) {
         b.cell_count = carve<int>(p, ncells + 1);
         h->zero_bytes = (size_t)(p - h->zero_region);
         b.cell_start = carve<int>(p, ncells + 1);
+        b.dgrid = carve<GridDesc>(p, 1);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
         b.cell_key = carve<int>(p, N); b.cell_rank = carve<int>(p, N); b.skey = carve<int>(p, N);
@@ -259,6 +272,7 @@ void fill_static(mor_handle* h) {
     b.moving_confidence = c.n_bad; b.static_confidence = c.n_good;
     b.kmax = (int)h->kmax; b.momax = (int)h->momax; b.ring_depth = h->ring_depth;
     b.grid = h->grid;
+    b.dynamic_grid = h->dynamic_grid ? 1 : 0; b.max_cells = h->max_cells; b.cell_h = h->cell_h;
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
     b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((size_t)h->grid.ncells / kTile + 2);
@@ -284,7 +298,12 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
 
     const unsigned gb = blocks_for(n);
     MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<(h->grid.ncells + kTile - 1) / kTile, kBlock, 0, st>>>(a)));
+    if (h->dynamic_grid) MOR_LAUNCH(KID_KEYS, (k_keys<<<gb, kBlock, 0, st>>>(a)));
+    {
+        const int tiles = (h->grid.ncells + kTile - 1) / kTile;
+        const int scan_blocks = h->dynamic_grid ? h->num_sms * 8 : (tiles < h->num_sms * 8 ? tiles : h->num_sms * 8);
+        MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<scan_blocks, kBlock, 0, st>>>(a)));
+    }
     MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<1><<<dim3(gb, 5), kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_LINK_FAR, (k_link_cells<2><<<dim3(gb, 13), kBlock, 0, st>>>(a)));
@@ -360,7 +379,7 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     if (n_out) *n_out = no;
     if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
         char msg[96];
-        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice)", h->h_counts[MOR_CNT_ERRFLAGS]);
+        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice 16=grid cells)", h->h_counts[MOR_CNT_ERRFLAGS]);
         h->last_error = msg;
         return MOR_ERR_CAPACITY;
     }
@@ -392,7 +411,7 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     h->nmax = limits && limits->max_points ? limits->max_points : 300000u;
     h->kmax = limits && limits->max_clusters ? limits->max_clusters : 8192u;
     h->momax = limits && limits->max_moving ? limits->max_moving : 1024u;
-    if (h->kmax > 32768u) h->kmax = 32768u;  // 15 bits of match id in the lattice key
+    if (h->kmax > 16384u) h->kmax = 16384u;  // k_select_clusters sorts the clusters of a frame in shared memory (128 KB of keys)
     h->ring_depth = (n_bad > 1 ? n_bad : 1) + 2;
     st = build_grid(h);
     if (st != MOR_OK) { delete h; return st; }
@@ -402,6 +421,13 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     st = allocate(h);
     if (st != MOR_OK) { if (h->arena) cudaFree(h->arena); cudaStreamDestroy(h->stream); delete h; return st; }
     fill_static(h);
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
+        GridDesc g0 = h->grid;
+        if (h->dynamic_grid) { g0.nx = g0.ny = g0.nz = 1; g0.ncells = 1; }
+        if (cudaMemcpy(h->base.dgrid, &g0, sizeof(g0), cudaMemcpyHostToDevice) != cudaSuccess) { mor_destroy(h); return MOR_ERR_CUDA; }
+    }
     *out = h;
     return MOR_OK;
 }

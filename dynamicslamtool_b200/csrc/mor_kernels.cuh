@@ -12,7 +12,7 @@ constexpr int kSingle = 1024;  // threads of the single-block bookkeeping kernel
 constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
 constexpr int kRootCheckCount = 48;  // far pass: cells above this size are first checked for a common root
 
-enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8 };
+enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_CAP = 16 };
 
 struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-10): two points of one cell are always
                    // within r (one union-find node per cell) and d<r => |dcell| <= 2 per axis
@@ -23,6 +23,8 @@ struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-1
 struct Scratch {  // zeroed at the start of every frame (one memset, together with cell_count)
     int ticket_ingest, ticket_cells, ticket_out, n_roots;
     int moving_total, stats_blocks_done, pad1, pad2;
+    unsigned box_inv_min[3], box_max[3];  // dynamic grid: bbox of `cloud` (ordered keys; mins stored inverted so 0 is neutral)
+    int pad3, pad4;
     unsigned long long dbg[8];  // MOR_DEBUG&4 instrumentation of k_link_cells
 };
 
@@ -44,7 +46,10 @@ struct FramePtrs {
     long long min_cluster, max_cluster;
     int method, opc_factor, moving_confidence, static_confidence;
     int kmax, momax, ring_depth;
-    GridDesc grid;
+    GridDesc grid;            // static mode: the config crop box (known at create)
+    GridDesc* dgrid;          // the grid every kernel after k_ingest/k_keys reads (device copy; rewritten per frame in dynamic mode)
+    int dynamic_grid;         // 1: the config box would need too many cells -> per-frame grid over the bounding box of `cloud`
+    int max_cells; double cell_h;
     // ---- per-frame scratch
     Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cells; unsigned long long* st_out;
     int* cell_count; int* cell_start;
@@ -127,20 +132,32 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
         const int c = (int)(mine & 0x7FFFFFFFull);
         a.pts[c] = make_float4(x, y, z, w);
         a.cloud_src[c] = (int)i;
-        const GridDesc& g = a.grid;
-        int cx = (int)floor(((double)x - g.ox) * g.inv_h);
-        int cy = (int)floor(((double)y - g.oy) * g.inv_h);
-        int cz = (int)floor(((double)z - g.oz) * g.inv_h);
-        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
-        const int key = (cz * g.ny + cy) * g.nx + cx;
-        a.cell_key[c] = key;
-        a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
         a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // slot c doubles as a sorted position
         a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
+        if (!a.dynamic_grid) {
+            const GridDesc& g = a.grid;
+            int cx = (int)floor(((double)x - g.ox) * g.inv_h);
+            int cy = (int)floor(((double)y - g.oy) * g.inv_h);
+            int cz = (int)floor(((double)z - g.oz) * g.inv_h);
+            cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+            const int key = (cz * g.ny + cy) * g.nx + cx;
+            a.cell_key[c] = key;
+            a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+        }
     } else if (cls == 2) {
         const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
         a.gpts[gi] = make_float4(x, y, z, w);
         a.gsrc[gi] = (int)i;
+    }
+    if (a.dynamic_grid) {  // bounding box of `cloud`: warp redux, then one set of atomics per warp
+        const bool v = cls == 1;
+        const unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
+        const unsigned ix = __reduce_max_sync(kFull, v ? ~kx : 0u), iy = __reduce_max_sync(kFull, v ? ~ky : 0u), iz = __reduce_max_sync(kFull, v ? ~kz : 0u);
+        const unsigned mx = __reduce_max_sync(kFull, v ? kx : 0u), my = __reduce_max_sync(kFull, v ? ky : 0u), mz = __reduce_max_sync(kFull, v ? kz : 0u);
+        if ((threadIdx.x & 31) == 0 && (ix | mx)) {
+            atomicMax(&a.scratch->box_inv_min[0], ix); atomicMax(&a.scratch->box_inv_min[1], iy); atomicMax(&a.scratch->box_inv_min[2], iz);
+            atomicMax(&a.scratch->box_max[0], mx); atomicMax(&a.scratch->box_max[1], my); atomicMax(&a.scratch->box_max[2], mz);
+        }
     }
     const int last_tile = a.n ? (int)((a.n - 1) / kBlock) : 0;
     if (tile == last_tile && threadIdx.x == 0) {
@@ -156,35 +173,86 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
     }
 }
 
+// ===================================================================================== K1b (dynamic grid only)
+// When the config crop box would need more cells than the table holds (e.g. trim "disabled" with huge
+// values), the grid is laid over the bounding box of this frame's `cloud` instead. Every block derives
+// the same GridDesc from the reduced box; block 0 publishes it for the later kernels.
+__device__ __forceinline__ GridDesc grid_from_box(const FramePtrs& a, bool* too_big) {
+    GridDesc g;
+    const Scratch* sc = a.scratch;
+    const double inv_h = 1.0 / a.cell_h;
+    double lo[3], hi[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { lo[q] = (double)fkey_inv(~sc->box_inv_min[q]); hi[q] = (double)fkey_inv(sc->box_max[q]); }
+    if (a.counts[MOR_CNT_NC] == 0) { lo[0] = lo[1] = lo[2] = 0; hi[0] = hi[1] = hi[2] = 0; }
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv_h = inv_h;
+    const double fx = floor((hi[0] - lo[0]) * inv_h) + 1.0, fy = floor((hi[1] - lo[1]) * inv_h) + 1.0, fz = floor((hi[2] - lo[2]) * inv_h) + 1.0;
+    *too_big = fx * fy * fz > (double)a.max_cells;
+    if (*too_big) { g.nx = g.ny = g.nz = 1; }  // memory-safe degenerate grid; the frame is flagged
+    else { g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; }
+    g.ncells = g.nx * g.ny * g.nz;
+    return g;
+}
+
+__global__ void __launch_bounds__(kBlock) k_keys(FramePtrs a) {
+    __shared__ GridDesc s_g;
+    if (threadIdx.x == 0) {
+        bool too_big;
+        s_g = grid_from_box(a, &too_big);
+        if (blockIdx.x == 0) {
+            *a.dgrid = s_g;
+            if (too_big) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_GRID_CAP);
+        }
+    }
+    __syncthreads();
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= a.counts[MOR_CNT_NC]) return;
+    const GridDesc& g = s_g;
+    const float4 p = a.pts[c];
+    int cx = (int)floor(((double)p.x - g.ox) * g.inv_h);
+    int cy = (int)floor(((double)p.y - g.oy) * g.inv_h);
+    int cz = (int)floor(((double)p.z - g.oz) * g.inv_h);
+    cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+    const int key = (cz * g.ny + cy) * g.nx + cx;
+    a.cell_key[c] = key;
+    a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+}
+
 // ===================================================================================== K2
 // Exclusive scan of the per-cell histogram -> cell_start[0..ncells] (counting sort of the cell keys).
+// Persistent blocks pull tiles by ticket, so the launch does not depend on the (possibly device-side)
+// cell count; the histogram is zeroed as it is consumed, ready for the next frame.
 __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
     __shared__ int s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_cells, 1);
-    __syncthreads();
-    const int tile = s_tile;
-    const int ncells = a.grid.ncells;
-    const int base = tile * kTile + threadIdx.x * kItems;
-    int v[kItems];
+    const int ncells = a.dgrid->ncells;
+    const int ntiles = (ncells + kTile - 1) / kTile;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_cells, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) return;
+        const int base = tile * kTile + threadIdx.x * kItems;
+        int v[kItems];
 #pragma unroll
-    for (int k = 0; k < kItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
+        for (int k = 0; k < kItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
 #pragma unroll
-    for (int k = 0; k < kItems; k++)
-        if (base + k < ncells && v[k]) a.cell_count[base + k] = 0;  // histogram consumed: ready for the next frame
-    int sum = 0;
+        for (int k = 0; k < kItems; k++)
+            if (base + k < ncells && v[k]) a.cell_count[base + k] = 0;
+        int sum = 0;
 #pragma unroll
-    for (int k = 0; k < kItems; k++) sum += v[k];
-    int total;
-    const int in_block = block_exclusive_scan<int>(sum, &total);
-    const int before = (int)tile_exclusive_prefix(a.st_cells, tile, (unsigned long long)total);
-    int run = before + in_block;
+        for (int k = 0; k < kItems; k++) sum += v[k];
+        int total;
+        const int in_block = block_exclusive_scan<int>(sum, &total);
+        const int before = (int)tile_exclusive_prefix(a.st_cells, tile, (unsigned long long)total);
+        int run = before + in_block;
 #pragma unroll
-    for (int k = 0; k < kItems; k++) {
-        if (base + k < ncells) a.cell_start[base + k] = run;
-        run += v[k];
+        for (int k = 0; k < kItems; k++) {
+            if (base + k < ncells) a.cell_start[base + k] = run;
+            run += v[k];
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) a.cell_start[ncells] = before + total;
     }
-    const int last_tile = (ncells - 1) / kTile;
-    if (tile == last_tile && threadIdx.x == 0) a.cell_start[ncells] = before + total;
 }
 
 // ===================================================================================== K3
@@ -308,7 +376,7 @@ __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
     const int dy = row < 10 ? (row % 5) - 2 : row - 12;
     const bool near_row = dz >= -1 && dy >= -1 && dy <= 1;
     const int key = a.skey[s];
-    const GridDesc& g = a.grid;
+    const GridDesc g = *a.dgrid;
     const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
     const int zz = cz + dz, yy = cy + dy;
     if (zz < 0 || yy < 0 || yy >= g.ny) return;
@@ -410,6 +478,7 @@ __global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kSingle) a.st_ingest[t] = 0ull;
     for (int t = threadIdx.x; t < a.tiles_cells; t += kSingle) a.st_cells[t] = 0ull;
     if (threadIdx.x == 0) { a.scratch->ticket_ingest = 0; a.scratch->ticket_cells = 0; a.scratch->n_roots = 0; a.scratch->stats_blocks_done = 0; }
+    if (threadIdx.x < 3) { a.scratch->box_inv_min[threadIdx.x] = 0u; a.scratch->box_max[threadIdx.x] = 0u; }
 }
 
 // ===================================================================================== K7
@@ -743,7 +812,7 @@ __global__ void __launch_bounds__(kBlock) k_pde_count(FramePtrs a, int ring) {
     const int m = a.mid_of_prev[kp];
     if (m < 0) return;
     const int target = a.match_m[m];
-    const GridDesc& g = a.grid;
+    const GridDesc g = *a.dgrid;
     const int cx = (int)floor(((double)t.x - g.ox) * g.inv_h), cy = (int)floor(((double)t.y - g.oy) * g.inv_h), cz = (int)floor(((double)t.z - g.oz) * g.inv_h);
     float best = 3.402823466e+38f;
     const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.nx - 1);

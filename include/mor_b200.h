@@ -58,7 +58,7 @@ enum { MOR_GROUND_CROP = 0, MOR_GROUND_VOXEL_COV = 1, MOR_GROUND_VOXEL_EIGEN = 2
 /* Optional capacities; zero fields take defaults. */
 typedef struct mor_limits {
     uint32_t max_points;    /* largest frame accepted (default 300000) */
-    uint32_t max_clusters;  /* largest number of size-valid clusters per frame (default 8192) */
+    uint32_t max_clusters;  /* largest number of size-valid clusters per frame (default 8192, at most 16384) */
     uint32_t max_moving;    /* capacity of the confirmed-moving list mo_vec (default 1024) */
     uint32_t reserved[5];
 } mor_limits;

@@ -1,0 +1,141 @@
+"""GPU parity on the edge cases the oracle tests cover: empty / tiny / non-finite inputs, arbitrary
+point_step and field offsets, missing intensity, min_cluster_size 1, the ExtractIndices overflow quirk,
+push-push-filter call patterns, and a randomised property test of cluster membership."""
+import numpy as np
+import pytest
+
+from dynamicslamtool_b200 import MovingObjectRemoval
+from helpers import IDENTITY_POSE, OPEN_CFG, blob, components_min_label, f32_sqdist_matrix, with_intensity, write_cfg
+from parity import ParityStats, compare_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(product, oracle, cfg, **kw):
+    return MovingObjectRemoval(cfg, 4, 3, binding=product, **kw), MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+
+
+def step(gpu, orc, pts, pose=IDENTITY_POSE, **kw):
+    gpu.push_raw_cloud_and_pose(pts, pose, **kw)
+    orc.push_raw_cloud_and_pose(pts, pose, **kw)
+    og, oo = gpu.filter_cloud().copy(), orc.filter_cloud().copy()
+    bad = compare_frame(gpu, orc, og, oo)
+    assert not bad, bad
+    return og
+
+
+def test_empty_tiny_and_nonfinite(product, oracle, tmp_path):
+    gpu, orc = pair(product, oracle, write_cfg(tmp_path))
+    step(gpu, orc, np.zeros((0, 4), np.float32))
+    step(gpu, orc, np.zeros((1, 4), np.float32))
+    pts = np.array([[0, 0, 0, 1], [3.0, 0, 0, 1], [3.0000002, 0, 0, 1], [-3.0, -3.0, -0.5, 1], [0, 0, -0.50000006, 1], [0, 0, 5.0, 1],
+                    [0, 0, 5.000001, 1], [np.nan, 0, 0, 1], [0, np.inf, 0, 1], [0, 0, -np.inf, 1], [0, -3.1, 0, 1]], np.float32)
+    out = step(gpu, orc, pts)
+    assert out.shape == (6, 8)
+    step(gpu, orc, np.zeros((0, 4), np.float32))
+
+
+def test_point_step_and_offsets(product, oracle, tmp_path):
+    rng = np.random.default_rng(0)
+    gpu, orc = pair(product, oracle, write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=20, max_cluster_size=5000, **OPEN_CFG))
+    xyz = np.concatenate([blob(rng, (0, 0, 0), 300, 0.1), blob(rng, (3, 1, 0), 200, 0.1)])
+    # Velodyne-style record: x y z pad intensity ring(u16) pad time -> 32 B, intensity at 16 (PCL PointXYZI layout)
+    rec = np.zeros((len(xyz), 8), np.float32)
+    rec[:, :3] = xyz
+    rec[:, 4] = rng.uniform(0, 1, len(xyz))
+    rec[:, 5:] = 123.0
+    blob32 = rec.view(np.uint8).reshape(-1)
+    for f in range(3):
+        step(gpu, orc, blob32, point_step=32, offsets=(0, 4, 8, 16))
+    # 12-byte xyz-only points, no intensity field
+    gpu, orc = pair(product, oracle, write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=20, max_cluster_size=5000, **OPEN_CFG))
+    out = step(gpu, orc, np.ascontiguousarray(xyz))
+    assert np.all(out[:, 4] == 0.0)
+    # fields in a scrambled order: z, intensity, y, x at 20 B
+    rec = np.stack([xyz[:, 2], np.full(len(xyz), 0.25, np.float32), xyz[:, 1], xyz[:, 0], np.zeros(len(xyz), np.float32)], axis=1).astype(np.float32)
+    step(gpu, orc, np.ascontiguousarray(rec).view(np.uint8).reshape(-1), point_step=20, offsets=(12, 8, 0, 4))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_membership_property_random_clouds(product, oracle, tmp_path, seed):
+    rng = np.random.default_rng(100 + seed)
+    r = float(rng.choice([0.05, 0.11, 0.3, 0.7]))
+    n = int(rng.integers(500, 3000))
+    xyz = np.concatenate([rng.uniform(-3, 3, (n, 3)), *(blob(rng, rng.uniform(-3, 3, 3), n // 8, r * 0.6) for _ in range(6))]).astype(np.float32)
+    # duplicates and points exactly on cell boundaries / at the radius
+    xyz = np.concatenate([xyz, xyz[:50], xyz[:50] + np.float32([r, 0, 0])]).astype(np.float32)
+    cfg = write_cfg(tmp_path, ec_distance_threshold=r, min_cluster_size=1, max_cluster_size=100000, **OPEN_CFG)
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_clusters=16384)
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    step(gpu, orc, with_intensity(xyz))
+    r2 = np.float32(np.float64(np.float32(r)) * np.float64(np.float32(r)))
+    want = components_min_label(f32_sqdist_matrix(xyz) < r2)  # independent of both implementations
+    np.testing.assert_array_equal(gpu.tap("labels"), want)
+    # permutation invariance of the partition
+    perm = rng.permutation(len(xyz))
+    step(gpu, orc, with_intensity(xyz[perm]))
+    lab = gpu.tap("labels")
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    a, b = want, lab[inv]
+    assert len(set(zip(a.tolist(), b.tolist()))) == len(set(a.tolist())) == len(set(b.tolist()))
+
+
+def test_extract_overflow_and_tracker_timeline(product, oracle, tmp_path):
+    rng = np.random.default_rng(11)
+    gpu, orc = pair(product, oracle, write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000, **OPEN_CFG))
+    base = blob(rng, (0, 0, 0), 300, 0.1)
+    seen = False
+    for f in range(12):
+        out = step(gpu, orc, with_intensity(base + np.float32([0.45 * f, 0, 0])))
+        seen |= bool(gpu.counts()["EXTRACT_OVERFLOW"])
+    assert seen
+
+
+def test_push_push_filter_and_double_filter(product, oracle, tmp_path):
+    rng = np.random.default_rng(12)
+    gpu, orc = pair(product, oracle, write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000, **OPEN_CFG))
+    a, b = blob(rng, (2, 0, 0), 300, 0.12), blob(rng, (-2, 1, 0), 300, 0.12)
+    for f in range(8):
+        pts = with_intensity(np.concatenate([a, b + np.float32([0.12 * f, 0, 0])]))
+        if f % 3 == 1:  # push without filter
+            gpu.push_raw_cloud_and_pose(pts, IDENTITY_POSE)
+            orc.push_raw_cloud_and_pose(pts, IDENTITY_POSE)
+            assert not compare_frame(gpu, orc, None, None, after_filter=False)
+            continue
+        step(gpu, orc, pts)
+        if f % 3 == 2:  # filter twice
+            og, oo = gpu.filter_cloud().copy(), orc.filter_cloud().copy()
+            assert not compare_frame(gpu, orc, og, oo)
+
+
+def test_capacity_errors_are_reported(product, tmp_path):
+    from dynamicslamtool_b200 import MorError
+    gpu = MovingObjectRemoval(write_cfg(tmp_path), 4, 3, binding=product, max_points=1000)
+    with pytest.raises(MorError) as e:
+        gpu.push_raw_cloud_and_pose(np.zeros((1001, 4), np.float32), IDENTITY_POSE)
+    assert e.value.status == 6
+    with pytest.raises(MorError):
+        MovingObjectRemoval(tmp_path / "missing.txt", 4, 3, binding=product)
+
+
+def test_device_resident_api_matches_host_api(product, tmp_path):
+    import ctypes as C
+    rng = np.random.default_rng(13)
+    cfg = write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000, **OPEN_CFG)
+    host, dev = MovingObjectRemoval(cfg, 4, 3, binding=product), MovingObjectRemoval(cfg, 4, 3, binding=product)
+    a, b = blob(rng, (2, 0, 0), 300, 0.12), blob(rng, (-2, 1, 0), 300, 0.12)
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    assert product.device_alloc(0, 600 * 16, C.byref(d_in)) == 0 and product.device_alloc(0, 600 * 32, C.byref(d_out)) == 0
+    for f in range(7):
+        pts = with_intensity(np.concatenate([a, b + np.float32([0.12 * f, 0, 0])]))
+        host.push_raw_cloud_and_pose(pts, IDENTITY_POSE)
+        want = host.filter_cloud().copy()
+        assert product.device_upload(0, d_in, pts.ctypes.data_as(C.c_void_p), pts.nbytes) == 0
+        dev.push_device(d_in.value, 600, IDENTITY_POSE)
+        n = dev.filter_device(d_out.value, 600)
+        got = np.empty((n, 8), np.float32)
+        assert product.device_download(0, got.ctypes.data_as(C.c_void_p), d_out, n * 32) == 0
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    product.device_free(0, d_in)
+    product.device_free(0, d_out)
