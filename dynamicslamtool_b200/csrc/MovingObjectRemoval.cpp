@@ -1,0 +1,70 @@
+// MovingObjectRemoval.cpp — host C++ class over the C ABI (see include/MOR/MovingObjectRemoval.h).
+#include "../../include/MOR/MovingObjectRemoval.h"
+
+#include <cstring>
+#include <stdexcept>
+
+namespace {
+
+// pcl::fromPCLPointCloud2 maps fields by name (reference cpp:523); FLOAT32 only, like PointXYZI.
+uint32_t find_field(const pcl::PCLPointCloud2& c, const char* name) {
+    for (const auto& f : c.fields)
+        if (f.name == name && f.datatype == 7 /*FLOAT32*/) return f.offset;
+    return UINT32_MAX;
+}
+
+}  // namespace
+
+void MovingObjectRemoval::init(const std::string& path, int n_bad, int n_good, int device, const mor_limits* limits) {
+    status_ = mor_create_ex(path.c_str(), n_bad, n_good, device, limits, &h_);
+    if (status_ != MOR_OK) throw std::runtime_error(std::string("MovingObjectRemoval: ") + mor_status_string(status_) + " (" + path + ")");
+    mor_get_config(h_, &cfg_);
+}
+
+MovingObjectRemoval::MovingObjectRemoval(ros::NodeHandle, std::string config_path, int n_bad, int n_good) { init(config_path, n_bad, n_good, 0, nullptr); }
+MovingObjectRemoval::MovingObjectRemoval(ros::NodeHandle, std::string config_path, int n_bad, int n_good, int device, const mor_limits* limits) {
+    init(config_path, n_bad, n_good, device, limits);
+}
+
+MovingObjectRemoval::~MovingObjectRemoval() {
+    if (pinned_out_) mor_free_pinned(pinned_out_);
+    mor_destroy(h_);
+}
+
+void MovingObjectRemoval::pushRawCloudAndPose(pcl::PCLPointCloud2& cloud, geometry_msgs::Pose pose) {
+    const uint32_t ox = find_field(cloud, "x"), oy = find_field(cloud, "y"), oz = find_field(cloud, "z"), oi = find_field(cloud, "intensity");
+    if (ox == UINT32_MAX || oy == UINT32_MAX || oz == UINT32_MAX) { status_ = MOR_ERR_ARG; return; }  // PCL: "Failed to find match for field"
+    const uint32_t n = cloud.width * cloud.height;
+    const double p7[7] = {pose.position.x, pose.position.y, pose.position.z, pose.orientation.x, pose.orientation.y, pose.orientation.z, pose.orientation.w};
+    n_in_ = n;
+    status_ = mor_push_raw_cloud_and_pose(h_, cloud.data.data(), n, cloud.point_step, ox, oy, oz, oi, p7);
+}
+
+bool MovingObjectRemoval::filterCloud(pcl::PCLPointCloud2& out_cloud, std::string f_id) {
+    const size_t need = (size_t)(n_in_ ? n_in_ : 1) * 32;
+    if (need > pinned_cap_) {
+        if (pinned_out_) mor_free_pinned(pinned_out_);
+        pinned_out_ = nullptr; pinned_cap_ = 0;
+        if (mor_alloc_pinned(need, &pinned_out_) != MOR_OK) { status_ = MOR_ERR_CUDA; return false; }
+        pinned_cap_ = need;
+    }
+    uint32_t n_out = 0;
+    status_ = mor_filter_cloud(h_, pinned_out_, (uint32_t)(pinned_cap_ / 32), &n_out);
+    if (status_ != MOR_OK) return false;
+    // pcl::toPCLPointCloud2 of a pcl::PointCloud<PointXYZI> (cpp:690): 32-byte records, fields x@0 y@4 z@8 intensity@16
+    static const char* const names[4] = {"x", "y", "z", "intensity"};
+    static const uint32_t offs[4] = {0, 4, 8, 16};
+    out_cloud.header = pcl::PCLHeader();
+    out_cloud.height = 1; out_cloud.width = n_out; out_cloud.is_bigendian = 0; out_cloud.point_step = 32; out_cloud.row_step = 32 * n_out; out_cloud.is_dense = 1;
+    out_cloud.fields.resize(4);
+    for (int i = 0; i < 4; i++) { out_cloud.fields[i].name = names[i]; out_cloud.fields[i].offset = offs[i]; out_cloud.fields[i].datatype = 7; out_cloud.fields[i].count = 1; }
+    out_cloud.data.resize((size_t)n_out * 32);
+    if (n_out) std::memcpy(out_cloud.data.data(), pinned_out_, (size_t)n_out * 32);
+    // pcl_conversions::fromPCL(out_cloud, output); output.header.frame_id = f_id (cpp:691-692)
+    output.header.seq = out_cloud.header.seq; output.header.frame_id = f_id;
+    output.height = 1; output.width = n_out; output.is_bigendian = 0; output.point_step = 32; output.row_step = 32 * n_out; output.is_dense = 1;
+    output.fields.resize(4);
+    for (int i = 0; i < 4; i++) { output.fields[i].name = names[i]; output.fields[i].offset = offs[i]; output.fields[i].datatype = 7; output.fields[i].count = 1; }
+    output.data = out_cloud.data;
+    return true;
+}

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "mor_kernels.cuh"
+#include "mor_ground.cuh"
 
 using namespace mor;
 
@@ -103,6 +104,7 @@ struct mor_handle {
     size_t zero_bytes = 0;
     size_t lattice_cap = 0;
     FramePtrs base;  // pointers that do not change from frame to frame
+    GroundPtrs ground;  // voxel-covariance ground removal state (ground_mode 1/2 only)
     // ping-pong
     float4* pts[2]; float4* spts[2]; int* cid[2]; int* cl_root[2]; int* cl_size[2]; float* cl_centroid[2]; uint8_t* cl_flags[2]; float* cl_bbox[2]; int* counts[2];
     int cur = 0;
@@ -123,19 +125,20 @@ struct mor_handle {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_pool;
     std::vector<int> prof_ids;  // kernel id of every recorded pair of the current frame
-    double prof_ms[32] = {0};
-    uint64_t prof_n[32] = {0};
+    double prof_ms[40] = {0};
+    uint64_t prof_n[40] = {0};
 };
 
 namespace {
 
 enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
                 KID_INIT_PREV, KID_TRANSFORM_PREV, KID_MATCH, KID_CLEAR_LATTICE, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE, KID_CHAIN,
-                KID_TRACK, KID_OUTPUT, KID__COUNT };
+                KID_TRACK, KID_OUTPUT, KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
 const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten", "k_select_clusters",
                                               "k_cluster_stats", "k_finalize_clusters", "k_init_prev_boxes", "k_transform_prev", "k_match",
                                               "memset_lattice", "k_lattice_insert", "k_lattice_count", "k_pde_count", "k_flags_and_chain", "k_track",
-                                              "k_output"};
+                                              "k_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter", "k_voxel_eval", "k_ground_mode",
+                                              "k_ground_mark", "k_ground_partition"};
 
 inline void prof_begin(mor_handle* h, int id) {
     if (!h->profiling) return;
@@ -203,7 +206,7 @@ int build_grid(mor_handle* h) {
 
 int allocate(mor_handle* h) {
     const size_t N = h->nmax, K = h->kmax, MO = h->momax, D = (size_t)h->ring_depth;
-    const size_t ncells = (size_t)h->grid.ncells;
+    const size_t ncells = h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells;
     const size_t tiles_pts = N / kBlock + 2, tiles_cells = ncells / kTile + 2;
     size_t lat = 1;
     while (lat < 2 * N) lat <<= 1;
@@ -242,6 +245,15 @@ int allocate(mor_handle* h) {
             h->cl_root[f] = carve<int>(p, K); h->cl_size[f] = carve<int>(p, K); h->cl_centroid[f] = carve<float>(p, K * 3);
             h->cl_flags[f] = carve<uint8_t>(p, K); h->cl_bbox[f] = carve<float>(p, K * 6); h->counts[f] = carve<int>(p, MOR_NCOUNTS);
         }
+        if (h->cfg.ground_mode != MOR_GROUND_CROP) {
+            GroundPtrs& g = h->ground;
+            const size_t vc = (size_t)h->max_cells;
+            g.rpts = carve<float4>(p, N); g.rsrc = carve<int>(p, N); g.is_ground = carve<uint8_t>(p, N); g.vkey = carve<int>(p, N);
+            g.vox_count = carve<int>(p, vc + 1); g.vox_ord = carve<int>(p, vc + 1); g.tiles_vox = (int)(vc / kTile + 2);
+            g.st_vox = carve<unsigned long long>(p, g.tiles_vox);
+            g.vox_n = carve<int>(p, N); g.vacc = carve<unsigned long long>(p, N * 6); g.vox_info = carve<float>(p, N * 8);
+            g.bin_hist = carve<int>(p, 65536); g.ggrid = carve<GridDesc>(p, 1); g.vdesc = carve<VoxDesc>(p, 1); g.gstate = carve<int>(p, 8);
+        }
         b.track = carve<TrackState>(p, 1); b.mo_centroid = carve<float>(p, MO * 3); b.mo_conf = carve<int>(p, MO);
         b.res_ring = carve<uint8_t>(p, D * K); b.res_len = carve<int>(p, D); b.corr_ring = carve<int>(p, D * K); b.corr_len = carve<int>(p, D);
         return p;
@@ -275,7 +287,13 @@ void fill_static(mor_handle* h) {
     b.dynamic_grid = h->dynamic_grid ? 1 : 0; b.max_cells = h->max_cells; b.cell_h = h->cell_h;
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
-    b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((size_t)h->grid.ncells / kTile + 2);
+    b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells) / kTile + 2);
+    if (c.ground_mode != MOR_GROUND_CROP) {
+        GroundPtrs& g = h->ground;
+        g.mode = c.ground_mode; g.leaf = c.gp_leaf; g.inv_leaf = 1.0f / c.gp_leaf; g.r2 = (float)((double)c.gp_leaf * (double)c.gp_leaf);
+        g.bin_gap = c.bin_gap; g.planarity = c.gp_planarity; g.bin_width = c.gp_bin_width;
+        g.ball_cell_h = (double)c.gp_leaf * (1.0 + 1.0 / 1024.0);
+    }
     const char* dbg = std::getenv("MOR_DEBUG");
     b.debug = dbg ? std::atoi(dbg) : 0;
 }
@@ -297,7 +315,23 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     std::memcpy(a.M.m, h->M, sizeof(h->M));
 
     const unsigned gb = blocks_for(n);
-    MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
+    if (h->cfg.ground_mode != MOR_GROUND_CROP) {
+        // voxel-covariance ground removal (reference cpp:90-200, repaired): 8 launches, then the common pipeline
+        const GroundPtrs& g = h->ground;
+        FramePtrs ag = a;
+        ag.dgrid = g.ggrid;  // the cell scan of this stage runs over the ball-query grid
+        MOR_LAUNCH(KID_G_INGEST, (k_ingest_raw<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_KEYS, (k_ground_keys<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<h->num_sms * 8, kBlock, 0, st>>>(ag)));
+        MOR_LAUNCH(KID_G_SCAN_VOX, (k_scan_voxels<<<h->num_sms * 8, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_SCATTER, (k_ground_scatter<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_EVAL, (k_voxel_eval<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_MODE, (k_ground_mode<<<1, kSingle, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_MARK, (k_ground_mark<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_PARTITION, (k_ground_partition<<<gb, kBlock, 0, st>>>(a, g)));
+    } else {
+        MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
+    }
     if (h->dynamic_grid) MOR_LAUNCH(KID_KEYS, (k_keys<<<gb, kBlock, 0, st>>>(a)));
     {
         const int tiles = (h->grid.ncells + kTile - 1) / kTile;
@@ -378,8 +412,8 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     const uint32_t no = (uint32_t)h->h_counts[MOR_CNT_NOUT];
     if (n_out) *n_out = no;
     if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
-        char msg[96];
-        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice 16=grid cells)", h->h_counts[MOR_CNT_ERRFLAGS]);
+        char msg[160];
+        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice 8=ground grid 16=grid cells)", h->h_counts[MOR_CNT_ERRFLAGS]);
         h->last_error = msg;
         return MOR_ERR_CAPACITY;
     }
@@ -405,7 +439,7 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     int st = mor_parse_config(config_path, &cfg);
     if (st != MOR_OK) return st;
     cfg.n_bad = n_bad; cfg.n_good = n_good;
-    if (cfg.ground_mode != MOR_GROUND_CROP) return MOR_ERR_CONFIG_VALUE;  // voxel-covariance modes: see mor_ground.cuh (next milestone)
+    if (cfg.ground_mode != MOR_GROUND_CROP && !(cfg.gp_leaf > 0.f)) return MOR_ERR_CONFIG_VALUE;
     mor_handle* h = new mor_handle();
     h->cfg = cfg; h->device = device;
     h->nmax = limits && limits->max_points ? limits->max_points : 300000u;
@@ -593,7 +627,7 @@ int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes
         case MOR_TAP_CLUSTER_REMOVED: if (!h->filtered) return MOR_ERR_STATE; src = a.cluster_removed; bytes = K; break;
         case MOR_TAP_RECIP_QUERY: src = a.recip_q; bytes = MU * 4; break;
         case MOR_TAP_RECIP_MATCH: src = a.recip_m; bytes = MU * 4; break;
-        case MOR_TAP_GROUND_VOXELS: bytes = 0; break;
+        case MOR_TAP_GROUND_VOXELS: if (h->cfg.ground_mode != MOR_GROUND_CROP) { src = h->ground.vox_info; bytes = (size_t)c[MOR_CNT_NVOX] * 32; } break;
         case MOR_TAP_CLUSTER_BBOX: src = a.cl_bbox; bytes = K * 24; break;
         case MOR_TAP_PREV_BBOX_T: src = a.pbbox; bytes = KP * 24; break;
         case 99: src = a.scratch; bytes = sizeof(Scratch); break;  // debug instrumentation (MOR_DEBUG)

@@ -449,8 +449,15 @@ struct mor_handle {
         }
     }
 
-    // ---------------- groundPlaneRemoval(x,y), cpp:90-200 (DEAD + crashing in the reference;
-    // repaired semantics). mode 1 = literal, mode 2 = eigen-normal generalisation.
+    // ---------------- groundPlaneRemoval(x,y), cpp:90-200 (DEAD + crashing in the reference: the call is commented
+    // out at cpp:527 and gp_i is a null shared_ptr at cpp:182-188). Repaired semantics:
+    //   * gp_i allocated; ground indices deduplicated and ascending; no accepted voxel => nothing removed;
+    //   * mode bin tie => smallest key;
+    //   * order-independent arithmetic so a parallel implementation can reproduce it: voxel centroids and ball
+    //     statistics are accumulated in double (relative to the voxel centroid) instead of float in index order.
+    // mode 1 = literal test (|S_xz|, |S_yz|, |S_zz| < 0.001 on the un-normalised scatter, Z bins of cpp:166);
+    // mode 2 = eigen-normal generalisation (north_star item 2; no reference behaviour): planarity + normal test,
+    //          bins along each voxel's own normal, every bin holding >= 25 % of the mode bin is ground.
     void ground_voxel(FrameCloud& fc, int mode) {
         const std::vector<PointXYZI>& raw = fc.raw_cloud;
         const int n = (int)raw.size();
@@ -458,118 +465,108 @@ struct mor_handle {
         std::vector<uint8_t> is_ground(n, 0);
         const float leaf = cfg.gp_leaf;
         if (n > 0 && leaf > 0) {
-            // --- VoxelGrid (A14), cpp:110-113
+            // --- VoxelGrid (A14), cpp:110-113: float index arithmetic, output in ascending voxel index
             const float inv_leaf = 1.0f / leaf;
             float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             for (const auto& p : raw) {
                 mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
                 mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
             }
-            int64_t minb[3], maxb[3], div[3];
+            int64_t minb[3], div[3];
             for (int d = 0; d < 3; d++) {
                 minb[d] = (int64_t)std::floor(mn[d] * inv_leaf);
-                maxb[d] = (int64_t)std::floor(mx[d] * inv_leaf);
-                div[d] = maxb[d] - minb[d] + 1;
+                div[d] = (int64_t)std::floor(mx[d] * inv_leaf) - minb[d] + 1;
             }
-            std::vector<PointXYZI> dsc;
-            if (div[0] * div[1] * div[2] > (int64_t)std::numeric_limits<int32_t>::max()) {
-                dsc = raw;  // PCL warns "Leaf size is too small" and returns the input unfiltered
-            } else {
-                std::vector<std::pair<int32_t, int>> keyed(n);
+            struct Vox { int64_t idx; double sx, sy, sz; int n; };
+            std::vector<Vox> vox;
+            {
+                std::vector<std::pair<int64_t, int>> keyed(n);
                 for (int i = 0; i < n; i++) {
-                    int64_t ijk0 = (int64_t)std::floor(raw[i].x * inv_leaf) - minb[0];
-                    int64_t ijk1 = (int64_t)std::floor(raw[i].y * inv_leaf) - minb[1];
-                    int64_t ijk2 = (int64_t)std::floor(raw[i].z * inv_leaf) - minb[2];
-                    keyed[i] = {(int32_t)(ijk0 + ijk1 * div[0] + ijk2 * div[0] * div[1]), i};
+                    int64_t i0 = (int64_t)std::floor(raw[i].x * inv_leaf) - minb[0];
+                    int64_t i1 = (int64_t)std::floor(raw[i].y * inv_leaf) - minb[1];
+                    int64_t i2 = (int64_t)std::floor(raw[i].z * inv_leaf) - minb[2];
+                    keyed[i] = {i0 + i1 * div[0] + i2 * div[0] * div[1], i};
                 }
-                std::stable_sort(keyed.begin(), keyed.end(),
-                                 [](const std::pair<int32_t, int>& a, const std::pair<int32_t, int>& b) { return a.first < b.first; });
+                std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a.first < b.first; });
                 for (int s = 0; s < n;) {
                     int e = s;
-                    float sx = 0, sy = 0, sz = 0, si = 0;  // CentroidPoint: float accumulators, all fields
+                    Vox v{keyed[s].first, 0, 0, 0, 0};
                     while (e < n && keyed[e].first == keyed[s].first) {
                         const PointXYZI& p = raw[keyed[e].second];
-                        sx += p.x; sy += p.y; sz += p.z; si += p.intensity; e++;
+                        v.sx += p.x; v.sy += p.y; v.sz += p.z; v.n++; e++;
                     }
-                    float cnt = (float)(e - s);
-                    dsc.push_back(PointXYZI{sx / cnt, sy / cnt, sz / cnt, si / cnt});
+                    vox.push_back(v);
                     s = e;
                 }
             }
-            // --- kd-tree over raw_cloud, ball query r = gp_leaf (cpp:115-125), strict < (A6)
+            // --- ball query r = gp_leaf around every voxel centroid (cpp:115-125), strict < (A6, A7)
             std::vector<float> rx(n), ry(n), rz(n);
             for (int i = 0; i < n; i++) { rx[i] = raw[i].x; ry[i] = raw[i].y; rz[i] = raw[i].z; }
             KdTree tree; tree.build(rx, ry, rz);
-            const float r2 = (float)((double)leaf * (double)leaf);  // A7
+            const float r2 = (float)((double)leaf * (double)leaf);
             std::vector<int> ind;
-            struct Acc { int voxel; double key; };
-            std::vector<Acc> accepted;
+            std::vector<long long> acc_key;
             std::vector<std::vector<int>> index_bank;
-            fc.ground_voxels.assign(dsc.size() * 8, 0.f);
-            for (size_t v = 0; v < dsc.size(); v++) {
+            fc.ground_voxels.assign(vox.size() * 8, 0.f);
+            for (size_t v = 0; v < vox.size(); v++) {
+                const float qx = (float)(vox[v].sx / vox[v].n), qy = (float)(vox[v].sy / vox[v].n), qz = (float)(vox[v].sz / vox[v].n);
                 float* gv = &fc.ground_voxels[v * 8];
-                gv[0] = dsc[v].x; gv[1] = dsc[v].y; gv[2] = dsc[v].z; gv[3] = 0; gv[4] = 0; gv[5] = 0; gv[6] = 0; gv[7] = 0;
-                tree.radius(dsc[v].x, dsc[v].y, dsc[v].z, r2, ind);
+                gv[0] = qx; gv[1] = qy; gv[2] = qz;
+                tree.radius(qx, qy, qz, r2, ind);
                 if (ind.size() <= 3) continue;  // cpp:131
-                std::sort(ind.begin(), ind.end());  // canonical accumulation order: ascending index
-                bool ok; double key;
+                double m[3] = {0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};  // moments of d = p - q
+                for (int j : ind) {
+                    const double dx = (double)raw[j].x - (double)qx, dy = (double)raw[j].y - (double)qy, dz = (double)raw[j].z - (double)qz;
+                    m[0] += dx; m[1] += dy; m[2] += dz;
+                    a[0] += dx * dx; a[1] += dx * dy; a[2] += dx * dz; a[3] += dy * dy; a[4] += dy * dz; a[5] += dz * dz;
+                }
+                const double nn = (double)ind.size();
+                // un-normalised scatter about the mean (computeCovarianceMatrix, A15): S_ab = sum(d_a d_b) - sum(d_a) sum(d_b) / n
+                const double S[6] = {a[0] - m[0] * m[0] / nn, a[1] - m[0] * m[1] / nn, a[2] - m[0] * m[2] / nn,
+                                     a[3] - m[1] * m[1] / nn, a[4] - m[1] * m[2] / nn, a[5] - m[2] * m[2] / nn};
+                bool ok; long long key;
                 if (mode == MOR_GROUND_VOXEL_COV) {
-                    // compute3DCentroid<float> + computeCovarianceMatrix (un-normalised scatter) (A15), cpp:141-145
-                    float cx = 0, cy = 0, cz = 0;
-                    for (int j : ind) { cx += raw[j].x; cy += raw[j].y; cz += raw[j].z; }
-                    const float fn = (float)ind.size();
-                    cx /= fn; cy /= fn; cz /= fn;
-                    float sxz = 0, syz = 0, szz = 0;
-                    for (int j : ind) {
-                        float dx = raw[j].x - cx, dy = raw[j].y - cy, dz = raw[j].z - cz;
-                        sxz += dx * dz; syz += dy * dz; szz += dz * dz;
-                    }
-                    ok = std::fabs(sxz) < 0.001 && std::fabs(syz) < 0.001 && std::fabs(szz) < 0.001;  // cpp:145
-                    // cpp:166: key = (float)((int)(z*10))/bin_gap  (float mul, trunc toward 0)
-                    key = (double)((float)((int)(dsc[v].z * 10)) / cfg.bin_gap);
+                    ok = std::fabs(S[2]) < 0.001 && std::fabs(S[4]) < 0.001 && std::fabs(S[5]) < 0.001;  // cpp:145
+                    key = (long long)(int)(qz * 10);  // cpp:166: (float)((int)(z*10))/bin_gap is monotone in this integer
                     gv[5] = 0; gv[6] = 0; gv[7] = 1;
                 } else {
-                    // eigen-normal generalisation: covariance in double about the double mean
-                    double cx = 0, cy = 0, cz = 0;
-                    for (int j : ind) { cx += raw[j].x; cy += raw[j].y; cz += raw[j].z; }
-                    const double dn = (double)ind.size();
-                    cx /= dn; cy /= dn; cz /= dn;
-                    double a[6] = {0, 0, 0, 0, 0, 0};
-                    for (int j : ind) {
-                        double dx = raw[j].x - cx, dy = raw[j].y - cy, dz = raw[j].z - cz;
-                        a[0] += dx * dx; a[1] += dx * dy; a[2] += dx * dz; a[3] += dy * dy; a[4] += dy * dz; a[5] += dz * dz;
-                    }
                     double lmin, nrm[3], tr;
-                    smallest_eigvec_sym3(a, lmin, nrm, tr);
+                    smallest_eigvec_sym3(S, lmin, nrm, tr);
                     ok = tr > 0 && (lmin / tr) < (double)cfg.gp_planarity && nrm[2] > 0.7;
                     gv[5] = (float)nrm[0]; gv[6] = (float)nrm[1]; gv[7] = (float)nrm[2];
-                    // bin along the voxel's own normal: signed plane offset n.c
-                    double off = nrm[0] * dsc[v].x + nrm[1] * dsc[v].y + nrm[2] * dsc[v].z;
-                    key = std::floor(off / (double)cfg.gp_bin_width);
+                    const double off = nrm[0] * (double)qx + nrm[1] * (double)qy + nrm[2] * (double)qz;  // plane offset along the voxel's own normal
+                    key = (long long)std::floor(off / (double)cfg.gp_bin_width);
                 }
+                if (key < -32768) key = -32768;
+                if (key > 32767) key = 32767;
+                gv[4] = (float)key;
                 if (ok) {
-                    gv[3] = 1; gv[4] = (float)key;
-                    accepted.push_back(Acc{(int)v, key});
+                    gv[3] = 1;
+                    acc_key.push_back(key);
                     index_bank.push_back(ind);
                 }
             }
-            // --- Z-bin mode (cpp:161-178); repaired: empty => no ground; tie => smallest key
-            if (!accepted.empty()) {
-                std::unordered_map<double, int> bins;
-                for (const auto& a : accepted) bins[a.key]++;
-                double tracked = 0; int mode_cnt = -1;
-                for (const auto& kv : bins)
-                    if (kv.second > mode_cnt || (kv.second == mode_cnt && kv.first < tracked)) { mode_cnt = kv.second; tracked = kv.first; }
-                // ground = union of balls of accepted voxels in the mode bin (cpp:184-191); mode 2 also
-                // takes the two adjacent bins (a sloped plane straddles bins)
-                for (size_t a = 0; a < accepted.size(); a++) {
-                    bool take = accepted[a].key == tracked;
-                    if (mode == MOR_GROUND_VOXEL_EIGEN) take = std::fabs(accepted[a].key - tracked) <= 1.0;
-                    if (take) for (int j : index_bank[a]) is_ground[j] = 1;
+            // --- bin histogram and mode (cpp:161-178)
+            if (!acc_key.empty()) {
+                std::vector<int> hist(65536, 0);
+                for (long long k : acc_key) hist[k + 32768]++;
+                // mode 1: the reference compares keys (float)kz/bin_gap; "smallest key" is the smallest kz for bin_gap > 0
+                // and the largest kz for bin_gap < 0
+                const bool ascending = !(mode == MOR_GROUND_VOXEL_COV && cfg.bin_gap < 0);
+                int best = -1, best_cnt = 0;
+                for (int t = 0; t < 65536; t++) {
+                    const int k = ascending ? t : 65535 - t;
+                    if (hist[k] > best_cnt) { best_cnt = hist[k]; best = k; }
+                }
+                const int thr = mode == MOR_GROUND_VOXEL_EIGEN ? std::max(1, (best_cnt + 3) / 4) : best_cnt;
+                for (size_t a2 = 0; a2 < acc_key.size(); a2++) {
+                    const int k = (int)(acc_key[a2] + 32768);
+                    const bool take = mode == MOR_GROUND_VOXEL_EIGEN ? hist[k] >= thr : k == best;
+                    if (take) for (int j : index_bank[a2]) is_ground[j] = 1;  // cpp:184-191
                 }
             }
         }
-        // ExtractIndices(negative) (cpp:194-198) + repaired gp_indices: deduped, ascending
+        // ExtractIndices(negative) (cpp:194-198) + repaired gp_indices: deduplicated, ascending
         for (int i = 0; i < n; i++) {
             if (is_ground[i]) fc.gp_indices.push_back(i);
             else { fc.cloud.push_back(raw[i]); fc.cloud_src.push_back(i); }

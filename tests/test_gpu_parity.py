@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from dynamicslamtool_b200 import MovingObjectRemoval, Synth
-from parity import ParityStats, run_sequence
+from parity import ParityStats, compare_frame, run_sequence
 
 pytestmark = pytest.mark.gpu
 
@@ -37,3 +37,36 @@ def test_sequence_parity(product, oracle, cfg_dir, tmp_path, scenario, cfg, fram
     assert stats.matches > 0
     if scenario == 1 and method == 2:
         assert stats.removed_points > 0 and stats.mo_frames > 0  # the removal path was exercised
+
+
+@pytest.mark.parametrize("scenario,base,frames,overrides", [
+    (4, "MOR_config_terrain.txt", 8, {}),                                                  # C4: eigen-normal mode on sloped / multi-plane terrain
+    (4, "MOR_config_terrain.txt", 6, {"ground_mode": 1, "gp_leaf": 0.5}),                  # literal voxel-covariance test, outdoor leaf
+    (1, "MOR_config.txt", 8, {"ground_mode": 1}),                                          # literal mode with the reference defaults (leaf 0.1, bin_gap 10)
+    (1, "MOR_config.txt", 6, {"ground_mode": 2, "gp_bin_width": 0.1}),
+])
+def test_voxel_covariance_ground_modes(product, oracle, cfg_dir, tmp_path, scenario, base, frames, overrides):
+    """Ground removal by voxel covariance (reference cpp:90-200, dead code there): parity against the oracle's repaired
+    restatement, including the per-voxel taps (centroids / normals within 1e-5, accepted flags and bins exact)."""
+    import numpy as np
+    from helpers import write_cfg
+    cfg = write_cfg(tmp_path, base=cfg_dir / base, **overrides)
+    maxp = Synth(scenario, scenario).max_points
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=maxp)
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    stats = ParityStats()
+    for f, (pts, pose) in enumerate(_frames(scenario, scenario, frames)):
+        gpu.push_raw_cloud_and_pose(pts, pose)
+        orc.push_raw_cloud_and_pose(pts, pose)
+        vg, vo = gpu.tap("ground_voxels"), orc.tap("ground_voxels")
+        assert vg.shape == vo.shape and vg.shape[0] > 0, f"frame {f}: voxel count {vg.shape} vs {vo.shape}"
+        np.testing.assert_allclose(vg[:, :3], vo[:, :3], rtol=1e-5, atol=1e-7, err_msg=f"frame {f}: voxel centroids")
+        assert np.array_equal(vg[:, 3], vo[:, 3]), f"frame {f}: accepted flags differ in {int(np.sum(vg[:, 3] != vo[:, 3]))} voxels"
+        acc = vo[:, 3] > 0
+        assert np.array_equal(vg[acc, 4], vo[acc, 4]), f"frame {f}: bin keys"
+        np.testing.assert_allclose(vg[acc, 5:], vo[acc, 5:], rtol=1e-5, atol=1e-6, err_msg=f"frame {f}: normals")
+        og, oo = gpu.filter_cloud().copy(), orc.filter_cloud().copy()
+        bad = compare_frame(gpu, orc, og, oo, stats)
+        assert not bad, f"frame {f}: {bad}"
+        assert gpu.counts()["NG"] > 0
+    print("ground parity stats", stats.as_dict())
