@@ -281,7 +281,7 @@ def run_product(args, rank, local_rank, world):
         dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_us"] * per_kernel[k]["launches"])
         peak, which = measured_peak_gbs()
         # SURVEY §8(d) per-unit figures (bytes per cloud point of the stage the kernel implements)
-        per_unit = {"k_link_cells": 20, "k_ingest": 33, "k_scatter": 40, "k_flatten": 8, "k_cluster_stats": 16, "k_output": 36,
+        per_unit = {"k_link_cells": 20, "k_ingest": 33, "k_scatter": 40, "k_flatten": 8, "k_cluster_stats": 16, "k_filter_output": 36,
                     "k_lattice_insert": 16, "k_lattice_count": 16, "k_transform_prev": 24, "k_scan_cells": 8}
         unit_bytes = per_unit.get(dom, 20)
         mean_nc = nc_sum / max(nprof, 1)

@@ -109,6 +109,7 @@ struct mor_handle {
     float4* pts[2]; float4* spts[2]; int* cid[2]; int* cl_root[2]; int* cl_size[2]; float* cl_centroid[2]; uint8_t* cl_flags[2]; float* cl_bbox[2]; int* counts[2];
     int cur = 0;
     bool have_cur = false, have_prev = false, filtered = false;
+    int mo_parity = 0;
     double cur_pose[7], prev_pose[7];
     float M[12];
     bool two_frames = false;
@@ -137,7 +138,7 @@ enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER
 const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten", "k_select_clusters",
                                               "k_cluster_stats", "k_finalize_clusters", "k_init_prev_boxes", "k_transform_prev", "k_match",
                                               "memset_lattice", "k_lattice_insert", "k_lattice_count", "k_pde_count", "k_flags_and_chain", "k_track",
-                                              "k_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter", "k_voxel_eval", "k_ground_mode",
+                                              "k_filter_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter", "k_voxel_eval", "k_ground_mode",
                                               "k_ground_mark", "k_ground_partition"};
 
 inline void prof_begin(mor_handle* h, int id) {
@@ -254,7 +255,7 @@ int allocate(mor_handle* h) {
             g.vox_n = carve<int>(p, N); g.vacc = carve<unsigned long long>(p, N * 6); g.vox_info = carve<float>(p, N * 8);
             g.bin_hist = carve<int>(p, 65536); g.ggrid = carve<GridDesc>(p, 1); g.vdesc = carve<VoxDesc>(p, 1); g.gstate = carve<int>(p, 8);
         }
-        b.track = carve<TrackState>(p, 1); b.mo_centroid = carve<float>(p, MO * 3); b.mo_conf = carve<int>(p, MO);
+        b.track = carve<TrackState>(p, 1); b.mo_centroid = carve<float>(p, 2 * MO * 3); b.mo_conf = carve<int>(p, 2 * MO);
         b.res_ring = carve<uint8_t>(p, D * K); b.res_len = carve<int>(p, D); b.corr_ring = carve<int>(p, D * K); b.corr_len = carve<int>(p, D);
         return p;
     };
@@ -312,6 +313,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     a.p_pts = h->pts[prev]; a.p_spts = h->spts[prev]; a.p_cid = h->cid[prev]; a.p_cl_root = h->cl_root[prev]; a.p_cl_size = h->cl_size[prev];
     a.p_cl_centroid = h->cl_centroid[prev]; a.p_cl_flags = h->cl_flags[prev]; a.p_counts = h->counts[prev];
     a.two_frames = h->two_frames ? 1 : 0;
+    a.mo_parity = h->mo_parity;
     std::memcpy(a.M.m, h->M, sizeof(h->M));
 
     const unsigned gb = blocks_for(n);
@@ -330,7 +332,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         MOR_LAUNCH(KID_G_MARK, (k_ground_mark<<<gb, kBlock, 0, st>>>(a, g)));
         MOR_LAUNCH(KID_G_PARTITION, (k_ground_partition<<<gb, kBlock, 0, st>>>(a, g)));
     } else {
-        MOR_LAUNCH(KID_INGEST, (k_ingest<<<gb, kBlock, 0, st>>>(a)));
+        MOR_LAUNCH(KID_INGEST, (k_ingest<<<n ? (n + kIngestTile - 1) / kIngestTile : 1, kBlock, 0, st>>>(a)));
     }
     if (h->dynamic_grid) MOR_LAUNCH(KID_KEYS, (k_keys<<<gb, kBlock, 0, st>>>(a)));
     {
@@ -400,8 +402,10 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     if (on_device && out) a.out = (float4*)out;  // write the records straight into the caller's device buffer
     else a.out = h->base.out;
     if (on_device && out && cap_points < h->n_input) { h->last_error = "device output buffer must hold n_input points"; return MOR_ERR_CAPACITY; }
-    MOR_LAUNCH(KID_TRACK, (k_track<<<1, kSingle, 0, st>>>(a)));
-    MOR_LAUNCH(KID_OUTPUT, (k_output<<<blocks_for(h->n_input), kBlock, 0, st>>>(a)));
+    a.mo_parity = h->mo_parity;
+    MOR_LAUNCH(KID_OUTPUT, (k_filter_output<<<h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kBlock, 0, st>>>(a)));
+    h->mo_parity ^= 1;  // the kernel wrote the updated mo_vec into the other half
+    a.mo_parity = h->mo_parity;
     MOR_CUDA(cudaGetLastError());
     h->filtered = true;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[3], st));
@@ -621,8 +625,8 @@ int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes
         case MOR_TAP_MATCH_DIST: src = a.match_dist; bytes = M * 4; break;
         case MOR_TAP_MATCH_SCORE: src = a.match_score; bytes = M * 8; break;
         case MOR_TAP_FLAGS: src = a.cl_flags; bytes = K; break;
-        case MOR_TAP_MO_CENTROIDS: src = a.mo_centroid; bytes = NMO * 12; break;
-        case MOR_TAP_MO_CONF: src = a.mo_conf; bytes = NMO * 4; break;
+        case MOR_TAP_MO_CENTROIDS: src = a.mo_centroid + (size_t)h->mo_parity * h->momax * 3; bytes = NMO * 12; break;
+        case MOR_TAP_MO_CONF: src = a.mo_conf + (size_t)h->mo_parity * h->momax; bytes = NMO * 4; break;
         case MOR_TAP_REMOVED_MASK: if (!h->filtered) return MOR_ERR_STATE; src = a.removed_mask; bytes = N; break;
         case MOR_TAP_CLUSTER_REMOVED: if (!h->filtered) return MOR_ERR_STATE; src = a.cluster_removed; bytes = K; break;
         case MOR_TAP_RECIP_QUERY: src = a.recip_q; bytes = MU * 4; break;

@@ -22,19 +22,18 @@ struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-1
 
 struct Scratch {  // zeroed at the start of every frame (one memset, together with cell_count)
     int ticket_ingest, ticket_cells, ticket_out, n_roots;
-    int moving_total, stats_blocks_done, pad1, pad2;
+    int moving_total, stats_blocks_done, out_blocks_done, pad2;
     unsigned box_inv_min[3], box_max[3];  // dynamic grid: bbox of `cloud` (ordered keys; mins stored inverted so 0 is neutral)
     int pad3, pad4;
     unsigned long long dbg[8];  // MOR_DEBUG&4 instrumentation of k_link_cells
 };
 
 struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:109-128)
-    int n_mo;         // mo_vec.size()
+    int n_mo[2];      // mo_vec.size(), double-buffered like mo_centroid / mo_conf (see k_filter_output)
     int res_count, res_head;    // res_vec deque
     int corr_count, corr_head;  // corrs_vec deque
     int frames;
     int extract_overflow;
-    int pad;
 };
 
 // Everything a kernel needs, passed by value (fits the 4 KB parameter space comfortably).
@@ -78,6 +77,7 @@ struct FramePtrs {
     TrackState* track; float* mo_centroid; int* mo_conf;
     uint8_t* res_ring; int* res_len; int* corr_ring; int* corr_len;
     Affine12 M; int two_frames;
+    int mo_parity;  // which half of the mo_vec double buffer is current
     int tiles_pts, tiles_cells;  // sizes of the scan status arrays
     unsigned lattice_words16;    // lattice size in 16-byte units (cleared by k_ingest)
     int debug;  // MOR_DEBUG env (profiling experiments only; 0 in production)
@@ -86,80 +86,108 @@ struct FramePtrs {
 // ===================================================================================== K1
 // pcl::fromPCLPointCloud2 (cpp:523) + PassThrough x, y (cpp:66-74, A1) + CropBox with removed indices
 // (cpp:78-86, A2), fused with the stable two-way partition into `cloud` / gp_indices order, the grid
-// cell key of every cloud point and the per-cell histogram. One point per thread, coalesced AoS read.
+// cell key of every cloud point and the per-cell histogram. kIngestItems consecutive points per thread
+// (tile = 1024 points): the decoupled look-back chain has n/1024 links instead of n/256.
+constexpr int kIngestItems = 4;
+constexpr int kIngestTile = kBlock * kIngestItems;
+
 __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
     __syncthreads();
     const int tile = s_tile;
-    const uint32_t i = (uint32_t)tile * kBlock + threadIdx.x;
+    const uint32_t gtid = (uint32_t)tile * kBlock + threadIdx.x;
     if (a.two_frames) {
         // housekeeping for the two-frame stages, spread over the grid: empty octree-lattice hash set,
         // neutral bounding boxes for the transformed previous clusters
         const uint32_t stride = gridDim.x * kBlock;
         if (a.method == 2) {
             uint4* lat = reinterpret_cast<uint4*>(a.lattice);
-            for (uint32_t t = i; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (uint32_t t = gtid; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         }
         const uint32_t kp6 = (uint32_t)a.p_counts[MOR_CNT_K] * 6u;
-        for (uint32_t t = i; t < kp6; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
+        for (uint32_t t = gtid; t < kp6; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
     }
-    float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
-    int cls = 0;
-    if (i < a.n) {
-        const uint8_t* p = a.in + (size_t)i * a.step;
-        if (a.vec16) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(p));
-            x = v.x; y = v.y; z = v.z; w = v.w;
-        } else {
-            x = __ldg(reinterpret_cast<const float*>(p + a.off_x));
-            y = __ldg(reinterpret_cast<const float*>(p + a.off_y));
-            z = __ldg(reinterpret_cast<const float*>(p + a.off_z));
-            w = a.off_i != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float*>(p + a.off_i)) : 0.f;
+    const uint32_t i0 = (uint32_t)tile * kIngestTile + threadIdx.x * kIngestItems;
+    float4 v[kIngestItems];
+    int cls[kIngestItems];
+    unsigned long long packed = 0ull;
+#pragma unroll
+    for (int k = 0; k < kIngestItems; k++) {
+        const uint32_t i = i0 + k;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cls[k] = 0;
+        if (i < a.n) {
+            const uint8_t* p = a.in + (size_t)i * a.step;
+            if (a.vec16) {
+                v[k] = __ldg(reinterpret_cast<const float4*>(p));
+            } else {
+                v[k].x = __ldg(reinterpret_cast<const float*>(p + a.off_x));
+                v[k].y = __ldg(reinterpret_cast<const float*>(p + a.off_y));
+                v[k].z = __ldg(reinterpret_cast<const float*>(p + a.off_z));
+                v[k].w = a.off_i != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float*>(p + a.off_i)) : 0.f;
+            }
         }
-        const bool fin = isfinite(x) && isfinite(y) && isfinite(z);
-        const bool in_xy = fin && !(x < -a.trim_x || x > a.trim_x) && !(y < -a.trim_y || y > a.trim_y);
-        if (in_xy) cls = (z < a.gp_limit || z > a.trim_z) ? 2 : 1;  // x,y box tests of CropBox are implied by the trim
-        a.point_class[i] = (uint8_t)cls;
-        a.removed_mask[i] = cls ? 1 : 0;
     }
-    unsigned long long packed = (cls == 1 ? 1ull : 0ull) | (cls == 2 ? (1ull << 31) : 0ull);
+#pragma unroll
+    for (int k = 0; k < kIngestItems; k++) {
+        const uint32_t i = i0 + k;
+        if (i < a.n) {
+            const float x = v[k].x, y = v[k].y, z = v[k].z;
+            const bool fin = isfinite(x) && isfinite(y) && isfinite(z);
+            const bool in_xy = fin && !(x < -a.trim_x || x > a.trim_x) && !(y < -a.trim_y || y > a.trim_y);
+            if (in_xy) cls[k] = (z < a.gp_limit || z > a.trim_z) ? 2 : 1;  // x,y box tests of CropBox are implied by the trim
+            a.point_class[i] = (uint8_t)cls[k];
+            a.removed_mask[i] = cls[k] ? 1 : 0;
+            packed += (cls[k] == 1 ? 1ull : 0ull) | (cls[k] == 2 ? (1ull << 31) : 0ull);
+        }
+    }
     unsigned long long total;
     const unsigned long long in_block = block_exclusive_scan<unsigned long long>(packed, &total);
     const unsigned long long before = tile_exclusive_prefix(a.st_ingest, tile, total);
-    const unsigned long long mine = before + in_block;
-    if (cls == 1) {
-        const int c = (int)(mine & 0x7FFFFFFFull);
-        a.pts[c] = make_float4(x, y, z, w);
-        a.cloud_src[c] = (int)i;
-        a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // slot c doubles as a sorted position
-        a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
-        if (!a.dynamic_grid) {
-            const GridDesc& g = a.grid;
-            int cx = (int)floor(((double)x - g.ox) * g.inv_h);
-            int cy = (int)floor(((double)y - g.oy) * g.inv_h);
-            int cz = (int)floor(((double)z - g.oz) * g.inv_h);
-            cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
-            const int key = (cz * g.ny + cy) * g.nx + cx;
-            a.cell_key[c] = key;
-            a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+    unsigned long long mine = before + in_block;
+#pragma unroll
+    for (int k = 0; k < kIngestItems; k++) {
+        if (cls[k] == 1) {
+            const int c = (int)(mine & 0x7FFFFFFFull);
+            mine += 1ull;
+            a.pts[c] = v[k];
+            a.cloud_src[c] = (int)(i0 + k);
+            a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // slot c doubles as a sorted position
+            a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
+            if (!a.dynamic_grid) {
+                const GridDesc& g = a.grid;
+                int cx = (int)floor(((double)v[k].x - g.ox) * g.inv_h);
+                int cy = (int)floor(((double)v[k].y - g.oy) * g.inv_h);
+                int cz = (int)floor(((double)v[k].z - g.oz) * g.inv_h);
+                cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+                const int key = (cz * g.ny + cy) * g.nx + cx;
+                a.cell_key[c] = key;
+                a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+            }
+        } else if (cls[k] == 2) {
+            const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
+            mine += 1ull << 31;
+            a.gpts[gi] = v[k];
+            a.gsrc[gi] = (int)(i0 + k);
         }
-    } else if (cls == 2) {
-        const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
-        a.gpts[gi] = make_float4(x, y, z, w);
-        a.gsrc[gi] = (int)i;
     }
     if (a.dynamic_grid) {  // bounding box of `cloud`: warp redux, then one set of atomics per warp
-        const bool v = cls == 1;
-        const unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
-        const unsigned ix = __reduce_max_sync(kFull, v ? ~kx : 0u), iy = __reduce_max_sync(kFull, v ? ~ky : 0u), iz = __reduce_max_sync(kFull, v ? ~kz : 0u);
-        const unsigned mx = __reduce_max_sync(kFull, v ? kx : 0u), my = __reduce_max_sync(kFull, v ? ky : 0u), mz = __reduce_max_sync(kFull, v ? kz : 0u);
+        unsigned ix = 0u, iy = 0u, iz = 0u, mx = 0u, my = 0u, mz = 0u;
+#pragma unroll
+        for (int k = 0; k < kIngestItems; k++)
+            if (cls[k] == 1) {
+                const unsigned kx = fkey(v[k].x), ky = fkey(v[k].y), kz = fkey(v[k].z);
+                ix = max(ix, ~kx); iy = max(iy, ~ky); iz = max(iz, ~kz); mx = max(mx, kx); my = max(my, ky); mz = max(mz, kz);
+            }
+        ix = __reduce_max_sync(kFull, ix); iy = __reduce_max_sync(kFull, iy); iz = __reduce_max_sync(kFull, iz);
+        mx = __reduce_max_sync(kFull, mx); my = __reduce_max_sync(kFull, my); mz = __reduce_max_sync(kFull, mz);
         if ((threadIdx.x & 31) == 0 && (ix | mx)) {
             atomicMax(&a.scratch->box_inv_min[0], ix); atomicMax(&a.scratch->box_inv_min[1], iy); atomicMax(&a.scratch->box_inv_min[2], iz);
             atomicMax(&a.scratch->box_max[0], mx); atomicMax(&a.scratch->box_max[1], my); atomicMax(&a.scratch->box_max[2], mz);
         }
     }
-    const int last_tile = a.n ? (int)((a.n - 1) / kBlock) : 0;
+    const int last_tile = a.n ? (int)((a.n - 1) / kIngestTile) : 0;
     if (tile == last_tile && threadIdx.x == 0) {
         const unsigned long long all = before + total;
         const int nc = (int)(all & 0x7FFFFFFFull), ng = (int)((all >> 31) & 0x7FFFFFFFull);
@@ -876,7 +904,9 @@ __global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
     const int corr_count = ts->corr_count + 1;
     const int corr_head = ts->corr_head;
     __syncthreads();
-    int n_mo = ts->n_mo;
+    float* const mo_centroid = a.mo_centroid + (size_t)a.mo_parity * a.momax * 3;
+    int* const mo_conf = a.mo_conf + (size_t)a.mo_parity * a.momax;
+    int n_mo = ts->n_mo[a.mo_parity];
     if (res_count >= a.moving_confidence) {
         const int r0 = res_head % D;
         const int len0 = a.res_len[r0];
@@ -914,8 +944,8 @@ __global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
             __syncthreads();
             bool close = false;
             for (int t = threadIdx.x; t < n_mo; t += kSingle) {
-                const double dx = (double)__fsub_rn(px, a.mo_centroid[t * 3]), dy = (double)__fsub_rn(py, a.mo_centroid[t * 3 + 1]),
-                             dz = (double)__fsub_rn(pz, a.mo_centroid[t * 3 + 2]);
+                const double dx = (double)__fsub_rn(px, mo_centroid[t * 3]), dy = (double)__fsub_rn(py, mo_centroid[t * 3 + 1]),
+                             dz = (double)__fsub_rn(pz, mo_centroid[t * 3 + 2]);
                 const double dist = sqrt(dx * dx + dy * dy + dz * dz);
                 close |= dist < (double)a.catch_up;
             }
@@ -925,8 +955,8 @@ __global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
             if (!any) {
                 if (n_mo < a.momax) {
                     if (threadIdx.x == 0) {
-                        a.mo_centroid[n_mo * 3] = px; a.mo_centroid[n_mo * 3 + 1] = py; a.mo_centroid[n_mo * 3 + 2] = pz;
-                        a.mo_conf[n_mo] = a.static_confidence + 1;  // MovingObjectCentroid ctor, .h:91
+                        mo_centroid[n_mo * 3] = px; mo_centroid[n_mo * 3 + 1] = py; mo_centroid[n_mo * 3 + 2] = pz;
+                        mo_conf[n_mo] = a.static_confidence + 1;  // MovingObjectCentroid ctor, .h:91
                     }
                     n_mo++;
                 } else if (threadIdx.x == 0) {
@@ -943,104 +973,141 @@ __global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
         } else {
             ts->corr_count = corr_count; ts->res_count = res_count; ts->res_head = res_head % D;
         }
-        ts->n_mo = n_mo;
+        ts->n_mo[a.mo_parity] = n_mo;
         a.counts[MOR_CNT_NMO] = n_mo;
     }
 }
 
-// ===================================================================================== K13
-// filterCloud tracking part (cpp:630-671): 1-NN of every confirmed mover among the current centroids,
-// unconditional selection of that cluster (cpp:644-648), confidence update and erase.
-__global__ void __launch_bounds__(kSingle) k_track(FramePtrs a) {
-    const int K = a.counts[MOR_CNT_K];
-    TrackState* ts = a.track;
-    const int n_mo = ts->n_mo;
-    __shared__ int s_total;
-    if (threadIdx.x == 0) { s_total = 0; a.scratch->ticket_out = 0; }
-    for (int t = threadIdx.x; t < a.tiles_pts; t += kSingle) a.st_out[t] = 0ull;  // look-back state of k_output
-    for (int k = threadIdx.x; k < K; k += kSingle) a.cluster_removed[k] = 0;
-    __syncthreads();
-    int kept_total = 0;
-    if (K > 0) {  // K == 0: un-built kd-tree in the reference (UB); defined here: entries untouched
-        for (int base = 0; base < n_mo; base += kSingle) {
-            const int t = base + threadIdx.x;
-            bool keep = false;
-            float cx = 0, cy = 0, cz = 0; int conf = 0;
-            if (t < n_mo) {
-                cx = a.mo_centroid[t * 3]; cy = a.mo_centroid[t * 3 + 1]; cz = a.mo_centroid[t * 3 + 2];
-                conf = a.mo_conf[t];
-                float d;
-                const int k = nn_brute(a.cl_centroid, K, cx, cy, cz, &d);
-                a.cluster_removed[k] = 1;
-                atomicAdd(&s_total, a.cl_size[k]);
-                if (!a.cl_flags[k] || d > a.leave_off) {  // cpp:650
-                    conf--;
-                    keep = conf != 0;
-                } else {
-                    cx = a.cl_centroid[k * 3]; cy = a.cl_centroid[k * 3 + 1]; cz = a.cl_centroid[k * 3 + 2];
-                    if (conf < a.static_confidence + 1) conf++;
-                    keep = true;
-                }
-            }
-            int tot;
-            const int r = single_block_rank(keep, &tot);  // barriers inside: all reads of this chunk precede the writes
-            if (keep) {
-                const int o = kept_total + r;
-                a.mo_centroid[o * 3] = cx; a.mo_centroid[o * 3 + 1] = cy; a.mo_centroid[o * 3 + 2] = cz;
-                a.mo_conf[o] = conf;
-            }
-            kept_total += tot;
-            __syncthreads();
-        }
-    } else {
-        kept_total = n_mo;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        ts->n_mo = kept_total;
-        a.counts[MOR_CNT_NMO] = kept_total;
-        // ExtractIndices: more indices than points => error, empty output (A18)
-        const int ov = s_total > a.counts[MOR_CNT_NC] ? 1 : 0;
-        ts->extract_overflow = ov;
-        a.counts[MOR_CNT_EXTRACT_OVERFLOW] = ov;
-    }
-}
+// ===================================================================================== K13 + K14
+// filterCloud (cpp:613-696) in one kernel.
+//  Tracking part (cpp:630-671): 1-NN of every confirmed mover among the current centroids, unconditional
+//  selection of that cluster (cpp:644-648), confidence update and erase. It is tiny (|mo_vec| x K distance
+//  evaluations), so EVERY block recomputes the selection into shared memory instead of waiting for a separate
+//  single-block kernel; block 0 alone writes the updated mo_vec into the other half of a double buffer.
+//  Output part: ExtractIndices(negative) of the moving points + append of the ground points (cpp:673-684),
+//  written as pcl::PointXYZI wire records (cpp:690); stable single-pass compaction over [cloud | ground],
+//  kOutItems consecutive points per thread.
+constexpr int kOutItems = 4;
+constexpr int kOutTile = kBlock * kOutItems;
+constexpr int kRemovedBits = 16384;  // = max kmax
 
-// ===================================================================================== K14
-// ExtractIndices(negative) of the moving points + append of the ground points (cpp:673-684), written
-// as pcl::PointXYZI wire records (cpp:690). Stable single-pass compaction over [cloud | ground].
-__global__ void __launch_bounds__(kBlock) k_output(FramePtrs a) {
-    __shared__ int s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_out, 1);
+__global__ void __launch_bounds__(kBlock) k_filter_output(FramePtrs a) {
+    const int mo_parity = a.mo_parity;
+    __shared__ unsigned s_removed[kRemovedBits / 32];
+    __shared__ int s_tile, s_total, s_keep_base;
+    const int K = a.counts[MOR_CNT_K];
+    const int nc = a.counts[MOR_CNT_NC], ng = a.counts[MOR_CNT_NG];
+    TrackState* ts = a.track;
+    const int n_mo = ts->n_mo[mo_parity];
+    const float* mo_c_in = a.mo_centroid + (size_t)mo_parity * a.momax * 3;
+    const int* mo_f_in = a.mo_conf + (size_t)mo_parity * a.momax;
+    float* mo_c_out = a.mo_centroid + (size_t)(mo_parity ^ 1) * a.momax * 3;
+    int* mo_f_out = a.mo_conf + (size_t)(mo_parity ^ 1) * a.momax;
+    if (threadIdx.x == 0) { s_tile = atomicAdd(&a.scratch->ticket_out, 1); s_total = 0; s_keep_base = 0; }
+    for (int t = threadIdx.x; t < (K + 31) / 32; t += kBlock) s_removed[t] = 0u;
     __syncthreads();
     const int tile = s_tile;
-    const int nc = a.counts[MOR_CNT_NC], ng = a.counts[MOR_CNT_NG];
+    const bool writer = tile == 0;  // the first block to start also owns the mo_vec update
+    // ---- tracking (redundant in every block; K == 0: un-built kd-tree in the reference (UB) -> entries untouched)
+    for (int base = 0; base < n_mo && K > 0; base += kBlock) {
+        const int t = base + threadIdx.x;
+        bool keep = false;
+        float cx = 0, cy = 0, cz = 0; int conf = 0;
+        if (t < n_mo) {
+            cx = mo_c_in[t * 3]; cy = mo_c_in[t * 3 + 1]; cz = mo_c_in[t * 3 + 2];
+            conf = mo_f_in[t];
+            float d;
+            const int k = nn_brute(a.cl_centroid, K, cx, cy, cz, &d);
+            atomicOr(&s_removed[k >> 5], 1u << (k & 31));
+            atomicAdd(&s_total, a.cl_size[k]);
+            if (!a.cl_flags[k] || d > a.leave_off) {  // cpp:650
+                conf--;
+                keep = conf != 0;
+            } else {
+                cx = a.cl_centroid[k * 3]; cy = a.cl_centroid[k * 3 + 1]; cz = a.cl_centroid[k * 3 + 2];
+                if (conf < a.static_confidence + 1) conf++;
+                keep = true;
+            }
+        }
+        if (writer) {  // ordered erase (cpp:655-660): survivors keep their relative order
+            int tot;
+            const int r = block_exclusive_scan<int>(keep ? 1 : 0, &tot);
+            if (keep) {
+                const int o = s_keep_base + r;
+                mo_c_out[o * 3] = cx; mo_c_out[o * 3 + 1] = cy; mo_c_out[o * 3 + 2] = cz;
+                mo_f_out[o] = conf;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_keep_base += tot;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int overflow = s_total > nc ? 1 : 0;  // ExtractIndices: more indices than points => error, empty output (A18)
+    if (writer) {
+        if (K == 0) {  // entries untouched: copy through
+            for (int t = threadIdx.x; t < n_mo; t += kBlock) {
+                mo_c_out[t * 3] = mo_c_in[t * 3]; mo_c_out[t * 3 + 1] = mo_c_in[t * 3 + 1]; mo_c_out[t * 3 + 2] = mo_c_in[t * 3 + 2];
+                mo_f_out[t] = mo_f_in[t];
+            }
+        }
+        for (int k = threadIdx.x; k < K; k += kBlock) a.cluster_removed[k] = (s_removed[k >> 5] >> (k & 31)) & 1u;
+        if (threadIdx.x == 0) {
+            const int kept = K > 0 ? s_keep_base : n_mo;
+            ts->n_mo[mo_parity ^ 1] = kept;  // the host flips the parity after this launch
+            a.counts[MOR_CNT_NMO] = kept;
+            ts->extract_overflow = overflow;
+            a.counts[MOR_CNT_EXTRACT_OVERFLOW] = overflow;
+        }
+    }
+    // ---- output compaction
     const int total_items = nc + ng;
-    const int last_tile = total_items ? (total_items - 1) / kBlock : 0;
-    if (tile > last_tile) return;
-    const int t = tile * kBlock + threadIdx.x;
-    const int overflow = a.track->extract_overflow;
-    bool keep = false;
-    float4 p = make_float4(0, 0, 0, 0);
-    if (t < nc) {
-        p = a.pts[t];
-        const int k = a.cid[t];
-        const bool removed = overflow || (k >= 0 && a.cluster_removed[k]);
-        keep = !removed;
-        if (removed) a.removed_mask[a.cloud_src[t]] = 2;
-    } else if (t < total_items) {
-        p = a.gpts[t - nc];
-        keep = true;
+    const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
+    if (tile <= last_tile) {
+    const int t0 = tile * kOutTile + threadIdx.x * kOutItems;
+    float4 p[kOutItems];
+    bool keep[kOutItems];
+    int nkeep = 0;
+#pragma unroll
+    for (int k = 0; k < kOutItems; k++) {
+        const int t = t0 + k;
+        keep[k] = false;
+        p[k] = make_float4(0, 0, 0, 0);
+        if (t < nc) {
+            p[k] = a.pts[t];
+            const int c = a.cid[t];
+            const bool removed = overflow || (c >= 0 && ((s_removed[c >> 5] >> (c & 31)) & 1u));
+            keep[k] = !removed;
+            if (removed) a.removed_mask[a.cloud_src[t]] = 2;
+        } else if (t < total_items) {
+            p[k] = a.gpts[t - nc];
+            keep[k] = true;
+        }
+        nkeep += keep[k] ? 1 : 0;
     }
     int tot;
-    const int in_block = block_exclusive_scan<int>(keep ? 1 : 0, &tot);
+    const int in_block = block_exclusive_scan<int>(nkeep, &tot);
     const int before = (int)tile_exclusive_prefix(a.st_out, tile, (unsigned long long)tot);
-    if (keep) {
-        const int o = before + in_block;
-        a.out[2 * o] = make_float4(p.x, p.y, p.z, 1.0f);
-        a.out[2 * o + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+    int o = before + in_block;
+#pragma unroll
+    for (int k = 0; k < kOutItems; k++) {
+        if (keep[k]) {
+            a.out[2 * o] = make_float4(p[k].x, p[k].y, p[k].z, 1.0f);
+            a.out[2 * o + 1] = make_float4(p[k].w, 0.f, 0.f, 0.f);
+            o++;
+        }
     }
     if (tile == last_tile && threadIdx.x == 0) a.counts[MOR_CNT_NOUT] = before + tot;
+    }
+    // the last block to finish resets the look-back state, so filterCloud may be called again at any time
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&a.scratch->out_blocks_done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        for (int t = threadIdx.x; t < a.tiles_pts; t += kBlock) a.st_out[t] = 0ull;
+        if (threadIdx.x == 0) { a.scratch->ticket_out = 0; a.scratch->out_blocks_done = 0; }
+    }
 }
 
 }  // namespace mor
