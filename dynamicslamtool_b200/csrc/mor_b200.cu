@@ -208,7 +208,7 @@ int build_grid(mor_handle* h) {
 int allocate(mor_handle* h) {
     const size_t N = h->nmax, K = h->kmax, MO = h->momax, D = (size_t)h->ring_depth;
     const size_t ncells = h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells;
-    const size_t tiles_pts = N / kBlock + 2, tiles_cells = ncells / kTile + 2;
+    const size_t tiles_pts = N / kBlock + 2, tiles_cells = ncells / kScanTile + 2;
     size_t lat = 1;
     while (lat < 2 * N) lat <<= 1;
     h->lattice_cap = lat;
@@ -223,13 +223,14 @@ int allocate(mor_handle* h) {
         b.st_ingest = carve<unsigned long long>(p, tiles_pts);
         b.st_cells = carve<unsigned long long>(p, tiles_cells);
         b.st_out = carve<unsigned long long>(p, tiles_pts);
-        b.cell_count = carve<int>(p, ncells + 1);
+        b.cell_count = carve<int>(p, ncells + 16);
         h->zero_bytes = (size_t)(p - h->zero_region);
-        b.cell_start = carve<int>(p, ncells + 1);
+        b.cell_start = carve<int>(p, ncells + 16);
+        b.cell_cursor = carve<int>(p, ncells + 16);
         b.dgrid = carve<GridDesc>(p, 1);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
-        b.cell_key = carve<int>(p, N); b.cell_rank = carve<int>(p, N); b.skey = carve<int>(p, N);
+        b.cell_key = carve<int>(p, N); b.skey = carve<int>(p, N);
         b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
         b.comp = carve<int>(p, N); b.minidx = carve<int>(p, N); b.done = carve<unsigned long long>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
@@ -250,7 +251,7 @@ int allocate(mor_handle* h) {
             GroundPtrs& g = h->ground;
             const size_t vc = (size_t)h->max_cells;
             g.rpts = carve<float4>(p, N); g.rsrc = carve<int>(p, N); g.is_ground = carve<uint8_t>(p, N); g.vkey = carve<int>(p, N);
-            g.vox_count = carve<int>(p, vc + 1); g.vox_ord = carve<int>(p, vc + 1); g.tiles_vox = (int)(vc / kTile + 2);
+            g.vox_count = carve<int>(p, vc + 1); g.vox_ord = carve<int>(p, vc + 1); g.tiles_vox = (int)(vc / kScanTile + 2);
             g.st_vox = carve<unsigned long long>(p, g.tiles_vox);
             g.vox_n = carve<int>(p, N); g.vacc = carve<unsigned long long>(p, N * 6); g.vox_info = carve<float>(p, N * 8);
             g.bin_hist = carve<int>(p, 65536); g.ggrid = carve<GridDesc>(p, 1); g.vdesc = carve<VoxDesc>(p, 1); g.gstate = carve<int>(p, 8);
@@ -288,7 +289,7 @@ void fill_static(mor_handle* h) {
     b.dynamic_grid = h->dynamic_grid ? 1 : 0; b.max_cells = h->max_cells; b.cell_h = h->cell_h;
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
-    b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells) / kTile + 2);
+    b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells) / kScanTile + 2);
     if (c.ground_mode != MOR_GROUND_CROP) {
         GroundPtrs& g = h->ground;
         g.mode = c.ground_mode; g.leaf = c.gp_leaf; g.inv_leaf = 1.0f / c.gp_leaf; g.r2 = (float)((double)c.gp_leaf * (double)c.gp_leaf);
@@ -336,7 +337,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     }
     if (h->dynamic_grid) MOR_LAUNCH(KID_KEYS, (k_keys<<<gb, kBlock, 0, st>>>(a)));
     {
-        const int tiles = (h->grid.ncells + kTile - 1) / kTile;
+        const int tiles = (h->grid.ncells + kScanTile - 1) / kScanTile;
         const int scan_blocks = h->dynamic_grid ? h->num_sms * 8 : (tiles < h->num_sms * 8 ? tiles : h->num_sms * 8);
         MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<scan_blocks, kBlock, 0, st>>>(a)));
     }

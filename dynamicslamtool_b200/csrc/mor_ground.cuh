@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_keys(FramePtrs a, GroundPtrs 
     cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
     const int key = (cz * g.ny + cy) * g.nx + cx;
     a.cell_key[r] = key;
-    a.cell_rank[r] = atomicAdd(&a.cell_count[key], 1);
+    atomicAdd(&a.cell_count[key], 1);
     const VoxDesc& v = s_v;
     long long i0 = (long long)floorf(__fmul_rn(p.x, gp.inv_leaf)) - v.minb[0];
     long long i1 = (long long)floorf(__fmul_rn(p.y, gp.inv_leaf)) - v.minb[1];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_scatter(FramePtrs a, GroundPt
     const int r = blockIdx.x * kBlock + threadIdx.x;
     if (r >= a.counts[MOR_CNT_NT]) return;
     const int key = a.cell_key[r];
-    const int pos = a.cell_start[key] + a.cell_rank[r];
+    const int pos = atomicAdd(&a.cell_cursor[key], 1);
     float4 p = gp.rpts[r];
     const int ord = gp.vox_ord[gp.vkey[r]];
     long long h, l;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_partition(FramePtrs a, Ground
             cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
             const int key = (cz * g.ny + cy) * g.nx + cx;
             a.cell_key[c] = key;
-            a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+            atomicAdd(&a.cell_count[key], 1);
         }
     } else if (cls == 2) {
         const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);

@@ -54,7 +54,7 @@ struct FramePtrs {
     int* cell_count; int* cell_start;
     uint8_t* point_class; uint8_t* removed_mask;
     int* cloud_src; float4* gpts; int* gsrc;
-    int* cell_key; int* cell_rank; int* skey;
+    int* cell_key; int* cell_cursor; int* skey;  // cell_cursor: copy of cell_start consumed by the scatter (fill cursors)
     int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
     int* comp; int* minidx; unsigned long long* done;  // indexed by sorted position (cell leaders)
     uint4* cell_box;  // [2*N] per leader position: {min x,y,z keys, count}, {max x,y,z keys, 0}
@@ -94,13 +94,10 @@ constexpr int kIngestTile = kBlock * kIngestItems;
 __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
-    __syncthreads();
-    const int tile = s_tile;
-    const uint32_t gtid = (uint32_t)tile * kBlock + threadIdx.x;
     if (a.two_frames) {
-        // housekeeping for the two-frame stages, spread over the grid: empty octree-lattice hash set,
-        // neutral bounding boxes for the transformed previous clusters
-        const uint32_t stride = gridDim.x * kBlock;
+        // housekeeping for the two-frame stages, spread over the grid and overlapped with the ticket's round
+        // trip: empty octree-lattice hash set, neutral bounding boxes for the transformed previous clusters
+        const uint32_t gtid = blockIdx.x * kBlock + threadIdx.x, stride = gridDim.x * kBlock;
         if (a.method == 2) {
             uint4* lat = reinterpret_cast<uint4*>(a.lattice);
             for (uint32_t t = gtid; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -108,6 +105,8 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
         const uint32_t kp6 = (uint32_t)a.p_counts[MOR_CNT_K] * 6u;
         for (uint32_t t = gtid; t < kp6; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
     }
+    __syncthreads();
+    const int tile = s_tile;
     const uint32_t i0 = (uint32_t)tile * kIngestTile + threadIdx.x * kIngestItems;
     float4 v[kIngestItems];
     int cls[kIngestItems];
@@ -148,6 +147,16 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
     unsigned long long mine = before + in_block;
 #pragma unroll
     for (int k = 0; k < kIngestItems; k++) {
+        int key = -1;
+        if (cls[k] == 1 && !a.dynamic_grid) {
+            const GridDesc& g = a.grid;
+            int cx = (int)floor(((double)v[k].x - g.ox) * g.inv_h);
+            int cy = (int)floor(((double)v[k].y - g.oy) * g.inv_h);
+            int cz = (int)floor(((double)v[k].z - g.oz) * g.inv_h);
+            cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+            key = (cz * g.ny + cy) * g.nx + cx;
+            atomicAdd(&a.cell_count[key], 1);  // result unused: a fire-and-forget RED, no round trip on the critical path
+        }
         if (cls[k] == 1) {
             const int c = (int)(mine & 0x7FFFFFFFull);
             mine += 1ull;
@@ -155,16 +164,7 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
             a.cloud_src[c] = (int)(i0 + k);
             a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // slot c doubles as a sorted position
             a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
-            if (!a.dynamic_grid) {
-                const GridDesc& g = a.grid;
-                int cx = (int)floor(((double)v[k].x - g.ox) * g.inv_h);
-                int cy = (int)floor(((double)v[k].y - g.oy) * g.inv_h);
-                int cz = (int)floor(((double)v[k].z - g.oz) * g.inv_h);
-                cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
-                const int key = (cz * g.ny + cy) * g.nx + cx;
-                a.cell_key[c] = key;
-                a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
-            }
+            if (!a.dynamic_grid) a.cell_key[c] = key;
         } else if (cls[k] == 2) {
             const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
             mine += 1ull << 31;
@@ -243,41 +243,69 @@ __global__ void __launch_bounds__(kBlock) k_keys(FramePtrs a) {
     cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
     const int key = (cz * g.ny + cy) * g.nx + cx;
     a.cell_key[c] = key;
-    a.cell_rank[c] = atomicAdd(&a.cell_count[key], 1);
+    atomicAdd(&a.cell_count[key], 1);
 }
 
 // ===================================================================================== K2
-// Exclusive scan of the per-cell histogram -> cell_start[0..ncells] (counting sort of the cell keys).
-// Persistent blocks pull tiles by ticket, so the launch does not depend on the (possibly device-side)
+// Exclusive scan of the per-cell histogram (counting sort of the cell keys) -> cell_start[0..ncells] and a second
+// copy, cell_cursor[], that k_scatter consumes as per-cell fill cursors (so k_ingest needs no returning atomic).
+// Persistent blocks pull 4096-cell tiles by ticket, so the launch does not depend on the (possibly device-side)
 // cell count; the histogram is zeroed as it is consumed, ready for the next frame.
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kBlock * kScanItems;
+
 __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
     __shared__ int s_tile;
     const int ncells = a.dgrid->ncells;
-    const int ntiles = (ncells + kTile - 1) / kTile;
+    const int ntiles = (ncells + kScanTile - 1) / kScanTile;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_cells, 1);
         __syncthreads();
         const int tile = s_tile;
         if (tile >= ntiles) return;
-        const int base = tile * kTile + threadIdx.x * kItems;
-        int v[kItems];
+        const int base = tile * kScanTile + threadIdx.x * kScanItems;
+        int v[kScanItems];
+        if (base + kScanItems <= ncells) {
+            int4* src = reinterpret_cast<int4*>(a.cell_count + base);
 #pragma unroll
-        for (int k = 0; k < kItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
+            for (int k = 0; k < kScanItems / 4; k++) {
+                const int4 t = src[k];
+                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+                if (t.x | t.y | t.z | t.w) src[k] = make_int4(0, 0, 0, 0);
+            }
+        } else {
 #pragma unroll
-        for (int k = 0; k < kItems; k++)
-            if (base + k < ncells && v[k]) a.cell_count[base + k] = 0;
+            for (int k = 0; k < kScanItems; k++) {
+                v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
+                if (v[k]) a.cell_count[base + k] = 0;
+            }
+        }
         int sum = 0;
 #pragma unroll
-        for (int k = 0; k < kItems; k++) sum += v[k];
+        for (int k = 0; k < kScanItems; k++) sum += v[k];
         int total;
         const int in_block = block_exclusive_scan<int>(sum, &total);
         const int before = (int)tile_exclusive_prefix(a.st_cells, tile, (unsigned long long)total);
         int run = before + in_block;
+        if (base + kScanItems <= ncells) {
+            int4* d0 = reinterpret_cast<int4*>(a.cell_start + base);
+            int4* d1 = reinterpret_cast<int4*>(a.cell_cursor + base);
 #pragma unroll
-        for (int k = 0; k < kItems; k++) {
-            if (base + k < ncells) a.cell_start[base + k] = run;
-            run += v[k];
+            for (int k = 0; k < kScanItems / 4; k++) {
+                int4 t;
+                t.x = run; run += v[4 * k];
+                t.y = run; run += v[4 * k + 1];
+                t.z = run; run += v[4 * k + 2];
+                t.w = run; run += v[4 * k + 3];
+                d0[k] = t; d1[k] = t;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k++) {
+                if (base + k < ncells) { a.cell_start[base + k] = run; a.cell_cursor[base + k] = run; }
+                run += v[k];
+            }
         }
         if (tile == ntiles - 1 && threadIdx.x == 0) a.cell_start[ncells] = before + total;
     }
@@ -291,7 +319,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) {
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.counts[MOR_CNT_NC]) return;
     const int key = a.cell_key[c];
-    const int pos = a.cell_start[key] + a.cell_rank[c];
+    const int pos = atomicAdd(&a.cell_cursor[key], 1);  // fill cursor of the cell
     float4 p = a.pts[c];
     p.w = __int_as_float(c);
     a.spts[pos] = p;
