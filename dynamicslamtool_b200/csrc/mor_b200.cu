@@ -87,6 +87,9 @@ struct mor_handle {
     mor_config cfg;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;  // runs k_transform_prev (depends only on the previous frame + pose) beside the clustering chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint32_t spec_out = 0;        // speculative size of the output D2H copy (points), from the previous frame
     uint32_t nmax = 0, kmax = 0, momax = 0;
     int ring_depth = 0, pde_ring = 0;
     bool dynamic_grid = false; int max_cells = 0; double cell_h = 0;
@@ -328,12 +331,23 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<h->num_sms * 8, kBlock, 0, st>>>(ag)));
         MOR_LAUNCH(KID_G_SCAN_VOX, (k_scan_voxels<<<h->num_sms * 8, kBlock, 0, st>>>(a, g)));
         MOR_LAUNCH(KID_G_SCATTER, (k_ground_scatter<<<gb, kBlock, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_EVAL, (k_voxel_eval<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_EVAL, (k_voxel_eval<<<gb * 32, kBlock, 0, st>>>(a, g)));  // one warp per voxel, V <= n
         MOR_LAUNCH(KID_G_MODE, (k_ground_mode<<<1, kSingle, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_MARK, (k_ground_mark<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_LAUNCH(KID_G_MARK, (k_ground_mark<<<gb * 32, kBlock, 0, st>>>(a, g)));
         MOR_LAUNCH(KID_G_PARTITION, (k_ground_partition<<<gb, kBlock, 0, st>>>(a, g)));
     } else {
         MOR_LAUNCH(KID_INGEST, (k_ingest<<<n ? (n + kIngestTile - 1) / kIngestTile : 1, kBlock, 0, st>>>(a)));
+    }
+    // The transform of the previous frame's clusters needs only the previous frame, the pose delta and the neutral
+    // boxes written by the ingest kernel: it runs on a side stream beside the clustering chain and is joined before
+    // k_match. (With per-kernel profiling on it stays in line so that its events bracket it alone.)
+    const bool fork = h->two_frames && !h->profiling;
+    if (fork) {
+        MOR_CUDA(cudaEventRecord(h->ev_fork, st));
+        MOR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, h->side>>>(a);
+        h->launches++;
+        MOR_CUDA(cudaEventRecord(h->ev_join, h->side));
     }
     if (h->dynamic_grid) MOR_LAUNCH(KID_KEYS, (k_keys<<<gb, kBlock, 0, st>>>(a)));
     {
@@ -349,7 +363,8 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<(n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, st>>>(a)));
     if (h->two_frames) {
         const unsigned gp = blocks_for(h->n_prev_input);
-        MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
+        if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+        else MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
         MOR_LAUNCH(KID_MATCH, (k_match<<<1, kSingle, 0, st>>>(a)));
         if (h->cfg.method_choice == 2) {
             MOR_LAUNCH(KID_LATTICE_INSERT, (k_lattice_insert<<<gp, kBlock, 0, st>>>(a)));
@@ -412,10 +427,21 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[3], st));
     if (on_device && !n_out && !h->profiling) return MOR_OK;  // fully asynchronous device-resident mode
     MOR_CUDA(cudaMemcpyAsync(h->h_counts, a.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, st));
+    // The size of the output is only known on the device. Instead of a second round trip (sync on the count, then
+    // copy), the cloud copy is issued speculatively with the previous frame's size plus a margin and topped up in
+    // the rare case the frame turned out larger.
+    uint32_t spec = 0;
+    if (!on_device && out) {
+        spec = h->spec_out ? h->spec_out + h->spec_out / 32 + 1024 : h->n_input;
+        if (spec > h->n_input) spec = h->n_input;
+        if (spec > cap_points) spec = cap_points;
+        if (spec) MOR_CUDA(cudaMemcpyAsync(out, a.out, (size_t)spec * 32, cudaMemcpyDeviceToHost, st));
+    }
     MOR_CUDA(cudaStreamSynchronize(st));
     if (h->profiling) prof_harvest(h);
     const uint32_t no = (uint32_t)h->h_counts[MOR_CNT_NOUT];
     if (n_out) *n_out = no;
+    h->spec_out = no;
     if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
         char msg[160];
         std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice 8=ground grid 16=grid cells)", h->h_counts[MOR_CNT_ERRFLAGS]);
@@ -424,8 +450,8 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     }
     if (!on_device) {
         if (no > cap_points) return MOR_ERR_CAPACITY;
-        if (no) {
-            MOR_CUDA(cudaMemcpyAsync(out, a.out, (size_t)no * 32, cudaMemcpyDeviceToHost, st));
+        if (no > spec) {
+            MOR_CUDA(cudaMemcpyAsync((uint8_t*)out + (size_t)spec * 32, (const uint8_t*)a.out + (size_t)spec * 32, (size_t)(no - spec) * 32, cudaMemcpyDeviceToHost, st));
             MOR_CUDA(cudaStreamSynchronize(st));
         }
     }
@@ -456,6 +482,9 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     if (st != MOR_OK) { delete h; return st; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete h; return MOR_ERR_CUDA; }
     st = allocate(h);
     if (st != MOR_OK) { if (h->arena) cudaFree(h->arena); cudaStreamDestroy(h->stream); delete h; return st; }
@@ -479,6 +508,9 @@ int mor_destroy(mor_handle* h) {
     if (!h) return MOR_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->slot_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->prof_pool) cudaEventDestroy(e);

@@ -79,8 +79,6 @@ __global__ void __launch_bounds__(kBlock) k_ingest_raw(FramePtrs a, GroundPtrs g
         gp.rpts[r] = make_float4(x, y, z, w);
         gp.rsrc[r] = (int)i;
         gp.is_ground[r] = 0;
-#pragma unroll
-        for (int q = 0; q < 6; q++) gp.vacc[(size_t)r * 6 + q] = 0ull;
     }
     {
         const unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
@@ -186,7 +184,12 @@ __global__ void __launch_bounds__(kBlock) k_scan_voxels(FramePtrs a, GroundPtrs 
         int run = before + in_block;
 #pragma unroll
         for (int k = 0; k < kItems; k++) {
-            if (base + k < ncells && v[k]) { gp.vox_ord[base + k] = run; gp.vox_n[run] = v[k]; run++; }
+            if (base + k < ncells && v[k]) {
+                gp.vox_ord[base + k] = run; gp.vox_n[run] = v[k];
+#pragma unroll
+                for (int q = 0; q < 6; q++) gp.vacc[(size_t)run * 6 + q] = 0ull;
+                run++;
+            }
         }
         if (tile == ntiles - 1 && threadIdx.x == 0) { gp.gstate[1] = before + total; a.counts[MOR_CNT_NVOX] = before + total; }
     }
@@ -196,19 +199,37 @@ __global__ void __launch_bounds__(kBlock) k_scan_voxels(FramePtrs a, GroundPtrs 
 // Raw points into ball-grid order; exact fixed-point coordinate sums per voxel.
 __global__ void __launch_bounds__(kBlock) k_ground_scatter(FramePtrs a, GroundPtrs gp) {
     const int r = blockIdx.x * kBlock + threadIdx.x;
-    if (r >= a.counts[MOR_CNT_NT]) return;
-    const int key = a.cell_key[r];
-    const int pos = atomicAdd(&a.cell_cursor[key], 1);
-    float4 p = gp.rpts[r];
-    const int ord = gp.vox_ord[gp.vkey[r]];
-    long long h, l;
-    unsigned long long* acc = gp.vacc + (size_t)ord * 6;
-    split_fixed(p.x, h, l); atomicAdd(acc + 0, (unsigned long long)h); atomicAdd(acc + 1, (unsigned long long)l);
-    split_fixed(p.y, h, l); atomicAdd(acc + 2, (unsigned long long)h); atomicAdd(acc + 3, (unsigned long long)l);
-    split_fixed(p.z, h, l); atomicAdd(acc + 4, (unsigned long long)h); atomicAdd(acc + 5, (unsigned long long)l);
-    p.w = __int_as_float(r);
-    a.spts[pos] = p;
-    a.skey[pos] = key;
+    const int nraw = a.counts[MOR_CNT_NT];
+    if ((r & ~31) >= nraw) return;  // whole warps stay for the group reductions
+    const bool in = r < nraw;
+    float4 p = make_float4(0, 0, 0, 0);
+    int ord = -1;
+    if (in) {
+        const int key = a.cell_key[r];
+        const int pos = atomicAdd(&a.cell_cursor[key], 1);
+        p = gp.rpts[r];
+        ord = gp.vox_ord[gp.vkey[r]];
+        float4 sp = p;
+        sp.w = __int_as_float(r);
+        a.spts[pos] = sp;
+        a.skey[pos] = key;
+    }
+    // exact voxel sums: neighbouring beams fall into the same voxel, so lanes are grouped by voxel (match.any) and
+    // reduced with redux in 16/15-bit pieces before one set of 64-bit atomics per group
+    const unsigned grp = __match_any_sync(kFull, ord);
+    const bool leader = in && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31);
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        long long h, l;
+        split_fixed(v[q], h, l);
+        const long long sh = ((long long)__reduce_add_sync(grp, (int)(h >> 16)) << 16) + (long long)__reduce_add_sync(grp, (int)(h & 0xFFFF));
+        const long long sl = ((long long)__reduce_add_sync(grp, (int)(l >> 15)) << 15) + (long long)__reduce_add_sync(grp, (int)(l & 0x7FFF));
+        if (leader) {
+            atomicAdd(gp.vacc + (size_t)ord * 6 + q * 2, (unsigned long long)sh);
+            atomicAdd(gp.vacc + (size_t)ord * 6 + q * 2 + 1, (unsigned long long)sl);
+        }
+    }
 }
 
 // Closed-form smallest eigenpair of a symmetric PSD 3x3 matrix (trigonometric method), same operation order
@@ -241,9 +262,10 @@ __device__ __forceinline__ void smallest_eig_sym3(const double a[6], double& lmi
 }
 
 // Visits every raw point within the ball B(q, leaf) (strict, float predicate) through the 27-cell block of
-// the ball grid: 9 x-rows, each one contiguous run of the sorted array.
+// the ball grid: 9 x-rows, each one contiguous run of the sorted array. One WARP per voxel: the lanes stride
+// over each run (balls near the sensor hold thousands of points).
 template <typename F>
-__device__ __forceinline__ void for_each_in_ball(const FramePtrs& a, const GroundPtrs& gp, const GridDesc& g, float qx, float qy, float qz, F&& f) {
+__device__ __forceinline__ void for_each_in_ball_warp(const FramePtrs& a, const GroundPtrs& gp, const GridDesc& g, float qx, float qy, float qz, int lane, F&& f) {
     int cx = (int)floor(((double)qx - g.ox) * g.inv_h), cy = (int)floor(((double)qy - g.oy) * g.inv_h), cz = (int)floor(((double)qz - g.oz) * g.inv_h);
     cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
@@ -251,17 +273,24 @@ __device__ __forceinline__ void for_each_in_ball(const FramePtrs& a, const Groun
         for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); yy++) {
             const int base = (zz * g.ny + yy) * g.nx;
             const int b = a.cell_start[base + x0], e = a.cell_start[base + x1 + 1];
-            for (int j = b; j < e; j++) {
+            for (int j = b + lane; j < e; j += 32) {
                 const float4 p = a.spts[j];
                 if (sqdist3(qx, qy, qz, p.x, p.y, p.z) < gp.r2) f(p);
             }
         }
 }
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
 // ===================================================================================== G5
-// One thread per voxel: centroid, ball statistics (moments of d = p - q in double), acceptance test, bin.
+// One warp per voxel: centroid, ball statistics (moments of d = p - q in double), acceptance test, bin.
 __global__ void __launch_bounds__(kBlock) k_voxel_eval(FramePtrs a, GroundPtrs gp) {
-    const int v = blockIdx.x * kBlock + threadIdx.x;
+    const int v = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (v >= gp.gstate[1]) return;
     const GridDesc g = *gp.ggrid;
     const double nv = (double)gp.vox_n[v];
@@ -271,12 +300,18 @@ __global__ void __launch_bounds__(kBlock) k_voxel_eval(FramePtrs a, GroundPtrs g
     const float qz = (float)join_fixed_mean((long long)acc[4], (long long)acc[5], nv);
     int n = 0;
     double m[3] = {0, 0, 0}, s[6] = {0, 0, 0, 0, 0, 0};
-    for_each_in_ball(a, gp, g, qx, qy, qz, [&](const float4& p) {
+    for_each_in_ball_warp(a, gp, g, qx, qy, qz, lane, [&](const float4& p) {
         const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;
         n++;
         m[0] += dx; m[1] += dy; m[2] += dz;
         s[0] += dx * dx; s[1] += dx * dy; s[2] += dx * dz; s[3] += dy * dy; s[4] += dy * dz; s[5] += dz * dz;
     });
+    n = __reduce_add_sync(kFull, n);
+#pragma unroll
+    for (int q = 0; q < 3; q++) m[q] = warp_sum_d(m[q]);
+#pragma unroll
+    for (int q = 0; q < 6; q++) s[q] = warp_sum_d(s[q]);
+    if (lane != 0) return;
     float* info = gp.vox_info + (size_t)v * 8;
     info[0] = qx; info[1] = qy; info[2] = qz;
     float acc_flag = 0.f, keyf = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
@@ -339,7 +374,8 @@ __global__ void __launch_bounds__(kSingle) k_ground_mode(FramePtrs a, GroundPtrs
 // ===================================================================================== G7
 // ground = union of the balls of the accepted voxels in the selected bins (cpp:184-191).
 __global__ void __launch_bounds__(kBlock) k_ground_mark(FramePtrs a, GroundPtrs gp) {
-    const int v = blockIdx.x * kBlock + threadIdx.x;
+    const int v = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (v >= gp.gstate[1]) return;
     const float* info = gp.vox_info + (size_t)v * 8;
     if (info[3] == 0.f || gp.gstate[2] < 0) return;
@@ -347,7 +383,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_mark(FramePtrs a, GroundPtrs 
     const bool take = gp.mode == MOR_GROUND_VOXEL_EIGEN ? gp.bin_hist[k] >= gp.gstate[3] : k == gp.gstate[2];
     if (!take) return;
     const GridDesc g = *gp.ggrid;
-    for_each_in_ball(a, gp, g, info[0], info[1], info[2], [&](const float4& p) { gp.is_ground[__float_as_int(p.w)] = 1; });
+    for_each_in_ball_warp(a, gp, g, info[0], info[1], info[2], lane, [&](const float4& p) { gp.is_ground[__float_as_int(p.w)] = 1; });
 }
 
 // ===================================================================================== G8
