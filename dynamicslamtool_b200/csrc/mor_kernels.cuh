@@ -378,12 +378,16 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
             if (PHASE == 2 && !skip && cell_end - j > kRootCheckCount) {
                 // far pass: the near pass has already merged most of a dense surface; two cells of one
                 // component need no point tests (the pair is marked done, which is all the mask means)
-                if (uf_find(a.parent, lead) == uf_find(a.parent, j)) {
-                    const unsigned grp = __match_any_sync(__activemask(), (lead << 6) | bit);
-                    if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicOr(a.done + lead, 1ull << bit);
-                    dmask |= 1ull << bit;
-                    skip = true;
+                // one lane per (cell pair) of the converged lanes walks the two paths and shares the verdict
+                const unsigned grp = __match_any_sync(__activemask(), (lead << 6) | bit);
+                const int leader_lane = __ffs(grp) - 1;
+                int same = 0;
+                if ((int)(threadIdx.x & 31) == leader_lane) {
+                    same = uf_find(a.parent, lead) == uf_find(a.parent, j) ? 1 : 0;
+                    if (same) atomicOr(a.done + lead, 1ull << bit);
                 }
+                same = __shfl_sync(grp, same, leader_lane);
+                if (same) { dmask |= 1ull << bit; skip = true; }
             }
         }
         if (!skip) {
