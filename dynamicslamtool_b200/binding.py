@@ -56,7 +56,6 @@ TAPS = {
     "ground_voxels": (21, np.float32, (8,)),
     "cluster_bbox": (22, np.float32, (6,)),
     "prev_bbox_t": (23, np.float32, (6,)),
-    "debug_scratch": (99, np.uint64, ()),
 }
 
 COUNT_NAMES = ["N", "NT", "NC", "NG", "K", "KPREV", "M", "NMO", "NOUT", "NKPREV", "P1", "P2", "TWO_FRAMES",

@@ -135,14 +135,13 @@ struct mor_handle {
 
 namespace {
 
-enum KernelId { KID_CLEAR = 0, KID_INGEST, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_SELECT, KID_STATS, KID_FINALIZE,
-                KID_INIT_PREV, KID_TRANSFORM_PREV, KID_MATCH, KID_CLEAR_LATTICE, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE, KID_CHAIN,
-                KID_TRACK, KID_OUTPUT, KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"memset_scratch", "k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten", "k_select_clusters",
-                                              "k_cluster_stats", "k_finalize_clusters", "k_init_prev_boxes", "k_transform_prev", "k_match",
-                                              "memset_lattice", "k_lattice_insert", "k_lattice_count", "k_pde_count", "k_flags_and_chain", "k_track",
-                                              "k_filter_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter", "k_voxel_eval", "k_ground_mode",
-                                              "k_ground_mark", "k_ground_partition"};
+enum KernelId { KID_INGEST = 0, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_STATS,
+                KID_TRANSFORM_PREV, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE,
+                KID_OUTPUT, KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
+const char* const kKernelNames[KID__COUNT] = {"k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten+select",
+                                              "k_cluster_stats+match", "k_transform_prev", "k_lattice_insert", "k_lattice_count+chain", "k_pde_count+chain",
+                                              "k_filter_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter",
+                                              "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
 
 inline void prof_begin(mor_handle* h, int id) {
     if (!h->profiling) return;
@@ -272,7 +271,7 @@ int allocate(mor_handle* h) {
     int P = 1;
     while (P < (int)K) P <<= 1;
     h->select_smem = (size_t)P * sizeof(unsigned long long);
-    MOR_CUDA(cudaFuncSetAttribute(k_select_clusters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
+    MOR_CUDA(cudaFuncSetAttribute(k_flatten, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     return MOR_OK;
 }
@@ -299,8 +298,6 @@ void fill_static(mor_handle* h) {
         g.bin_gap = c.bin_gap; g.planarity = c.gp_planarity; g.bin_width = c.gp_bin_width;
         g.ball_cell_h = (double)c.gp_leaf * (1.0 + 1.0 / 1024.0);
     }
-    const char* dbg = std::getenv("MOR_DEBUG");
-    b.debug = dbg ? std::atoi(dbg) : 0;
 }
 
 inline unsigned blocks_for(uint32_t n) { return n ? (n + kBlock - 1) / kBlock : 1; }
@@ -358,21 +355,20 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<1><<<dim3(gb, 5), kBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_LINK_FAR, (k_link_cells<2><<<dim3(gb, 13), kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_SELECT, (k_select_clusters<<<1, kSingle, h->select_smem, st>>>(a)));
+    const unsigned g1k = n ? (n + kSingle - 1) / kSingle : 1;
+    MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<g1k, kSingle, h->select_smem, st>>>(a)));  // + cluster selection in its last block
+    if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));  // k_cluster_stats' last block runs the correspondences
+    else if (h->two_frames) MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
     MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<(n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, st>>>(a)));
     if (h->two_frames) {
         const unsigned gp = blocks_for(h->n_prev_input);
-        if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-        else MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
-        MOR_LAUNCH(KID_MATCH, (k_match<<<1, kSingle, 0, st>>>(a)));
         if (h->cfg.method_choice == 2) {
             MOR_LAUNCH(KID_LATTICE_INSERT, (k_lattice_insert<<<gp, kBlock, 0, st>>>(a)));
-            MOR_LAUNCH(KID_LATTICE_COUNT, (k_lattice_count<<<gb, kBlock, 0, st>>>(a)));
+            MOR_LAUNCH(KID_LATTICE_COUNT, (k_lattice_count<<<g1k, kSingle, 0, st>>>(a)));  // + flags and consistency chain in its last block
         } else {
-            MOR_LAUNCH(KID_PDE, (k_pde_count<<<gp, kBlock, 0, st>>>(a, h->pde_ring)));
+            const unsigned gp1k = h->n_prev_input ? (h->n_prev_input + kSingle - 1) / kSingle : 1;
+            MOR_LAUNCH(KID_PDE, (k_pde_count<<<gp1k, kSingle, 0, st>>>(a, h->pde_ring)));
         }
-        MOR_LAUNCH(KID_CHAIN, (k_flags_and_chain<<<1, kSingle, 0, st>>>(a)));
     }
     MOR_CUDA(cudaGetLastError());
     return MOR_OK;
@@ -667,7 +663,6 @@ int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes
         case MOR_TAP_GROUND_VOXELS: if (h->cfg.ground_mode != MOR_GROUND_CROP) { src = h->ground.vox_info; bytes = (size_t)c[MOR_CNT_NVOX] * 32; } break;
         case MOR_TAP_CLUSTER_BBOX: src = a.cl_bbox; bytes = K * 24; break;
         case MOR_TAP_PREV_BBOX_T: src = a.pbbox; bytes = KP * 24; break;
-        case 99: src = a.scratch; bytes = sizeof(Scratch); break;  // debug instrumentation (MOR_DEBUG)
         default: return MOR_ERR_ARG;
     }
     if (!host.empty() || tap == MOR_TAP_PREV_POINTS_T) bytes = host.size();

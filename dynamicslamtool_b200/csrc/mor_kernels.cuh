@@ -22,10 +22,10 @@ struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-1
 
 struct Scratch {  // zeroed at the start of every frame (one memset, together with cell_count)
     int ticket_ingest, ticket_cells, ticket_out, n_roots;
-    int moving_total, stats_blocks_done, out_blocks_done, pad2;
+    int moving_total, stats_blocks_done, out_blocks_done, flatten_blocks_done;
+    int moving_blocks_done, pad5, pad6, pad7;
     unsigned box_inv_min[3], box_max[3];  // dynamic grid: bbox of `cloud` (ordered keys; mins stored inverted so 0 is neutral)
     int pad3, pad4;
-    unsigned long long dbg[8];  // MOR_DEBUG&4 instrumentation of k_link_cells
 };
 
 struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:109-128)
@@ -80,7 +80,6 @@ struct FramePtrs {
     int mo_parity;  // which half of the mo_vec double buffer is current
     int tiles_pts, tiles_cells;  // sizes of the scan status arrays
     unsigned lattice_words16;    // lattice size in 16-byte units (cleared by k_ingest)
-    int debug;  // MOR_DEBUG env (profiling experiments only; 0 in production)
 };
 
 // ===================================================================================== K1
@@ -458,37 +457,53 @@ __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
 // ===================================================================================== K5
 // Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud
 // index of every component (the canonical label) with warp-aggregated atomics, collect the roots.
-__global__ void __launch_bounds__(kBlock) k_flatten(FramePtrs a) {
-    const int s = blockIdx.x * kBlock + threadIdx.x;
+__device__ void select_block(const FramePtrs& a);
+
+__global__ void __launch_bounds__(kSingle) k_flatten(FramePtrs a) {
+    const int s = blockIdx.x * kSingle + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int nc = a.counts[MOR_CNT_NC];
-    if (s >= nc) return;
-    const int c = __float_as_int(a.spts[s].w);
-    const int lead = a.cell_start[a.skey[s]];
-    const int r = uf_find(a.parent, lead);
-    a.comp[s] = r;
-    if (r == s) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s;
-    const unsigned active = __activemask();
-    const unsigned same = __match_any_sync(active, r);
+    const bool act = s < nc;
+    int c = 0, r = -1 - lane;
+    if (act) {
+        c = __float_as_int(a.spts[s].w);
+        const int lead = a.cell_start[a.skey[s]];
+        r = uf_find(a.parent, lead);
+        a.comp[s] = r;
+        if (r == s) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s;
+    }
+    const unsigned same = __match_any_sync(kFull, r);
     const int mn = __reduce_min_sync(same, c);
-    if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
+    if (act && (int)(__ffs(same) - 1) == lane) {
         atomicAdd(&a.comp_size[r], __popc(same));
         atomicMin(&a.minidx[r], mn);
     }
+    // the last block to finish selects and orders the clusters (K6) - no separate single-block launch
+    __shared__ int s_last;
+    __threadfence();  // root_list entries are plain stores of arbitrary threads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.scratch->flatten_blocks_done, 1) == (int)gridDim.x - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last) select_block(a);
 }
 
 // ===================================================================================== K6
 // Size filter min <= size <= max (cpp:215-216), cluster order = size descending then min index
 // ascending (A9 canonical rule) by a shared-memory bitonic sort of (~size, root) keys.
-__global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
+__device__ void select_block(const FramePtrs& a) {
     extern __shared__ unsigned long long keys[];
     __shared__ int s_k;
     if (threadIdx.x == 0) s_k = 0;
     __syncthreads();
-    const int n_roots = a.scratch->n_roots;
+    const int n_roots = __ldcg(&a.scratch->n_roots);
     for (int t = threadIdx.x; t < n_roots; t += kSingle) {
         const int rpos = a.root_list[t];
-        const int sz = a.comp_size[rpos];
-        const int root = a.minidx[rpos];  // min cloud index of the component = canonical label
+        const int sz = __ldcg(&a.comp_size[rpos]);
+        const int root = __ldcg(&a.minidx[rpos]);  // min cloud index of the component = canonical label
         if ((long long)sz >= a.min_cluster && (long long)sz <= a.max_cluster) {
             const int slot = atomicAdd(&s_k, 1);
             if (slot < a.kmax) keys[slot] = ((unsigned long long)(0xFFFFFFFFu - (unsigned)sz) << 32) | (unsigned)root;
@@ -501,7 +516,7 @@ __global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
     if (K > a.kmax) {  // capacity exceeded: keep the first kmax found, flag the frame
         if (threadIdx.x == 0) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_CLUSTER_CAP);
         // the dropped roots must not keep a stale cluster id
-        for (int t = threadIdx.x; t < n_roots; t += kSingle) a.cid_of_root[a.minidx[a.root_list[t]]] = -1;
+        for (int t = threadIdx.x; t < n_roots; t += kSingle) a.cid_of_root[__ldcg(&a.minidx[a.root_list[t]])] = -1;
         K = a.kmax;
     }
     int P = 1;
@@ -537,7 +552,10 @@ __global__ void __launch_bounds__(kSingle) k_select_clusters(FramePtrs a) {
     // the ingest / cell scans of this frame are complete: reset their look-back state for the next frame
     for (int t = threadIdx.x; t < a.tiles_pts; t += kSingle) a.st_ingest[t] = 0ull;
     for (int t = threadIdx.x; t < a.tiles_cells; t += kSingle) a.st_cells[t] = 0ull;
-    if (threadIdx.x == 0) { a.scratch->ticket_ingest = 0; a.scratch->ticket_cells = 0; a.scratch->n_roots = 0; a.scratch->stats_blocks_done = 0; }
+    if (threadIdx.x == 0) {
+        a.scratch->ticket_ingest = 0; a.scratch->ticket_cells = 0; a.scratch->n_roots = 0; a.scratch->stats_blocks_done = 0;
+        a.scratch->flatten_blocks_done = 0; a.scratch->moving_blocks_done = 0;
+    }
     if (threadIdx.x < 3) { a.scratch->box_inv_min[threadIdx.x] = 0u; a.scratch->box_max[threadIdx.x] = 0u; }
 }
 
@@ -639,10 +657,12 @@ __device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc
     }
 }
 
+__device__ void match_block(const FramePtrs& a);
+
 __global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) {
     const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
-    if (blockIdx.x * kStatBlock >= nc) return;  // whole blocks stay alive for the barriers
+    if (blockIdx.x * kStatBlock >= nc && !(nc == 0 && blockIdx.x == 0)) return;  // whole blocks stay alive for the barriers
     float4 p = make_float4(0, 0, 0, 0);
     int k = -1;
     if (s < nc) {
@@ -660,7 +680,7 @@ __global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();  // the block's accumulator atomics are ordered before the ticket
-        s_last = atomicAdd(&a.scratch->stats_blocks_done, 1) == (nc + kStatBlock - 1) / kStatBlock - 1;
+        s_last = atomicAdd(&a.scratch->stats_blocks_done, 1) == max((nc + kStatBlock - 1) / kStatBlock, 1) - 1;
         __threadfence();
     }
     __syncthreads();
@@ -673,6 +693,11 @@ __global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) {
             a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
 #pragma unroll
         for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
+    }
+    // ... and, with two frames, goes straight on to the cluster correspondences (K9)
+    if (a.two_frames) {
+        __syncthreads();
+        match_block(a);
     }
 }
 
@@ -739,14 +764,14 @@ __device__ __forceinline__ int nn_brute(const float* pts, int n, float qx, float
     return best;
 }
 
-__global__ void __launch_bounds__(kSingle) k_match(FramePtrs a) {
+__device__ void match_block(const FramePtrs& a) {
     const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K];
     // previous centroids and boxes into the current frame
     for (int i = threadIdx.x; i < Kp; i += kSingle) {
         const float3 t = xform(a.M, a.p_cl_centroid[i * 3], a.p_cl_centroid[i * 3 + 1], a.p_cl_centroid[i * 3 + 2]);
         a.pct[i * 3] = t.x; a.pct[i * 3 + 1] = t.y; a.pct[i * 3 + 2] = t.z;
 #pragma unroll
-        for (int q = 0; q < 6; q++) a.pbbox[i * 6 + q] = fkey_inv(a.pacc_box[i * 6 + q]);
+        for (int q = 0; q < 6; q++) a.pbbox[i * 6 + q] = fkey_inv(__ldcg(&a.pacc_box[i * 6 + q]));
         a.match_of_prev[i] = -1; a.mid_of_prev[i] = -1;
     }
     for (int j = threadIdx.x; j < K; j += kSingle) a.mid_of_cur[j] = -1;
@@ -840,63 +865,81 @@ __global__ void __launch_bounds__(kBlock) k_lattice_insert(FramePtrs a) {
     hset_insert(a.lattice, a.lattice_mask, key);
 }
 
-__global__ void __launch_bounds__(kBlock) k_lattice_count(FramePtrs a) {
-    const int s = blockIdx.x * kBlock + threadIdx.x;
-    if (s >= a.counts[MOR_CNT_NC]) return;
-    const float4 p = a.spts[s];
-    const int c = __float_as_int(p.w);
-    const int k = a.cid[c];
-    const int m = k >= 0 ? a.mid_of_cur[k] : -1;
+__device__ void chain_block(const FramePtrs& a);
+
+// Shared tail of the two moving-test kernels: the last block to finish turns the scores into flags and runs the
+// consistency chain (K12).
+__device__ __forceinline__ void moving_test_epilogue(const FramePtrs& a) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.scratch->moving_blocks_done, 1) == (int)gridDim.x - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last) chain_block(a);
+}
+
+__global__ void __launch_bounds__(kSingle) k_lattice_count(FramePtrs a) {
+    const int s = blockIdx.x * kSingle + threadIdx.x;
+    int m = -1;
     bool is_new = false;
-    if (m >= 0) {
-        unsigned long long key;
-        if (lattice_key(a, m, p.x, p.y, p.z, &key)) is_new = !hset_contains(a.lattice, a.lattice_mask, key);
-        else { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); is_new = true; }
+    if (s < a.counts[MOR_CNT_NC]) {
+        const float4 p = a.spts[s];
+        const int c = __float_as_int(p.w);
+        const int k = a.cid[c];
+        m = k >= 0 ? a.mid_of_cur[k] : -1;
+        if (m >= 0) {
+            unsigned long long key;
+            if (lattice_key(a, m, p.x, p.y, p.z, &key)) is_new = !hset_contains(a.lattice, a.lattice_mask, key);
+            else { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); is_new = true; }
+        }
     }
-    if (is_new) {
-        const unsigned same = __match_any_sync(__activemask(), m);
-        if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.newcount[m], __popc(same));
-    }
+    const unsigned same = __match_any_sync(kFull, is_new ? m : -1 - (int)(threadIdx.x & 31));
+    if (is_new && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.newcount[m], __popc(same));
+    moving_test_epilogue(a);
 }
 
 // ===================================================================================== K10' (method 1)
 // CorrespondenceEstimation::determineCorrespondences (cpp:343-361): for every point of the transformed
 // previous cluster the nearest point of the matched current cluster; only squared distances inside
 // (pde_lb, pde_ub) count, so the search is bounded by sqrt(pde_ub) on the clustering grid.
-__global__ void __launch_bounds__(kBlock) k_pde_count(FramePtrs a, int ring) {
-    const int c = blockIdx.x * kBlock + threadIdx.x;
-    if (c >= a.p_counts[MOR_CNT_NC]) return;
-    const float4 t = a.tpts[c];
-    const int kp = __float_as_int(t.w);
-    if (kp < 0) return;
-    const int m = a.mid_of_prev[kp];
-    if (m < 0) return;
-    const int target = a.match_m[m];
-    const GridDesc g = *a.dgrid;
-    const int cx = (int)floor(((double)t.x - g.ox) * g.inv_h), cy = (int)floor(((double)t.y - g.oy) * g.inv_h), cz = (int)floor(((double)t.z - g.oz) * g.inv_h);
-    float best = 3.402823466e+38f;
-    const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.nx - 1);
-    if (x0 <= x1) {
-        for (int zz = max(cz - ring, 0); zz <= min(cz + ring, g.nz - 1); zz++)
-            for (int yy = max(cy - ring, 0); yy <= min(cy + ring, g.ny - 1); yy++) {
-                const int base = (zz * g.ny + yy) * g.nx;
-                const int b = a.cell_start[base + x0], e = a.cell_start[base + x1 + 1];
-                for (int j = b; j < e; j++) {
-                    const float4 q = a.spts[j];
-                    if (a.cid[__float_as_int(q.w)] != target) continue;
-                    const float d = sqdist3(t.x, t.y, t.z, q.x, q.y, q.z);
-                    best = fminf(best, d);
-                }
+__global__ void __launch_bounds__(kSingle) k_pde_count(FramePtrs a, int ring) {
+    const int c = blockIdx.x * kSingle + threadIdx.x;
+    if (c < a.p_counts[MOR_CNT_NC]) {
+        const float4 t = a.tpts[c];
+        const int kp = __float_as_int(t.w);
+        const int m = kp >= 0 ? a.mid_of_prev[kp] : -1;
+        if (m >= 0) {
+            const int target = a.match_m[m];
+            const GridDesc g = *a.dgrid;
+            const int cx = (int)floor(((double)t.x - g.ox) * g.inv_h), cy = (int)floor(((double)t.y - g.oy) * g.inv_h), cz = (int)floor(((double)t.z - g.oz) * g.inv_h);
+            float best = 3.402823466e+38f;
+            const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.nx - 1);
+            if (x0 <= x1) {
+                for (int zz = max(cz - ring, 0); zz <= min(cz + ring, g.nz - 1); zz++)
+                    for (int yy = max(cy - ring, 0); yy <= min(cy + ring, g.ny - 1); yy++) {
+                        const int base = (zz * g.ny + yy) * g.nx;
+                        const int b = a.cell_start[base + x0], e = a.cell_start[base + x1 + 1];
+                        for (int j = b; j < e; j++) {
+                            const float4 q = a.spts[j];
+                            if (a.cid[__float_as_int(q.w)] != target) continue;
+                            best = fminf(best, sqdist3(t.x, t.y, t.z, q.x, q.y, q.z));
+                        }
+                    }
             }
+            if (best > a.pde_lb && best < a.pde_ub) atomicAdd(&a.newcount[m], 1);
+        }
     }
-    if (best > a.pde_lb && best < a.pde_ub) atomicAdd(&a.newcount[m], 1);
+    moving_test_epilogue(a);
 }
 
 // ===================================================================================== K12
 // Detection flags (cpp:580-606) and the N-frame consistency chain: checkMovingClusterChain
 // (cpp:478-514), recurseFindClusterChain (cpp:415-453), pushCentroid (cpp:455-476). corrs_vec /
 // res_vec are device-resident ring buffers; a correspondence map is stored as match_of_prev[].
-__global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
+__device__ void chain_block(const FramePtrs& a) {
     const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K], M = a.counts[MOR_CNT_M];
     const int D = a.ring_depth, kmax = a.kmax;
     TrackState* ts = a.track;
@@ -905,10 +948,10 @@ __global__ void __launch_bounds__(kSingle) k_flags_and_chain(FramePtrs a) {
         const unsigned long long n1 = (unsigned long long)a.p_cl_size[a.match_q[m]], n2 = (unsigned long long)a.cl_size[a.match_m[m]];
         double score, thr;
         if (a.method == 1) {
-            score = (double)a.newcount[m] / (double)((n1 + n2) / 2ull);  // cpp:361
+            score = (double)__ldcg(&a.newcount[m]) / (double)((n1 + n2) / 2ull);  // cpp:361
             thr = (double)a.pde_thr;                                       // cpp:586
         } else {
-            score = (double)a.newcount[m];                                                 // cpp:330
+            score = (double)__ldcg(&a.newcount[m]);                                        // cpp:330
             thr = (double)((n1 + n2) / (unsigned long long)(long long)a.opc_factor);      // cpp:590, unsigned division
         }
         a.match_score[m] = score;
