@@ -9,7 +9,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from bench import algorithmic_bytes, measured_peak_gbs, pinned_array  # noqa: E402
 from dynamicslamtool_b200 import MorBinding, MovingObjectRemoval, Synth, load_product  # noqa: E402

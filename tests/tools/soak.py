@@ -1,7 +1,7 @@
 """Long parity soak: N frames of a scenario through the CUDA path and the oracle, all taps compared per frame."""
 import ctypes as C, sys, time
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from dynamicslamtool_b200 import MorBinding, MovingObjectRemoval, Synth, load_product
 from parity import ParityStats, compare_frame
