@@ -275,43 +275,31 @@ def run_product(args, rank, local_rank, world):
             d_outs.append(p)
         offs = [(si * F) // S for si in range(S)]  # every sequence starts at its own frame of the pool and wraps around once
 
-        def round_robin(t0, t1):
+        from dynamicslamtool_b200 import SequenceBatch
+        batch = SequenceBatch(hs)
+        outs = [p.value for p in d_outs]
+
+        def steps(t0, t1):
             for t in range(t0, t1):
-                for si, hh in enumerate(hs):
-                    f = (offs[si] + t) % F
-                    hh.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-                    hh.filter_device(d_outs[si].value, maxp, want_count=False)
+                fs = [(offs[si] + t) % F for si in range(S)]
+                batch.step_device([d_frames.value + f * frame_bytes for f in fs], [int(npts[f]) for f in fs], [poses[f] for f in fs], outs)
 
         Wm = max(3, W)
-        round_robin(0, Wm)
-        for hh in hs:
-            hh.sync()
+        steps(0, Wm)
+        hs[0].sync()
         barrier()
-        # host side: T launcher threads, each owning S/T sequences (ctypes releases the GIL inside the C ABI calls)
-        T = max(1, min(args.launch_threads, S))
-
-        def launcher(tid):
-            for t in range(Wm, Wm + K):
-                for si in range(tid, S, T):
-                    f = (offs[si] + t) % F
-                    hs[si].push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-                    hs[si].filter_device(d_outs[si].value, maxp, want_count=False)
-
-        for hh in hs:
-            hh.event_record(0)
-        ths = [threading.Thread(target=launcher, args=(tid,)) for tid in range(T)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        for hh in hs:
-            hh.event_record(1)
-        multi_ms = max(hh.event_elapsed_ms(0, 1) for hh in hs)
+        l0m = hs[0].launch_count()
+        hs[0].event_record(0)
+        steps(Wm, Wm + K)
+        hs[0].event_record(1)
+        multi_ms = hs[0].event_elapsed_ms(0, 1)
         barrier()
         multi_ms = max_over_ranks(multi_ms)
+        T = 1
+        multi_launches = hs[0].launch_count() - l0m
         multi = {"sequences_per_gpu": S, "value": world * S * K / (multi_ms * 1e-3), "unit": "frames/s", "ms_per_round": multi_ms / K,
-                 "launch_threads": T,
-                 "note": "device-resident, S handles = S streams, T host launcher threads; aggregate over all sequences and GPUs"}
+                 "launches": multi_launches,
+                 "note": "device-resident, mor_batch_step_device: S sequences per set of launches (blockIdx.z = sequence); aggregate over all sequences and GPUs"}
         for hh in hs:
             hh.close()
         for p in d_outs:

@@ -114,6 +114,8 @@ class MorBinding:
         self.get_last_device_ms = f("get_last_device_ms", [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)], True)
         self.set_timing = f("set_timing", [vp, C.c_int], True)
         self.last_error = f("last_error", [vp], True, C.c_char_p)
+        self.batch_step_device = f("batch_step_device", [C.POINTER(vp), u32, C.POINTER(vp), C.POINTER(u32), u32, u32, u32, u32, u32,
+                                                         C.POINTER(C.c_double), C.POINTER(vp)], True)
         self.event_record = f("event_record", [vp, C.c_int], True)
         self.event_elapsed_ms = f("event_elapsed_ms", [vp, C.c_int, C.c_int, C.POINTER(C.c_float)], True)
         self.set_kernel_profiling = f("set_kernel_profiling", [vp, C.c_int], True)
@@ -287,6 +289,33 @@ class MovingObjectRemoval:
         v = C.c_uint64(0)
         self._check(self.b.get_launch_count(self.h, C.byref(v)), "get_launch_count")
         return v.value
+
+
+class SequenceBatch:
+    """S independent sequences stepped with one set of kernel launches (mor_batch_step_device, BASELINE config 5)."""
+
+    def __init__(self, handles: list[MovingObjectRemoval]):
+        self.handles = handles
+        self.b = handles[0].b
+        S = len(handles)
+        self._hs = (C.c_void_p * S)(*[h.h.value for h in handles])
+        self._data = (C.c_void_p * S)()
+        self._out = (C.c_void_p * S)()
+        self._n = (C.c_uint32 * S)()
+        self._poses = (C.c_double * (7 * S))()
+
+    def step_device(self, d_ptrs, ns, poses, d_outs, point_step=16, offsets=(0, 4, 8, 12)):
+        S = len(self.handles)
+        for s in range(S):
+            self._data[s] = d_ptrs[s]
+            self._out[s] = d_outs[s]
+            self._n[s] = int(ns[s])
+            self.handles[s].n_input = int(ns[s])
+            for k in range(7):
+                self._poses[7 * s + k] = float(poses[s][k])
+        st = self.b.batch_step_device(self._hs, S, self._data, self._n, point_step, *offsets, self._poses, self._out)
+        if st:
+            self.handles[0]._check(st, "batch_step_device")
 
 
 class Synth:

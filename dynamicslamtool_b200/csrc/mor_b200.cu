@@ -90,6 +90,10 @@ struct mor_handle {
     cudaStream_t side = nullptr;  // runs k_transform_prev (depends only on the previous frame + pose) beside the clustering chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t spec_out = 0;        // speculative size of the output D2H copy (points), from the previous frame
+    cudaStream_t last_stream = nullptr;  // stream that carries this handle's latest work (differs after a batched step)
+    // batched stepping (this handle as the leader of a batch): device array of per-sequence arguments + pinned ring
+    FramePtrs* d_batch = nullptr; FramePtrs* h_batch = nullptr; uint32_t batch_cap = 0; int batch_slot = 0;
+    cudaEvent_t batch_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t nmax = 0, kmax = 0, momax = 0;
     int ring_depth = 0, pde_ring = 0;
     bool dynamic_grid = false; int max_cells = 0; double cell_h = 0;
@@ -228,7 +232,6 @@ int allocate(mor_handle* h) {
         b.cell_count = carve<int>(p, ncells + 16);
         h->zero_bytes = (size_t)(p - h->zero_region);
         b.cell_start = carve<int>(p, ncells + 16);
-        b.cell_cursor = carve<int>(p, ncells + 16);
         b.dgrid = carve<GridDesc>(p, 1);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
@@ -272,6 +275,7 @@ int allocate(mor_handle* h) {
     while (P < (int)K) P <<= 1;
     h->select_smem = (size_t)P * sizeof(unsigned long long);
     MOR_CUDA(cudaFuncSetAttribute(k_flatten, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
+    MOR_CUDA(cudaFuncSetAttribute(k_flatten_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     return MOR_OK;
 }
@@ -290,6 +294,7 @@ void fill_static(mor_handle* h) {
     b.grid = h->grid;
     b.dynamic_grid = h->dynamic_grid ? 1 : 0; b.max_cells = h->max_cells; b.cell_h = h->cell_h;
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
+    b.pde_ring = h->pde_ring;
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
     b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells) / kScanTile + 2);
     if (c.ground_mode != MOR_GROUND_CROP) {
@@ -302,8 +307,8 @@ void fill_static(mor_handle* h) {
 
 inline unsigned blocks_for(uint32_t n) { return n ? (n + kBlock - 1) / kBlock : 1; }
 
-int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
-    cudaStream_t st = h->stream;
+// Arguments of the current frame (everything the kernels read) from the handle's host-side state.
+void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
     FramePtrs& a = h->frame;
     a = h->base;
     const int cur = h->cur, prev = cur ^ 1;
@@ -316,7 +321,12 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     a.two_frames = h->two_frames ? 1 : 0;
     a.mo_parity = h->mo_parity;
     std::memcpy(a.M.m, h->M, sizeof(h->M));
+}
 
+int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
+    cudaStream_t st = h->stream;
+    fill_frame(h, d_points, n, step, ox, oy, oz, oi);
+    FramePtrs& a = h->frame;
     const unsigned gb = blocks_for(n);
     if (h->cfg.ground_mode != MOR_GROUND_CROP) {
         // voxel-covariance ground removal (reference cpp:90-200, repaired): 8 launches, then the common pipeline
@@ -367,10 +377,31 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
             MOR_LAUNCH(KID_LATTICE_COUNT, (k_lattice_count<<<g1k, kSingle, 0, st>>>(a)));  // + flags and consistency chain in its last block
         } else {
             const unsigned gp1k = h->n_prev_input ? (h->n_prev_input + kSingle - 1) / kSingle : 1;
-            MOR_LAUNCH(KID_PDE, (k_pde_count<<<gp1k, kSingle, 0, st>>>(a, h->pde_ring)));
+            MOR_LAUNCH(KID_PDE, (k_pde_count<<<gp1k, kSingle, 0, st>>>(a)));
         }
     }
     MOR_CUDA(cudaGetLastError());
+    return MOR_OK;
+}
+
+// ca = cb; cb = new frame (cpp:520-521), pose delta cb.ps^-1 * ca.ps (cpp:536)
+void advance_frame(mor_handle* h, uint32_t n, const double pose7[7]) {
+    if (h->have_cur) { h->cur ^= 1; std::memcpy(h->prev_pose, h->cur_pose, sizeof(h->cur_pose)); h->have_prev = true; h->n_prev_input = h->n_input; }
+    std::memcpy(h->cur_pose, pose7, sizeof(h->cur_pose));
+    h->n_input = n;
+    h->two_frames = h->have_prev;  // ca->init && cb->init (cpp:534)
+    std::memset(h->M, 0, sizeof(h->M));
+    if (h->two_frames) pose_delta_affine(h->prev_pose, h->cur_pose, h->M);
+    h->have_cur = true;
+    h->filtered = false;
+}
+
+// Work of a handle may have been enqueued on another handle's stream by mor_batch_step_device.
+int join_foreign_stream(mor_handle* h) {
+    if (h->last_stream && h->last_stream != h->stream) {
+        MOR_CUDA(cudaStreamSynchronize(h->last_stream));
+        h->last_stream = h->stream;
+    }
     return MOR_OK;
 }
 
@@ -380,6 +411,7 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
     if (ox + 4 > step || oy + 4 > step || oz + 4 > step || (oi != 0xFFFFFFFFu && oi + 4 > step)) return MOR_ERR_ARG;
     if (n > h->nmax) { h->last_error = "frame larger than mor_limits.max_points"; return MOR_ERR_CAPACITY; }
     MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (h->profiling && !h->prof_ids.empty()) { MOR_CUDA(cudaStreamSynchronize(h->stream)); prof_harvest(h); }
     const uint8_t* d_points = (const uint8_t*)data;
@@ -389,15 +421,7 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
         if (bytes) MOR_CUDA(cudaMemcpyAsync(h->d_in, data, bytes, cudaMemcpyHostToDevice, h->stream));
         d_points = h->d_in;
     }
-    // ca = cb; cb = new frame (cpp:520-521)
-    if (h->have_cur) { h->cur ^= 1; std::memcpy(h->prev_pose, h->cur_pose, sizeof(h->cur_pose)); h->have_prev = true; h->n_prev_input = h->n_input; }
-    std::memcpy(h->cur_pose, pose7, sizeof(h->cur_pose));
-    h->n_input = n;
-    h->two_frames = h->have_prev;  // ca->init && cb->init (cpp:534)
-    std::memset(h->M, 0, sizeof(h->M));
-    if (h->two_frames) pose_delta_affine(h->prev_pose, h->cur_pose, h->M);
-    h->have_cur = true;
-    h->filtered = false;
+    advance_frame(h, n, pose7);
     int st = enqueue_push(h, d_points, n, step, ox, oy, oz, oi);
     if (st != MOR_OK) return st;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -408,6 +432,7 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     if (!h) return MOR_ERR_ARG;
     if (!h->have_cur) return MOR_ERR_STATE;
     MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     cudaStream_t st = h->stream;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[2], st));
     FramePtrs& a = h->frame;
@@ -511,6 +536,9 @@ int mor_destroy(mor_handle* h) {
     for (auto& e : h->slot_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->prof_pool) cudaEventDestroy(e);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->d_batch) cudaFree(h->d_batch);
+    if (h->h_batch) cudaFreeHost(h->h_batch);
+    for (auto& e : h->batch_ev) if (e) cudaEventDestroy(e);
     if (h->arena) cudaFree(h->arena);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -539,9 +567,105 @@ int mor_filter_cloud(mor_handle* h, void* out, uint32_t cap_points, uint32_t* n_
 }
 int mor_filter_cloud_device(mor_handle* h, void* d_out, uint32_t cap_points, uint32_t* n_out) { return do_filter(h, d_out, true, cap_points, n_out); }
 
+// One pushRawCloudAndPose + filterCloud for S independent sequences in one set of launches (BASELINE config 5).
+int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* d_data, const uint32_t* n, uint32_t point_step, uint32_t off_x,
+                          uint32_t off_y, uint32_t off_z, uint32_t off_i, const double* poses7, void* const* d_out) {
+    if (!hs || !S || !d_data || !n || !poses7 || !d_out || !hs[0]) return MOR_ERR_ARG;
+    mor_handle* h = hs[0];  // leader: owns the stream and the argument array of the batch
+    if (point_step < 12 || point_step % 4 || off_x % 4 || off_y % 4 || off_z % 4 || (off_i != 0xFFFFFFFFu && off_i % 4)) return MOR_ERR_ARG;
+    uint32_t n_max = 0, np_max = 0;
+    for (uint32_t s = 0; s < S; s++) {
+        mor_handle* g = hs[s];
+        if (!g || g->device != h->device || g->nmax != h->nmax || g->kmax != h->kmax || g->cfg.method_choice != h->cfg.method_choice ||
+            g->dynamic_grid != h->dynamic_grid || g->grid.ncells != h->grid.ncells || g->have_prev != h->have_prev || g->have_cur != h->have_cur ||
+            g->profiling) { h->last_error = "batched handles must share device, limits, config and frame count"; return MOR_ERR_ARG; }
+        if (g->cfg.ground_mode != MOR_GROUND_CROP) { h->last_error = "batched stepping supports ground_mode 0 only"; return MOR_ERR_ARG; }
+        if (n[s] > g->nmax || (!d_data[s] && n[s]) || !d_out[s]) return n[s] > g->nmax ? MOR_ERR_CAPACITY : MOR_ERR_ARG;
+        for (uint32_t t = 0; t < s; t++) if (hs[t] == g) return MOR_ERR_ARG;
+    }
+    MOR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (S > h->batch_cap) {
+        MOR_CUDA(cudaStreamSynchronize(st));
+        if (h->d_batch) cudaFree(h->d_batch);
+        if (h->h_batch) cudaFreeHost(h->h_batch);
+        h->d_batch = nullptr; h->h_batch = nullptr; h->batch_cap = 0;
+        MOR_CUDA(cudaMalloc(&h->d_batch, sizeof(FramePtrs) * S * 4));
+        MOR_CUDA(cudaMallocHost(&h->h_batch, sizeof(FramePtrs) * S * 4));
+        for (auto& e : h->batch_ev) if (!e) MOR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->batch_cap = S;
+    }
+    // ring of 4 argument slots: the H2D copy of a slot runs later on the stream, so a slot is only rewritten once the
+    // step that used it four steps ago has consumed it
+    const int slot = h->batch_slot;
+    h->batch_slot = (slot + 1) & 3;
+    MOR_CUDA(cudaEventSynchronize(h->batch_ev[slot]));
+    FramePtrs* hp = h->h_batch + (size_t)slot * h->batch_cap;
+    FramePtrs* dp = h->d_batch + (size_t)slot * h->batch_cap;
+    for (uint32_t s = 0; s < S; s++) {
+        mor_handle* g = hs[s];
+        if (g->last_stream != st) {  // earlier work of this handle ran elsewhere (its own stream or another batch): wait for it once
+            if (g->last_stream) MOR_CUDA(cudaStreamSynchronize(g->last_stream));
+            if (g->stream != st) MOR_CUDA(cudaStreamSynchronize(g->stream));
+        }
+        advance_frame(g, n[s], poses7 + 7 * s);
+        fill_frame(g, (const uint8_t*)d_data[s], n[s], point_step, off_x, off_y, off_z, off_i);
+        g->frame.out = (float4*)d_out[s];
+        hp[s] = g->frame;
+        n_max = n[s] > n_max ? n[s] : n_max;
+        np_max = g->n_prev_input > np_max ? g->n_prev_input : np_max;
+        g->last_stream = st;
+    }
+    MOR_CUDA(cudaMemcpyAsync(dp, hp, sizeof(FramePtrs) * S, cudaMemcpyHostToDevice, st));
+    MOR_CUDA(cudaEventRecord(h->batch_ev[slot], st));
+    const bool two = h->two_frames;
+    const unsigned gb = blocks_for(n_max), g1k = n_max ? (n_max + kSingle - 1) / kSingle : 1;
+    k_ingest_batch<<<dim3(n_max ? (n_max + kIngestTile - 1) / kIngestTile : 1, 1, S), kBlock, 0, st>>>(dp);
+    if (two) {  // the transform of the previous clusters runs beside the clustering chain (see enqueue_push)
+        MOR_CUDA(cudaEventRecord(h->ev_fork, st));
+        MOR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        k_transform_prev_batch<<<dim3(np_max ? (np_max + kStatBlock - 1) / kStatBlock : 1, 1, S), kStatBlock, 0, h->side>>>(dp);
+        MOR_CUDA(cudaEventRecord(h->ev_join, h->side));
+    }
+    if (h->dynamic_grid) k_keys_batch<<<dim3(gb, 1, S), kBlock, 0, st>>>(dp);
+    {
+        const int tiles = (h->grid.ncells + kScanTile - 1) / kScanTile;
+        const int per_seq = h->num_sms * 8 / (int)S > 8 ? h->num_sms * 8 / (int)S : 8;
+        const int scan_blocks = h->dynamic_grid ? per_seq : (tiles < per_seq ? tiles : per_seq);
+        k_scan_cells_batch<<<dim3(scan_blocks, 1, S), kBlock, 0, st>>>(dp);
+    }
+    k_scatter_batch<<<dim3(gb, 1, S), kBlock, 0, st>>>(dp);
+    k_link_cells_batch<1><<<dim3(gb, 5, S), kBlock, 0, st>>>(dp);
+    k_link_cells_batch<2><<<dim3(gb, 13, S), kBlock, 0, st>>>(dp);
+    k_flatten_batch<<<dim3(g1k, 1, S), kSingle, h->select_smem, st>>>(dp);
+    if (two) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    k_cluster_stats_batch<<<dim3(g1k, 1, S), kStatBlock, 0, st>>>(dp);
+    h->launches += 7 + (h->dynamic_grid ? 1 : 0);
+    if (two) {
+        if (h->cfg.method_choice == 2) {
+            k_lattice_insert_batch<<<dim3(blocks_for(np_max), 1, S), kBlock, 0, st>>>(dp);
+            k_lattice_count_batch<<<dim3(g1k, 1, S), kSingle, 0, st>>>(dp);
+            h->launches += 3;
+        } else {
+            k_pde_count_batch<<<dim3(np_max ? (np_max + kSingle - 1) / kSingle : 1, 1, S), kSingle, 0, st>>>(dp);
+            h->launches += 2;
+        }
+    }
+    k_filter_output_batch<<<dim3(n_max ? (n_max + kOutTile - 1) / kOutTile : 1, 1, S), kBlock, 0, st>>>(dp);
+    h->launches += 1;
+    MOR_CUDA(cudaGetLastError());
+    for (uint32_t s = 0; s < S; s++) {
+        hs[s]->mo_parity ^= 1;
+        hs[s]->frame.mo_parity = hs[s]->mo_parity;
+        hs[s]->filtered = true;
+    }
+    return MOR_OK;
+}
+
 int mor_sync(mor_handle* h) {
     if (!h) return MOR_ERR_ARG;
     MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     return MOR_OK;
 }
@@ -619,6 +743,7 @@ int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes
     if (!h) return MOR_ERR_ARG;
     if (!h->have_cur) return MOR_ERR_STATE;
     MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     const FramePtrs& a = h->frame;
     int32_t c[MOR_NCOUNTS];

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_scatter(FramePtrs a, GroundPt
     int ord = -1;
     if (in) {
         const int key = a.cell_key[r];
-        const int pos = atomicAdd(&a.cell_cursor[key], 1);
+        const int pos = a.cell_start[key] + atomicSub(&a.cell_count[key], 1) - 1;
         p = gp.rpts[r];
         ord = gp.vox_ord[gp.vkey[r]];
         float4 sp = p;

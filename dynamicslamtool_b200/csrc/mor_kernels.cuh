@@ -2,6 +2,9 @@
 // moving tests + tracking + output. Launched by mor_b200.cu. Every kernel cites the reference lines
 // (src/MovingObjectRemoval.cpp unless noted) whose behaviour it reproduces; DESIGN.md has the data
 // layout and the roofline of each.
+// Every kernel exists twice: NAME(FramePtrs) for one sequence (arguments in the constant bank) and
+// NAME_batch(const FramePtrs*) for S sequences in one launch (blockIdx.z selects the sequence; the per-sequence
+// state - scratch, tickets, tables - is disjoint, so the bodies are identical).
 #pragma once
 #include "mor_device.cuh"
 #include "../../include/mor_b200.h"
@@ -54,7 +57,7 @@ struct FramePtrs {
     int* cell_count; int* cell_start;
     uint8_t* point_class; uint8_t* removed_mask;
     int* cloud_src; float4* gpts; int* gsrc;
-    int* cell_key; int* cell_cursor; int* skey;  // cell_cursor: copy of cell_start consumed by the scatter (fill cursors)
+    int* cell_key; int* skey;
     int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
     int* comp; int* minidx; unsigned long long* done;  // indexed by sorted position (cell leaders)
     uint4* cell_box;  // [2*N] per leader position: {min x,y,z keys, count}, {max x,y,z keys, 0}
@@ -78,6 +81,7 @@ struct FramePtrs {
     uint8_t* res_ring; int* res_len; int* corr_ring; int* corr_len;
     Affine12 M; int two_frames;
     int mo_parity;  // which half of the mo_vec double buffer is current
+    int pde_ring;   // method 1: search reach in cells, ceil(sqrt(pde_ub)/h)
     int tiles_pts, tiles_cells;  // sizes of the scan status arrays
     unsigned lattice_words16;    // lattice size in 16-byte units (cleared by k_ingest)
 };
@@ -90,7 +94,7 @@ struct FramePtrs {
 constexpr int kIngestItems = 4;
 constexpr int kIngestTile = kBlock * kIngestItems;
 
-__global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
+__device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
     if (a.two_frames) {
@@ -199,6 +203,9 @@ __global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) {
         a.track->frames += 1;
     }
 }
+__global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) { k_ingest_body(a); }
+__global__ void __launch_bounds__(kBlock) k_ingest_batch(const FramePtrs* __restrict__ P) { k_ingest_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K1b (dynamic grid only)
 // When the config crop box would need more cells than the table holds (e.g. trim "disabled" with huge
@@ -221,7 +228,7 @@ __device__ __forceinline__ GridDesc grid_from_box(const FramePtrs& a, bool* too_
     return g;
 }
 
-__global__ void __launch_bounds__(kBlock) k_keys(FramePtrs a) {
+__device__ __forceinline__ void k_keys_body(const FramePtrs& a) {
     __shared__ GridDesc s_g;
     if (threadIdx.x == 0) {
         bool too_big;
@@ -244,16 +251,20 @@ __global__ void __launch_bounds__(kBlock) k_keys(FramePtrs a) {
     a.cell_key[c] = key;
     atomicAdd(&a.cell_count[key], 1);
 }
+__global__ void __launch_bounds__(kBlock) k_keys(FramePtrs a) { k_keys_body(a); }
+__global__ void __launch_bounds__(kBlock) k_keys_batch(const FramePtrs* __restrict__ P) { k_keys_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K2
-// Exclusive scan of the per-cell histogram (counting sort of the cell keys) -> cell_start[0..ncells] and a second
-// copy, cell_cursor[], that k_scatter consumes as per-cell fill cursors (so k_ingest needs no returning atomic).
+// Exclusive scan of the per-cell histogram (counting sort of the cell keys) -> cell_start[0..ncells]. The histogram
+// itself is left in place: k_scatter counts it back down to zero (rank = atomicSub - 1), which both hands out the
+// slots of a cell and leaves the table clean for the next frame - the dense table is read once and written once.
 // Persistent blocks pull 4096-cell tiles by ticket, so the launch does not depend on the (possibly device-side)
-// cell count; the histogram is zeroed as it is consumed, ready for the next frame.
+// cell count.
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kBlock * kScanItems;
 
-__global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
+__device__ __forceinline__ void k_scan_cells_body(const FramePtrs& a) {
     __shared__ int s_tile;
     const int ncells = a.dgrid->ncells;
     const int ntiles = (ncells + kScanTile - 1) / kScanTile;
@@ -266,19 +277,15 @@ __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
         const int base = tile * kScanTile + threadIdx.x * kScanItems;
         int v[kScanItems];
         if (base + kScanItems <= ncells) {
-            int4* src = reinterpret_cast<int4*>(a.cell_count + base);
+            const int4* src = reinterpret_cast<const int4*>(a.cell_count + base);
 #pragma unroll
             for (int k = 0; k < kScanItems / 4; k++) {
                 const int4 t = src[k];
                 v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-                if (t.x | t.y | t.z | t.w) src[k] = make_int4(0, 0, 0, 0);
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < kScanItems; k++) {
-                v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
-                if (v[k]) a.cell_count[base + k] = 0;
-            }
+            for (int k = 0; k < kScanItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
         }
         int sum = 0;
 #pragma unroll
@@ -289,7 +296,6 @@ __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
         int run = before + in_block;
         if (base + kScanItems <= ncells) {
             int4* d0 = reinterpret_cast<int4*>(a.cell_start + base);
-            int4* d1 = reinterpret_cast<int4*>(a.cell_cursor + base);
 #pragma unroll
             for (int k = 0; k < kScanItems / 4; k++) {
                 int4 t;
@@ -297,28 +303,31 @@ __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
                 t.y = run; run += v[4 * k + 1];
                 t.z = run; run += v[4 * k + 2];
                 t.w = run; run += v[4 * k + 3];
-                d0[k] = t; d1[k] = t;
+                d0[k] = t;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < kScanItems; k++) {
-                if (base + k < ncells) { a.cell_start[base + k] = run; a.cell_cursor[base + k] = run; }
+                if (base + k < ncells) a.cell_start[base + k] = run;
                 run += v[k];
             }
         }
         if (tile == ntiles - 1 && threadIdx.x == 0) a.cell_start[ncells] = before + total;
     }
 }
+__global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) { k_scan_cells_body(a); }
+__global__ void __launch_bounds__(kBlock) k_scan_cells_batch(const FramePtrs* __restrict__ P) { k_scan_cells_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K3
 // Scatter cloud points into cell-sorted order (float4 xyz + cloud index) for the neighbour search and
 // reset the per-position union-find state. The first point of a cell (its "leader" position
 // cell_start[key]) is the union-find node of the whole cell.
-__global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) {
+__device__ __forceinline__ void k_scatter_body(const FramePtrs& a) {
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.counts[MOR_CNT_NC]) return;
     const int key = a.cell_key[c];
-    const int pos = atomicAdd(&a.cell_cursor[key], 1);  // fill cursor of the cell
+    const int pos = a.cell_start[key] + atomicSub(&a.cell_count[key], 1) - 1;  // slots of a cell are handed out last to first
     float4 p = a.pts[c];
     p.w = __int_as_float(c);
     a.spts[pos] = p;
@@ -342,6 +351,9 @@ __global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) {
         }
     }
 }
+__global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) { k_scatter_body(a); }
+__global__ void __launch_bounds__(kBlock) k_scatter_batch(const FramePtrs* __restrict__ P) { k_scatter_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K4
 // pcl::EuclideanClusterExtraction radius graph (cpp:213-218; A5-A7) on cell granularity. Every point q
@@ -424,7 +436,7 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
 // chain of a thread is a handful of cells and a warp walks the same cells for neighbouring q.
 // PHASE 1 = the 13 backward cells of the 3x3x3 block (5 rows); PHASE 2 = the 49 cells at offset 2 (13 rows).
 template <int PHASE>
-__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
+__device__ __forceinline__ void k_link_cells_body(const FramePtrs& a) {
     const int s = blockIdx.x * kBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
@@ -453,13 +465,18 @@ __global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
         if (row != 12 && cx + 2 < g.nx) link_scan_range<2>(a, q, lead, row, base, cx, cx + 2, cx + 2, dmask);
     }
 }
+template <int PHASE>
+__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) { k_link_cells_body<PHASE>(a); }
+template <int PHASE>
+__global__ void __launch_bounds__(kBlock) k_link_cells_batch(const FramePtrs* __restrict__ P) { k_link_cells_body<PHASE>(P[blockIdx.z]); }
+
 
 // ===================================================================================== K5
 // Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud
 // index of every component (the canonical label) with warp-aggregated atomics, collect the roots.
 __device__ void select_block(const FramePtrs& a);
 
-__global__ void __launch_bounds__(kSingle) k_flatten(FramePtrs a) {
+__device__ __forceinline__ void k_flatten_body(const FramePtrs& a) {
     const int s = blockIdx.x * kSingle + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int nc = a.counts[MOR_CNT_NC];
@@ -490,6 +507,9 @@ __global__ void __launch_bounds__(kSingle) k_flatten(FramePtrs a) {
     __syncthreads();
     if (s_last) select_block(a);
 }
+__global__ void __launch_bounds__(kSingle) k_flatten(FramePtrs a) { k_flatten_body(a); }
+__global__ void __launch_bounds__(kSingle) k_flatten_batch(const FramePtrs* __restrict__ P) { k_flatten_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K6
 // Size filter min <= size <= max (cpp:215-216), cluster order = size descending then min index
@@ -659,7 +679,7 @@ __device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc
 
 __device__ void match_block(const FramePtrs& a);
 
-__global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) {
+__device__ __forceinline__ void k_cluster_stats_body(const FramePtrs& a) {
     const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (blockIdx.x * kStatBlock >= nc && !(nc == 0 && blockIdx.x == 0)) return;  // whole blocks stay alive for the barriers
@@ -700,11 +720,14 @@ __global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) {
         match_block(a);
     }
 }
+__global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) { k_cluster_stats_body(a); }
+__global__ void __launch_bounds__(kStatBlock) k_cluster_stats_batch(const FramePtrs* __restrict__ P) { k_cluster_stats_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K8
 // pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12) and the bounding box
 // of the transformed points (getMinMax3D runs after the transform, cpp:272).
-__global__ void __launch_bounds__(kStatBlock) k_transform_prev(FramePtrs a) {
+__device__ __forceinline__ void k_transform_prev_body(const FramePtrs& a) {
     const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int ncp = a.p_counts[MOR_CNT_NC];
     if (blockIdx.x * kStatBlock >= ncp) return;
@@ -723,6 +746,9 @@ __global__ void __launch_bounds__(kStatBlock) k_transform_prev(FramePtrs a) {
     }
     block_cluster_accumulate<false>(nullptr, a.pacc_box, k, k >= 0, t.x, t.y, t.z);
 }
+__global__ void __launch_bounds__(kStatBlock) k_transform_prev(FramePtrs a) { k_transform_prev_body(a); }
+__global__ void __launch_bounds__(kStatBlock) k_transform_prev_batch(const FramePtrs* __restrict__ P) { k_transform_prev_body(P[blockIdx.z]); }
+
 
 // Block-wide ordered compaction helper for the single-block kernels: returns the exclusive rank of
 // `flag` among all threads, *total = number of set flags. kSingle threads.
@@ -852,7 +878,7 @@ __device__ __forceinline__ bool lattice_key(const FramePtrs& a, int m, float x, 
     return ok;
 }
 
-__global__ void __launch_bounds__(kBlock) k_lattice_insert(FramePtrs a) {
+__device__ __forceinline__ void k_lattice_insert_body(const FramePtrs& a) {
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.p_counts[MOR_CNT_NC]) return;
     const float4 t = a.tpts[c];
@@ -864,6 +890,9 @@ __global__ void __launch_bounds__(kBlock) k_lattice_insert(FramePtrs a) {
     if (!lattice_key(a, m, t.x, t.y, t.z, &key)) { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); return; }
     hset_insert(a.lattice, a.lattice_mask, key);
 }
+__global__ void __launch_bounds__(kBlock) k_lattice_insert(FramePtrs a) { k_lattice_insert_body(a); }
+__global__ void __launch_bounds__(kBlock) k_lattice_insert_batch(const FramePtrs* __restrict__ P) { k_lattice_insert_body(P[blockIdx.z]); }
+
 
 __device__ void chain_block(const FramePtrs& a);
 
@@ -881,7 +910,7 @@ __device__ __forceinline__ void moving_test_epilogue(const FramePtrs& a) {
     if (s_last) chain_block(a);
 }
 
-__global__ void __launch_bounds__(kSingle) k_lattice_count(FramePtrs a) {
+__device__ __forceinline__ void k_lattice_count_body(const FramePtrs& a) {
     const int s = blockIdx.x * kSingle + threadIdx.x;
     int m = -1;
     bool is_new = false;
@@ -900,12 +929,16 @@ __global__ void __launch_bounds__(kSingle) k_lattice_count(FramePtrs a) {
     if (is_new && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.newcount[m], __popc(same));
     moving_test_epilogue(a);
 }
+__global__ void __launch_bounds__(kSingle) k_lattice_count(FramePtrs a) { k_lattice_count_body(a); }
+__global__ void __launch_bounds__(kSingle) k_lattice_count_batch(const FramePtrs* __restrict__ P) { k_lattice_count_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K10' (method 1)
 // CorrespondenceEstimation::determineCorrespondences (cpp:343-361): for every point of the transformed
 // previous cluster the nearest point of the matched current cluster; only squared distances inside
 // (pde_lb, pde_ub) count, so the search is bounded by sqrt(pde_ub) on the clustering grid.
-__global__ void __launch_bounds__(kSingle) k_pde_count(FramePtrs a, int ring) {
+__device__ __forceinline__ void k_pde_count_body(const FramePtrs& a) {
+    const int ring = a.pde_ring;
     const int c = blockIdx.x * kSingle + threadIdx.x;
     if (c < a.p_counts[MOR_CNT_NC]) {
         const float4 t = a.tpts[c];
@@ -934,6 +967,9 @@ __global__ void __launch_bounds__(kSingle) k_pde_count(FramePtrs a, int ring) {
     }
     moving_test_epilogue(a);
 }
+__global__ void __launch_bounds__(kSingle) k_pde_count(FramePtrs a) { k_pde_count_body(a); }
+__global__ void __launch_bounds__(kSingle) k_pde_count_batch(const FramePtrs* __restrict__ P) { k_pde_count_body(P[blockIdx.z]); }
+
 
 // ===================================================================================== K12
 // Detection flags (cpp:580-606) and the N-frame consistency chain: checkMovingClusterChain
@@ -1066,7 +1102,7 @@ constexpr int kOutItems = 4;
 constexpr int kOutTile = kBlock * kOutItems;
 constexpr int kRemovedBits = 16384;  // = max kmax
 
-__global__ void __launch_bounds__(kBlock) k_filter_output(FramePtrs a) {
+__device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
     const int mo_parity = a.mo_parity;
     __shared__ unsigned s_removed[kRemovedBits / 32];
     __shared__ int s_tile, s_total, s_keep_base;
@@ -1184,5 +1220,8 @@ __global__ void __launch_bounds__(kBlock) k_filter_output(FramePtrs a) {
         if (threadIdx.x == 0) { a.scratch->ticket_out = 0; a.scratch->out_blocks_done = 0; }
     }
 }
+__global__ void __launch_bounds__(kBlock) k_filter_output(FramePtrs a) { k_filter_output_body(a); }
+__global__ void __launch_bounds__(kBlock) k_filter_output_batch(const FramePtrs* __restrict__ P) { k_filter_output_body(P[blockIdx.z]); }
+
 
 }  // namespace mor

@@ -115,6 +115,15 @@ int mor_push_raw_cloud_and_pose_device(mor_handle* h, const void* d_data, uint32
 int mor_filter_cloud_device(mor_handle* h, void* d_out, uint32_t cap_points, uint32_t* n_out);
 int mor_sync(mor_handle* h);
 
+/* Batched device-resident step (BASELINE config 5: many independent sequences per GPU): one pushRawCloudAndPose +
+ * filterCloud for S sequences in ONE set of kernel launches (blockIdx.z selects the sequence). All handles must
+ * live on the same device with the same config, limits and frame count, ground_mode 0. d_data[s] / d_out[s] are
+ * device pointers (d_out[s] must hold n[s] records), poses7 = S x 7 doubles. Asynchronous on hs[0]'s stream;
+ * mor_sync / mor_tap on any of the handles waits for it. */
+int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* d_data, const uint32_t* n,
+                          uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, uint32_t off_i,
+                          const double* poses7, void* const* d_out);
+
 /* cudaMallocHost / cudaFreeHost passthroughs so callers can stage frames in pinned memory. */
 int mor_alloc_pinned(size_t bytes, void** out);
 int mor_free_pinned(void* p);

@@ -139,3 +139,45 @@ def test_device_resident_api_matches_host_api(product, tmp_path):
         np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
     product.device_free(0, d_in)
     product.device_free(0, d_out)
+
+
+def test_batched_step_matches_oracle_per_sequence(product, oracle, cfg_dir):
+    """mor_batch_step_device: S sequences advanced by one set of launches give, per sequence, exactly what the
+    oracle gives for that sequence alone (independence of the replicas, SURVEY §8e / BASELINE config 5)."""
+    import ctypes as C
+    from dynamicslamtool_b200 import SequenceBatch, Synth
+    cfg = cfg_dir / "MOR_config.txt"
+    S, frames = 3, 8
+    syn = [Synth(1, 40 + s) for s in range(S)]
+    maxp = syn[0].max_points
+    gpus = [MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=maxp) for _ in range(S)]
+    orcs = [MovingObjectRemoval(cfg, 4, 3, binding=oracle) for _ in range(S)]
+    batch = SequenceBatch(gpus)
+    d_in, d_out = [], []
+    for s in range(S):
+        a, b = C.c_void_p(), C.c_void_p()
+        assert product.device_alloc(0, maxp * 16, C.byref(a)) == 0 and product.device_alloc(0, maxp * 32, C.byref(b)) == 0
+        d_in.append(a); d_out.append(b)
+    for f in range(frames):
+        data = [syn[s].frame(f) for s in range(S)]
+        for s in range(S):
+            pts = data[s][0]
+            assert product.device_upload(0, d_in[s], pts.ctypes.data_as(C.c_void_p), pts.nbytes) == 0
+        batch.step_device([p.value for p in d_in], [d[0].shape[0] for d in data], [d[1] for d in data], [p.value for p in d_out])
+        for s in range(S):
+            orcs[s].push_raw_cloud_and_pose(*data[s])
+            oo = orcs[s].filter_cloud().copy()
+            gpus[s].sync()
+            n_out = gpus[s].counts()["NOUT"]
+            og = np.empty((n_out, 8), np.float32)
+            if n_out:
+                assert product.device_download(0, og.ctypes.data_as(C.c_void_p), d_out[s], n_out * 32) == 0
+            bad = compare_frame(gpus[s], orcs[s], og, oo)
+            assert not bad, f"sequence {s} frame {f}: {bad}"
+    # a batched handle can go back to single stepping
+    pts, pose = syn[0].frame(frames)
+    gpus[0].push_raw_cloud_and_pose(pts, pose); orcs[0].push_raw_cloud_and_pose(pts, pose)
+    og, oo = gpus[0].filter_cloud().copy(), orcs[0].filter_cloud().copy()
+    assert not compare_frame(gpus[0], orcs[0], og, oo)
+    for p in d_in + d_out:
+        product.device_free(0, p)
