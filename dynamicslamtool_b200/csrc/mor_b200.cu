@@ -185,13 +185,14 @@ int build_grid(mor_handle* h) {
     if (!(r2 > 0.f) || !(c.trim_x > 0.f) || !(c.trim_y > 0.f)) return MOR_ERR_CONFIG_VALUE;
     const double hcell = std::sqrt((double)r2) / std::sqrt(3.0) * (1.0 - 1.0 / 1024.0);
     GridDesc g;
-    g.ox = -(double)c.trim_x; g.oy = -(double)c.trim_y;
+    const double pad = (double)kGridPad * hcell;  // empty low-side cells: see k_link_cells
+    g.ox = -(double)c.trim_x - pad; g.oy = -(double)c.trim_y - pad;
     double zlo, zhi;
     if (c.ground_mode == MOR_GROUND_CROP) { zlo = (double)c.gp_limit; zhi = (double)c.trim_z; }
     else { zlo = -64.0; zhi = 64.0; }  // voxel modes: z is not cropped; generous fixed slab
     if (!(zhi >= zlo)) zhi = zlo;
-    g.oz = zlo; g.inv_h = 1.0 / hcell;
-    const double fx = std::floor(2.0 * (double)c.trim_x / hcell) + 1, fy = std::floor(2.0 * (double)c.trim_y / hcell) + 1, fz = std::floor((zhi - zlo) / hcell) + 1;
+    g.oz = zlo - pad; g.inv_h = 1.0 / hcell;
+    const double fx = std::floor(((double)c.trim_x - g.ox) / hcell) + 1, fy = std::floor(((double)c.trim_y - g.oy) / hcell) + 1, fz = std::floor((zhi - g.oz) / hcell) + 1;
     if (fx < 1 || fy < 1 || fz < 1) return MOR_ERR_CONFIG_VALUE;
     h->cell_h = hcell;
     h->max_cells = 1 << 24;  // 16.7 M cells: 2 x 64 MB of cell tables, ~15 us to scan
@@ -200,7 +201,7 @@ int build_grid(mor_handle* h) {
         // lay the grid over the bounding box of each frame's cloud instead (k_keys); a frame whose box
         // still needs more than max_cells cells is rejected with MOR_ERR_CAPACITY
         h->dynamic_grid = true;
-        g.nx = g.ny = g.nz = 1; g.ncells = h->max_cells;
+        g.nx = g.ny = g.nz = kGridPad + 1; g.ncells = h->max_cells;
     } else {
         h->dynamic_grid = false;
         g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
@@ -514,7 +515,7 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
         GridDesc g0 = h->grid;
-        if (h->dynamic_grid) { g0.nx = g0.ny = g0.nz = 1; g0.ncells = 1; }
+        if (h->dynamic_grid) { g0.nx = g0.ny = g0.nz = kGridPad + 1; g0.ncells = g0.nx * g0.ny * g0.nz; }
         if (cudaMemcpy(h->base.dgrid, &g0, sizeof(g0), cudaMemcpyHostToDevice) != cudaSuccess) { mor_destroy(h); return MOR_ERR_CUDA; }
     }
     *out = h;

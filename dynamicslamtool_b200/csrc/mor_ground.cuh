@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_partition(FramePtrs a, Ground
         if (!a.dynamic_grid) {
             const GridDesc& g = a.grid;
             int cx = (int)floor(((double)p.x - g.ox) * g.inv_h), cy = (int)floor(((double)p.y - g.oy) * g.inv_h), cz = (int)floor(((double)p.z - g.oz) * g.inv_h);
-            cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+            cx = min(max(cx, kGridPad), g.nx - 1); cy = min(max(cy, kGridPad), g.ny - 1); cz = min(max(cz, kGridPad), g.nz - 1);
             const int key = (cz * g.ny + cy) * g.nx + cx;
             a.cell_key[c] = key;
             atomicAdd(&a.cell_count[key], 1);

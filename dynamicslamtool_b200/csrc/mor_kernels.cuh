@@ -13,12 +13,14 @@ namespace mor {
 
 constexpr int kSingle = 1024;  // threads of the single-block bookkeeping kernels
 constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
+constexpr int kGridPad = 2;  // empty cells on the low side of every axis: backward neighbour look-ups need no bounds checks
 constexpr int kRootCheckCount = 48;  // far pass: cells above this size are first checked for a common root
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_CAP = 16 };
 
 struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-10): two points of one cell are always
-                   // within r (one union-find node per cell) and d<r => |dcell| <= 2 per axis
+                   // within r (one union-find node per cell) and d<r => |dcell| <= 2 per axis. The origin lies kGridPad
+                   // cells below the data on every axis, so every real cell has coordinates >= kGridPad
     double ox, oy, oz, inv_h;
     int nx, ny, nz, ncells;
 };
@@ -156,7 +158,7 @@ __device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
             int cx = (int)floor(((double)v[k].x - g.ox) * g.inv_h);
             int cy = (int)floor(((double)v[k].y - g.oy) * g.inv_h);
             int cz = (int)floor(((double)v[k].z - g.oz) * g.inv_h);
-            cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+            cx = min(max(cx, kGridPad), g.nx - 1); cy = min(max(cy, kGridPad), g.ny - 1); cz = min(max(cz, kGridPad), g.nz - 1);
             key = (cz * g.ny + cy) * g.nx + cx;
             atomicAdd(&a.cell_count[key], 1);  // result unused: a fire-and-forget RED, no round trip on the critical path
         }
@@ -219,10 +221,11 @@ __device__ __forceinline__ GridDesc grid_from_box(const FramePtrs& a, bool* too_
 #pragma unroll
     for (int q = 0; q < 3; q++) { lo[q] = (double)fkey_inv(~sc->box_inv_min[q]); hi[q] = (double)fkey_inv(sc->box_max[q]); }
     if (a.counts[MOR_CNT_NC] == 0) { lo[0] = lo[1] = lo[2] = 0; hi[0] = hi[1] = hi[2] = 0; }
-    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv_h = inv_h;
-    const double fx = floor((hi[0] - lo[0]) * inv_h) + 1.0, fy = floor((hi[1] - lo[1]) * inv_h) + 1.0, fz = floor((hi[2] - lo[2]) * inv_h) + 1.0;
+    const double pad = (double)kGridPad * a.cell_h;
+    g.ox = lo[0] - pad; g.oy = lo[1] - pad; g.oz = lo[2] - pad; g.inv_h = inv_h;
+    const double fx = floor((hi[0] - g.ox) * inv_h) + 1.0, fy = floor((hi[1] - g.oy) * inv_h) + 1.0, fz = floor((hi[2] - g.oz) * inv_h) + 1.0;
     *too_big = fx * fy * fz > (double)a.max_cells;
-    if (*too_big) { g.nx = g.ny = g.nz = 1; }  // memory-safe degenerate grid; the frame is flagged
+    if (*too_big) { g.nx = g.ny = g.nz = kGridPad + 1; }  // memory-safe degenerate grid (one real cell); the frame is flagged
     else { g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; }
     g.ncells = g.nx * g.ny * g.nz;
     return g;
@@ -246,7 +249,7 @@ __device__ __forceinline__ void k_keys_body(const FramePtrs& a) {
     int cx = (int)floor(((double)p.x - g.ox) * g.inv_h);
     int cy = (int)floor(((double)p.y - g.oy) * g.inv_h);
     int cz = (int)floor(((double)p.z - g.oz) * g.inv_h);
-    cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+    cx = min(max(cx, kGridPad), g.nx - 1); cy = min(max(cy, kGridPad), g.ny - 1); cz = min(max(cz, kGridPad), g.nz - 1);
     const int key = (cz * g.ny + cy) * g.nx + cx;
     a.cell_key[c] = key;
     atomicAdd(&a.cell_count[key], 1);
@@ -367,17 +370,18 @@ __device__ __forceinline__ unsigned long long ld_done(const unsigned long long* 
     return v;
 }
 
-// Examines the cells of one x-range of one row for point q; see k_link_cells.
+// Examines the cells ka..kb (linear keys, one x-run of a neighbour row) for point q; see k_link_cells.
+// `rowkey` is the key of the cell straight "above" q's cell in that row: the pair bit of cell kj is row*5 + (kj - rowkey + 2).
 template <int PHASE>
-__device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4 q, int lead, int row, int base, int cx, int xa, int xb,
+__device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4 q, int lead, int row, int rowkey, int ka, int kb,
                                                 unsigned long long& dmask) {
-    int j = a.cell_start[base + xa];
-    const int e = a.cell_start[base + xb + 1];
+    int j = a.cell_start[ka];
+    const int e = a.cell_start[kb + 1];
     const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
     while (j < e) {
         const int kj = a.skey[j];
         const int cell_end = a.cell_start[kj + 1];
-        const int bit = row * 5 + (kj - base - cx + 2);
+        const int bit = row * 5 + (kj - rowkey + 2);
         bool skip = (dmask >> bit) & 1ull;
         if (!skip && cell_end - j > kBoxMinCount) {
             // conservative point-to-box distance: no point of the cell can be closer than this
@@ -403,6 +407,7 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
         }
         if (!skip) {
             bool hit = false;
+            const int other = j;  // leader position of the neighbour cell
             const int last = cell_end - 1;
             for (int it = 0; j < cell_end && !hit; j += 4) {  // always 4 independent loads in flight (indices clamped)
                 const float4 p0 = a.spts[j], p1 = a.spts[min(j + 1, last)], p2 = a.spts[min(j + 2, last)], p3 = a.spts[min(j + 3, last)];
@@ -422,7 +427,7 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
                     dmask |= ld_done(a.done + lead);
                     if (!((dmask >> bit) & 1ull)) {
                         const unsigned long long old = atomicOr(a.done + lead, 1ull << bit);
-                        if (!((old >> bit) & 1ull)) uf_union(a.parent, lead, a.cell_start[kj]);
+                        if (!((old >> bit) & 1ull)) uf_union(a.parent, lead, other);
                     }
                 }
                 dmask |= 1ull << bit;
@@ -435,6 +440,9 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
 // grid = (point tiles, rows): one thread per (point q, x-row of the backward neighbourhood), so the serial
 // chain of a thread is a handful of cells and a warp walks the same cells for neighbouring q.
 // PHASE 1 = the 13 backward cells of the 3x3x3 block (5 rows); PHASE 2 = the 49 cells at offset 2 (13 rows).
+// Neighbour rows are addressed linearly from the point's own key (key + dy*nx + dz*nx*ny +- 2): the grid carries
+// kGridPad empty cells on the low side of every axis, so a backward offset never leaves the table and an offset
+// that runs over the high end of a row / layer lands in the next row's / layer's padding, which is always empty.
 template <int PHASE>
 __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a) {
     const int s = blockIdx.x * kBlock + threadIdx.x;
@@ -447,22 +455,18 @@ __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a) {
     const int dy = row < 10 ? (row % 5) - 2 : row - 12;
     const bool near_row = dz >= -1 && dy >= -1 && dy <= 1;
     const int key = a.skey[s];
-    const GridDesc g = *a.dgrid;
-    const int cx = key % g.nx, t = key / g.nx, cy = t % g.ny, cz = t / g.ny;
-    const int zz = cz + dz, yy = cy + dy;
-    if (zz < 0 || yy < 0 || yy >= g.ny) return;
-    const int base = (zz * g.ny + yy) * g.nx;
+    const int nx = a.dgrid->nx, ny = a.dgrid->ny;
+    const int rowkey = key + dy * nx + dz * nx * ny;
     const float4 q = a.spts[s];
     const int lead = a.cell_start[key];
     unsigned long long dmask = ld_done(a.done + lead);
     if (PHASE == 1) {
-        const int xa = max(cx - 1, 0), xb = row == 12 ? cx - 1 : min(cx + 1, g.nx - 1);
-        if (xb >= xa) link_scan_range<1>(a, q, lead, row, base, cx, xa, xb, dmask);
+        link_scan_range<1>(a, q, lead, row, rowkey, rowkey - 1, row == 12 ? rowkey - 1 : rowkey + 1, dmask);
     } else if (!near_row) {
-        link_scan_range<2>(a, q, lead, row, base, cx, max(cx - 2, 0), min(cx + 2, g.nx - 1), dmask);
+        link_scan_range<2>(a, q, lead, row, rowkey, rowkey - 2, rowkey + 2, dmask);
     } else {
-        if (cx - 2 >= 0) link_scan_range<2>(a, q, lead, row, base, cx, cx - 2, cx - 2, dmask);
-        if (row != 12 && cx + 2 < g.nx) link_scan_range<2>(a, q, lead, row, base, cx, cx + 2, cx + 2, dmask);
+        link_scan_range<2>(a, q, lead, row, rowkey, rowkey - 2, rowkey - 2, dmask);
+        if (row != 12) link_scan_range<2>(a, q, lead, row, rowkey, rowkey + 2, rowkey + 2, dmask);
     }
 }
 template <int PHASE>
