@@ -139,10 +139,10 @@ struct mor_handle {
 
 namespace {
 
-enum KernelId { KID_INGEST = 0, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_LINK_FAR, KID_FLATTEN, KID_STATS,
+enum KernelId { KID_INGEST = 0, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_FLATTEN, KID_STATS,
                 KID_TRANSFORM_PREV, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE,
                 KID_OUTPUT, KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells<1>", "k_link_cells<2>", "k_flatten+select",
+const char* const kKernelNames[KID__COUNT] = {"k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells", "k_flatten+select",
                                               "k_cluster_stats+match", "k_transform_prev", "k_lattice_insert", "k_lattice_count+chain", "k_pde_count+chain",
                                               "k_filter_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter",
                                               "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
@@ -364,8 +364,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<scan_blocks, kBlock, 0, st>>>(a)));
     }
     MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<1><<<dim3(gb, 5), kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_LINK_FAR, (k_link_cells<2><<<dim3(gb, 13), kBlock, 0, st>>>(a)));
+    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<<<dim3(gb, 18), kBlock, 0, st>>>(a)));  // near pass (5 rows) + far pass (13 rows)
     const unsigned g1k = n ? (n + kSingle - 1) / kSingle : 1;
     MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<g1k, kSingle, h->select_smem, st>>>(a)));  // + cluster selection in its last block
     if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));  // k_cluster_stats' last block runs the correspondences
@@ -636,12 +635,11 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
         k_scan_cells_batch<<<dim3(scan_blocks, 1, S), kBlock, 0, st>>>(dp);
     }
     k_scatter_batch<<<dim3(gb, 1, S), kBlock, 0, st>>>(dp);
-    k_link_cells_batch<1><<<dim3(gb, 5, S), kBlock, 0, st>>>(dp);
-    k_link_cells_batch<2><<<dim3(gb, 13, S), kBlock, 0, st>>>(dp);
+    k_link_cells_batch<<<dim3(gb, 18, S), kBlock, 0, st>>>(dp);
     k_flatten_batch<<<dim3(g1k, 1, S), kSingle, h->select_smem, st>>>(dp);
     if (two) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     k_cluster_stats_batch<<<dim3(g1k, 1, S), kStatBlock, 0, st>>>(dp);
-    h->launches += 7 + (h->dynamic_grid ? 1 : 0);
+    h->launches += 6 + (h->dynamic_grid ? 1 : 0);
     if (two) {
         if (h->cfg.method_choice == 2) {
             k_lattice_insert_batch<<<dim3(blocks_for(np_max), 1, S), kBlock, 0, st>>>(dp);

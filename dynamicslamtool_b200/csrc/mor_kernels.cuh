@@ -444,13 +444,13 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
 // kGridPad empty cells on the low side of every axis, so a backward offset never leaves the table and an offset
 // that runs over the high end of a row / layer lands in the next row's / layer's padding, which is always empty.
 template <int PHASE>
-__device__ __forceinline__ void k_link_cells_body(const FramePtrs& a) {
+__device__ __forceinline__ void k_link_cells_body(const FramePtrs& a, int row_index) {
     const int s = blockIdx.x * kBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
     // canonical row ids (they fix the bit layout): 0-4: dz=-2, 5-9: dz=-1, 10-12: dz=0 with dy=-2,-1,0
-    int row = blockIdx.y;
-    if (PHASE == 1) row = blockIdx.y == 0 ? 12 : (blockIdx.y == 1 ? 11 : 4 + blockIdx.y);  // near rows: 12, 11, 6, 7, 8
+    int row = row_index;
+    if (PHASE == 1) row = row_index == 0 ? 12 : (row_index == 1 ? 11 : 4 + row_index);  // near rows: 12, 11, 6, 7, 8
     const int dz = row < 5 ? -2 : (row < 10 ? -1 : 0);
     const int dy = row < 10 ? (row % 5) - 2 : row - 12;
     const bool near_row = dz >= -1 && dy >= -1 && dy <= 1;
@@ -469,11 +469,16 @@ __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a) {
         if (row != 12) link_scan_range<2>(a, q, lead, row, rowkey, rowkey + 2, rowkey + 2, dmask);
     }
 }
-template <int PHASE>
-__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) { k_link_cells_body<PHASE>(a); }
-template <int PHASE>
-__global__ void __launch_bounds__(kBlock) k_link_cells_batch(const FramePtrs* __restrict__ P) { k_link_cells_body<PHASE>(P[blockIdx.z]); }
-
+// One launch for both passes: blockIdx.y 0..4 = near pass, 5..17 = far pass. Blocks are dispatched y-major, so the
+// near rows start first and most of their unions are in place when the far rows run their root checks; the two
+// passes' tails overlap instead of adding up (the far pass is correct with any amount of near-pass progress: its
+// root check is only a shortcut).
+__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
+    if (blockIdx.y < 5) k_link_cells_body<1>(a, blockIdx.y); else k_link_cells_body<2>(a, blockIdx.y - 5);
+}
+__global__ void __launch_bounds__(kBlock) k_link_cells_batch(const FramePtrs* __restrict__ P) {
+    if (blockIdx.y < 5) k_link_cells_body<1>(P[blockIdx.z], blockIdx.y); else k_link_cells_body<2>(P[blockIdx.z], blockIdx.y - 5);
+}
 
 // ===================================================================================== K5
 // Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud
