@@ -181,3 +181,40 @@ def test_batched_step_matches_oracle_per_sequence(product, oracle, cfg_dir):
     assert not compare_frame(gpus[0], orcs[0], og, oo)
     for p in d_in + d_out:
         product.device_free(0, p)
+
+
+@pytest.mark.parametrize("n_bad,n_good", [(1, 0), (2, 1), (3, 5), (6, 2)])
+def test_confidence_parameters(product, oracle, tmp_path, n_bad, n_good):
+    """moving_confidence / static_confidence other than the node's 4, 3 (external_sync_test.cpp:37): ring-buffer depth,
+    confirmation frame and confidence caps must follow the reference for every combination."""
+    rng = np.random.default_rng(20 + n_bad)
+    cfg = write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000, **OPEN_CFG)
+    gpu = MovingObjectRemoval(cfg, n_bad, n_good, binding=product)
+    orc = MovingObjectRemoval(cfg, n_bad, n_good, binding=oracle)
+    a, b, c = blob(rng, (2, 0, 0), 300, 0.12), blob(rng, (-2, 1, 0), 300, 0.12), blob(rng, (0, -3, 0.5), 250, 0.1)
+    confirmed_at = None
+    for f in range(14):
+        move = np.float32([0.12 * min(f, 8), 0, 0])  # the mover stops after frame 8: decay path
+        pts = with_intensity(np.concatenate([a, b + move, c + np.float32([0, 0.1 * f, 0])]))
+        step(gpu, orc, pts)
+        if confirmed_at is None and gpu.counts()["NMO"]:
+            confirmed_at = f
+    assert confirmed_at is not None  # the mover was confirmed for every (n_bad, n_good); parity is checked frame by frame in step()
+
+
+def test_many_movers_exceed_one_block(product, oracle, tmp_path):
+    """More confirmed movers than threads in a block (256) and more clusters than a warp: exercises the chunked,
+    order-preserving paths of the chain / tracking code."""
+    rng = np.random.default_rng(31)
+    cfg = write_cfg(tmp_path, ec_distance_threshold=0.2, min_cluster_size=10, max_cluster_size=5000, opc_normalization_factor=20,
+                    leave_off_distance=0.5, **OPEN_CFG)
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_clusters=4096, max_moving=2048)
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    centers = np.array([[2.0 * i, 2.0 * j, 0.0] for i in range(20) for j in range(16)], np.float32)  # 320 blobs, 2 m apart
+    blobs = [blob(rng, c, 24, 0.03) for c in centers]
+    n_mo = []
+    for f in range(8):
+        pts = with_intensity(np.concatenate([bl + np.float32([0.13 * f, 0, 0]) for bl in blobs]) + rng.normal(0, 0.001, (320 * 24, 3)).astype(np.float32))
+        step(gpu, orc, pts)
+        n_mo.append(gpu.counts()["NMO"])
+    assert max(n_mo) > 256, n_mo
