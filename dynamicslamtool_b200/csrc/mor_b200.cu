@@ -165,6 +165,25 @@ void prof_harvest(mor_handle* h) {  // stream must be idle
     }
     h->prof_ids.clear();
 }
+// Launch with the programmatic-stream-serialisation attribute (see pdl_prologue in mor_device.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// Kernel launch of the frame chain: PDL normally, plain (and bracketed by events) under per-kernel profiling.
+#define MOR_KLAUNCH(id, kernel, grid, block, smem, ...)                                           \
+    do {                                                                                           \
+        if (h->profiling) { prof_begin(h, id); kernel<<<grid, block, smem, st>>>(__VA_ARGS__); prof_end(h); } \
+        else launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__);                  \
+        h->launches++;                                                                             \
+    } while (0)
+
 // Every device operation of the hot path goes through this: counted (mor_get_launch_count) and, when
 // profiling is on, bracketed by events on the handle's stream.
 #define MOR_LAUNCH(id, ...) do { prof_begin(h, id); __VA_ARGS__; prof_end(h); h->launches++; } while (0)
@@ -344,7 +363,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         MOR_LAUNCH(KID_G_MARK, (k_ground_mark<<<gb * 32, kBlock, 0, st>>>(a, g)));
         MOR_LAUNCH(KID_G_PARTITION, (k_ground_partition<<<gb, kBlock, 0, st>>>(a, g)));
     } else {
-        MOR_LAUNCH(KID_INGEST, (k_ingest<<<n ? (n + kIngestTile - 1) / kIngestTile : 1, kBlock, 0, st>>>(a)));
+        MOR_KLAUNCH(KID_INGEST, k_ingest, n ? (n + kIngestTile - 1) / kIngestTile : 1, kBlock, 0, a);
     }
     // The transform of the previous frame's clusters needs only the previous frame, the pose delta and the neutral
     // boxes written by the ingest kernel: it runs on a side stream beside the clustering chain and is joined before
@@ -357,27 +376,27 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         h->launches++;
         MOR_CUDA(cudaEventRecord(h->ev_join, h->side));
     }
-    if (h->dynamic_grid) MOR_LAUNCH(KID_KEYS, (k_keys<<<gb, kBlock, 0, st>>>(a)));
+    if (h->dynamic_grid) MOR_KLAUNCH(KID_KEYS, k_keys, gb, kBlock, 0, a);
     {
         const int tiles = (h->grid.ncells + kScanTile - 1) / kScanTile;
         const int scan_blocks = h->dynamic_grid ? h->num_sms * 8 : (tiles < h->num_sms * 8 ? tiles : h->num_sms * 8);
-        MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<scan_blocks, kBlock, 0, st>>>(a)));
+        MOR_KLAUNCH(KID_SCAN_CELLS, k_scan_cells, scan_blocks, kBlock, 0, a);
     }
-    MOR_LAUNCH(KID_SCATTER, (k_scatter<<<gb, kBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_NEIGHBORS, (k_link_cells<<<dim3(gb, 18), kBlock, 0, st>>>(a)));  // near pass (5 rows) + far pass (13 rows)
+    MOR_KLAUNCH(KID_SCATTER, k_scatter, gb, kBlock, 0, a);
+    MOR_KLAUNCH(KID_NEIGHBORS, k_link_cells, dim3(gb, 18), kBlock, 0, a);  // near pass (5 rows) + far pass (13 rows)
     const unsigned g1k = n ? (n + kSingle - 1) / kSingle : 1;
-    MOR_LAUNCH(KID_FLATTEN, (k_flatten<<<g1k, kSingle, h->select_smem, st>>>(a)));  // + cluster selection in its last block
+    MOR_KLAUNCH(KID_FLATTEN, k_flatten, g1k, kSingle, h->select_smem, a);  // + cluster selection in its last block
     if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));  // k_cluster_stats' last block runs the correspondences
     else if (h->two_frames) MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
-    MOR_LAUNCH(KID_STATS, (k_cluster_stats<<<(n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, st>>>(a)));
+    MOR_KLAUNCH(KID_STATS, k_cluster_stats, (n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, a);
     if (h->two_frames) {
         const unsigned gp = blocks_for(h->n_prev_input);
         if (h->cfg.method_choice == 2) {
-            MOR_LAUNCH(KID_LATTICE_INSERT, (k_lattice_insert<<<gp, kBlock, 0, st>>>(a)));
-            MOR_LAUNCH(KID_LATTICE_COUNT, (k_lattice_count<<<g1k, kSingle, 0, st>>>(a)));  // + flags and consistency chain in its last block
+            MOR_KLAUNCH(KID_LATTICE_INSERT, k_lattice_insert, gp, kBlock, 0, a);
+            MOR_KLAUNCH(KID_LATTICE_COUNT, k_lattice_count, g1k, kSingle, 0, a);  // + flags and consistency chain in its last block
         } else {
             const unsigned gp1k = h->n_prev_input ? (h->n_prev_input + kSingle - 1) / kSingle : 1;
-            MOR_LAUNCH(KID_PDE, (k_pde_count<<<gp1k, kSingle, 0, st>>>(a)));
+            MOR_KLAUNCH(KID_PDE, k_pde_count, gp1k, kSingle, 0, a);
         }
     }
     MOR_CUDA(cudaGetLastError());
@@ -440,7 +459,7 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     else a.out = h->base.out;
     if (on_device && out && cap_points < h->n_input) { h->last_error = "device output buffer must hold n_input points"; return MOR_ERR_CAPACITY; }
     a.mo_parity = h->mo_parity;
-    MOR_LAUNCH(KID_OUTPUT, (k_filter_output<<<h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kBlock, 0, st>>>(a)));
+    MOR_KLAUNCH(KID_OUTPUT, k_filter_output, h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kBlock, 0, a);
     h->mo_parity ^= 1;  // the kernel wrote the updated mo_vec into the other half
     a.mo_parity = h->mo_parity;
     MOR_CUDA(cudaGetLastError());
@@ -620,37 +639,37 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
     MOR_CUDA(cudaEventRecord(h->batch_ev[slot], st));
     const bool two = h->two_frames;
     const unsigned gb = blocks_for(n_max), g1k = n_max ? (n_max + kSingle - 1) / kSingle : 1;
-    k_ingest_batch<<<dim3(n_max ? (n_max + kIngestTile - 1) / kIngestTile : 1, 1, S), kBlock, 0, st>>>(dp);
+    launch_pdl(k_ingest_batch, dim3(n_max ? (n_max + kIngestTile - 1) / kIngestTile : 1, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
     if (two) {  // the transform of the previous clusters runs beside the clustering chain (see enqueue_push)
         MOR_CUDA(cudaEventRecord(h->ev_fork, st));
         MOR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         k_transform_prev_batch<<<dim3(np_max ? (np_max + kStatBlock - 1) / kStatBlock : 1, 1, S), kStatBlock, 0, h->side>>>(dp);
         MOR_CUDA(cudaEventRecord(h->ev_join, h->side));
     }
-    if (h->dynamic_grid) k_keys_batch<<<dim3(gb, 1, S), kBlock, 0, st>>>(dp);
+    if (h->dynamic_grid) launch_pdl(k_keys_batch, dim3(gb, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
     {
         const int tiles = (h->grid.ncells + kScanTile - 1) / kScanTile;
         const int per_seq = h->num_sms * 8 / (int)S > 8 ? h->num_sms * 8 / (int)S : 8;
         const int scan_blocks = h->dynamic_grid ? per_seq : (tiles < per_seq ? tiles : per_seq);
-        k_scan_cells_batch<<<dim3(scan_blocks, 1, S), kBlock, 0, st>>>(dp);
+        launch_pdl(k_scan_cells_batch, dim3(scan_blocks, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
     }
-    k_scatter_batch<<<dim3(gb, 1, S), kBlock, 0, st>>>(dp);
-    k_link_cells_batch<<<dim3(gb, 18, S), kBlock, 0, st>>>(dp);
-    k_flatten_batch<<<dim3(g1k, 1, S), kSingle, h->select_smem, st>>>(dp);
+    launch_pdl(k_scatter_batch, dim3(gb, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+    launch_pdl(k_link_cells_batch, dim3(gb, 18, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+    launch_pdl(k_flatten_batch, dim3(g1k, 1, S), dim3(kSingle), h->select_smem, st, (const FramePtrs*)dp);
     if (two) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-    k_cluster_stats_batch<<<dim3(g1k, 1, S), kStatBlock, 0, st>>>(dp);
+    launch_pdl(k_cluster_stats_batch, dim3(g1k, 1, S), dim3(kStatBlock), 0, st, (const FramePtrs*)dp);
     h->launches += 6 + (h->dynamic_grid ? 1 : 0);
     if (two) {
         if (h->cfg.method_choice == 2) {
-            k_lattice_insert_batch<<<dim3(blocks_for(np_max), 1, S), kBlock, 0, st>>>(dp);
-            k_lattice_count_batch<<<dim3(g1k, 1, S), kSingle, 0, st>>>(dp);
+            launch_pdl(k_lattice_insert_batch, dim3(blocks_for(np_max), 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+            launch_pdl(k_lattice_count_batch, dim3(g1k, 1, S), dim3(kSingle), 0, st, (const FramePtrs*)dp);
             h->launches += 3;
         } else {
-            k_pde_count_batch<<<dim3(np_max ? (np_max + kSingle - 1) / kSingle : 1, 1, S), kSingle, 0, st>>>(dp);
+            launch_pdl(k_pde_count_batch, dim3(np_max ? (np_max + kSingle - 1) / kSingle : 1, 1, S), dim3(kSingle), 0, st, (const FramePtrs*)dp);
             h->launches += 2;
         }
     }
-    k_filter_output_batch<<<dim3(n_max ? (n_max + kOutTile - 1) / kOutTile : 1, 1, S), kBlock, 0, st>>>(dp);
+    launch_pdl(k_filter_output_batch, dim3(n_max ? (n_max + kOutTile - 1) / kOutTile : 1, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
     h->launches += 1;
     MOR_CUDA(cudaGetLastError());
     for (uint32_t s = 0; s < S; s++) {

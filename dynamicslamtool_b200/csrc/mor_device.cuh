@@ -19,6 +19,16 @@ constexpr int kItems = 4;            // items per thread in the scan kernels
 constexpr int kTile = kBlock * kItems;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the frame chain starts with this: it lets the NEXT kernel of the stream be scheduled right away
+// (its blocks become resident and park in griddepcontrol.wait) and then waits until the PREVIOUS kernel has
+// completed and its writes are visible. With kernels that last 7-50 us and never fill the GPU this hides the launch
+// and block-dispatch latency of every boundary. A kernel launched without the PDL attribute passes straight through.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- arithmetic (A6, A12)
 // FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz, every op rounded to float, no FMA.
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {

@@ -97,6 +97,7 @@ constexpr int kIngestItems = 4;
 constexpr int kIngestTile = kBlock * kIngestItems;
 
 __device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
+    pdl_prologue();
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
     if (a.two_frames) {
@@ -232,6 +233,7 @@ __device__ __forceinline__ GridDesc grid_from_box(const FramePtrs& a, bool* too_
 }
 
 __device__ __forceinline__ void k_keys_body(const FramePtrs& a) {
+    pdl_prologue();
     __shared__ GridDesc s_g;
     if (threadIdx.x == 0) {
         bool too_big;
@@ -268,6 +270,7 @@ constexpr int kScanItems = 16;
 constexpr int kScanTile = kBlock * kScanItems;
 
 __device__ __forceinline__ void k_scan_cells_body(const FramePtrs& a) {
+    pdl_prologue();
     __shared__ int s_tile;
     const int ncells = a.dgrid->ncells;
     const int ntiles = (ncells + kScanTile - 1) / kScanTile;
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_cells_batch(const FramePtrs* __
 // reset the per-position union-find state. The first point of a cell (its "leader" position
 // cell_start[key]) is the union-find node of the whole cell.
 __device__ __forceinline__ void k_scatter_body(const FramePtrs& a) {
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.counts[MOR_CNT_NC]) return;
     const int key = a.cell_key[c];
@@ -445,6 +449,7 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
 // that runs over the high end of a row / layer lands in the next row's / layer's padding, which is always empty.
 template <int PHASE>
 __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a, int row_index) {
+    pdl_prologue();
     const int s = blockIdx.x * kBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
@@ -486,6 +491,7 @@ __global__ void __launch_bounds__(kBlock) k_link_cells_batch(const FramePtrs* __
 __device__ void select_block(const FramePtrs& a);
 
 __device__ __forceinline__ void k_flatten_body(const FramePtrs& a) {
+    pdl_prologue();
     const int s = blockIdx.x * kSingle + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int nc = a.counts[MOR_CNT_NC];
@@ -689,6 +695,7 @@ __device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc
 __device__ void match_block(const FramePtrs& a);
 
 __device__ __forceinline__ void k_cluster_stats_body(const FramePtrs& a) {
+    pdl_prologue();
     const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (blockIdx.x * kStatBlock >= nc && !(nc == 0 && blockIdx.x == 0)) return;  // whole blocks stay alive for the barriers
@@ -737,6 +744,7 @@ __global__ void __launch_bounds__(kStatBlock) k_cluster_stats_batch(const FrameP
 // pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12) and the bounding box
 // of the transformed points (getMinMax3D runs after the transform, cpp:272).
 __device__ __forceinline__ void k_transform_prev_body(const FramePtrs& a) {
+    pdl_prologue();
     const int s = blockIdx.x * kStatBlock + threadIdx.x;
     const int ncp = a.p_counts[MOR_CNT_NC];
     if (blockIdx.x * kStatBlock >= ncp) return;
@@ -888,6 +896,7 @@ __device__ __forceinline__ bool lattice_key(const FramePtrs& a, int m, float x, 
 }
 
 __device__ __forceinline__ void k_lattice_insert_body(const FramePtrs& a) {
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.p_counts[MOR_CNT_NC]) return;
     const float4 t = a.tpts[c];
@@ -920,6 +929,7 @@ __device__ __forceinline__ void moving_test_epilogue(const FramePtrs& a) {
 }
 
 __device__ __forceinline__ void k_lattice_count_body(const FramePtrs& a) {
+    pdl_prologue();
     const int s = blockIdx.x * kSingle + threadIdx.x;
     int m = -1;
     bool is_new = false;
@@ -947,6 +957,7 @@ __global__ void __launch_bounds__(kSingle) k_lattice_count_batch(const FramePtrs
 // previous cluster the nearest point of the matched current cluster; only squared distances inside
 // (pde_lb, pde_ub) count, so the search is bounded by sqrt(pde_ub) on the clustering grid.
 __device__ __forceinline__ void k_pde_count_body(const FramePtrs& a) {
+    pdl_prologue();
     const int ring = a.pde_ring;
     const int c = blockIdx.x * kSingle + threadIdx.x;
     if (c < a.p_counts[MOR_CNT_NC]) {
@@ -1112,6 +1123,7 @@ constexpr int kOutTile = kBlock * kOutItems;
 constexpr int kRemovedBits = 16384;  // = max kmax
 
 __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
+    pdl_prologue();
     const int mo_parity = a.mo_parity;
     __shared__ unsigned s_removed[kRemovedBits / 32];
     __shared__ int s_tile, s_total, s_keep_base;
