@@ -374,13 +374,11 @@ __device__ __forceinline__ unsigned long long ld_done(const unsigned long long* 
     return v;
 }
 
-// Examines the cells ka..kb (linear keys, one x-run of a neighbour row) for point q; see k_link_cells.
+// Examines the sorted positions j..e-1 (the cells of one x-run of a neighbour row) for point q; see k_link_cells.
 // `rowkey` is the key of the cell straight "above" q's cell in that row: the pair bit of cell kj is row*5 + (kj - rowkey + 2).
 template <int PHASE>
-__device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4 q, int lead, int row, int rowkey, int ka, int kb,
+__device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4 q, int lead, int row, int rowkey, int j, const int e,
                                                 unsigned long long& dmask) {
-    int j = a.cell_start[ka];
-    const int e = a.cell_start[kb + 1];
     const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
     while (j < e) {
         const int kj = a.skey[j];
@@ -462,17 +460,20 @@ __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a, int row_in
     const int key = a.skey[s];
     const int nx = a.dgrid->nx, ny = a.dgrid->ny;
     const int rowkey = key + dy * nx + dz * nx * ny;
+    // the x-runs of this (point, row): most of them are empty, so their bounds are fetched before anything else
+    int ka, kb, kc = 0, kd = -1;
+    if (PHASE == 1) { ka = rowkey - 1; kb = row == 12 ? rowkey - 1 : rowkey + 1; }
+    else if (!near_row) { ka = rowkey - 2; kb = rowkey + 2; }
+    else { ka = kb = rowkey - 2; if (row != 12) { kc = kd = rowkey + 2; } }
+    const int j0 = a.cell_start[ka], e0 = a.cell_start[kb + 1];
+    int j1 = 0, e1 = 0;
+    if (kd >= kc) { j1 = a.cell_start[kc]; e1 = a.cell_start[kd + 1]; }
+    if (j0 >= e0 && j1 >= e1) return;
     const float4 q = a.spts[s];
     const int lead = a.cell_start[key];
     unsigned long long dmask = ld_done(a.done + lead);
-    if (PHASE == 1) {
-        link_scan_range<1>(a, q, lead, row, rowkey, rowkey - 1, row == 12 ? rowkey - 1 : rowkey + 1, dmask);
-    } else if (!near_row) {
-        link_scan_range<2>(a, q, lead, row, rowkey, rowkey - 2, rowkey + 2, dmask);
-    } else {
-        link_scan_range<2>(a, q, lead, row, rowkey, rowkey - 2, rowkey - 2, dmask);
-        if (row != 12) link_scan_range<2>(a, q, lead, row, rowkey, rowkey + 2, rowkey + 2, dmask);
-    }
+    if (j0 < e0) link_scan_range<PHASE>(a, q, lead, row, rowkey, j0, e0, dmask);
+    if (j1 < e1) link_scan_range<PHASE>(a, q, lead, row, rowkey, j1, e1, dmask);
 }
 // One launch for both passes: blockIdx.y 0..4 = near pass, 5..17 = far pass. Blocks are dispatched y-major, so the
 // near rows start first and most of their unions are in place when the far rows run their root checks; the two
