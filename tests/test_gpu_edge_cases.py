@@ -218,3 +218,26 @@ def test_many_movers_exceed_one_block(product, oracle, tmp_path):
         step(gpu, orc, pts)
         n_mo.append(gpu.counts()["NMO"])
     assert max(n_mo) > 256, n_mo
+
+
+def test_run_to_run_determinism(product, cfg_dir):
+    """Intra-cell order, union order and atomic order vary from run to run; every observable (labels, cluster order,
+    centroids bit for bit, scores, flags, mo_vec, masks, output bytes) must not."""
+    from dynamicslamtool_b200 import Synth
+    from helpers import crc
+    cfg = cfg_dir / "MOR_config_hdl64.txt"
+    s = Synth(2, 2)
+    frames = [s.frame(f) for f in range(100, 108)]  # the dense stretch: cells with > 1000 points, 27k-point clusters
+
+    def run():
+        m = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=s.max_points)
+        sig = []
+        for pts, pose in frames:
+            m.push_raw_cloud_and_pose(pts, pose)
+            out = m.filter_cloud()
+            sig.append(tuple(crc(m.tap(t)) for t in ("labels", "cluster_id", "cluster_root", "cluster_size", "centroids", "cluster_bbox", "match_query",
+                                                       "match_match", "match_score", "flags", "mo_centroids", "mo_conf", "removed_mask")) + (crc(out),))
+        return sig
+
+    a, b, c = run(), run(), run()
+    assert a == b == c
