@@ -257,7 +257,7 @@ int allocate(mor_handle* h) {
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
         b.cell_key = carve<int>(p, N); b.skey = carve<int>(p, N);
         b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
-        b.comp = carve<int>(p, N); b.minidx = carve<int>(p, N); b.done = carve<unsigned long long>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
+        b.comp = carve<int>(p, N); b.scid = carve<int>(p, N); b.minidx = carve<int>(p, N); b.done = carve<unsigned long long>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
         b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
         b.recip_q = carve<int>(p, K); b.recip_m = carve<int>(p, K); b.match_q = carve<int>(p, K); b.match_m = carve<int>(p, K);

@@ -62,6 +62,7 @@ struct FramePtrs {
     int* cell_key; int* skey;
     int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
     int* comp; int* minidx; unsigned long long* done;  // indexed by sorted position (cell leaders)
+    int* scid;        // cluster id per sorted position (coalesced companion of spts for the method-1 search)
     uint4* cell_box;  // [2*N] per leader position: {min x,y,z keys, count}, {max x,y,z keys, 0}
     unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
     unsigned* acc_box;            // [kmax*6] min xyz, max xyz keys
@@ -709,6 +710,7 @@ __device__ __forceinline__ void k_cluster_stats_body(const FramePtrs& a) {
         a.label[c] = lab;
         k = a.cid_of_root[lab];
         a.cid[c] = k;
+        a.scid[s] = k;
     }
     block_cluster_accumulate<true>(a.acc_sum, a.acc_box, k, k >= 0, p.x, p.y, p.z);
     // the last block to finish turns the accumulators into centroids (compute3DCentroid<double>, A10)
@@ -969,19 +971,41 @@ __device__ __forceinline__ void k_pde_count_body(const FramePtrs& a) {
             const int target = a.match_m[m];
             const GridDesc g = *a.dgrid;
             const int cx = (int)floor(((double)t.x - g.ox) * g.inv_h), cy = (int)floor(((double)t.y - g.oy) * g.inv_h), cz = (int)floor(((double)t.z - g.oz) * g.inv_h);
+            const float h = (float)(1.0 / g.inv_h);
             float best = 3.402823466e+38f;
-            const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.nx - 1);
-            if (x0 <= x1) {
-                for (int zz = max(cz - ring, 0); zz <= min(cz + ring, g.nz - 1); zz++)
-                    for (int yy = max(cy - ring, 0); yy <= min(cy + ring, g.ny - 1); yy++) {
+            // Shells of growing Chebyshev distance r around the query's cell. A point in shell r is at least (r-1)*h away,
+            // so the search stops as soon as that bound exceeds the best distance (or pde_ub: farther neighbours never
+            // count), and a neighbour at d2 <= pde_lb settles the answer (the nearest one is then <= pde_lb: not counted).
+            bool settled = false;
+            for (int r = 0; r <= ring && !settled; r++) {
+                if (r > 1) {
+                    const float lb = (float)(r - 1) * h * 0.99999f;
+                    if (lb * lb >= fminf(best, a.pde_ub)) break;
+                }
+                for (int dz = -r; dz <= r && !settled; dz++) {
+                    const int zz = cz + dz;
+                    if (zz < 0 || zz >= g.nz) continue;
+                    for (int dy = -r; dy <= r && !settled; dy++) {
+                        const int yy = cy + dy;
+                        if (yy < 0 || yy >= g.ny) continue;
                         const int base = (zz * g.ny + yy) * g.nx;
-                        const int b = a.cell_start[base + x0], e = a.cell_start[base + x1 + 1];
-                        for (int j = b; j < e; j++) {
-                            const float4 q = a.spts[j];
-                            if (a.cid[__float_as_int(q.w)] != target) continue;
-                            best = fminf(best, sqdist3(t.x, t.y, t.z, q.x, q.y, q.z));
+                        const bool full = (dz == -r || dz == r || dy == -r || dy == r);  // rows on the shell's faces: whole x-run
+                        // otherwise only the two end cells x = cx -+ r belong to the shell
+                        for (int part = 0; part < (full || r == 0 ? 1 : 2); part++) {
+                            int xa, xb;
+                            if (full || r == 0) { xa = cx - r; xb = cx + r; } else if (part == 0) { xa = xb = cx - r; } else { xa = xb = cx + r; }
+                            xa = max(xa, 0); xb = min(xb, g.nx - 1);
+                            if (xa > xb) continue;
+                            const int b = a.cell_start[base + xa], e = a.cell_start[base + xb + 1];
+                            for (int j = b; j < e; j++) {
+                                if (a.scid[j] != target) continue;
+                                const float4 q = a.spts[j];
+                                best = fminf(best, sqdist3(t.x, t.y, t.z, q.x, q.y, q.z));
+                            }
+                            if (best <= a.pde_lb) { settled = true; break; }
                         }
                     }
+                }
             }
             if (best > a.pde_lb && best < a.pde_ub) atomicAdd(&a.newcount[m], 1);
         }
