@@ -76,8 +76,8 @@ class MorConfig(C.Structure):
 
 
 class MorLimits(C.Structure):
-    _fields_ = [("max_points", C.c_uint32), ("max_clusters", C.c_uint32), ("max_moving", C.c_uint32),
-                ("reserved", C.c_uint32 * 5)]
+    _fields_ = [("max_points", C.c_uint32), ("max_clusters", C.c_uint32), ("max_moving", C.c_uint32), ("max_cells", C.c_uint32),
+                ("reserved", C.c_uint32 * 4)]
 
 
 class MorError(RuntimeError):
@@ -165,10 +165,10 @@ class MovingObjectRemoval:
     """
 
     def __init__(self, config_path, n_bad: int = 4, n_good: int = 3, device: int = 0, binding: MorBinding | None = None,
-                 max_points: int = 0, max_clusters: int = 0, max_moving: int = 0):
+                 max_points: int = 0, max_clusters: int = 0, max_moving: int = 0, max_cells: int = 0):
         self.b = binding or load_product()
         self.h = C.c_void_p()
-        lim = MorLimits(max_points=max_points, max_clusters=max_clusters, max_moving=max_moving)
+        lim = MorLimits(max_points=max_points, max_clusters=max_clusters, max_moving=max_moving, max_cells=max_cells)
         st = self.b.create_ex(str(config_path).encode(), n_bad, n_good, device, C.byref(lim), C.byref(self.h))
         if st:
             self.h = C.c_void_p()

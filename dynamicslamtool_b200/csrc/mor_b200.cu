@@ -97,6 +97,7 @@ struct mor_handle {
     uint32_t nmax = 0, kmax = 0, momax = 0;
     int ring_depth = 0, pde_ring = 0;
     bool dynamic_grid = false; int max_cells = 0; double cell_h = 0;
+    uint32_t static_cell_cap = 0;
     int num_sms = 148;
     size_t select_smem = 0;
     GridDesc grid;
@@ -214,16 +215,19 @@ int build_grid(mor_handle* h) {
     const double fx = std::floor(((double)c.trim_x - g.ox) / hcell) + 1, fy = std::floor(((double)c.trim_y - g.oy) / hcell) + 1, fz = std::floor((zhi - g.oz) / hcell) + 1;
     if (fx < 1 || fy < 1 || fz < 1) return MOR_ERR_CONFIG_VALUE;
     h->cell_h = hcell;
-    h->max_cells = 1 << 24;  // 16.7 M cells: 2 x 64 MB of cell tables, ~15 us to scan
-    if (fx * fy * fz > (double)h->max_cells) {
-        // the crop box itself is too large for a dense table (e.g. trimming "disabled" with huge values):
-        // lay the grid over the bounding box of each frame's cloud instead (k_keys); a frame whose box
-        // still needs more than max_cells cells is rejected with MOR_ERR_CAPACITY
+    // Dense cell table. Up to static_cap cells (default 2^27 = 2 x 512 MB of tables; the scan then costs ~0.3 ms per
+    // frame) the grid covers the config crop box and is known at create time. Beyond that (e.g. trimming "disabled"
+    // with huge values) the grid is laid over the bounding box of each frame's cloud instead (k_keys), with at most
+    // 2^24 cells; a frame whose box still needs more is rejected with MOR_ERR_CAPACITY.
+    const double static_cap = h->static_cell_cap ? (double)h->static_cell_cap : 134217728.0;
+    if (fx * fy * fz > static_cap) {
         h->dynamic_grid = true;
+        h->max_cells = 1 << 24;
         g.nx = g.ny = g.nz = kGridPad + 1; g.ncells = h->max_cells;
     } else {
         h->dynamic_grid = false;
         g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
+        h->max_cells = g.ncells > (1 << 24) ? g.ncells : (1 << 24);
     }
     h->grid = g;
     h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / hcell);
@@ -516,6 +520,7 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     h->nmax = limits && limits->max_points ? limits->max_points : 300000u;
     h->kmax = limits && limits->max_clusters ? limits->max_clusters : 8192u;
     h->momax = limits && limits->max_moving ? limits->max_moving : 1024u;
+    h->static_cell_cap = limits ? limits->max_cells : 0u;
     if (h->kmax > 16384u) h->kmax = 16384u;  // k_select_clusters sorts the clusters of a frame in shared memory (128 KB of keys)
     h->ring_depth = (n_bad > 1 ? n_bad : 1) + 2;
     st = build_grid(h);

@@ -60,7 +60,9 @@ typedef struct mor_limits {
     uint32_t max_points;    /* largest frame accepted (default 300000) */
     uint32_t max_clusters;  /* largest number of size-valid clusters per frame (default 8192, at most 16384) */
     uint32_t max_moving;    /* capacity of the confirmed-moving list mo_vec (default 1024) */
-    uint32_t reserved[5];
+    uint32_t max_cells;     /* largest dense cell table laid over the config crop box (default 2^27 cells = 1 GB of
+                               tables); above it the grid follows each frame's bounding box (at most 2^24 cells) */
+    uint32_t reserved[4];
 } mor_limits;
 
 /* The 23 MOR_config.txt keys (config/MOR_config.txt:1-39) + extension keys, as parsed. */

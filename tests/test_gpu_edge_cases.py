@@ -241,3 +241,24 @@ def test_run_to_run_determinism(product, cfg_dir):
 
     a, b, c = run(), run(), run()
     assert a == b == c
+
+
+@pytest.mark.parametrize("max_cells", [0, 1 << 20])
+def test_small_radius_over_a_large_crop_box(product, oracle, cfg_dir, tmp_path, max_cells):
+    """Outdoor trim with the indoor clustering radius: 80 m x 80 m x 4.4 m at r = 0.11 m needs 1.1e8 cells. With the default
+    limits that is one big static table; with a small max_cells the grid follows each frame's bounding box instead
+    (which here is still too large => MOR_ERR_CAPACITY, reported, never a wrong answer)."""
+    from dynamicslamtool_b200 import MorError, Synth
+    cfg = write_cfg(tmp_path, base=cfg_dir / "MOR_config_hdl64.txt", ec_distance_threshold=0.11, min_cluster_size=20)
+    s = Synth(2, 2)
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=s.max_points, max_cells=max_cells)
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    if max_cells == 0:
+        for f in range(3):
+            step(gpu, orc, *s.frame(f))
+    else:
+        pts, pose = s.frame(0)
+        gpu.push_raw_cloud_and_pose(pts, pose)
+        with pytest.raises(MorError) as e:
+            gpu.filter_cloud()
+        assert e.value.status == 6 and "16" in str(e.value)
