@@ -262,3 +262,44 @@ def test_small_radius_over_a_large_crop_box(product, oracle, cfg_dir, tmp_path, 
         with pytest.raises(MorError) as e:
             gpu.filter_cloud()
         assert e.value.status == 6 and "16" in str(e.value)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_configs_and_scenes(product, oracle, tmp_path, seed):
+    """Randomised end-to-end parity: random crop box, radius, cluster size limits, method, thresholds and confidence
+    counts over a random scene of static / moving / appearing / vanishing blobs, a plane of ground points, NaNs and
+    out-of-range points, with a random rigid motion of the sensor between frames."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(1000 + seed)
+    r = float(rng.choice([0.08, 0.15, 0.3, 0.6]))
+    cfgkw = dict(
+        trim_x=float(rng.uniform(4, 9)), trim_y=float(rng.uniform(4, 9)), trim_z=float(rng.uniform(1.5, 4)), gp_limit=float(rng.uniform(-1.2, -0.4)),
+        ec_distance_threshold=r, min_cluster_size=int(rng.integers(5, 60)), max_cluster_size=int(rng.integers(400, 3000)),
+        method_choice=int(rng.integers(1, 3)), opc_normalization_factor=int(rng.integers(2, 25)), volume_constraint=float(rng.uniform(0.1, 0.6)),
+        pde_lb=float(rng.uniform(0.001, 0.01)), pde_ub=float(rng.uniform(0.2, 0.8)), pde_distance_threshold=float(rng.uniform(0.05, 0.4)),
+        leave_off_distance=float(rng.uniform(0.2, 1.0)), catch_up_distance=float(rng.uniform(0.1, 0.6)))
+    cfg = write_cfg(tmp_path, **cfgkw)
+    n_bad, n_good = int(rng.integers(1, 6)), int(rng.integers(0, 5))
+    gpu = MovingObjectRemoval(cfg, n_bad, n_good, binding=product)
+    orc = MovingObjectRemoval(cfg, n_bad, n_good, binding=oracle)
+    nb = int(rng.integers(4, 14))
+    centers = rng.uniform(-6, 6, (nb, 3)) * np.array([1, 1, 0.15])
+    vel = rng.uniform(-0.25, 0.25, (nb, 3)) * np.array([1, 1, 0]) * (rng.random((nb, 1)) < 0.5)
+    sizes = rng.integers(30, 900, nb)
+    sig = rng.uniform(0.5, 1.5, nb) * r
+    shapes = [rng.normal(0, 1, (int(sizes[b]), 3)) * sig[b] * np.array([1, 1, 0.6]) for b in range(nb)]
+    ground = np.concatenate([rng.uniform(-9, 9, (3000, 2)), rng.normal(-1.5, 0.02, (3000, 1))], axis=1)
+    pos, yaw = np.zeros(3), 0.0
+    for f in range(12):
+        pos = pos + rng.uniform(-0.15, 0.15, 3) * np.array([1, 1, 0.1])
+        yaw += float(rng.uniform(-0.05, 0.05))
+        rot = R.from_euler("zyx", [yaw, float(rng.uniform(-0.01, 0.01)), float(rng.uniform(-0.01, 0.01))])
+        world = [shapes[b] + centers[b] + vel[b] * f + rng.normal(0, 0.003, shapes[b].shape) for b in range(nb) if not (b % 5 == 4 and f % 6 >= 4)]
+        world.append(ground + rng.normal(0, 0.002, ground.shape))
+        w = np.concatenate(world)
+        sensor = rot.inv().apply(w - pos).astype(np.float32)  # world -> sensor frame, consistent with the odometry pose
+        pts = with_intensity(sensor, 0.3)
+        pts[rng.integers(0, len(pts), 5), rng.integers(0, 3, 5)] = np.nan
+        pts[rng.integers(0, len(pts), 3), 0] = np.inf
+        pose = np.concatenate([pos, rot.as_quat()])
+        step(gpu, orc, np.ascontiguousarray(pts), pose)
