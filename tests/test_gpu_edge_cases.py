@@ -264,7 +264,7 @@ def test_small_radius_over_a_large_crop_box(product, oracle, cfg_dir, tmp_path, 
         assert e.value.status == 6 and "16" in str(e.value)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(18))
 def test_fuzz_random_configs_and_scenes(product, oracle, tmp_path, seed):
     """Randomised end-to-end parity: random crop box, radius, cluster size limits, method, thresholds and confidence
     counts over a random scene of static / moving / appearing / vanishing blobs, a plane of ground points, NaNs and
@@ -278,6 +278,9 @@ def test_fuzz_random_configs_and_scenes(product, oracle, tmp_path, seed):
         method_choice=int(rng.integers(1, 3)), opc_normalization_factor=int(rng.integers(2, 25)), volume_constraint=float(rng.uniform(0.1, 0.6)),
         pde_lb=float(rng.uniform(0.001, 0.01)), pde_ub=float(rng.uniform(0.2, 0.8)), pde_distance_threshold=float(rng.uniform(0.05, 0.4)),
         leave_off_distance=float(rng.uniform(0.2, 1.0)), catch_up_distance=float(rng.uniform(0.1, 0.6)))
+    if seed >= 12:  # the voxel-covariance ground modes (reference cpp:90-200) instead of the crop
+        cfgkw.update(ground_mode=1 + seed % 2, gp_leaf=float(rng.choice([0.2, 0.35, 0.5])), gp_bin_width=float(rng.choice([0.2, 0.5])),
+                     gp_planarity=float(rng.choice([0.005, 0.02])))
     cfg = write_cfg(tmp_path, **cfgkw)
     n_bad, n_good = int(rng.integers(1, 6)), int(rng.integers(0, 5))
     gpu = MovingObjectRemoval(cfg, n_bad, n_good, binding=product)
