@@ -316,6 +316,44 @@ def run_product(args, rank, local_rank, world):
         for p in d_outs:
             b.device_free(local_rank, p)
 
+    # ------------------------------------------------------------------ multi-sequence, end to end: one host thread per sequence through
+    # the host C ABI (pinned input, H2D, kernels, D2H): copies of one sequence overlap the kernels of the others
+    multi_e2e = None
+    Se = min(args.e2e_sequences, 16)
+    if Se > 1:
+        hs2 = [MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp) for _ in range(Se)]
+        outs2 = [pinned_array(b, (maxp, 8), np.float32) for _ in range(Se)]
+        Ke = max(20, K // 2)
+        offs2 = [(si * F) // Se for si in range(Se)]
+        gate = threading.Barrier(Se + 1)
+
+        def drive(si):
+            hh, outp = hs2[si].h, C.c_void_p(outs2[si][0].ctypes.data)
+            no = C.c_uint32(0)
+            for phase, cnt in (("warm", 5), ("timed", Ke)):
+                if phase == "timed":
+                    gate.wait()
+                for t in range(cnt):
+                    f = (offs2[si] + (t if phase == "warm" else 5 + t)) % F
+                    if b.push(hh, in_ptrs[f], ns[f], 16, 0, 4, 8, 12, pose_arrs[f]) or b.filter(hh, outp, maxp, C.byref(no)):
+                        raise RuntimeError("C ABI error in the multi-sequence e2e leg")
+            gate.wait()
+
+        ths = [threading.Thread(target=drive, args=(si,)) for si in range(Se)]
+        for th in ths:
+            th.start()
+        gate.wait()
+        t0 = time.perf_counter()
+        gate.wait()
+        dt = time.perf_counter() - t0
+        for th in ths:
+            th.join()
+        dt = max_over_ranks(dt)
+        multi_e2e = {"sequences_per_gpu": Se, "value": world * Se * Ke / dt, "unit": "frames/s",
+                     "note": "host C ABI, one host thread + stream per sequence, pinned buffers, H2D and D2H inside; wall clock over all sequences"}
+        for hh in hs2:
+            hh.close()
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ per-kernel profile (rank 0; outside the timed regions)
@@ -407,6 +445,7 @@ def run_product(args, rank, local_rank, world):
                            "frac": frame_bytes_alg * (K / (dev_ms * 1e-3)) / 1e9 / peak, "peak": peak, "peak_source": which},
         "kernels": per_kernel,
         "multi_sequence": multi,
+        "multi_sequence_e2e": multi_e2e,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -419,7 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--launch-threads", type=int, default=4, help="host threads enqueueing the multi-sequence frames")
+    ap.add_argument("--e2e-sequences", type=int, default=8, help="sequences (= host threads) of the multi-sequence end-to-end figure (1 = skip)")
     ap.add_argument("--sequences", type=int, default=16, help="independent sequences per GPU for the extra multi_sequence figure (1 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
