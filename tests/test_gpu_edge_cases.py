@@ -174,11 +174,27 @@ def test_batched_step_matches_oracle_per_sequence(product, oracle, cfg_dir):
                 assert product.device_download(0, og.ctypes.data_as(C.c_void_p), d_out[s], n_out * 32) == 0
             bad = compare_frame(gpus[s], orcs[s], og, oo)
             assert not bad, f"sequence {s} frame {f}: {bad}"
-    # a batched handle can go back to single stepping
-    pts, pose = syn[0].frame(frames)
-    gpus[0].push_raw_cloud_and_pose(pts, pose); orcs[0].push_raw_cloud_and_pose(pts, pose)
-    og, oo = gpus[0].filter_cloud().copy(), orcs[0].filter_cloud().copy()
-    assert not compare_frame(gpus[0], orcs[0], og, oo)
+    # batched handles (the leader and a follower) can go back to single stepping, and back into a batch
+    for s in (0, 2):
+        pts, pose = syn[s].frame(frames)
+        gpus[s].push_raw_cloud_and_pose(pts, pose); orcs[s].push_raw_cloud_and_pose(pts, pose)
+        og, oo = gpus[s].filter_cloud().copy(), orcs[s].filter_cloud().copy()
+        assert not compare_frame(gpus[s], orcs[s], og, oo)
+    pts1, pose1 = syn[1].frame(frames)
+    gpus[1].push_raw_cloud_and_pose(pts1, pose1); orcs[1].push_raw_cloud_and_pose(pts1, pose1)
+    gpus[1].filter_cloud(); orcs[1].filter_cloud()
+    data = [syn[s].frame(frames + 1) for s in range(S)]
+    for s in range(S):
+        assert product.device_upload(0, d_in[s], data[s][0].ctypes.data_as(C.c_void_p), data[s][0].nbytes) == 0
+    batch.step_device([p.value for p in d_in], [d[0].shape[0] for d in data], [d[1] for d in data], [p.value for p in d_out])
+    for s in range(S):
+        orcs[s].push_raw_cloud_and_pose(*data[s])
+        oo = orcs[s].filter_cloud().copy()
+        gpus[s].sync()
+        n_out = gpus[s].counts()["NOUT"]
+        og = np.empty((n_out, 8), np.float32)
+        assert product.device_download(0, og.ctypes.data_as(C.c_void_p), d_out[s], n_out * 32) == 0
+        assert not compare_frame(gpus[s], orcs[s], og, oo)
     for p in d_in + d_out:
         product.device_free(0, p)
 
