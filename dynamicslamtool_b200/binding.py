@@ -102,6 +102,7 @@ class MorBinding:
         self.sync = f("sync", [vp])
         self.tap = f("tap", [vp, C.c_int, vp, sz, C.POINTER(sz)])
         # product-only entry points (absent from the oracle)
+        self.get_limits = f("get_limits", [vp, C.POINTER(MorLimits)], True)
         self.push_device = f("push_raw_cloud_and_pose_device", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)], True)
         self.filter_device = f("filter_cloud_device", [vp, vp, u32, C.POINTER(u32)], True)
         self.alloc_pinned = f("alloc_pinned", [sz, C.POINTER(vp)], True)
@@ -200,6 +201,12 @@ class MovingObjectRemoval:
         cfg = MorConfig()
         self._check(self.b.get_config(self.h, C.byref(cfg)), "get_config")
         return cfg
+
+    @property
+    def limits(self) -> MorLimits:
+        lim = MorLimits()
+        self._check(self.b.get_limits(self.h, C.byref(lim)), "get_limits")
+        return lim
 
     def push_raw_cloud_and_pose(self, points: np.ndarray, pose7, point_step=None, offsets=None):
         pose = (C.c_double * 7)(*[float(v) for v in pose7])

@@ -19,6 +19,15 @@ void MovingObjectRemoval::init(const std::string& path, int n_bad, int n_good, i
     status_ = mor_create_ex(path.c_str(), n_bad, n_good, device, limits, &h_);
     if (status_ != MOR_OK) throw std::runtime_error(std::string("MovingObjectRemoval: ") + mor_status_string(status_) + " (" + path + ")");
     mor_get_config(h_, &cfg_);
+    // one pinned staging buffer for the largest frame the handle accepts: re-pinning when a larger frame shows
+    // up costs tens of milliseconds
+    mor_limits lim;
+    mor_get_limits(h_, &lim);
+    pinned_cap_ = (size_t)lim.max_points * 32;
+    if (mor_alloc_pinned(pinned_cap_, &pinned_out_) != MOR_OK) {
+        mor_destroy(h_); h_ = nullptr;
+        throw std::runtime_error("MovingObjectRemoval: cannot pin the output staging buffer");
+    }
 }
 
 MovingObjectRemoval::MovingObjectRemoval(ros::NodeHandle, std::string config_path, int n_bad, int n_good) { init(config_path, n_bad, n_good, 0, nullptr); }
@@ -41,13 +50,6 @@ void MovingObjectRemoval::pushRawCloudAndPose(pcl::PCLPointCloud2& cloud, geomet
 }
 
 bool MovingObjectRemoval::filterCloud(pcl::PCLPointCloud2& out_cloud, std::string f_id) {
-    const size_t need = (size_t)(n_in_ ? n_in_ : 1) * 32;
-    if (need > pinned_cap_) {
-        if (pinned_out_) mor_free_pinned(pinned_out_);
-        pinned_out_ = nullptr; pinned_cap_ = 0;
-        if (mor_alloc_pinned(need, &pinned_out_) != MOR_OK) { status_ = MOR_ERR_CUDA; return false; }
-        pinned_cap_ = need;
-    }
     uint32_t n_out = 0;
     status_ = mor_filter_cloud(h_, pinned_out_, (uint32_t)(pinned_cap_ / 32), &n_out);
     if (status_ != MOR_OK) return false;
@@ -58,13 +60,13 @@ bool MovingObjectRemoval::filterCloud(pcl::PCLPointCloud2& out_cloud, std::strin
     out_cloud.height = 1; out_cloud.width = n_out; out_cloud.is_bigendian = 0; out_cloud.point_step = 32; out_cloud.row_step = 32 * n_out; out_cloud.is_dense = 1;
     out_cloud.fields.resize(4);
     for (int i = 0; i < 4; i++) { out_cloud.fields[i].name = names[i]; out_cloud.fields[i].offset = offs[i]; out_cloud.fields[i].datatype = 7; out_cloud.fields[i].count = 1; }
-    out_cloud.data.resize((size_t)n_out * 32);
-    if (n_out) std::memcpy(out_cloud.data.data(), pinned_out_, (size_t)n_out * 32);
+    const uint8_t* rec = (const uint8_t*)pinned_out_;
+    out_cloud.data.assign(rec, rec + (size_t)n_out * 32);  // assign, not resize + memcpy: no zero fill of 32 B/point
     // pcl_conversions::fromPCL(out_cloud, output); output.header.frame_id = f_id (cpp:691-692)
     output.header.seq = out_cloud.header.seq; output.header.frame_id = f_id;
     output.height = 1; output.width = n_out; output.is_bigendian = 0; output.point_step = 32; output.row_step = 32 * n_out; output.is_dense = 1;
     output.fields.resize(4);
     for (int i = 0; i < 4; i++) { output.fields[i].name = names[i]; output.fields[i].offset = offs[i]; output.fields[i].datatype = 7; output.fields[i].count = 1; }
-    output.data = out_cloud.data;
+    output.data.assign(rec, rec + (size_t)n_out * 32);  // `output` keeps its capacity from frame to frame
     return true;
 }

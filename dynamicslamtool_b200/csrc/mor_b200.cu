@@ -575,6 +575,13 @@ int mor_get_config(const mor_handle* h, mor_config* out) {
     return MOR_OK;
 }
 
+int mor_get_limits(const mor_handle* h, mor_limits* out) {
+    if (!h || !out) return MOR_ERR_ARG;
+    *out = mor_limits{};
+    out->max_points = h->nmax; out->max_clusters = h->kmax; out->max_moving = h->momax; out->max_cells = (uint32_t)h->max_cells;
+    return MOR_OK;
+}
+
 const char* mor_last_error(const mor_handle* h) { return h ? h->last_error.c_str() : ""; }
 
 int mor_push_raw_cloud_and_pose(mor_handle* h, const void* data, uint32_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,

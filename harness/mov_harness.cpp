@@ -6,6 +6,8 @@
 // runs can be compared across implementations.
 //
 //   mov_harness <MOR_config.txt> <scenario 1..4> <seed> <frames> [n_bad=4] [n_good=3] [--quiet]
+#include <malloc.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -39,6 +41,12 @@ int main(int argc, char** argv) {
     bool quiet = false;
     for (int i = 5; i < argc; i++) quiet |= !std::strcmp(argv[i], "--quiet");
 
+    // The callback allocates and frees ~6 MB of cloud buffers per frame (its local PCLPointCloud2, as in the
+    // reference). With glibc's defaults those are mapped and unmapped every time (0.25 ms of page faults per MB on
+    // the bench host); keep them in the heap instead.
+    mallopt(M_MMAP_THRESHOLD, 32 << 20);
+    mallopt(M_TRIM_THRESHOLD, 512 << 20);
+
     mor_synth* syn = nullptr;
     if (mor_synth_create(scenario, seed, &syn)) { std::fprintf(stderr, "bad scenario\n"); return 2; }
     uint32_t maxp = 0;
@@ -54,6 +62,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 4; i++) { pcl::PCLPointField f; f.name = names[i]; f.offset = 4 * i; f.datatype = 7; f.count = 1; cloud.fields.push_back(f); }
     std::vector<float> buf((size_t)maxp * 4);
     std::vector<double> ms;
+    double stage_ms[3] = {0, 0, 0};  // callback copy, pushRawCloudAndPose, filterCloud (frames after the fifth)
     for (int f = 0; f < frames; f++) {
         uint32_t n = 0;
         double p7[7];
@@ -66,9 +75,17 @@ int main(int argc, char** argv) {
 
         const auto t0 = std::chrono::steady_clock::now();
         pcl::PCLPointCloud2 work = cloud;  // the callback's own copy (external_sync_test.cpp:11-12)
+        const auto t1 = std::chrono::steady_clock::now();
         mor.pushRawCloudAndPose(work, pose);
+        const auto t2 = std::chrono::steady_clock::now();
         const bool ok = mor.filterCloud(work, "/filtered");
-        const double dt = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        const auto t3 = std::chrono::steady_clock::now();
+        const double dt = std::chrono::duration<double, std::milli>(t3 - t0).count();
+        if (f >= 5) {
+            stage_ms[0] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+            stage_ms[1] += std::chrono::duration<double, std::milli>(t2 - t1).count();
+            stage_ms[2] += std::chrono::duration<double, std::milli>(t3 - t2).count();
+        }
         if (!ok) { std::fprintf(stderr, "frame %d: %s\n", f, mor_status_string(mor.lastStatus())); return 1; }
         ms.push_back(dt);
         if (!quiet) std::printf("frame %d in %u out %u crc %08x ms %.3f\n", f, n, mor.output.width, crc32_buf(mor.output.data.data(), mor.output.data.size()), dt);
@@ -79,6 +96,7 @@ int main(int argc, char** argv) {
         double sum = 0;
         for (double v : s) sum += v;
         std::printf("summary frames %zu mean_ms %.3f p50_ms %.3f p99_ms %.3f fps %.1f\n", s.size(), sum / s.size(), s[s.size() / 2], s[(size_t)(s.size() * 0.99)], 1e3 * s.size() / sum);
+        std::printf("stages copy_ms %.3f push_ms %.3f filter_ms %.3f\n", stage_ms[0] / s.size(), stage_ms[1] / s.size(), stage_ms[2] / s.size());
     }
     mor_synth_destroy(syn);
     return 0;

@@ -85,6 +85,7 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device,
                   const mor_limits* limits, mor_handle** out);
 int mor_destroy(mor_handle* h);
 int mor_get_config(const mor_handle* h, mor_config* out);
+int mor_get_limits(const mor_handle* h, mor_limits* out); /* the capacities in effect (defaults filled in) */
 const char* mor_status_string(int status);
 const char* mor_last_error(const mor_handle* h);
 

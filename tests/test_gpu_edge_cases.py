@@ -112,6 +112,8 @@ def test_push_push_filter_and_double_filter(product, oracle, tmp_path):
 def test_capacity_errors_are_reported(product, tmp_path):
     from dynamicslamtool_b200 import MorError
     gpu = MovingObjectRemoval(write_cfg(tmp_path), 4, 3, binding=product, max_points=1000)
+    lim = gpu.limits
+    assert (lim.max_points, lim.max_clusters, lim.max_moving) == (1000, 8192, 1024) and lim.max_cells >= 1 << 24
     with pytest.raises(MorError) as e:
         gpu.push_raw_cloud_and_pose(np.zeros((1001, 4), np.float32), IDENTITY_POSE)
     assert e.value.status == 6
