@@ -95,6 +95,7 @@ class MorBinding:
         vp, u32, sz = C.c_void_p, C.c_uint32, C.c_size_t
         self.create_ex = f("create_ex", [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(MorLimits), C.POINTER(vp)])
         self.destroy = f("destroy", [vp])
+        self.reset = f("reset", [vp])
         self.get_config = f("get_config", [vp, C.POINTER(MorConfig)])
         self.parse_config = f("parse_config", [C.c_char_p, C.POINTER(MorConfig)])
         self.push = f("push_raw_cloud_and_pose", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)])
@@ -201,6 +202,10 @@ class MovingObjectRemoval:
         cfg = MorConfig()
         self._check(self.b.get_config(self.h, C.byref(cfg)), "get_config")
         return cfg
+
+    def reset(self):
+        """Forget every frame seen so far (a freshly constructed object with the same configuration)."""
+        self._check(self.b.reset(self.h), "reset")
 
     @property
     def limits(self) -> MorLimits:

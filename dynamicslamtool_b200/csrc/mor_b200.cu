@@ -292,7 +292,6 @@ int allocate(mor_handle* h) {
     h->arena_bytes = (size_t)(plan(nullptr) - (uint8_t*)nullptr) + 256;
     MOR_CUDA(cudaMalloc(&h->arena, h->arena_bytes));
     plan(h->arena);
-    MOR_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     MOR_CUDA(cudaMallocHost(&h->h_counts, sizeof(int32_t) * MOR_NCOUNTS));
     for (int i = 0; i < 4; i++) MOR_CUDA(cudaEventCreate(&h->ev[i]));
     int P = 1;
@@ -502,6 +501,20 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     return MOR_OK;
 }
 
+// The state of a handle that has seen no frame: all device tables zero, the grid descriptor in place, no tracked
+// objects, empty buffers (the reference's freshly constructed object, cpp:368-391). Ordered on the handle's stream.
+int reset_state(mor_handle* h) {
+    MOR_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+    GridDesc g0 = h->grid;
+    if (h->dynamic_grid) { g0.nx = g0.ny = g0.nz = kGridPad + 1; g0.ncells = g0.nx * g0.ny * g0.nz; }
+    MOR_CUDA(cudaMemcpyAsync(h->base.dgrid, &g0, sizeof(g0), cudaMemcpyHostToDevice, h->stream));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));  // g0 is on this stack frame
+    h->cur = 0; h->have_cur = h->have_prev = h->filtered = h->two_frames = false;
+    h->mo_parity = 0; h->n_input = h->n_prev_input = 0; h->spec_out = 0;
+    h->last_stream = h->stream;
+    return MOR_OK;
+}
+
 }  // namespace
 
 // ============================================================================================ C ABI
@@ -537,12 +550,18 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
-        GridDesc g0 = h->grid;
-        if (h->dynamic_grid) { g0.nx = g0.ny = g0.nz = kGridPad + 1; g0.ncells = g0.nx * g0.ny * g0.nz; }
-        if (cudaMemcpy(h->base.dgrid, &g0, sizeof(g0), cudaMemcpyHostToDevice) != cudaSuccess) { mor_destroy(h); return MOR_ERR_CUDA; }
     }
+    st = reset_state(h);
+    if (st != MOR_OK) { mor_destroy(h); return st; }
     *out = h;
     return MOR_OK;
+}
+
+int mor_reset(mor_handle* h) {
+    if (!h) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    return reset_state(h);
 }
 
 int mor_create(const char* config_path, int n_bad, int n_good, int device, mor_handle** out) {

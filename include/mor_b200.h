@@ -84,6 +84,9 @@ int mor_create(const char* config_path, int n_bad, int n_good, int device, mor_h
 int mor_create_ex(const char* config_path, int n_bad, int n_good, int device,
                   const mor_limits* limits, mor_handle** out);
 int mor_destroy(mor_handle* h);
+/* Back to the state of a freshly created handle (no frames seen, nothing tracked): what destroying the reference
+ * object and constructing a new one does (cpp:368-391), without re-allocating. For replaying several sequences. */
+int mor_reset(mor_handle* h);
 int mor_get_config(const mor_handle* h, mor_config* out);
 int mor_get_limits(const mor_handle* h, mor_limits* out); /* the capacities in effect (defaults filled in) */
 const char* mor_status_string(int status);

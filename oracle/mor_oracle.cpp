@@ -906,6 +906,17 @@ int oracle_create(const char* config_path, int n_bad, int n_good, int device, mo
     return oracle_create_ex(config_path, n_bad, n_good, device, nullptr, out);
 }
 int oracle_destroy(mor_handle* h) { delete h; return MOR_OK; }
+// a reset handle is a newly constructed object with the same configuration (cpp:368-391)
+int oracle_reset(mor_handle* h) {
+    if (!h) return MOR_ERR_ARG;
+    const mor_config c = h->cfg;
+    const int nb = h->moving_confidence, ng = h->static_confidence;
+    *h = mor_handle();
+    h->cfg = c; h->moving_confidence = nb; h->static_confidence = ng;
+    h->ca = std::make_shared<FrameCloud>();
+    h->cb = std::make_shared<FrameCloud>();
+    return MOR_OK;
+}
 int oracle_get_config(const mor_handle* h, mor_config* out) { if (!h || !out) return MOR_ERR_ARG; *out = h->cfg; return MOR_OK; }
 
 int oracle_push_raw_cloud_and_pose(mor_handle* h, const void* data, uint32_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y,

@@ -238,6 +238,34 @@ def test_many_movers_exceed_one_block(product, oracle, tmp_path):
     assert max(n_mo) > 256, n_mo
 
 
+def test_reset_starts_a_new_sequence(product, oracle, cfg_dir):
+    """mor_reset = destroy + construct without re-allocating: after it the handle behaves exactly like a new one
+    (no previous frame, empty buffers, nothing tracked), also in the middle of tracking and after a pushed frame
+    that was never filtered."""
+    from dynamicslamtool_b200 import Synth
+    from helpers import crc
+    cfg = cfg_dir / "MOR_config.txt"
+    s1, s2 = Synth(1, 1), Synth(1, 5)
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=s1.max_points)
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    for f in range(9):  # long enough for confirmed moving objects
+        pts, pose = s1.frame(f)
+        step(gpu, orc, pts, pose)
+    assert gpu.counts()["NMO"] > 0
+    pts, pose = s1.frame(9)
+    gpu.push_raw_cloud_and_pose(pts, pose)  # pushed, not filtered
+    gpu.reset(); orc.reset()
+    fresh = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=s1.max_points)
+    for f in range(8):
+        pts, pose = s2.frame(f)
+        fresh.push_raw_cloud_and_pose(pts, pose)
+        of = fresh.filter_cloud().copy()
+        og = step(gpu, orc, pts, pose)
+        assert crc(og) == crc(of)
+        for t in ("labels", "cluster_id", "centroids", "match_score", "flags", "mo_centroids", "mo_conf", "removed_mask"):
+            assert crc(gpu.tap(t)) == crc(fresh.tap(t)), t
+
+
 def test_run_to_run_determinism(product, cfg_dir):
     """Intra-cell order, union order and atomic order vary from run to run; every observable (labels, cluster order,
     centroids bit for bit, scores, flags, mo_vec, masks, output bytes) must not."""
