@@ -6,6 +6,9 @@
 // runs can be compared across implementations.
 //
 //   mov_harness <MOR_config.txt> <scenario 1..4> <seed> <frames> [n_bad=4] [n_good=3] [--quiet]
+//   mov_harness <MOR_config.txt> --replay <dir> [frames] [n_bad=4] [n_good=3] [--quiet] [--out <dir>]
+//       recorded data: KITTI-style .bin clouds + poses.txt (+ calib.txt), see replay_io.h; --out writes the filtered clouds
+//   mov_harness --pose-of <12 numbers>          the pose7 the replay front end derives from a 3x4 matrix (host only)
 #include <malloc.h>
 
 #include <algorithm>
@@ -18,6 +21,7 @@
 
 #include "../dynamicslamtool_b200/csrc/mor_synth.h"
 #include "../include/MOR/MovingObjectRemoval.h"
+#include "replay_io.h"
 
 static uint32_t crc32_buf(const uint8_t* p, size_t n) {
     static uint32_t table[256];
@@ -31,15 +35,91 @@ static uint32_t crc32_buf(const uint8_t* p, size_t n) {
     return c ^ 0xFFFFFFFFu;
 }
 
+// Where the frames come from: the seeded generator or a directory of recorded clouds + poses.
+struct FrameSource {
+    mor_synth* syn = nullptr;
+    std::vector<std::string> bins;
+    std::vector<std::array<double, 7>> poses;
+    uint32_t max_points = 0;
+    std::vector<float> buf;
+
+    bool open_synth(int scenario, uint64_t seed) {
+        if (mor_synth_create(scenario, seed, &syn)) return false;
+        mor_synth_info(syn, &max_points, nullptr, nullptr);
+        buf.resize((size_t)max_points * 4);
+        return true;
+    }
+    bool open_replay(const std::string& dir, std::string& err) {
+        bins = replay::list_bins(dir);
+        if (bins.empty()) bins = replay::list_bins(dir + "/velodyne");
+        if (bins.empty()) { err = "no .bin clouds in " + dir; return false; }
+        replay::Mat34 tr;
+        const bool have_calib = replay::read_calib(dir + "/calib.txt", tr);
+        if (!replay::read_poses(dir + "/poses.txt", have_calib ? &tr : nullptr, poses, err)) return false;
+        if (poses.size() < bins.size()) bins.resize(poses.size());  // a cloud without a pose cannot be processed
+        for (const std::string& b : bins) {
+            FILE* f = std::fopen(b.c_str(), "rb");
+            if (!f) { err = "cannot open " + b; return false; }
+            std::fseek(f, 0, SEEK_END);
+            max_points = std::max<uint32_t>(max_points, (uint32_t)(std::ftell(f) / 16));
+            std::fclose(f);
+        }
+        return true;
+    }
+    size_t frames() const { return syn ? SIZE_MAX : bins.size(); }
+    // fills cloud.data / width / row_step and p7
+    bool frame(uint32_t f, pcl::PCLPointCloud2& cloud, double p7[7]) {
+        uint32_t n = 0;
+        if (syn) {
+            if (mor_synth_frame(syn, f, buf.data(), max_points, &n, p7, 8)) return false;
+            cloud.data.assign((const uint8_t*)buf.data(), (const uint8_t*)buf.data() + (size_t)n * 16);
+        } else {
+            const long got = replay::read_bin(bins[f], cloud.data);
+            if (got < 0) return false;
+            n = (uint32_t)got;
+            std::copy(poses[f].begin(), poses[f].end(), p7);
+        }
+        cloud.width = n; cloud.row_step = 16 * n;
+        return true;
+    }
+    ~FrameSource() { if (syn) mor_synth_destroy(syn); }
+};
+
 int main(int argc, char** argv) {
-    if (argc < 5) { std::fprintf(stderr, "usage: %s <config> <scenario> <seed> <frames> [n_bad] [n_good] [--quiet]\n", argv[0]); return 2; }
+    if (argc >= 14 && !std::strcmp(argv[1], "--pose-of")) {
+        replay::Mat34 m;
+        for (int i = 0; i < 12; i++) m.m[i] = std::atof(argv[2 + i]);
+        double p7[7];
+        replay::to_pose7(m, p7);
+        std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p7[0], p7[1], p7[2], p7[3], p7[4], p7[5], p7[6]);
+        return 0;
+    }
+    if (argc < 4) { std::fprintf(stderr, "usage: %s <config> <scenario> <seed> <frames> [n_bad] [n_good] [--quiet]\n       %s <config> --replay <dir> [frames] [n_bad] [n_good] [--quiet] [--out <dir>]\n", argv[0], argv[0]); return 2; }
     const std::string cfg = argv[1];
-    const int scenario = std::atoi(argv[2]);
-    const uint64_t seed = std::strtoull(argv[3], nullptr, 10);
-    const int frames = std::atoi(argv[4]);
-    const int n_bad = argc > 5 && argv[5][0] != '-' ? std::atoi(argv[5]) : 4, n_good = argc > 6 && argv[6][0] != '-' ? std::atoi(argv[6]) : 3;
+    const bool replay_mode = !std::strcmp(argv[2], "--replay");
     bool quiet = false;
-    for (int i = 5; i < argc; i++) quiet |= !std::strcmp(argv[i], "--quiet");
+    std::string out_dir;
+    std::vector<std::string> pos;  // positional arguments after the source
+    for (int i = replay_mode ? 4 : 2; i < argc; i++) {
+        if (!std::strcmp(argv[i], "--quiet")) quiet = true;
+        else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out_dir = argv[++i];
+        else pos.push_back(argv[i]);
+    }
+    FrameSource src;
+    int frames = 0;
+    size_t next = 0;
+    if (replay_mode) {
+        std::string err;
+        if (!src.open_replay(argv[3], err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
+        frames = (int)src.frames();
+        if (pos.size() > next) frames = std::min(frames, std::atoi(pos[next++].c_str()));
+    } else {
+        if (pos.size() < 3) { std::fprintf(stderr, "scenario, seed and frame count expected\n"); return 2; }
+        if (!src.open_synth(std::atoi(pos[0].c_str()), std::strtoull(pos[1].c_str(), nullptr, 10))) { std::fprintf(stderr, "bad scenario\n"); return 2; }
+        frames = std::atoi(pos[2].c_str());
+        next = 3;
+    }
+    const int n_bad = pos.size() > next ? std::atoi(pos[next].c_str()) : 4, n_good = pos.size() > next + 1 ? std::atoi(pos[next + 1].c_str()) : 3;
 
     // The callback allocates and frees ~6 MB of cloud buffers per frame (its local PCLPointCloud2, as in the
     // reference). With glibc's defaults those are mapped and unmapped every time (0.25 ms of page faults per MB on
@@ -47,12 +127,8 @@ int main(int argc, char** argv) {
     mallopt(M_MMAP_THRESHOLD, 32 << 20);
     mallopt(M_TRIM_THRESHOLD, 512 << 20);
 
-    mor_synth* syn = nullptr;
-    if (mor_synth_create(scenario, seed, &syn)) { std::fprintf(stderr, "bad scenario\n"); return 2; }
-    uint32_t maxp = 0;
-    mor_synth_info(syn, &maxp, nullptr, nullptr);
     mor_limits lim{};
-    lim.max_points = maxp;
+    lim.max_points = std::max<uint32_t>(src.max_points, 1);
     ros::NodeHandle nh;
     MovingObjectRemoval mor(nh, cfg, n_bad, n_good, 0, &lim);  // mor.reset(new MovingObjectRemoval(nh, "...MOR_config.txt", 4, 3))
 
@@ -60,15 +136,12 @@ int main(int argc, char** argv) {
     cloud.height = 1; cloud.point_step = 16; cloud.is_dense = 1;
     const char* names[4] = {"x", "y", "z", "intensity"};
     for (int i = 0; i < 4; i++) { pcl::PCLPointField f; f.name = names[i]; f.offset = 4 * i; f.datatype = 7; f.count = 1; cloud.fields.push_back(f); }
-    std::vector<float> buf((size_t)maxp * 4);
     std::vector<double> ms;
     double stage_ms[3] = {0, 0, 0};  // callback copy, pushRawCloudAndPose, filterCloud (frames after the fifth)
     for (int f = 0; f < frames; f++) {
-        uint32_t n = 0;
         double p7[7];
-        if (mor_synth_frame(syn, (uint32_t)f, buf.data(), maxp, &n, p7, 8)) { std::fprintf(stderr, "generator failed\n"); return 1; }
-        cloud.width = n; cloud.row_step = 16 * n;
-        cloud.data.assign((const uint8_t*)buf.data(), (const uint8_t*)buf.data() + (size_t)n * 16);
+        if (!src.frame((uint32_t)f, cloud, p7)) { std::fprintf(stderr, "frame %d: cannot read the cloud\n", f); return 1; }
+        const uint32_t n = cloud.width;
         geometry_msgs::Pose pose;
         pose.position.x = p7[0]; pose.position.y = p7[1]; pose.position.z = p7[2];
         pose.orientation.x = p7[3]; pose.orientation.y = p7[4]; pose.orientation.z = p7[5]; pose.orientation.w = p7[6];
@@ -88,6 +161,11 @@ int main(int argc, char** argv) {
         }
         if (!ok) { std::fprintf(stderr, "frame %d: %s\n", f, mor_status_string(mor.lastStatus())); return 1; }
         ms.push_back(dt);
+        if (!out_dir.empty()) {
+            char name[32];
+            std::snprintf(name, sizeof name, "/%06d.bin", f);
+            if (!replay::write_bin(out_dir + name, mor.output.data.data(), mor.output.width)) { std::fprintf(stderr, "cannot write %s%s\n", out_dir.c_str(), name); return 1; }
+        }
         if (!quiet) std::printf("frame %d in %u out %u crc %08x ms %.3f\n", f, n, mor.output.width, crc32_buf(mor.output.data.data(), mor.output.data.size()), dt);
     }
     if (ms.size() > 5) {
@@ -98,6 +176,5 @@ int main(int argc, char** argv) {
         std::printf("summary frames %zu mean_ms %.3f p50_ms %.3f p99_ms %.3f fps %.1f\n", s.size(), sum / s.size(), s[s.size() / 2], s[(size_t)(s.size() * 0.99)], 1e3 * s.size() / sum);
         std::printf("stages copy_ms %.3f push_ms %.3f filter_ms %.3f\n", stage_ms[0] / s.size(), stage_ms[1] / s.size(), stage_ms[2] / s.size());
     }
-    mor_synth_destroy(syn);
     return 0;
 }
