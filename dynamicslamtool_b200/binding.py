@@ -80,6 +80,9 @@ class MorLimits(C.Structure):
                 ("reserved", C.c_uint32 * 4)]
 
 
+MARKER_DTYPE = np.dtype([("position", np.float32, 3), ("scale", np.float32, 3), ("color", np.float32, 4), ("id", np.int32), ("cluster", np.int32)])
+
+
 class MorError(RuntimeError):
     def __init__(self, status: int, where: str, detail: str = ""):
         self.status = status
@@ -102,6 +105,8 @@ class MorBinding:
         self.filter = f("filter_cloud", [vp, vp, u32, C.POINTER(u32)])
         self.sync = f("sync", [vp])
         self.tap = f("tap", [vp, C.c_int, vp, sz, C.POINTER(sz)])
+        self.get_cluster_collection = f("get_cluster_collection", [vp, vp, u32, C.POINTER(u32)])
+        self.get_moving_markers = f("get_moving_markers", [vp, vp, u32, C.POINTER(u32)])
         # product-only entry points (absent from the oracle)
         self.get_limits = f("get_limits", [vp, C.POINTER(MorLimits)], True)
         self.push_device = f("push_raw_cloud_and_pose_device", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)], True)
@@ -235,6 +240,24 @@ class MovingObjectRemoval:
         n_out = C.c_uint32(0)
         self._check(self.b.filter(self.h, out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n_out)), "filter_cloud")
         return out[: n_out.value]
+
+    def cluster_collection(self) -> np.ndarray:
+        """The reference's VISUALIZE debug cloud (cpp:226-229, :553-558): float32 [N_k, 8] PointXYZI records."""
+        n = C.c_uint32(0)
+        self._check(self.b.get_cluster_collection(self.h, None, 0, C.byref(n)), "get_cluster_collection")
+        out = np.empty((n.value, 8), np.float32)
+        if n.value:
+            self._check(self.b.get_cluster_collection(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "get_cluster_collection")
+        return out
+
+    def moving_markers(self) -> np.ndarray:
+        """Bounding-box markers of the last filter_cloud (cpp:640-642), structured array of MARKER_DTYPE."""
+        n = C.c_uint32(0)
+        self._check(self.b.get_moving_markers(self.h, None, 0, C.byref(n)), "get_moving_markers")
+        out = np.zeros(n.value, MARKER_DTYPE)
+        if n.value:
+            self._check(self.b.get_moving_markers(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "get_moving_markers")
+        return out
 
     def sync(self):
         self._check(self.b.sync(self.h), "sync")

@@ -70,3 +70,27 @@ bool MovingObjectRemoval::filterCloud(pcl::PCLPointCloud2& out_cloud, std::strin
     output.data.assign(rec, rec + (size_t)n_out * 32);  // `output` keeps its capacity from frame to frame
     return true;
 }
+
+bool MovingObjectRemoval::clusterCollection(pcl::PCLPointCloud2& debug_cloud) {
+    uint32_t n = 0;
+    status_ = mor_get_cluster_collection(h_, pinned_out_, (uint32_t)(pinned_cap_ / 32), &n);
+    if (status_ != MOR_OK) return false;
+    static const char* const names[4] = {"x", "y", "z", "intensity"};
+    static const uint32_t offs[4] = {0, 4, 8, 16};
+    debug_cloud.header = pcl::PCLHeader();
+    debug_cloud.height = 1; debug_cloud.width = n; debug_cloud.is_bigendian = 0; debug_cloud.point_step = 32; debug_cloud.row_step = 32 * n; debug_cloud.is_dense = 1;
+    debug_cloud.fields.resize(4);
+    for (int i = 0; i < 4; i++) { debug_cloud.fields[i].name = names[i]; debug_cloud.fields[i].offset = offs[i]; debug_cloud.fields[i].datatype = 7; debug_cloud.fields[i].count = 1; }
+    const uint8_t* rec = (const uint8_t*)pinned_out_;
+    debug_cloud.data.assign(rec, rec + (size_t)n * 32);
+    return true;
+}
+
+bool MovingObjectRemoval::movingMarkers(std::vector<mor_marker>& markers) {
+    uint32_t n = 0;
+    status_ = mor_get_moving_markers(h_, nullptr, 0, &n);
+    if (status_ != MOR_OK) return false;
+    markers.resize(n);
+    if (n) status_ = mor_get_moving_markers(h_, markers.data(), n, &n);
+    return status_ == MOR_OK;
+}

@@ -14,6 +14,7 @@
 
 #include "mor_kernels.cuh"
 #include "mor_ground.cuh"
+#include "mor_debug.cuh"
 
 using namespace mor;
 
@@ -112,6 +113,7 @@ struct mor_handle {
     size_t zero_bytes = 0;
     size_t lattice_cap = 0;
     FramePtrs base;  // pointers that do not change from frame to frame
+    int* coll_cursor = nullptr; int* coll_turn = nullptr;  // mor_get_cluster_collection scratch
     GroundPtrs ground;  // voxel-covariance ground removal state (ground_mode 1/2 only)
     // ping-pong
     float4* pts[2]; float4* spts[2]; int* cid[2]; int* cl_root[2]; int* cl_size[2]; float* cl_centroid[2]; uint8_t* cl_flags[2]; float* cl_bbox[2]; int* counts[2];
@@ -270,6 +272,7 @@ int allocate(mor_handle* h) {
         b.anchor = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
         b.lattice = carve<unsigned long long>(p, lat);
         b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
+        b.marker_cluster = carve<int>(p, MO); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
         b.out = carve<float4>(p, N * 2);
         for (int f = 0; f < 2; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
@@ -870,6 +873,65 @@ int mor_get_mo_vec(mor_handle* h, float* xyz, int32_t* conf, size_t n) {
     size_t nb = 0;
     int st = mor_tap(h, MOR_TAP_MO_CENTROIDS, xyz, n * 12, &nb);
     return st != MOR_OK ? st : mor_tap(h, MOR_TAP_MO_CONF, conf, n * 4, &nb);
+}
+
+// ---- VISUALIZE outputs (IncludeAll.h:32), on request
+int mor_get_cluster_collection(mor_handle* h, void* out, uint32_t cap_points, uint32_t* n_out) {
+    if (!h || !n_out) return MOR_ERR_ARG;
+    if (!h->have_cur) return MOR_ERR_STATE;
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    const FramePtrs& a = h->frame;
+    CollectionPtrs c;
+    c.cid = a.cid; c.pts = a.pts; c.cl_size = a.cl_size; c.counts = a.counts; c.cursor = h->coll_cursor; c.turn = h->coll_turn;
+    c.out = h->base.out;  // free between calls: mor_filter_cloud has copied its result out before it returns
+    k_collection_offsets<<<1, kCollBlock, 0, h->stream>>>(c);
+    k_cluster_collection<<<h->n_input ? (h->n_input + kCollBlock - 1) / kCollBlock : 1, kCollBlock, 0, h->stream>>>(c);
+    h->launches += 2;
+    MOR_CUDA(cudaGetLastError());
+    MOR_CUDA(cudaMemcpyAsync(h->h_counts, a.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, h->stream));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    const uint32_t nk = (uint32_t)h->h_counts[MOR_CNT_NK];
+    *n_out = nk;
+    if (!out) return MOR_OK;
+    if (nk > cap_points) return MOR_ERR_CAPACITY;
+    if (nk) MOR_CUDA(cudaMemcpy(out, c.out, (size_t)nk * 32, cudaMemcpyDeviceToHost));
+    return MOR_OK;
+}
+
+int mor_get_moving_markers(mor_handle* h, mor_marker* out, uint32_t cap, uint32_t* n_out) {
+    if (!h || !n_out) return MOR_ERR_ARG;
+    if (!h->have_cur || !h->filtered) return MOR_ERR_STATE;
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    const FramePtrs& a = h->frame;
+    TrackState ts;
+    MOR_CUDA(cudaMemcpy(&ts, a.track, sizeof ts, cudaMemcpyDeviceToHost));
+    const uint32_t n = (uint32_t)ts.n_markers;
+    *n_out = n;
+    if (!out || !n) return MOR_OK;
+    if (n > cap) return MOR_ERR_CAPACITY;
+    MOR_CUDA(cudaMemcpy(h->h_counts, a.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost));
+    const size_t K = (size_t)h->h_counts[MOR_CNT_K];
+    std::vector<int> which(n);
+    std::vector<float> cen(K * 3), box(K * 6);
+    MOR_CUDA(cudaMemcpy(which.data(), a.marker_cluster, n * sizeof(int), cudaMemcpyDeviceToHost));
+    MOR_CUDA(cudaMemcpy(cen.data(), a.cl_centroid, K * 12, cudaMemcpyDeviceToHost));
+    MOR_CUDA(cudaMemcpy(box.data(), a.cl_bbox, K * 24, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) {
+        const int k = which[i];
+        mor_marker& m = out[i];
+        for (int q = 0; q < 3; q++) {
+            m.position[q] = cen[(size_t)k * 3 + q];
+            const float ext = box[(size_t)k * 6 + 3 + q] - box[(size_t)k * 6 + q];
+            m.scale[q] = ext == 0.f ? 0.1f : ext;  // cpp:40-47
+        }
+        m.color[0] = 0.8f; m.color[1] = 0.1f; m.color[2] = 0.4f; m.color[3] = 0.5f;  // cpp:622, :53
+        m.id = 1;  // cpp:622: the counter is never advanced, every marker of a frame replaces the one before
+        m.cluster = k;
+    }
+    return MOR_OK;
 }
 
 }  // extern "C"

@@ -39,6 +39,7 @@ struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:
     int corr_count, corr_head;  // corrs_vec deque
     int frames;
     int extract_overflow;
+    int n_markers;    // mo_vec entries the last filterCloud looked up (one bounding-box marker each, cpp:640-642)
 };
 
 // Everything a kernel needs, passed by value (fits the 4 KB parameter space comfortably).
@@ -74,6 +75,7 @@ struct FramePtrs {
     int* match_of_prev; int* mid_of_prev; int* mid_of_cur; double* anchor; int* newcount;
     unsigned long long* lattice; unsigned lattice_mask;
     uint8_t* cluster_removed; int* found;
+    int* marker_cluster;          // [momax] cluster each mo_vec entry was matched to by the last filterCloud
     float4* out;
     // ---- ping-pong frame state: cur / prev
     float4* pts; float4* spts; int* cid; int* cl_root; int* cl_size; float* cl_centroid; uint8_t* cl_flags; float* cl_bbox; int* counts;
@@ -1175,6 +1177,7 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
             conf = mo_f_in[t];
             float d;
             const int k = nn_brute(a.cl_centroid, K, cx, cy, cz, &d);
+            if (writer) a.marker_cluster[t] = k;
             atomicOr(&s_removed[k >> 5], 1u << (k & 31));
             atomicAdd(&s_total, a.cl_size[k]);
             if (!a.cl_flags[k] || d > a.leave_off) {  // cpp:650
@@ -1214,6 +1217,7 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
             ts->n_mo[mo_parity ^ 1] = kept;  // the host flips the parity after this launch
             a.counts[MOR_CNT_NMO] = kept;
             ts->extract_overflow = overflow;
+            ts->n_markers = K > 0 ? n_mo : 0;
             a.counts[MOR_CNT_EXTRACT_OVERFLOW] = overflow;
         }
     }

@@ -7,6 +7,7 @@
 //
 //   mov_harness <MOR_config.txt> <scenario 1..4> <seed> <frames> [n_bad=4] [n_good=3] [--quiet]
 //   mov_harness <MOR_config.txt> --replay <dir> [frames] [n_bad=4] [n_good=3] [--quiet] [--out <dir>]
+//       (either form: --debug also fetches the VISUALIZE debug cloud and bounding-box markers of every frame)
 //       recorded data: KITTI-style .bin clouds + poses.txt (+ calib.txt), see replay_io.h; --out writes the filtered clouds
 //   mov_harness --pose-of <12 numbers>          the pose7 the replay front end derives from a 3x4 matrix (host only)
 #include <malloc.h>
@@ -97,11 +98,12 @@ int main(int argc, char** argv) {
     if (argc < 4) { std::fprintf(stderr, "usage: %s <config> <scenario> <seed> <frames> [n_bad] [n_good] [--quiet]\n       %s <config> --replay <dir> [frames] [n_bad] [n_good] [--quiet] [--out <dir>]\n", argv[0], argv[0]); return 2; }
     const std::string cfg = argv[1];
     const bool replay_mode = !std::strcmp(argv[2], "--replay");
-    bool quiet = false;
+    bool quiet = false, debug = false;  // --debug: also fetch the VISUALIZE outputs (debug cloud, markers) every frame
     std::string out_dir;
     std::vector<std::string> pos;  // positional arguments after the source
     for (int i = replay_mode ? 4 : 2; i < argc; i++) {
         if (!std::strcmp(argv[i], "--quiet")) quiet = true;
+        else if (!std::strcmp(argv[i], "--debug")) debug = true;
         else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out_dir = argv[++i];
         else pos.push_back(argv[i]);
     }
@@ -151,6 +153,8 @@ int main(int argc, char** argv) {
         const auto t1 = std::chrono::steady_clock::now();
         mor.pushRawCloudAndPose(work, pose);
         const auto t2 = std::chrono::steady_clock::now();
+        pcl::PCLPointCloud2 debug_cloud;
+        if (debug && !mor.clusterCollection(debug_cloud)) { std::fprintf(stderr, "frame %d: %s\n", f, mor_status_string(mor.lastStatus())); return 1; }  // cpp:553-558
         const bool ok = mor.filterCloud(work, "/filtered");
         const auto t3 = std::chrono::steady_clock::now();
         const double dt = std::chrono::duration<double, std::milli>(t3 - t0).count();
@@ -165,6 +169,13 @@ int main(int argc, char** argv) {
             char name[32];
             std::snprintf(name, sizeof name, "/%06d.bin", f);
             if (!replay::write_bin(out_dir + name, mor.output.data.data(), mor.output.width)) { std::fprintf(stderr, "cannot write %s%s\n", out_dir.c_str(), name); return 1; }
+        }
+        if (debug) {
+            std::vector<mor_marker> markers;
+            if (!mor.movingMarkers(markers)) { std::fprintf(stderr, "frame %d: %s\n", f, mor_status_string(mor.lastStatus())); return 1; }
+            std::printf("debug %d clustered %u crc %08x markers %zu", f, debug_cloud.width, crc32_buf(debug_cloud.data.data(), debug_cloud.data.size()), markers.size());
+            for (const mor_marker& m : markers) std::printf(" [cluster %d scale %.9g %.9g %.9g]", m.cluster, m.scale[0], m.scale[1], m.scale[2]);
+            std::printf("\n");
         }
         if (!quiet) std::printf("frame %d in %u out %u crc %08x ms %.3f\n", f, n, mor.output.width, crc32_buf(mor.output.data.data(), mor.output.data.size()), dt);
     }

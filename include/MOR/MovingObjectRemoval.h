@@ -18,7 +18,9 @@
 //   * a bad config throws std::runtime_error instead of calling exit(0) (cpp:703-707, :856-860);
 //   * filterCloud returns false if the device reported an error (the reference always returns true, cpp:695);
 //   * the VISUALIZE side effects (debug cloud published and copied over the caller's input cloud at cpp:553-558,
-//     bounding-box markers) are ROS publishing and are not reproduced; the input cloud is never modified.
+//     bounding-box markers published at cpp:640-642) are not performed behind the caller's back: the same data is
+//     available on request (clusterCollection, movingMarkers) for the node to publish; the input cloud is never
+//     modified by pushRawCloudAndPose.
 #ifndef MOR_MOVING_OBJECT_REMOVAL_H
 #define MOR_MOVING_OBJECT_REMOVAL_H
 
@@ -80,6 +82,12 @@ public:
     // Output: the filtered cloud (cloud minus confirmed moving clusters, plus the ground points) is written to `cloud`
     // and to `output` with header.frame_id = f_id (cpp:613-696).
     bool filterCloud(pcl::PCLPointCloud2& cloud, std::string f_id);
+
+    // The reference's VISUALIZE outputs, on request (nothing is computed unless these are called):
+    // cb->cluster_collection as published on the debug topic (cpp:553-558), valid after pushRawCloudAndPose ...
+    bool clusterCollection(pcl::PCLPointCloud2& debug_cloud);
+    // ... and the bounding-box markers of the clusters the last filterCloud matched to mo_vec (cpp:640-642).
+    bool movingMarkers(std::vector<mor_marker>& markers);
 
     mor_handle* handle() { return h_; }       // for the parity taps / device-resident calls of mor_b200.h
     const mor_config& config() const { return cfg_; }

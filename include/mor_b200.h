@@ -156,6 +156,24 @@ int mor_event_elapsed_ms(mor_handle* h, int slot_a, int slot_b, float* ms);
 int mor_set_kernel_profiling(mor_handle* h, int enabled);
 int mor_get_kernel_profile(mor_handle* h, int index, char name[32], double* total_ms, uint64_t* launches);
 
+/* ---- the reference's VISUALIZE outputs (IncludeAll.h:32), on request ---------------------- */
+/* cb->cluster_collection as published on the debug topic (cpp:226-229, :553-558): the points of all size-valid
+ * clusters, cluster after cluster in cluster order, ascending cloud index inside a cluster; 32-byte pcl::PointXYZI
+ * records like mor_filter_cloud. Valid after mor_push_raw_cloud_and_pose. out == NULL: only the count. */
+int mor_get_cluster_collection(mor_handle* h, void* out, uint32_t cap_points, uint32_t* n_out);
+/* One bounding-box marker per mo_vec entry the last mor_filter_cloud looked up, in mo_vec order (marker_pub,
+ * cpp:640-642; mark_cluster, cpp:7-58), from the per-cluster statistics kept on the device. `position` is the
+ * cluster centroid of the hot path (double sums rounded to float; the reference's marker uses a float-accumulated
+ * centroid, equal to ~1e-6 relative), `scale` the exact bounding-box extents with 0 replaced by 0.1. */
+typedef struct mor_marker {
+    float position[3];
+    float scale[3];
+    float color[4];  /* 0.8, 0.1, 0.4, alpha 0.5 */
+    int32_t id;      /* always 1, as in the reference (cpp:622) */
+    int32_t cluster; /* index into this frame's cluster list */
+} mor_marker;
+int mor_get_moving_markers(mor_handle* h, mor_marker* out, uint32_t cap, uint32_t* n_out);
+
 /* ---- parity taps ------------------------------------------------------------------------ */
 typedef enum mor_tap_id {
     MOR_TAP_COUNTS = 0,          /* int32[MOR_NCOUNTS], see below */

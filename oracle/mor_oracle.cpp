@@ -421,7 +421,27 @@ struct mor_handle {
     int n_out = 0, extract_overflow = 0, P1 = 0, P2 = 0, n_kprev = 0, frames = 0;
     bool filtered = false;
     std::vector<PointXYZI> f_cloud;
+    std::vector<mor_marker> markers;  // VISUALIZE: marker_pub.publish(mark_cluster(...)) calls of the last filterCloud
     std::string last_error;
+
+    // ---------------- mark_cluster, cpp:7-58: pcl::compute3DCentroid into a Vector4f (float sums in index order,
+    // divided by n), getMinMax3D extents, zero extents widened to 0.1; id is 1 for every marker (cpp:622)
+    static mor_marker mark_cluster(const std::vector<PointXYZI>& pts, int k) {
+        mor_marker m;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (const PointXYZI& p : pts) {
+            sx += p.x; sy += p.y; sz += p.z;
+            const float v[3] = {p.x, p.y, p.z};
+            for (int q = 0; q < 3; q++) { mn[q] = std::min(mn[q], v[q]); mx[q] = std::max(mx[q], v[q]); }
+        }
+        const float n = (float)pts.size();
+        m.position[0] = sx / n; m.position[1] = sy / n; m.position[2] = sz / n;
+        for (int q = 0; q < 3; q++) { const float e = mx[q] - mn[q]; m.scale[q] = e == 0.f ? 0.1f : e; }
+        m.color[0] = 0.8f; m.color[1] = 0.1f; m.color[2] = 0.4f; m.color[3] = 0.5f;
+        m.id = 1; m.cluster = k;
+        return m;
+    }
 
     // ---------------- groundPlaneRemoval(x,y,z), cpp:62-88 (ACTIVE path, cpp:526)
     void trim_xy(FrameCloud& fc, const std::vector<PointXYZI>& in, float x, float y) {
@@ -846,10 +866,12 @@ struct mor_handle {
         const size_t K = cb->clusters.size();
         std::vector<int> moving_points;
         cluster_removed.assign(K, 0);
+        markers.clear();
         for (int i = 0; i < (int)mo_vec.size(); i++) {  // cpp:630
             if (K == 0) continue;  // defined behaviour for the un-built tree: entries untouched
             float d;
             int k = nn_centroid(cb->centroid_collection, mo_vec[i].centroid, &d);  // cpp:636
+            markers.push_back(mark_cluster(cb->clusters[k].points, k));            // cpp:640-642 (VISUALIZE)
             for (int j : cb->clusters[k].indices) moving_points.push_back(j);      // cpp:644-648
             cluster_removed[k] = 1;
             if (!cb->detection_results[k] || d > cfg.leave_off_distance) {         // cpp:650
@@ -915,6 +937,29 @@ int oracle_reset(mor_handle* h) {
     h->cfg = c; h->moving_confidence = nb; h->static_confidence = ng;
     h->ca = std::make_shared<FrameCloud>();
     h->cb = std::make_shared<FrameCloud>();
+    return MOR_OK;
+}
+// VISUALIZE outputs: cluster_collection (cpp:226-229, :553-558) and the markers of the last filterCloud
+int oracle_get_cluster_collection(mor_handle* h, void* out, uint32_t cap_points, uint32_t* n_out) {
+    if (!h || !n_out) return MOR_ERR_ARG;
+    if (!h->cb || !h->cb->init) return MOR_ERR_STATE;
+    size_t n = 0;
+    for (const Cluster& c : h->cb->clusters) n += c.points.size();
+    *n_out = (uint32_t)n;
+    if (!out) return MOR_OK;
+    if (n > cap_points) return MOR_ERR_CAPACITY;
+    float* o = (float*)out;
+    for (const Cluster& c : h->cb->clusters)
+        for (const PointXYZI& p : c.points) { o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = 1.0f; o[4] = p.intensity; o[5] = o[6] = o[7] = 0.f; o += 8; }
+    return MOR_OK;
+}
+int oracle_get_moving_markers(mor_handle* h, mor_marker* out, uint32_t cap, uint32_t* n_out) {
+    if (!h || !n_out) return MOR_ERR_ARG;
+    if (!h->filtered) return MOR_ERR_STATE;
+    *n_out = (uint32_t)h->markers.size();
+    if (!out || h->markers.empty()) return MOR_OK;
+    if (h->markers.size() > cap) return MOR_ERR_CAPACITY;
+    std::copy(h->markers.begin(), h->markers.end(), out);
     return MOR_OK;
 }
 int oracle_get_config(const mor_handle* h, mor_config* out) { if (!h || !out) return MOR_ERR_ARG; *out = h->cfg; return MOR_OK; }

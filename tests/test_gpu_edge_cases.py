@@ -266,6 +266,34 @@ def test_reset_starts_a_new_sequence(product, oracle, cfg_dir):
             assert crc(gpu.tap(t)) == crc(fresh.tap(t)), t
 
 
+def test_visualize_outputs_cluster_collection_and_markers(product, oracle, cfg_dir):
+    """The reference's VISUALIZE side outputs: cluster_collection (cpp:226-229, :553-558) byte for byte - a stable
+    partition of the cloud by cluster - and one marker per mo_vec entry (cpp:640-642): cluster, id, colour and
+    bounding-box scale exact, position = centroid (the reference accumulates it in float: 1e-5 relative)."""
+    from dynamicslamtool_b200 import Synth
+    for scen, cfg, frames in ((1, "MOR_config.txt", range(0, 12)), (2, "MOR_config_hdl64.txt", range(100, 108))):
+        s = Synth(scen, scen)
+        gpu = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
+        orc = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=oracle)
+        seen_markers = 0
+        for f in frames:
+            pts, pose = s.frame(f)
+            gpu.push_raw_cloud_and_pose(pts, pose); orc.push_raw_cloud_and_pose(pts, pose)
+            cg, co = gpu.cluster_collection(), orc.cluster_collection()   # between push and filter, as the reference publishes it
+            assert cg.shape == co.shape and cg.tobytes() == co.tobytes(), f"scenario {scen} frame {f}"
+            assert cg.shape[0] == gpu.counts()["NK"]
+            og, oo = gpu.filter_cloud().copy(), orc.filter_cloud().copy()
+            assert og.tobytes() == oo.tobytes()
+            assert gpu.cluster_collection().tobytes() == co.tobytes()       # and after filter: same frame, same answer
+            mg, mo = gpu.moving_markers(), orc.moving_markers()
+            assert mg.shape == mo.shape
+            seen_markers += mg.shape[0]
+            for name in ("cluster", "id", "color", "scale"):
+                assert np.array_equal(mg[name], mo[name]), name
+            np.testing.assert_allclose(mg["position"], mo["position"], rtol=1e-5, atol=1e-5)
+        assert seen_markers > 0
+
+
 def test_run_to_run_determinism(product, cfg_dir):
     """Intra-cell order, union order and atomic order vary from run to run; every observable (labels, cluster order,
     centroids bit for bit, scores, flags, mo_vec, masks, output bytes) must not."""

@@ -31,6 +31,33 @@ def test_cpp_class_matches_oracle(oracle, built):
         assert int(lines[f][7], 16) == crc(out), f"frame {f}: C++ class output differs from the oracle"
 
 
+def test_cpp_class_visualize_outputs(oracle, built):
+    """clusterCollection / movingMarkers of the C++ class against the oracle (CRC of the debug cloud, marker clusters
+    and scales)."""
+    exe = ROOT / "harness" / "mov_harness"
+    cfg = ROOT / "config" / "MOR_config.txt"
+    n = 10
+    res = subprocess.run([str(exe), str(cfg), "1", "1", str(n), "--debug"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    dbg = [l for l in res.stdout.splitlines() if l.startswith("debug ")]
+    assert len(dbg) == n
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    s = Synth(1, 1)
+    markers_seen = 0
+    for f in range(n):
+        pts, pose = s.frame(f)
+        orc.push_raw_cloud_and_pose(pts, pose)
+        coll = orc.cluster_collection()
+        orc.filter_cloud()
+        marks = orc.moving_markers()
+        tok = dbg[f].split()
+        assert int(tok[3]) == coll.shape[0] and int(tok[5], 16) == crc(coll) and int(tok[7]) == marks.shape[0]
+        want = "".join(" [cluster %d scale %.9g %.9g %.9g]" % (m["cluster"], *m["scale"]) for m in marks)
+        assert dbg[f].endswith(want) or not want
+        markers_seen += marks.shape[0]
+    assert markers_seen > 0
+
+
 def test_harness_config_error_is_an_exception_not_exit0(built):
     exe = ROOT / "harness" / "mov_harness"
     res = subprocess.run([str(exe), "/nonexistent.txt", "1", "1", "1"], capture_output=True, text=True, timeout=60)
