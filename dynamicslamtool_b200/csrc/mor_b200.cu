@@ -217,19 +217,24 @@ int build_grid(mor_handle* h) {
     const double fx = std::floor(((double)c.trim_x - g.ox) / hcell) + 1, fy = std::floor(((double)c.trim_y - g.oy) / hcell) + 1, fz = std::floor((zhi - g.oz) / hcell) + 1;
     if (fx < 1 || fy < 1 || fz < 1) return MOR_ERR_CONFIG_VALUE;
     h->cell_h = hcell;
-    // Dense cell table. Up to static_cap cells (default 2^27 = 2 x 512 MB of tables; the scan then costs ~0.3 ms per
-    // frame) the grid covers the config crop box and is known at create time. Beyond that (e.g. trimming "disabled"
-    // with huge values) the grid is laid over the bounding box of each frame's cloud instead (k_keys), with at most
-    // 2^24 cells; a frame whose box still needs more is rejected with MOR_ERR_CAPACITY.
+    // Dense cell table, three regimes by the number of cells the config crop box needs:
+    //  * up to 2^22: the grid covers the crop box and is fixed at create time (scanning it costs ~10 us per frame);
+    //  * up to static_cap (mor_limits.max_cells, default 2^27 = 2 x 512 MB of tables): tables for the whole box are
+    //    allocated, but each frame's grid is laid over the bounding box of its cloud (k_keys), so the scan pays for
+    //    the occupied extent only - a small radius over a large box, or the voxel modes' uncropped z slab;
+    //  * beyond (e.g. trimming "disabled" with huge values): per-frame bounding-box grid in tables of 2^24 cells (or
+    //    mor_limits.max_cells); a frame whose box needs more is rejected with MOR_ERR_CAPACITY.
+    const double need = fx * fy * fz;
     const double static_cap = h->static_cell_cap ? (double)h->static_cell_cap : 134217728.0;
-    if (fx * fy * fz > static_cap) {
-        h->dynamic_grid = true;
-        h->max_cells = 1 << 24;
-        g.nx = g.ny = g.nz = kGridPad + 1; g.ncells = h->max_cells;
-    } else {
+    if (need <= 4194304.0) {
         h->dynamic_grid = false;
         g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
-        h->max_cells = g.ncells > (1 << 24) ? g.ncells : (1 << 24);
+        h->max_cells = 1 << 24;  // the voxel modes' ball-query grid shares the tables
+    } else {
+        h->dynamic_grid = true;
+        if (need <= static_cap) h->max_cells = need > 16777216.0 ? (int)need : (1 << 24);
+        else h->max_cells = h->static_cell_cap ? (int)h->static_cell_cap : (1 << 24);
+        g.nx = g.ny = g.nz = kGridPad + 1; g.ncells = h->max_cells;
     }
     h->grid = g;
     h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / hcell);

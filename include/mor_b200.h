@@ -60,8 +60,10 @@ typedef struct mor_limits {
     uint32_t max_points;    /* largest frame accepted (default 300000) */
     uint32_t max_clusters;  /* largest number of size-valid clusters per frame (default 8192, at most 16384) */
     uint32_t max_moving;    /* capacity of the confirmed-moving list mo_vec (default 1024) */
-    uint32_t max_cells;     /* largest dense cell table laid over the config crop box (default 2^27 cells = 1 GB of
-                               tables); above it the grid follows each frame's bounding box (at most 2^24 cells) */
+    uint32_t max_cells;     /* largest dense cell table (default 2^27 cells = 1 GB). A crop box that needs up to 2^22 cells
+                               gets a fixed grid; up to max_cells the tables cover the box and each frame's grid follows
+                               the bounding box of its cloud; a box that needs more gets bounding-box grids in tables of
+                               max_cells (default then 2^24) cells, and a frame that does not fit is MOR_ERR_CAPACITY */
     uint32_t reserved[4];
 } mor_limits;
 
