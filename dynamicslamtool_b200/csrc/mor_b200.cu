@@ -364,15 +364,15 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         const GroundPtrs& g = h->ground;
         FramePtrs ag = a;
         ag.dgrid = g.ggrid;  // the cell scan of this stage runs over the ball-query grid
-        MOR_LAUNCH(KID_G_INGEST, (k_ingest_raw<<<gb, kBlock, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_KEYS, (k_ground_keys<<<gb, kBlock, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_SCAN_CELLS, (k_scan_cells<<<h->num_sms * 8, kBlock, 0, st>>>(ag)));
-        MOR_LAUNCH(KID_G_SCAN_VOX, (k_scan_voxels<<<h->num_sms * 8, kBlock, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_SCATTER, (k_ground_scatter<<<gb, kBlock, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_EVAL, (k_voxel_eval<<<gb * 32, kBlock, 0, st>>>(a, g)));  // one warp per voxel, V <= n
-        MOR_LAUNCH(KID_G_MODE, (k_ground_mode<<<1, kSingle, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_MARK, (k_ground_mark<<<gb * 32, kBlock, 0, st>>>(a, g)));
-        MOR_LAUNCH(KID_G_PARTITION, (k_ground_partition<<<gb, kBlock, 0, st>>>(a, g)));
+        MOR_KLAUNCH(KID_G_INGEST, k_ingest_raw, gb, kBlock, 0, a, g);
+        MOR_KLAUNCH(KID_G_KEYS, k_ground_keys, gb, kBlock, 0, a, g);
+        MOR_KLAUNCH(KID_SCAN_CELLS, k_scan_cells, h->num_sms * 8, kBlock, 0, ag);
+        MOR_KLAUNCH(KID_G_SCAN_VOX, k_scan_voxels, h->num_sms * 8, kBlock, 0, a, g);
+        MOR_KLAUNCH(KID_G_SCATTER, k_ground_scatter, gb, kBlock, 0, a, g);
+        MOR_KLAUNCH(KID_G_EVAL, k_voxel_eval, h->num_sms * 8, kBlock, 0, a, g);  // warps stride over the voxels
+        MOR_KLAUNCH(KID_G_MODE, k_ground_mode, 1, kSingle, 0, a, g);
+        MOR_KLAUNCH(KID_G_MARK, k_ground_mark, h->num_sms * 8, kBlock, 0, a, g);
+        MOR_KLAUNCH(KID_G_PARTITION, k_ground_partition, gb, kBlock, 0, a, g);
     } else {
         MOR_KLAUNCH(KID_INGEST, k_ingest, n ? (n + kIngestTile - 1) / kIngestTile : 1, kBlock, 0, a);
     }

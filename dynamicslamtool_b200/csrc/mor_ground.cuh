@@ -39,6 +39,7 @@ struct GroundPtrs {
 // fromPCLPointCloud2 + PassThrough x,y (cpp:94-102): stable compaction of the in-range points into
 // raw_cloud, bounding box of raw_cloud, resets of the per-frame ground state.
 __global__ void __launch_bounds__(kBlock) k_ingest_raw(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
     __syncthreads();
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kBlock) k_ingest_raw(FramePtrs a, GroundPtrs g
 // Ball-query grid (cell edge leaf*(1+2^-10) over the raw bounding box) and VoxelGrid index of every raw
 // point; both histograms. Every block derives the two descriptors from the reduced box.
 __global__ void __launch_bounds__(kBlock) k_ground_keys(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
     __shared__ GridDesc s_g;
     __shared__ VoxDesc s_v;
     const int nraw = a.counts[MOR_CNT_NT];
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(kBlock) k_ground_keys(FramePtrs a, GroundPtrs 
 // Occupancy scan of the voxel histogram: ordinal of every occupied voxel in ascending voxel index (the
 // order pcl::VoxelGrid emits its centroids in), point count per ordinal, total number of voxels.
 __global__ void __launch_bounds__(kBlock) k_scan_voxels(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
     __shared__ int s_tile;
     const int ncells = gp.vdesc->ncells;
     const int ntiles = (ncells + kTile - 1) / kTile;
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_voxels(FramePtrs a, GroundPtrs 
 // ===================================================================================== G4
 // Raw points into ball-grid order; exact fixed-point coordinate sums per voxel.
 __global__ void __launch_bounds__(kBlock) k_ground_scatter(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
     const int r = blockIdx.x * kBlock + threadIdx.x;
     const int nraw = a.counts[MOR_CNT_NT];
     if ((r & ~31) >= nraw) return;  // whole warps stay for the group reductions
@@ -288,11 +292,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // ===================================================================================== G5
 // One warp per voxel: centroid, ball statistics (moments of d = p - q in double), acceptance test, bin.
-__global__ void __launch_bounds__(kBlock) k_voxel_eval(FramePtrs a, GroundPtrs gp) {
-    const int v = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (v >= gp.gstate[1]) return;
-    const GridDesc g = *gp.ggrid;
+__device__ __forceinline__ void voxel_eval_one(const FramePtrs& a, const GroundPtrs& gp, const GridDesc& g, const int v, const int lane) {
     const double nv = (double)gp.vox_n[v];
     const unsigned long long* acc = gp.vacc + (size_t)v * 6;
     const float qx = (float)join_fixed_mean((long long)acc[0], (long long)acc[1], nv);
@@ -339,11 +339,21 @@ __global__ void __launch_bounds__(kBlock) k_voxel_eval(FramePtrs a, GroundPtrs g
     }
     info[3] = acc_flag; info[4] = keyf; info[5] = n0; info[6] = n1; info[7] = n2;
 }
+// The number of voxels is only known on the device (and is far below the number of points): a fixed grid of warps
+// strides over them instead of launching one warp per point's worth of blocks that would mostly exit.
+__global__ void __launch_bounds__(kBlock) k_voxel_eval(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
+    const int lane = threadIdx.x & 31;
+    const int nvox = gp.gstate[1], warps = (gridDim.x * kBlock) >> 5;
+    const GridDesc g = *gp.ggrid;
+    for (int v = (blockIdx.x * kBlock + threadIdx.x) >> 5; v < nvox; v += warps) voxel_eval_one(a, gp, g, v, lane);
+}
 
 // ===================================================================================== G6
 // Mode bin (cpp:169-178, tie => smallest key) and the selection threshold; resets the look-back state that the
 // clustering stage reuses.
 __global__ void __launch_bounds__(kSingle) k_ground_mode(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
     __shared__ unsigned long long s_best[kSingle / 32];
     const bool ascending = !(gp.mode == MOR_GROUND_VOXEL_COV && gp.bin_gap < 0.f);
     unsigned long long best = 0ull;  // (count << 32) | (65535 - rank-of-key): max => largest count, then smallest key
@@ -374,22 +384,26 @@ __global__ void __launch_bounds__(kSingle) k_ground_mode(FramePtrs a, GroundPtrs
 // ===================================================================================== G7
 // ground = union of the balls of the accepted voxels in the selected bins (cpp:184-191).
 __global__ void __launch_bounds__(kBlock) k_ground_mark(FramePtrs a, GroundPtrs gp) {
-    const int v = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
-    if (v >= gp.gstate[1]) return;
-    const float* info = gp.vox_info + (size_t)v * 8;
-    if (info[3] == 0.f || gp.gstate[2] < 0) return;
-    const int k = (int)info[4] + 32768;
-    const bool take = gp.mode == MOR_GROUND_VOXEL_EIGEN ? gp.bin_hist[k] >= gp.gstate[3] : k == gp.gstate[2];
-    if (!take) return;
+    const int nvox = gp.gstate[1], warps = (gridDim.x * kBlock) >> 5;
+    if (gp.gstate[2] < 0) return;
     const GridDesc g = *gp.ggrid;
-    for_each_in_ball_warp(a, gp, g, info[0], info[1], info[2], lane, [&](const float4& p) { gp.is_ground[__float_as_int(p.w)] = 1; });
+    for (int v = (blockIdx.x * kBlock + threadIdx.x) >> 5; v < nvox; v += warps) {
+        const float* info = gp.vox_info + (size_t)v * 8;
+        if (info[3] == 0.f) continue;
+        const int k = (int)info[4] + 32768;
+        const bool take = gp.mode == MOR_GROUND_VOXEL_EIGEN ? gp.bin_hist[k] >= gp.gstate[3] : k == gp.gstate[2];
+        if (!take) continue;
+        for_each_in_ball_warp(a, gp, g, info[0], info[1], info[2], lane, [&](const float4& p) { gp.is_ground[__float_as_int(p.w)] = 1; });
+    }
 }
 
 // ===================================================================================== G8
 // ExtractIndices(negative) (cpp:194-198): stable partition of raw_cloud into cloud / gp_indices, fused with
 // the clustering-grid key + histogram (static grid) or the cloud bounding box (dynamic grid).
 __global__ void __launch_bounds__(kBlock) k_ground_partition(FramePtrs a, GroundPtrs gp) {
+    pdl_prologue();
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
     __syncthreads();
