@@ -394,7 +394,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         MOR_KLAUNCH(KID_SCAN_CELLS, k_scan_cells, scan_blocks, kBlock, 0, a);
     }
     MOR_KLAUNCH(KID_SCATTER, k_scatter, gb, kBlock, 0, a);
-    MOR_KLAUNCH(KID_NEIGHBORS, k_link_cells, dim3(gb, 18), kBlock, 0, a);  // near pass (5 rows) + far pass (13 rows)
+    MOR_KLAUNCH(KID_NEIGHBORS, k_link_cells, dim3((n + kLinkBlock - 1) / kLinkBlock + (n ? 0 : 1), 18), kLinkBlock, 0, a);  // near pass (5 rows) + far pass (13 rows)
     const unsigned g1k = n ? (n + kSingle - 1) / kSingle : 1;
     MOR_KLAUNCH(KID_FLATTEN, k_flatten, g1k, kSingle, h->select_smem, a);  // + cluster selection in its last block
     if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));  // k_cluster_stats' last block runs the correspondences
@@ -693,7 +693,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
         launch_pdl(k_scan_cells_batch, dim3(scan_blocks, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
     }
     launch_pdl(k_scatter_batch, dim3(gb, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
-    launch_pdl(k_link_cells_batch, dim3(gb, 18, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+    launch_pdl(k_link_cells_batch, dim3((n_max + kLinkBlockBatch - 1) / kLinkBlockBatch + (n_max ? 0 : 1), 18, S), dim3(kLinkBlockBatch), 0, st, (const FramePtrs*)dp);
     launch_pdl(k_flatten_batch, dim3(g1k, 1, S), dim3(kSingle), h->select_smem, st, (const FramePtrs*)dp);
     if (two) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     launch_pdl(k_cluster_stats_batch, dim3(g1k, 1, S), dim3(kStatBlock), 0, st, (const FramePtrs*)dp);

@@ -6,6 +6,9 @@
 // NAME_batch(const FramePtrs*) for S sequences in one launch (blockIdx.z selects the sequence; the per-sequence
 // state - scratch, tickets, tables - is disjoint, so the bodies are identical).
 #pragma once
+#ifndef LINK_BLOCK_SINGLE
+#define LINK_BLOCK_SINGLE 128
+#endif
 #include "mor_device.cuh"
 #include "../../include/mor_b200.h"
 
@@ -448,10 +451,14 @@ __device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4
 // Neighbour rows are addressed linearly from the point's own key (key + dy*nx + dz*nx*ny +- 2): the grid carries
 // kGridPad empty cells on the low side of every axis, so a backward offset never leaves the table and an offset
 // that runs over the high end of a row / layer lands in the next row's / layer's padding, which is always empty.
-template <int PHASE>
+// Block size: at 32 registers an SM holds 64 warps either way; one sequence alone is a latency chain in which a
+// block should retire as soon as its slowest warp does (small blocks), a batch of sequences keeps the SMs full and
+// pays per block (large blocks).
+constexpr int kLinkBlock = LINK_BLOCK_SINGLE, kLinkBlockBatch = 256;
+template <int PHASE, int BLOCK>
 __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a, int row_index) {
     pdl_prologue();
-    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int s = blockIdx.x * BLOCK + threadIdx.x;
     const int nc = a.counts[MOR_CNT_NC];
     if (s >= nc) return;
     // canonical row ids (they fix the bit layout): 0-4: dz=-2, 5-9: dz=-1, 10-12: dz=0 with dy=-2,-1,0
@@ -482,11 +489,11 @@ __device__ __forceinline__ void k_link_cells_body(const FramePtrs& a, int row_in
 // near rows start first and most of their unions are in place when the far rows run their root checks; the two
 // passes' tails overlap instead of adding up (the far pass is correct with any amount of near-pass progress: its
 // root check is only a shortcut).
-__global__ void __launch_bounds__(kBlock) k_link_cells(FramePtrs a) {
-    if (blockIdx.y < 5) k_link_cells_body<1>(a, blockIdx.y); else k_link_cells_body<2>(a, blockIdx.y - 5);
+__global__ void __launch_bounds__(kLinkBlock, 2048 / kLinkBlock) k_link_cells(FramePtrs a) {
+    if (blockIdx.y < 5) k_link_cells_body<1, kLinkBlock>(a, blockIdx.y); else k_link_cells_body<2, kLinkBlock>(a, blockIdx.y - 5);
 }
-__global__ void __launch_bounds__(kBlock) k_link_cells_batch(const FramePtrs* __restrict__ P) {
-    if (blockIdx.y < 5) k_link_cells_body<1>(P[blockIdx.z], blockIdx.y); else k_link_cells_body<2>(P[blockIdx.z], blockIdx.y - 5);
+__global__ void __launch_bounds__(kLinkBlockBatch, 2048 / kLinkBlockBatch) k_link_cells_batch(const FramePtrs* __restrict__ P) {
+    if (blockIdx.y < 5) k_link_cells_body<1, kLinkBlockBatch>(P[blockIdx.z], blockIdx.y); else k_link_cells_body<2, kLinkBlockBatch>(P[blockIdx.z], blockIdx.y - 5);
 }
 
 // ===================================================================================== K5
