@@ -328,7 +328,7 @@ __device__ __forceinline__ void k_scan_cells_body(const FramePtrs& a) {
     }
 }
 __global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) { k_scan_cells_body(a); }
-__global__ void __launch_bounds__(kBlock) k_scan_cells_batch(const FramePtrs* __restrict__ P) { k_scan_cells_body(P[blockIdx.z]); }
+__global__ void __launch_bounds__(kBlock, 8) k_scan_cells_batch(const FramePtrs* __restrict__ P) { k_scan_cells_body(P[blockIdx.z]); }
 
 
 // ===================================================================================== K3
@@ -749,7 +749,7 @@ __device__ __forceinline__ void k_cluster_stats_body(const FramePtrs& a) {
     }
 }
 __global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) { k_cluster_stats_body(a); }
-__global__ void __launch_bounds__(kStatBlock) k_cluster_stats_batch(const FramePtrs* __restrict__ P) { k_cluster_stats_body(P[blockIdx.z]); }
+__global__ void __launch_bounds__(kStatBlock, 2) k_cluster_stats_batch(const FramePtrs* __restrict__ P) { k_cluster_stats_body(P[blockIdx.z]); }
 
 
 // ===================================================================================== K8
@@ -961,7 +961,7 @@ __device__ __forceinline__ void k_lattice_count_body(const FramePtrs& a) {
     moving_test_epilogue(a);
 }
 __global__ void __launch_bounds__(kSingle) k_lattice_count(FramePtrs a) { k_lattice_count_body(a); }
-__global__ void __launch_bounds__(kSingle) k_lattice_count_batch(const FramePtrs* __restrict__ P) { k_lattice_count_body(P[blockIdx.z]); }
+__global__ void __launch_bounds__(kSingle, 2) k_lattice_count_batch(const FramePtrs* __restrict__ P) { k_lattice_count_body(P[blockIdx.z]); }
 
 
 // ===================================================================================== K10' (method 1)
@@ -1278,7 +1278,7 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
     }
 }
 __global__ void __launch_bounds__(kBlock) k_filter_output(FramePtrs a) { k_filter_output_body(a); }
-__global__ void __launch_bounds__(kBlock) k_filter_output_batch(const FramePtrs* __restrict__ P) { k_filter_output_body(P[blockIdx.z]); }
+__global__ void __launch_bounds__(kBlock, 8) k_filter_output_batch(const FramePtrs* __restrict__ P) { k_filter_output_body(P[blockIdx.z]); }
 
 
 }  // namespace mor
