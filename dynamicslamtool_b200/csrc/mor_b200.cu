@@ -374,7 +374,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
         MOR_KLAUNCH(KID_G_MARK, k_ground_mark, h->num_sms * 8, kBlock, 0, a, g);
         MOR_KLAUNCH(KID_G_PARTITION, k_ground_partition, gb, kBlock, 0, a, g);
     } else {
-        MOR_KLAUNCH(KID_INGEST, k_ingest, n ? (n + kIngestTile - 1) / kIngestTile : 1, kBlock, 0, a);
+        MOR_KLAUNCH(KID_INGEST, k_ingest, n ? (n + kIngestTile - 1) / kIngestTile : 1, kIngestBlock, 0, a);
     }
     // The transform of the previous frame's clusters needs only the previous frame, the pose delta and the neutral
     // boxes written by the ingest kernel: it runs on a side stream beside the clustering chain and is joined before
@@ -470,7 +470,7 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     else a.out = h->base.out;
     if (on_device && out && cap_points < h->n_input) { h->last_error = "device output buffer must hold n_input points"; return MOR_ERR_CAPACITY; }
     a.mo_parity = h->mo_parity;
-    MOR_KLAUNCH(KID_OUTPUT, k_filter_output, h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kBlock, 0, a);
+    MOR_KLAUNCH(KID_OUTPUT, k_filter_output, h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kOutBlock, 0, a);
     h->mo_parity ^= 1;  // the kernel wrote the updated mo_vec into the other half
     a.mo_parity = h->mo_parity;
     MOR_CUDA(cudaGetLastError());
@@ -678,7 +678,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
     MOR_CUDA(cudaEventRecord(h->batch_ev[slot], st));
     const bool two = h->two_frames;
     const unsigned gb = blocks_for(n_max), g1k = n_max ? (n_max + kSingle - 1) / kSingle : 1;
-    launch_pdl(k_ingest_batch, dim3(n_max ? (n_max + kIngestTile - 1) / kIngestTile : 1, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+    launch_pdl(k_ingest_batch, dim3(n_max ? (n_max + kIngestTile - 1) / kIngestTile : 1, 1, S), dim3(kIngestBlock), 0, st, (const FramePtrs*)dp);
     if (two) {  // the transform of the previous clusters runs beside the clustering chain (see enqueue_push)
         MOR_CUDA(cudaEventRecord(h->ev_fork, st));
         MOR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
@@ -708,7 +708,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
             h->launches += 2;
         }
     }
-    launch_pdl(k_filter_output_batch, dim3(n_max ? (n_max + kOutTile - 1) / kOutTile : 1, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+    launch_pdl(k_filter_output_batch, dim3(n_max ? (n_max + kOutTile - 1) / kOutTile : 1, 1, S), dim3(kOutBlock), 0, st, (const FramePtrs*)dp);
     h->launches += 1;
     MOR_CUDA(cudaGetLastError());
     for (uint32_t s = 0; s < S; s++) {

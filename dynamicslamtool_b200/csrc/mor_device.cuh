@@ -172,9 +172,9 @@ __device__ __forceinline__ unsigned long long tile_exclusive_prefix(unsigned lon
 
 // Block-wide exclusive scan of one value per thread (kBlock threads). Returns exclusive prefix within
 // the block; *total (valid in all threads) = block sum.
-template <typename T>
+template <typename T, int BLOCK = kBlock>
 __device__ __forceinline__ T block_exclusive_scan(T v, T* total) {
-    __shared__ T s_warp[kBlock / 32];
+    __shared__ T s_warp[BLOCK / 32];
     __shared__ T s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T inc = v;

@@ -99,8 +99,12 @@ struct FramePtrs {
 // (cpp:78-86, A2), fused with the stable two-way partition into `cloud` / gp_indices order, the grid
 // cell key of every cloud point and the per-cell histogram. kIngestItems consecutive points per thread
 // (tile = 1024 points): the decoupled look-back chain has n/1024 links instead of n/256.
-constexpr int kIngestItems = 4;
-constexpr int kIngestTile = kBlock * kIngestItems;
+#ifndef INGEST_BLOCK
+#define INGEST_BLOCK 256
+#endif
+constexpr int kIngestBlock = INGEST_BLOCK;
+constexpr int kIngestTile = 1024;
+constexpr int kIngestItems = kIngestTile / kIngestBlock;
 
 __device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
     pdl_prologue();
@@ -109,7 +113,7 @@ __device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
     if (a.two_frames) {
         // housekeeping for the two-frame stages, spread over the grid and overlapped with the ticket's round
         // trip: empty octree-lattice hash set, neutral bounding boxes for the transformed previous clusters
-        const uint32_t gtid = blockIdx.x * kBlock + threadIdx.x, stride = gridDim.x * kBlock;
+        const uint32_t gtid = blockIdx.x * kIngestBlock + threadIdx.x, stride = gridDim.x * kIngestBlock;
         if (a.method == 2) {
             uint4* lat = reinterpret_cast<uint4*>(a.lattice);
             for (uint32_t t = gtid; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -154,7 +158,7 @@ __device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
         }
     }
     unsigned long long total;
-    const unsigned long long in_block = block_exclusive_scan<unsigned long long>(packed, &total);
+    const unsigned long long in_block = block_exclusive_scan<unsigned long long, kIngestBlock>(packed, &total);
     const unsigned long long before = tile_exclusive_prefix(a.st_ingest, tile, total);
     unsigned long long mine = before + in_block;
 #pragma unroll
@@ -212,8 +216,8 @@ __device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
         a.track->frames += 1;
     }
 }
-__global__ void __launch_bounds__(kBlock) k_ingest(FramePtrs a) { k_ingest_body(a); }
-__global__ void __launch_bounds__(kBlock) k_ingest_batch(const FramePtrs* __restrict__ P) { k_ingest_body(P[blockIdx.z]); }
+__global__ void __launch_bounds__(kIngestBlock) k_ingest(FramePtrs a) { k_ingest_body(a); }
+__global__ void __launch_bounds__(kIngestBlock) k_ingest_batch(const FramePtrs* __restrict__ P) { k_ingest_body(P[blockIdx.z]); }
 
 
 // ===================================================================================== K1b (dynamic grid only)
@@ -1152,8 +1156,12 @@ __device__ void chain_block(const FramePtrs& a) {
 //  Output part: ExtractIndices(negative) of the moving points + append of the ground points (cpp:673-684),
 //  written as pcl::PointXYZI wire records (cpp:690); stable single-pass compaction over [cloud | ground],
 //  kOutItems consecutive points per thread.
-constexpr int kOutItems = 4;
-constexpr int kOutTile = kBlock * kOutItems;
+#ifndef OUT_BLOCK
+#define OUT_BLOCK 256
+#endif
+constexpr int kOutBlock = OUT_BLOCK;
+constexpr int kOutTile = 1024;
+constexpr int kOutItems = kOutTile / kOutBlock;
 constexpr int kRemovedBits = 16384;  // = max kmax
 
 __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
@@ -1170,12 +1178,12 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
     float* mo_c_out = a.mo_centroid + (size_t)(mo_parity ^ 1) * a.momax * 3;
     int* mo_f_out = a.mo_conf + (size_t)(mo_parity ^ 1) * a.momax;
     if (threadIdx.x == 0) { s_tile = atomicAdd(&a.scratch->ticket_out, 1); s_total = 0; s_keep_base = 0; }
-    for (int t = threadIdx.x; t < (K + 31) / 32; t += kBlock) s_removed[t] = 0u;
+    for (int t = threadIdx.x; t < (K + 31) / 32; t += kOutBlock) s_removed[t] = 0u;
     __syncthreads();
     const int tile = s_tile;
     const bool writer = tile == 0;  // the first block to start also owns the mo_vec update
     // ---- tracking (redundant in every block; K == 0: un-built kd-tree in the reference (UB) -> entries untouched)
-    for (int base = 0; base < n_mo && K > 0; base += kBlock) {
+    for (int base = 0; base < n_mo && K > 0; base += kOutBlock) {
         const int t = base + threadIdx.x;
         bool keep = false;
         float cx = 0, cy = 0, cz = 0; int conf = 0;
@@ -1198,7 +1206,7 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
         }
         if (writer) {  // ordered erase (cpp:655-660): survivors keep their relative order
             int tot;
-            const int r = block_exclusive_scan<int>(keep ? 1 : 0, &tot);
+            const int r = block_exclusive_scan<int, kOutBlock>(keep ? 1 : 0, &tot);
             if (keep) {
                 const int o = s_keep_base + r;
                 mo_c_out[o * 3] = cx; mo_c_out[o * 3 + 1] = cy; mo_c_out[o * 3 + 2] = cz;
@@ -1213,12 +1221,12 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
     const int overflow = s_total > nc ? 1 : 0;  // ExtractIndices: more indices than points => error, empty output (A18)
     if (writer) {
         if (K == 0) {  // entries untouched: copy through
-            for (int t = threadIdx.x; t < n_mo; t += kBlock) {
+            for (int t = threadIdx.x; t < n_mo; t += kOutBlock) {
                 mo_c_out[t * 3] = mo_c_in[t * 3]; mo_c_out[t * 3 + 1] = mo_c_in[t * 3 + 1]; mo_c_out[t * 3 + 2] = mo_c_in[t * 3 + 2];
                 mo_f_out[t] = mo_f_in[t];
             }
         }
-        for (int k = threadIdx.x; k < K; k += kBlock) a.cluster_removed[k] = (s_removed[k >> 5] >> (k & 31)) & 1u;
+        for (int k = threadIdx.x; k < K; k += kOutBlock) a.cluster_removed[k] = (s_removed[k >> 5] >> (k & 31)) & 1u;
         if (threadIdx.x == 0) {
             const int kept = K > 0 ? s_keep_base : n_mo;
             ts->n_mo[mo_parity ^ 1] = kept;  // the host flips the parity after this launch
@@ -1254,7 +1262,7 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
         nkeep += keep[k] ? 1 : 0;
     }
     int tot;
-    const int in_block = block_exclusive_scan<int>(nkeep, &tot);
+    const int in_block = block_exclusive_scan<int, kOutBlock>(nkeep, &tot);
     const int before = (int)tile_exclusive_prefix(a.st_out, tile, (unsigned long long)tot);
     int o = before + in_block;
 #pragma unroll
@@ -1273,12 +1281,12 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
     if (threadIdx.x == 0) s_last = atomicAdd(&a.scratch->out_blocks_done, 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (s_last) {
-        for (int t = threadIdx.x; t < a.tiles_pts; t += kBlock) a.st_out[t] = 0ull;
+        for (int t = threadIdx.x; t < a.tiles_pts; t += kOutBlock) a.st_out[t] = 0ull;
         if (threadIdx.x == 0) { a.scratch->ticket_out = 0; a.scratch->out_blocks_done = 0; }
     }
 }
-__global__ void __launch_bounds__(kBlock) k_filter_output(FramePtrs a) { k_filter_output_body(a); }
-__global__ void __launch_bounds__(kBlock, 8) k_filter_output_batch(const FramePtrs* __restrict__ P) { k_filter_output_body(P[blockIdx.z]); }
+__global__ void __launch_bounds__(kOutBlock) k_filter_output(FramePtrs a) { k_filter_output_body(a); }
+__global__ void __launch_bounds__(kOutBlock, 2048 / kOutBlock) k_filter_output_batch(const FramePtrs* __restrict__ P) { k_filter_output_body(P[blockIdx.z]); }
 
 
 }  // namespace mor
