@@ -551,9 +551,9 @@ int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, co
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-    if (e != cudaSuccess) { delete h; return MOR_ERR_CUDA; }
+    if (e != cudaSuccess) { cudaGetLastError(); mor_destroy(h); return MOR_ERR_CUDA; }  // mor_destroy releases whatever exists
     st = allocate(h);
-    if (st != MOR_OK) { if (h->arena) cudaFree(h->arena); cudaStreamDestroy(h->stream); delete h; return st; }
+    if (st != MOR_OK) { cudaGetLastError(); mor_destroy(h); return st; }
     fill_static(h);
     {
         int sms = 0;
