@@ -1,5 +1,5 @@
 """Small driver for ncu captures and per-kernel timing experiments (not part of the product).
-usage: prof_run.py [config] [scenario] [frames] [--profile]"""
+usage: prof_run.py [config] [scenario] [frames] [--profile] [--debug]   (--debug also fetches the VISUALIZE outputs)"""
 import sys, numpy as np
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -14,7 +14,10 @@ frames = [s.frame(f) for f in range(nfr)]
 if '--profile' in sys.argv:
     m.set_kernel_profiling(True)
 for pts, pose in frames:
-    m.push_raw_cloud_and_pose(pts, pose); out = m.filter_cloud()
+    m.push_raw_cloud_and_pose(pts, pose)
+    if '--debug' in sys.argv: m.cluster_collection()
+    out = m.filter_cloud()
+    if '--debug' in sys.argv: m.moving_markers()
 print(m.counts())
 if '--profile' in sys.argv:
     for k, (ms, n) in m.kernel_profile().items():
