@@ -12,7 +12,9 @@
 // restatement of src/MovingObjectRemoval.cpp that encodes the third-party semantics listed
 // as A1..A18 in SURVEY.md §8c (PCL 1.8 / FLANN / tf source knowledge). Each function cites
 // the reference file:line it follows. Cross-checks that ARE available offline
-// (scipy cKDTree + connected_components, brute force) live in tests/test_oracle_*.py.
+// (scipy cKDTree + connected_components, brute force) live in tests/test_oracle_*.py; the check
+// against a real PCL installation is oracle/pcl_probe/ (one probe per assumption; needs PCL, so it
+// has never been run from this repository).
 //
 // Build: g++ -O2 -ffp-contract=off (no -march=native: FMA contraction would break the float
 // bit-parity with a default x86-64 PCL/FLANN build). Single-threaded like the reference.
