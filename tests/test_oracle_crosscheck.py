@@ -274,3 +274,31 @@ def test_cluster_collection_markers_and_reset(oracle, tmp_path):
         m.filter_cloud()
         sig2.append((m.counts()["NMO"], m.tap("removed_mask").tobytes()))
     assert sig2 == sig
+
+
+# ------------------------------------------------------------------ order independence
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_partition_and_output_do_not_depend_on_point_order(oracle, tmp_path, seed):
+    """EuclideanClusterExtraction grows whole components before the size test (A5), so the partition of the cloud into
+    clusters - and with it the set of removed points - cannot depend on the order of the points in the message. Labels
+    (minimum index) and the order inside clusters do; the sets must not."""
+    rng = np.random.default_rng(seed)
+    kw = dict(ec_distance_threshold=0.3, min_cluster_size=40, max_cluster_size=5000, **OPEN_CFG)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    a, b = make(oracle, tmp_path / "a", **kw), make(oracle, tmp_path / "b", **kw)
+    static = [blob(rng, (rng.uniform(-8, 8), rng.uniform(-8, 8), 0), int(rng.integers(60, 300)), 0.15) for _ in range(4)]
+    mover = blob(rng, (0, -5, 0), 250, 0.12)
+    small = blob(rng, (6, 6, 2), 20, 0.05)                      # below min_cluster_size
+    for f in range(8):
+        pts = with_intensity(np.concatenate(static + [mover + np.float32([0.13 * f, 0, 0]), small]))
+        perm = rng.permutation(len(pts))
+        a.push_raw_cloud_and_pose(pts, IDENTITY_POSE)
+        b.push_raw_cloud_and_pose(pts[perm], IDENTITY_POSE)
+        ca, cb = a.tap("cluster_id"), b.tap("cluster_id")
+        sets_a = {frozenset(np.flatnonzero(ca == k).tolist()) for k in range(a.counts()["K"])}
+        sets_b = {frozenset(perm[np.flatnonzero(cb == k)].tolist()) for k in range(b.counts()["K"])}
+        assert sets_a == sets_b and a.counts()["K"] == 5
+        oa, ob = a.filter_cloud().copy(), b.filter_cloud().copy()
+        assert sorted(map(bytes, oa)) == sorted(map(bytes, ob))
+        assert a.counts()["NMO"] == b.counts()["NMO"]
+    assert a.counts()["NMO"] == 1
