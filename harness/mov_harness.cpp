@@ -9,6 +9,7 @@
 //   mov_harness <MOR_config.txt> --replay <dir> [frames] [n_bad=4] [n_good=3] [--quiet] [--out <dir>]
 //       (either form: --debug also fetches the VISUALIZE debug cloud and bounding-box markers of every frame)
 //       recorded data: KITTI-style .bin clouds + poses.txt (+ calib.txt), see replay_io.h; --out writes the filtered clouds
+//   mov_harness --inspect <dir>                 the frames and poses --replay would feed (host only)
 //   mov_harness --pose-of <12 numbers>          the pose7 the replay front end derives from a 3x4 matrix (host only)
 #include <malloc.h>
 
@@ -93,6 +94,19 @@ int main(int argc, char** argv) {
         double p7[7];
         replay::to_pose7(m, p7);
         std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p7[0], p7[1], p7[2], p7[3], p7[4], p7[5], p7[6]);
+        return 0;
+    }
+    if (argc >= 3 && !std::strcmp(argv[1], "--inspect")) {  // what --replay would feed, without touching a GPU
+        FrameSource src;
+        std::string err;
+        if (!src.open_replay(argv[2], err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
+        std::printf("frames %zu max_points %u\n", src.frames(), src.max_points);
+        pcl::PCLPointCloud2 cloud;
+        for (size_t f = 0; f < src.frames(); f++) {
+            double p7[7];
+            if (!src.frame((uint32_t)f, cloud, p7)) { std::fprintf(stderr, "frame %zu: cannot read the cloud\n", f); return 1; }
+            std::printf("frame %zu points %u pose %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", f, cloud.width, p7[0], p7[1], p7[2], p7[3], p7[4], p7[5], p7[6]);
+        }
         return 0;
     }
     if (argc < 4) { std::fprintf(stderr, "usage: %s <config> <scenario> <seed> <frames> [n_bad] [n_good] [--quiet]\n       %s <config> --replay <dir> [frames] [n_bad] [n_good] [--quiet] [--out <dir>]\n", argv[0], argv[0]); return 2; }

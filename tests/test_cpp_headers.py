@@ -35,3 +35,74 @@ def test_replay_front_end_pose_conversion(built):
         q = r.as_quat()
         assert min(np.abs(p[3:] - q).max(), np.abs(p[3:] + q).max()) < 1e-7
         assert abs(np.linalg.norm(p[3:]) - 1) < 1e-12
+
+
+def test_replay_front_end_reads_recorded_directories(built, tmp_path):
+    """CPU: the recorded-data front end (harness/replay_io.h) through `mov_harness --inspect`: .bin clouds in lexical
+    order (also under velodyne/), 7- / 8- / 12-column pose files, comments, calib.txt Tr, clouds without a pose
+    dropped, malformed inputs rejected."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    exe = ROOT / "harness" / "mov_harness"
+    subprocess.check_call(["make", "-C", str(ROOT / "harness")], stdout=subprocess.DEVNULL)
+    rng = np.random.default_rng(9)
+
+    def inspect(d):
+        return subprocess.run([str(exe), "--inspect", str(d)], capture_output=True, text=True, timeout=60)
+
+    def rows(res):
+        return [l.split() for l in res.stdout.splitlines() if l.startswith("frame ")]
+
+    sizes = [5, 11, 3, 8]
+    poses = [np.concatenate([rng.normal(size=3), Rotation.random(random_state=i).as_quat()]) for i in range(4)]
+    # 7 columns, clouds directly in the directory, one cloud more than poses
+    d = tmp_path / "seven"
+    d.mkdir()
+    for i, n in enumerate(sizes + [2]):
+        rng.normal(size=(n, 4)).astype(np.float32).tofile(d / f"{i:06d}.bin")
+    (d / "poses.txt").write_text("# comment\n" + "\n".join(" ".join(repr(float(v)) for v in p) for p in poses) + "\n")
+    res = inspect(d)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.splitlines()[0] == "frames 4 max_points 11"
+    got = rows(res)
+    assert [int(r[3]) for r in got] == sizes
+    assert np.array_equal(np.array([[float(v) for v in r[5:12]] for r in got]), np.array(poses))
+    # 8 columns (TUM), clouds under velodyne/
+    d = tmp_path / "tum"
+    (d / "velodyne").mkdir(parents=True)
+    for i, n in enumerate(sizes):
+        rng.normal(size=(n, 4)).astype(np.float32).tofile(d / "velodyne" / f"{i:06d}.bin")
+    (d / "poses.txt").write_text("\n".join(" ".join([repr(0.1 * i)] + [repr(float(v)) for v in p]) for i, p in enumerate(poses)) + "\n")
+    got = rows(inspect(d))
+    assert np.array_equal(np.array([[float(v) for v in r[5:12]] for r in got]), np.array(poses))
+    # 12 columns + calib: sensor pose = Tr^-1 P Tr
+    d = tmp_path / "kitti"
+    d.mkdir()
+    tr = np.eye(4)
+    tr[:3, :3] = Rotation.from_euler("xyz", [-90, 0, -90], degrees=True).as_matrix()
+    tr[:3, 3] = [0.1, -0.2, 0.3]
+    lines = []
+    for i, (n, p) in enumerate(zip(sizes, poses)):
+        rng.normal(size=(n, 4)).astype(np.float32).tofile(d / f"{i:06d}.bin")
+        m = np.eye(4)
+        m[:3, :3] = Rotation.from_quat(p[3:]).as_matrix()
+        m[:3, 3] = p[:3]
+        lines.append(" ".join(repr(float(v)) for v in (tr @ m @ np.linalg.inv(tr))[:3].reshape(-1)))
+    (d / "poses.txt").write_text("\n".join(lines) + "\n")
+    (d / "calib.txt").write_text("P0: 1 0 0 0 0 1 0 0 0 0 1 0\nTr: " + " ".join(repr(float(v)) for v in tr[:3].reshape(-1)) + "\n")
+    got = rows(inspect(d))
+    for r, p in zip(got, poses):
+        q = np.array([float(v) for v in r[5:12]])
+        assert np.allclose(q[:3], p[:3], atol=1e-9)
+        assert min(np.abs(q[3:] - p[3:]).max(), np.abs(q[3:] + p[3:]).max()) < 1e-9
+    # malformed: a pose line with 5 numbers; a cloud whose size is not a multiple of 16 bytes; an empty directory
+    (d / "poses.txt").write_text("1 2 3 4 5\n")
+    assert inspect(d).returncode != 0
+    d2 = tmp_path / "badbin"
+    d2.mkdir()
+    (d2 / "000000.bin").write_bytes(b"\0" * 20)
+    (d2 / "poses.txt").write_text("0 0 0 0 0 0 1\n")
+    assert inspect(d2).returncode != 0
+    d3 = tmp_path / "empty"
+    d3.mkdir()
+    assert inspect(d3).returncode != 0
