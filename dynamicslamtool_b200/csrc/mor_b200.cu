@@ -288,7 +288,7 @@ int allocate(mor_handle* h) {
             GroundPtrs& g = h->ground;
             const size_t vc = (size_t)h->max_cells;
             g.rpts = carve<float4>(p, N); g.rsrc = carve<int>(p, N); g.is_ground = carve<uint8_t>(p, N); g.vkey = carve<int>(p, N);
-            g.vox_count = carve<int>(p, vc + 1); g.vox_ord = carve<int>(p, vc + 1); g.tiles_vox = (int)(vc / kScanTile + 2);
+            g.vox_count = carve<int>(p, vc + 1); g.vox_ord = carve<int>(p, vc + 1); g.tiles_vox = (int)(vc / kTile + 2);  // k_scan_voxels pulls kTile-voxel tiles
             g.st_vox = carve<unsigned long long>(p, g.tiles_vox);
             g.vox_n = carve<int>(p, N); g.vacc = carve<unsigned long long>(p, N * 6); g.vox_info = carve<float>(p, N * 8);
             g.bin_hist = carve<int>(p, 65536); g.ggrid = carve<GridDesc>(p, 1); g.vdesc = carve<VoxDesc>(p, 1); g.gstate = carve<int>(p, 8);
@@ -687,7 +687,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
     }
     if (h->dynamic_grid) launch_pdl(k_keys_batch, dim3(gb, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
     {
-        const int tiles = (h->grid.ncells + kScanTile - 1) / kScanTile;
+        const int tiles = (h->grid.ncells + kScanTileBatch - 1) / kScanTileBatch;
         const int per_seq = h->num_sms * 8 / (int)S > 8 ? h->num_sms * 8 / (int)S : 8;
         const int scan_blocks = h->dynamic_grid ? per_seq : (tiles < per_seq ? tiles : per_seq);
         launch_pdl(k_scan_cells_batch, dim3(scan_blocks, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);

@@ -44,6 +44,7 @@ def test_sequence_parity(product, oracle, cfg_dir, tmp_path, scenario, cfg, fram
     (4, "MOR_config_terrain.txt", 6, {"ground_mode": 1, "gp_leaf": 0.5}),                  # literal voxel-covariance test, outdoor leaf
     (1, "MOR_config.txt", 8, {"ground_mode": 1}),                                          # literal mode with the reference defaults (leaf 0.1, bin_gap 10)
     (1, "MOR_config.txt", 6, {"ground_mode": 2, "gp_bin_width": 0.1}),
+    (4, "MOR_config_terrain.txt", 3, {"gp_leaf": 0.1}),                                    # a voxel grid of ~10 million cells (> 9000 scan tiles)
 ])
 def test_voxel_covariance_ground_modes(product, oracle, cfg_dir, tmp_path, scenario, base, frames, overrides):
     """Ground removal by voxel covariance (reference cpp:90-200, dead code there): parity against the oracle's repaired
