@@ -102,6 +102,8 @@ int mor_parse_config(const char* config_path, mor_config* out);
  * (the PCLPointCloud2 fields named x, y, z, intensity: pcl::fromPCLPointCloud2, cpp:523).
  * off_i == UINT32_MAX => no intensity field (intensity 0, as PCL does).
  * pose7 = position x,y,z then orientation x,y,z,w (geometry_msgs::Pose), doubles.
+ * n <= mor_limits.max_points, and n * point_step <= 32 B x max_points (the device staging buffer; records wider than
+ * 32 bytes need a proportionally larger max_points), else MOR_ERR_CAPACITY.
  * Asynchronous: returns after enqueueing the H2D copy and the kernels on the handle's stream. */
 int mor_push_raw_cloud_and_pose(mor_handle* h, const void* data, uint32_t n, uint32_t point_step,
                                 uint32_t off_x, uint32_t off_y, uint32_t off_z, uint32_t off_i,
