@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kCollBlock) k_cluster_collection(CollectionPtr
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) st_parent(a.turn + 1, tile + 1);
+    if (threadIdx.x == 0) { __threadfence(); st_parent(a.turn + 1, tile + 1); }  // release: cursors before the turn
     const int base = __shfl_sync(grp, slot >= 0 ? s_base[slot] + before_in_tile : 0, leader);
     if (k >= 0) {
         const float4 p = a.pts[c];
