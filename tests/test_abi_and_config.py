@@ -75,3 +75,36 @@ def test_product_fails_loudly_without_a_device(product):
     h = C.c_void_p()
     st = product.create_ex(str(DEFAULT_CFG).encode(), 4, 3, 0, None, C.byref(h))
     assert st == 7 and not h.value
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_config_parser_differential_fuzz(seed, product, oracle, tmp_path):
+    """The product's parser (csrc/mor_config.cpp) and the oracle's are two independent restatements of setVariables
+    (cpp:698-864). Random mutations of the default file - shuffled lines, comments, short lines, extra colons, spaces,
+    odd numbers, dropped / duplicated / unknown keys - must give the same status and, on success, the same struct."""
+    import random
+    rnd = random.Random(seed)
+    lines = [l for l in DEFAULT_CFG.read_text().splitlines() if len(l) >= 3 and not l.startswith("#")]
+    rnd.shuffle(lines)
+    out = []
+    for l in lines:
+        key, val = l.split(":", 1)
+        r = rnd.random()
+        if r < 0.01:
+            continue                                                     # dropped key
+        if r < 0.05:
+            out.append(l)                                                # duplicated key (the later line wins)
+        if r < 0.10:
+            val = rnd.choice(["1e-1", "007", "+3", "-0.5", "2.", ".5", "0x10", "1,5", "nan", "abc", "", " 4", "4 ", "3:3", "1e400"])
+        if r > 0.99:
+            key = key + "_x"                                             # unknown key
+        out.append(f"{key}:{val}")
+        if rnd.random() < 0.2:
+            out.append(rnd.choice(["# note: with colon", "#", "ab", "", "  ", "#x", "a:" if rnd.random() < 0.1 else "# a:"]))
+    p = tmp_path / "fuzz.txt"
+    p.write_text("\n".join(out) + ("\n" if rnd.random() < 0.5 else ""))
+    ca, cb = MorConfig(), MorConfig()
+    sa, sb = product.parse_config(str(p).encode(), C.byref(ca)), oracle.parse_config(str(p).encode(), C.byref(cb))
+    assert sa == sb, f"status product {sa} vs oracle {sb} for\n{p.read_text()}"
+    if sa == 0:
+        assert bytes(ca) == bytes(cb), p.read_text()
