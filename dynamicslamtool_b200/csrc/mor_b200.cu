@@ -933,7 +933,7 @@ int mor_get_moving_markers(mor_handle* h, mor_marker* out, uint32_t cap, uint32_
             m.scale[q] = ext == 0.f ? 0.1f : ext;  // cpp:40-47
         }
         m.color[0] = 0.8f; m.color[1] = 0.1f; m.color[2] = 0.4f; m.color[3] = 0.5f;  // cpp:622, :53
-        m.id = 1;  // cpp:622: the counter is never advanced, every marker of a frame replaces the one before
+        m.id = (int32_t)i + 1;  // cpp:622, :669: filterCloud's counter starts at 1 and advances once per looked-up entry
         m.cluster = k;
     }
     return MOR_OK;

@@ -173,7 +173,7 @@ typedef struct mor_marker {
     float position[3];
     float scale[3];
     float color[4];  /* 0.8, 0.1, 0.4, alpha 0.5 */
-    int32_t id;      /* always 1, as in the reference (cpp:622) */
+    int32_t id;      /* 1, 2, 3, ... in mo_vec order: the reference's counter starts at 1 (cpp:622) and advances per entry (cpp:669) */
     int32_t cluster; /* index into this frame's cluster list */
 } mor_marker;
 int mor_get_moving_markers(mor_handle* h, mor_marker* out, uint32_t cap, uint32_t* n_out);

@@ -427,8 +427,8 @@ struct mor_handle {
     std::string last_error;
 
     // ---------------- mark_cluster, cpp:7-58: pcl::compute3DCentroid into a Vector4f (float sums in index order,
-    // divided by n), getMinMax3D extents, zero extents widened to 0.1; id is 1 for every marker (cpp:622)
-    static mor_marker mark_cluster(const std::vector<PointXYZI>& pts, int k) {
+    // divided by n), getMinMax3D extents, zero extents widened to 0.1; `id` is filterCloud's running counter (cpp:622, :669)
+    static mor_marker mark_cluster(const std::vector<PointXYZI>& pts, int k, int id) {
         mor_marker m;
         float sx = 0.f, sy = 0.f, sz = 0.f;
         float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -441,7 +441,7 @@ struct mor_handle {
         m.position[0] = sx / n; m.position[1] = sy / n; m.position[2] = sz / n;
         for (int q = 0; q < 3; q++) { const float e = mx[q] - mn[q]; m.scale[q] = e == 0.f ? 0.1f : e; }
         m.color[0] = 0.8f; m.color[1] = 0.1f; m.color[2] = 0.4f; m.color[3] = 0.5f;
-        m.id = 1; m.cluster = k;
+        m.id = id; m.cluster = k;
         return m;
     }
 
@@ -869,11 +869,12 @@ struct mor_handle {
         std::vector<int> moving_points;
         cluster_removed.assign(K, 0);
         markers.clear();
+        int id = 1;  // cpp:622; advanced once per looked-up entry (cpp:669), so the markers of a frame carry 1, 2, 3, ...
         for (int i = 0; i < (int)mo_vec.size(); i++) {  // cpp:630
             if (K == 0) continue;  // defined behaviour for the un-built tree: entries untouched
             float d;
             int k = nn_centroid(cb->centroid_collection, mo_vec[i].centroid, &d);  // cpp:636
-            markers.push_back(mark_cluster(cb->clusters[k].points, k));            // cpp:640-642 (VISUALIZE)
+            markers.push_back(mark_cluster(cb->clusters[k].points, k, id));        // cpp:640-642 (VISUALIZE)
             for (int j : cb->clusters[k].indices) moving_points.push_back(j);      // cpp:644-648
             cluster_removed[k] = 1;
             if (!cb->detection_results[k] || d > cfg.leave_off_distance) {         // cpp:650
@@ -882,6 +883,7 @@ struct mor_handle {
                 mo_vec[i].centroid = cb->centroid_collection[k];                   // cpp:664
                 mo_vec[i].increaseConfidence();
             }
+            id++;  // cpp:669
         }
         // ExtractIndices(negative) (A18), cpp:673-678
         f_cloud.clear();

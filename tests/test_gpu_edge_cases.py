@@ -290,6 +290,8 @@ def test_visualize_outputs_cluster_collection_and_markers(product, oracle, cfg_d
             seen_markers += mg.shape[0]
             for name in ("cluster", "id", "color", "scale"):
                 assert np.array_equal(mg[name], mo[name]), name
+            # filterCloud's marker counter starts at 1 and advances once per looked-up entry (reference cpp:622, :669)
+            assert np.array_equal(mg["id"], np.arange(1, mg.shape[0] + 1)), mg["id"]
             np.testing.assert_allclose(mg["position"], mo["position"], rtol=1e-5, atol=1e-5)
         assert seen_markers > 0
 

@@ -1,0 +1,85 @@
+"""Long-running GPU parity (-m gpu): the benchmarked configurations at their own sizes.
+
+* C2 (the bench workload, BASELINE.json configs[1]) for 200 consecutive frames and C1 for 100, every tap compared
+  with the oracle on every frame (the round-1 soak tool, promoted into the driver-run suite).
+* mor_batch_step_device at the configuration bench.py's `multi_sequence` / C5 legs run: C2 config, 16 sequences per
+  set of launches, 34 frames each, including the dense stretch (frames 101-107: cells with > 1000 points, 27k-point
+  clusters); every sequence compared tap by tap.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dynamicslamtool_b200 import MovingObjectRemoval, SequenceBatch, Synth
+from parity import ParityStats, compare_frame
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scenario,cfg,frames", [(2, "MOR_config_hdl64.txt", 200), (1, "MOR_config.txt", 100)])
+def test_soak_every_tap_every_frame(product, oracle, cfg_dir, scenario, cfg, frames):
+    s = Synth(scenario, scenario)
+    gpu = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
+    orc = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=oracle)
+    st = ParityStats()
+    for f in range(frames):
+        pts, pose = s.frame(f)
+        gpu.push_raw_cloud_and_pose(pts, pose)
+        orc.push_raw_cloud_and_pose(pts, pose)
+        og, oo = gpu.filter_cloud().copy(), orc.filter_cloud().copy()
+        bad = compare_frame(gpu, orc, og, oo, st)
+        assert not bad, f"scenario {scenario} frame {f}: {bad}"
+    print("soak", scenario, st.as_dict())
+    assert st.matches > 0 and st.flagged > 0 and st.removed_points > 0 and st.mo_frames > 0
+    # north_star tolerance: centroids within 1e-5 relative (checked per frame); report how many are not even bit-equal
+    assert st.centroid_not_bitexact <= st.centroid_values // 1000
+
+
+def test_batched_step_at_the_benchmarked_configuration(product, oracle, cfg_dir):
+    """S = 16 sequences per launch on the C2 workload (bench.py multi_sequence, tools/c5_run.py). 8 distinct streams
+    (seed, first frame), each run twice inside the batch: the copies must agree with each other bit for bit and with
+    the oracle tap by tap. Streams 0-3 cross the dense stretch of seed 2 (frames 101-107)."""
+    cfg = cfg_dir / "MOR_config_hdl64.txt"
+    streams = [(2, 76), (2, 80), (2, 90), (2, 100), (1000, 0), (1001, 0), (1002, 3), (1003, 7)]
+    frames, S = 34, 16
+    syn = [Synth(2, seed) for seed, _ in streams]
+    maxp = syn[0].max_points
+    gpus = [MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=maxp) for _ in range(S)]
+    orcs = [MovingObjectRemoval(cfg, 4, 3, binding=oracle) for _ in streams]
+    batch = SequenceBatch(gpus)
+    d_in, d_out = [], []
+    for _ in range(S):
+        a, b = C.c_void_p(), C.c_void_p()
+        assert product.device_alloc(0, maxp * 16, C.byref(a)) == 0 and product.device_alloc(0, maxp * 32, C.byref(b)) == 0
+        d_in.append(a); d_out.append(b)
+    stats = ParityStats()
+    dense = 0
+    for f in range(frames):
+        data = [syn[t].frame(streams[t][1] + f) for t in range(len(streams))]
+        for s in range(S):
+            pts = data[s % 8][0]
+            assert product.device_upload(0, d_in[s], pts.ctypes.data_as(C.c_void_p), pts.nbytes) == 0
+        batch.step_device([p.value for p in d_in], [data[s % 8][0].shape[0] for s in range(S)], [data[s % 8][1] for s in range(S)],
+                          [p.value for p in d_out])
+        outs = []
+        for s in range(S):
+            gpus[s].sync()
+            n_out = gpus[s].counts()["NOUT"]
+            og = np.empty((n_out, 8), np.float32)
+            if n_out:
+                assert product.device_download(0, og.ctypes.data_as(C.c_void_p), d_out[s], n_out * 32) == 0
+            outs.append(og)
+        for t in range(len(streams)):
+            orcs[t].push_raw_cloud_and_pose(*data[t])
+            oo = orcs[t].filter_cloud().copy()
+            bad = compare_frame(gpus[t], orcs[t], outs[t], oo, stats)
+            assert not bad, f"stream {t} frame {f}: {bad}"
+            assert outs[t].tobytes() == outs[t + 8].tobytes(), f"copies of stream {t} differ at frame {f}"
+            for tap in ("labels", "cluster_id", "centroids", "match_score", "flags", "mo_conf", "removed_mask"):
+                assert gpus[t].tap(tap).tobytes() == gpus[t + 8].tap(tap).tobytes(), f"{tap}: copies of stream {t} differ at frame {f}"
+            dense = max(dense, int(gpus[t].tap("cluster_size").max(initial=0)))
+    print("batched parity", stats.as_dict(), "largest cluster", dense)
+    assert stats.matches > 0 and dense > 20000
+    for p in d_in + d_out:
+        product.device_free(0, p)

@@ -242,7 +242,7 @@ def test_extract_overflow_quirk(oracle, tmp_path):
 def test_cluster_collection_markers_and_reset(oracle, tmp_path):
     """cluster_collection (cpp:226-229) = the clustered points, cluster after cluster, ascending cloud index inside a
     cluster - rebuilt here from the cluster_id tap; markers (cpp:7-58, :640-642): float centroid, extents with the
-    0 -> 0.1 rule, id 1; oracle_reset = a newly constructed object."""
+    0 -> 0.1 rule, ids 1, 2, 3, ... in mo_vec order (the counter of cpp:622 advances at cpp:669); oracle_reset = a newly constructed object."""
     rng = np.random.default_rng(7)
     m = make(oracle, tmp_path, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000, **OPEN_CFG)
     frames = list(two_blob_frames(rng, 9, 0.12))
@@ -259,12 +259,12 @@ def test_cluster_collection_markers_and_reset(oracle, tmp_path):
         m.filter_cloud()
         marks = m.moving_markers()
         assert marks.shape[0] == n_tracked
-        for mk in marks:
+        for i, mk in enumerate(marks):
             p = pts[cid == mk["cluster"], :3]
             ext = p.max(0) - p.min(0)
             assert np.array_equal(mk["scale"], np.where(ext == 0, np.float32(0.1), ext))
             np.testing.assert_allclose(mk["position"], p.astype(np.float64).mean(0), rtol=1e-5, atol=1e-5)
-            assert mk["id"] == 1 and np.allclose(mk["color"], [0.8, 0.1, 0.4, 0.5])
+            assert mk["id"] == i + 1 and np.allclose(mk["color"], [0.8, 0.1, 0.4, 0.5])
         sig.append((m.counts()["NMO"], m.tap("removed_mask").tobytes()))
     assert any(s[0] for s in sig)
     m.reset()
