@@ -111,6 +111,7 @@ class MorBinding:
         self.get_limits = f("get_limits", [vp, C.POINTER(MorLimits)], True)
         self.push_device = f("push_raw_cloud_and_pose_device", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)], True)
         self.filter_device = f("filter_cloud_device", [vp, vp, u32, C.POINTER(u32)], True)
+        self.get_output_device = f("get_output_device", [vp, C.POINTER(vp)], True)
         self.alloc_pinned = f("alloc_pinned", [sz, C.POINTER(vp)], True)
         self.free_pinned = f("free_pinned", [vp], True)
         self.device_alloc = f("device_alloc", [C.c_int, sz, C.POINTER(vp)], True)
@@ -284,10 +285,16 @@ class MovingObjectRemoval:
         self.n_input = n
         self._check(self.b.push_device(self.h, C.c_void_p(d_ptr), n, point_step, *offsets, pose), "push_device")
 
-    def filter_device(self, d_out: int, cap: int, want_count=True) -> int:
+    def filter_device(self, d_out: int | None, cap: int, want_count=True) -> int:
+        """d_out None: the records stay in the handle's own device buffer (output_device())."""
         n_out = C.c_uint32(0)
-        self._check(self.b.filter_device(self.h, C.c_void_p(d_out), cap, C.byref(n_out) if want_count else None), "filter_device")
+        self._check(self.b.filter_device(self.h, C.c_void_p(d_out) if d_out else None, cap, C.byref(n_out) if want_count else None), "filter_device")
         return n_out.value
+
+    def output_device(self) -> int:
+        p = C.c_void_p()
+        self._check(self.b.get_output_device(self.h, C.byref(p)), "get_output_device")
+        return p.value
 
     def event_record(self, slot: int):
         self._check(self.b.event_record(self.h, slot), "event_record")

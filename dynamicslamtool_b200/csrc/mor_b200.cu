@@ -2,8 +2,9 @@
 //
 // One handle = one CUDA device + one stream + device-resident SoA frame state that persists across
 // frames (previous frame's clusters, mo_vec, the corrs_vec / res_vec ring buffers). A frame is
-// pushRawCloudAndPose (reference cpp:516-611) = one H2D copy + ~14 kernel launches with no host
-// synchronisation, then filterCloud (cpp:613-696) = 2 launches + the D2H copy of the output cloud.
+// pushRawCloudAndPose (reference cpp:516-611) = one H2D copy + ONE cooperative kernel launch (k_frame, all phases
+// of the frame incl. the filter phase, no host synchronisation), then filterCloud (cpp:613-696) = commit of the
+// filter phase's result + the D2H copy of the output cloud.
 // There is no CPU fallback: every entry point that computes needs the device.
 #include <cmath>
 #include <cstdio>
@@ -88,8 +89,6 @@ struct mor_handle {
     mor_config cfg;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;  // runs k_transform_prev (depends only on the previous frame + pose) beside the clustering chain
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t spec_out = 0;        // speculative size of the output D2H copy (points), from the previous frame
     cudaStream_t last_stream = nullptr;  // stream that carries this handle's latest work (differs after a batched step)
     // batched stepping (this handle as the leader of a batch): device array of per-sequence arguments + pinned ring
@@ -97,11 +96,9 @@ struct mor_handle {
     cudaEvent_t batch_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t nmax = 0, kmax = 0, momax = 0;
     int ring_depth = 0, pde_ring = 0;
-    bool dynamic_grid = false; int max_cells = 0; double cell_h = 0;
-    uint32_t static_cell_cap = 0;
-    int num_sms = 148;
-    size_t select_smem = 0;
-    GridDesc grid;
+    int max_cells = 0; double cell_h = 0;  // max_cells: dense tables of the voxel ground modes
+    int num_sms = 148, frame_ctas = 148;
+    size_t frame_smem = 0;
     std::string last_error;
 
     // one big device arena + carved pointers
@@ -109,11 +106,9 @@ struct mor_handle {
     size_t arena_bytes = 0;
     uint8_t* d_in = nullptr;
     size_t d_in_bytes = 0;
-    uint8_t* zero_region = nullptr;  // Scratch + scan status + cell_count: one memset per frame
-    size_t zero_bytes = 0;
-    size_t lattice_cap = 0;
+    size_t lattice_cap = 0, table_cap = 0;
     FramePtrs base;  // pointers that do not change from frame to frame
-    int* coll_cursor = nullptr; int* coll_turn = nullptr;  // mor_get_cluster_collection scratch
+    int* coll_cursor = nullptr; int* coll_turn = nullptr; float4* coll_out = nullptr;  // mor_get_cluster_collection scratch
     GroundPtrs ground;  // voxel-covariance ground removal state (ground_mode 1/2 only)
     // ping-pong
     float4* pts[2]; float4* spts[2]; int* cid[2]; int* cl_root[2]; int* cl_size[2]; float* cl_centroid[2]; uint8_t* cl_flags[2]; float* cl_bbox[2]; int* counts[2];
@@ -132,7 +127,7 @@ struct mor_handle {
     int32_t* h_counts = nullptr;  // pinned
     // generic event slots (bench.py brackets its timed regions with these, on the handle's stream)
     cudaEvent_t slot_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    // per-kernel profiling (off by default: two extra event records per launch)
+    // per-phase profiling (off by default): every phase of the frame kernel is launched as its own kernel between events
     bool profiling = false;
     std::vector<cudaEvent_t> prof_pool;
     std::vector<int> prof_ids;  // kernel id of every recorded pair of the current frame
@@ -142,13 +137,13 @@ struct mor_handle {
 
 namespace {
 
-enum KernelId { KID_INGEST = 0, KID_KEYS, KID_SCAN_CELLS, KID_SCATTER, KID_NEIGHBORS, KID_FLATTEN, KID_STATS,
-                KID_TRANSFORM_PREV, KID_LATTICE_INSERT, KID_LATTICE_COUNT, KID_PDE,
-                KID_OUTPUT, KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"k_ingest", "k_keys", "k_scan_cells", "k_scatter", "k_link_cells", "k_flatten+select",
-                                              "k_cluster_stats+match", "k_transform_prev", "k_lattice_insert", "k_lattice_count+chain", "k_pde_count+chain",
-                                              "k_filter_output", "k_ingest_raw", "k_ground_keys", "k_scan_voxels", "k_ground_scatter",
+enum KernelId { KID_PHASE0 = 0, KID_FRAME = PH__COUNT, KID_FILTER_AGAIN,
+                KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_CELLS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
+const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells+transform", "ph_scatter", "ph_link", "ph_flatten", "ph_select", "ph_stats", "ph_match",
+                                              "ph_moving_test", "ph_chain+cleanup", "ph_filter", "k_frame", "k_filter_again",
+                                              "k_ingest_raw", "k_ground_keys", "k_scan_cells", "k_scan_voxels", "k_ground_scatter",
                                               "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
+static_assert(KID__COUNT <= 40, "profile table too small");
 
 inline void prof_begin(mor_handle* h, int id) {
     if (!h->profiling) return;
@@ -168,7 +163,8 @@ void prof_harvest(mor_handle* h) {  // stream must be idle
     }
     h->prof_ids.clear();
 }
-// Launch with the programmatic-stream-serialisation attribute (see pdl_prologue in mor_device.cuh).
+// Launch with the programmatic-stream-serialisation attribute (see pdl_prologue in mor_device.cuh): the chain of
+// short kernels of the voxel ground modes.
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -179,17 +175,21 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
-// Kernel launch of the frame chain: PDL normally, plain (and bracketed by events) under per-kernel profiling.
 #define MOR_KLAUNCH(id, kernel, grid, block, smem, ...)                                           \
     do {                                                                                           \
-        if (h->profiling) { prof_begin(h, id); kernel<<<grid, block, smem, st>>>(__VA_ARGS__); prof_end(h); } \
-        else launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__);                  \
+        cudaError_t le__;                                                                          \
+        if (h->profiling) { prof_begin(h, id); kernel<<<grid, block, smem, st>>>(__VA_ARGS__); le__ = cudaGetLastError(); prof_end(h); } \
+        else le__ = launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__);           \
+        if (le__ != cudaSuccess) { h->last_error = std::string(#kernel) + ": " + cudaGetErrorString(le__); return MOR_ERR_CUDA; } \
         h->launches++;                                                                             \
     } while (0)
 
-// Every device operation of the hot path goes through this: counted (mor_get_launch_count) and, when
-// profiling is on, bracketed by events on the handle's stream.
-#define MOR_LAUNCH(id, ...) do { prof_begin(h, id); __VA_ARGS__; prof_end(h); h->launches++; } while (0)
+// All CTAs of the frame kernel must be resident at once (they meet at group barriers): cooperative launch.
+template <typename K, typename... Args>
+cudaError_t launch_coop(K kernel, unsigned grid, size_t smem, cudaStream_t st, Args... args) {
+    void* argv[] = {(void*)&args...};
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kT), argv, smem, st);
+}
 
 template <typename T>
 T* carve(uint8_t*& p, size_t count) {
@@ -203,90 +203,65 @@ int build_grid(mor_handle* h) {
     // A7: r2 = (float)((double)tol * (double)tol); effective radius = sqrt(r2). Cell edge h = r/sqrt(3) shrunk by
     // 2^-10: the diagonal of a cell stays below r even after float rounding of the distance (every two points of
     // a cell are neighbours), and d < r implies a cell offset of at most 2 per axis (r/h = 1.734).
+    // The grid is sparse (a hash table of the occupied cells), so neither the crop box nor the extent of a frame
+    // enters anywhere: any finite coordinate up to 2^20 cells from the origin is binned.
     const float r2 = (float)((double)c.ec_distance_threshold * (double)c.ec_distance_threshold);
     if (!(r2 > 0.f) || !(c.trim_x > 0.f) || !(c.trim_y > 0.f)) return MOR_ERR_CONFIG_VALUE;
-    const double hcell = std::sqrt((double)r2) / std::sqrt(3.0) * (1.0 - 1.0 / 1024.0);
-    GridDesc g;
-    const double pad = (double)kGridPad * hcell;  // empty low-side cells: see k_link_cells
-    g.ox = -(double)c.trim_x - pad; g.oy = -(double)c.trim_y - pad;
-    double zlo, zhi;
-    if (c.ground_mode == MOR_GROUND_CROP) { zlo = (double)c.gp_limit; zhi = (double)c.trim_z; }
-    else { zlo = -64.0; zhi = 64.0; }  // voxel modes: z is not cropped; generous fixed slab
-    if (!(zhi >= zlo)) zhi = zlo;
-    g.oz = zlo - pad; g.inv_h = 1.0 / hcell;
-    const double fx = std::floor(((double)c.trim_x - g.ox) / hcell) + 1, fy = std::floor(((double)c.trim_y - g.oy) / hcell) + 1, fz = std::floor((zhi - g.oz) / hcell) + 1;
-    if (fx < 1 || fy < 1 || fz < 1) return MOR_ERR_CONFIG_VALUE;
-    h->cell_h = hcell;
-    // Dense cell table, three regimes by the number of cells the config crop box needs:
-    //  * up to 2^22: the grid covers the crop box and is fixed at create time (scanning it costs ~10 us per frame);
-    //  * up to static_cap (mor_limits.max_cells, default 2^27 = 2 x 512 MB of tables): tables for the whole box are
-    //    allocated, but each frame's grid is laid over the bounding box of its cloud (k_keys), so the scan pays for
-    //    the occupied extent only - a small radius over a large box, or the voxel modes' uncropped z slab;
-    //  * beyond (e.g. trimming "disabled" with huge values): per-frame bounding-box grid in tables of 2^24 cells (or
-    //    mor_limits.max_cells); a frame whose box needs more is rejected with MOR_ERR_CAPACITY.
-    const double need = fx * fy * fz;
-    const double static_cap = h->static_cell_cap ? (double)h->static_cell_cap : 134217728.0;
-    if (need <= 4194304.0) {
-        h->dynamic_grid = false;
-        g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; g.ncells = g.nx * g.ny * g.nz;
-        h->max_cells = 1 << 24;  // the voxel modes' ball-query grid shares the tables
-    } else {
-        h->dynamic_grid = true;
-        if (need <= static_cap) h->max_cells = need > 16777216.0 ? (int)need : (1 << 24);
-        else h->max_cells = h->static_cell_cap ? (int)h->static_cell_cap : (1 << 24);
-        g.nx = g.ny = g.nz = kGridPad + 1; g.ncells = h->max_cells;
-    }
-    h->grid = g;
-    h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / hcell);
+    h->cell_h = std::sqrt((double)r2) / std::sqrt(3.0) * (1.0 - 1.0 / 1024.0);
+    if (!(h->cell_h > 0.0) || !std::isfinite(1.0 / h->cell_h)) return MOR_ERR_CONFIG_VALUE;
+    h->pde_ring = (int)std::ceil(std::sqrt((double)c.pde_ub) / h->cell_h);
     if (h->pde_ring < 1) h->pde_ring = 1;
+    if (h->pde_ring > 64) h->pde_ring = 64;
     return MOR_OK;
 }
 
 int allocate(mor_handle* h) {
     const size_t N = h->nmax, K = h->kmax, MO = h->momax, D = (size_t)h->ring_depth;
-    const size_t ncells = h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells;
-    const size_t tiles_pts = N / kBlock + 2, tiles_cells = ncells / kScanTile + 2;
+    const size_t tiles_pts = N / kBlock + 2;
     size_t lat = 1;
     while (lat < 2 * N) lat <<= 1;
     h->lattice_cap = lat;
+    size_t tab = 1024;
+    while (tab < 2 * N) tab <<= 1;  // load factor <= 1/2 even if every point had a cell of its own
+    h->table_cap = tab;
     h->d_in_bytes = N * 32;
+    const bool ground = h->cfg.ground_mode != MOR_GROUND_CROP;
     // ---- size pass (mirror of the carve pass below)
     auto plan = [&](uint8_t* p0) -> uint8_t* {
         uint8_t* p = p0;
         FramePtrs& b = h->base;
         h->d_in = carve<uint8_t>(p, h->d_in_bytes);
-        h->zero_region = p;
         b.scratch = carve<Scratch>(p, 1);
         b.st_ingest = carve<unsigned long long>(p, tiles_pts);
-        b.st_cells = carve<unsigned long long>(p, tiles_cells);
+        b.st_cscan = carve<unsigned long long>(p, tiles_pts);
         b.st_out = carve<unsigned long long>(p, tiles_pts);
-        b.cell_count = carve<int>(p, ncells + 16);
-        h->zero_bytes = (size_t)(p - h->zero_region);
-        b.cell_start = carve<int>(p, ncells + 16);
-        b.dgrid = carve<GridDesc>(p, 1);
+        b.table = carve<Cell>(p, tab);
+        b.cell_list = carve<int>(p, N); b.ckey = carve<unsigned long long>(p, N + 1); b.cstart = carve<int>(p, N + 1);
+        b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
-        b.cell_key = carve<int>(p, N); b.skey = carve<int>(p, N);
         b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
-        b.comp = carve<int>(p, N); b.scid = carve<int>(p, N); b.minidx = carve<int>(p, N); b.done = carve<unsigned long long>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
+        b.comp = carve<int>(p, N); b.scid = carve<int>(p, N); b.minidx = carve<int>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
         b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
         b.recip_q = carve<int>(p, K); b.recip_m = carve<int>(p, K); b.match_q = carve<int>(p, K); b.match_m = carve<int>(p, K);
         b.match_dist = carve<float>(p, K); b.match_score = carve<double>(p, K);
         b.match_of_prev = carve<int>(p, K); b.mid_of_prev = carve<int>(p, K); b.mid_of_cur = carve<int>(p, K);
-        b.anchor = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
+        b.anchorp = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
         b.lattice = carve<unsigned long long>(p, lat);
         b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
         b.marker_cluster = carve<int>(p, MO); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
-        b.out = carve<float4>(p, N * 2);
+        b.out = carve<float4>(p, N * 2); h->coll_out = carve<float4>(p, N * 2);
         for (int f = 0; f < 2; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
             h->cl_root[f] = carve<int>(p, K); h->cl_size[f] = carve<int>(p, K); h->cl_centroid[f] = carve<float>(p, K * 3);
             h->cl_flags[f] = carve<uint8_t>(p, K); h->cl_bbox[f] = carve<float>(p, K * 6); h->counts[f] = carve<int>(p, MOR_NCOUNTS);
         }
-        if (h->cfg.ground_mode != MOR_GROUND_CROP) {
+        if (ground) {  // dense ball-query grid and pcl::VoxelGrid index space over the bounding box of raw_cloud
             GroundPtrs& g = h->ground;
             const size_t vc = (size_t)h->max_cells;
+            b.cell_count = carve<int>(p, vc + 16); b.cell_start = carve<int>(p, vc + 16); b.cell_key = carve<int>(p, N); b.skey = carve<int>(p, N);
+            b.dgrid = carve<GridDesc>(p, 1); b.st_cells = carve<unsigned long long>(p, vc / kScanTile + 2);
             g.rpts = carve<float4>(p, N); g.rsrc = carve<int>(p, N); g.is_ground = carve<uint8_t>(p, N); g.vkey = carve<int>(p, N);
             g.vox_count = carve<int>(p, vc + 1); g.vox_ord = carve<int>(p, vc + 1); g.tiles_vox = (int)(vc / kTile + 2);  // k_scan_voxels pulls kTile-voxel tiles
             g.st_vox = carve<unsigned long long>(p, g.tiles_vox);
@@ -302,12 +277,30 @@ int allocate(mor_handle* h) {
     plan(h->arena);
     MOR_CUDA(cudaMallocHost(&h->h_counts, sizeof(int32_t) * MOR_NCOUNTS));
     for (int i = 0; i < 4; i++) MOR_CUDA(cudaEventCreate(&h->ev[i]));
+    // dynamic shared memory of the frame kernel: the cluster sort keys of the select phase / the link phase's point tile
     int P = 1;
     while (P < (int)K) P <<= 1;
-    h->select_smem = (size_t)P * sizeof(unsigned long long);
-    MOR_CUDA(cudaFuncSetAttribute(k_flatten, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
-    MOR_CUDA(cudaFuncSetAttribute(k_flatten_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->select_smem));
-    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    h->frame_smem = (size_t)P * sizeof(unsigned long long);
+    if (h->frame_smem < (size_t)kLinkTilePts * 16) h->frame_smem = (size_t)kLinkTilePts * 16;
+    return MOR_OK;
+}
+
+template <int PH>
+int set_phase_smem(mor_handle* h) {
+    MOR_CUDA(cudaFuncSetAttribute(k_phase<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
+    return MOR_OK;
+}
+int configure_kernels(mor_handle* h) {
+    MOR_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
+    MOR_CUDA(cudaFuncSetAttribute(k_frame_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
+    int st = set_phase_smem<PH_LINK>(h);
+    if (st == MOR_OK) st = set_phase_smem<PH_SELECT>(h);
+    if (st != MOR_OK) return st;
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->num_sms = sms;
+    MOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame, kT, h->frame_smem));
+    if (per_sm < 1) { h->last_error = "the frame kernel does not fit on an SM of this device"; return MOR_ERR_CUDA; }
+    h->frame_ctas = h->num_sms;  // one CTA per SM
     return MOR_OK;
 }
 
@@ -322,12 +315,15 @@ void fill_static(mor_handle* h) {
     b.method = c.method_choice; b.opc_factor = c.opc_normalization_factor;
     b.moving_confidence = c.n_bad; b.static_confidence = c.n_good;
     b.kmax = (int)h->kmax; b.momax = (int)h->momax; b.ring_depth = h->ring_depth;
-    b.grid = h->grid;
-    b.dynamic_grid = h->dynamic_grid ? 1 : 0; b.max_cells = h->max_cells; b.cell_h = h->cell_h;
+    b.cell_h = h->cell_h; b.inv_h = 1.0 / h->cell_h;
+    b.skip_ingest = c.ground_mode != MOR_GROUND_CROP ? 1 : 0;
+    b.table_mask = (unsigned)(h->table_cap - 1);
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
     b.pde_ring = h->pde_ring;
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
-    b.tiles_pts = (int)(h->nmax / kBlock + 2); b.tiles_cells = (int)((h->cfg.ground_mode != MOR_GROUND_CROP ? (size_t)h->max_cells : (size_t)h->grid.ncells) / kScanTile + 2);
+    b.tiles_pts = (int)(h->nmax / kBlock + 2);
+    b.max_cells = h->max_cells;
+    b.tiles_cells = (int)((size_t)h->max_cells / kScanTile + 2);
     if (c.ground_mode != MOR_GROUND_CROP) {
         GroundPtrs& g = h->ground;
         g.mode = c.ground_mode; g.leaf = c.gp_leaf; g.inv_leaf = 1.0f / c.gp_leaf; g.r2 = (float)((double)c.gp_leaf * (double)c.gp_leaf);
@@ -338,13 +334,26 @@ void fill_static(mor_handle* h) {
 
 inline unsigned blocks_for(uint32_t n) { return n ? (n + kBlock - 1) / kBlock : 1; }
 
+// pcl::fromPCLPointCloud2 accepts any record layout (cpp:523): float4 records and 4-byte aligned fields are read with
+// vector / word loads, anything else (e.g. the 22-byte velodyne XYZIRT record) byte by byte.
+int validate_layout(uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
+    if (step < 12) return MOR_ERR_ARG;
+    if (ox > step - 4 || oy > step - 4 || oz > step - 4 || (oi != 0xFFFFFFFFu && oi > step - 4)) return MOR_ERR_ARG;
+    return MOR_OK;
+}
+int input_mode(const void* d_points, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
+    if (step == 16 && ox == 0 && oy == 4 && oz == 8 && oi == 12 && ((uintptr_t)d_points % 16) == 0) return 0;
+    if (step % 4 == 0 && ox % 4 == 0 && oy % 4 == 0 && oz % 4 == 0 && (oi == 0xFFFFFFFFu || oi % 4 == 0) && ((uintptr_t)d_points % 4) == 0) return 1;
+    return 2;
+}
+
 // Arguments of the current frame (everything the kernels read) from the handle's host-side state.
 void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
     FramePtrs& a = h->frame;
     a = h->base;
     const int cur = h->cur, prev = cur ^ 1;
     a.in = d_points; a.n = n; a.step = step; a.off_x = ox; a.off_y = oy; a.off_z = oz; a.off_i = oi;
-    a.vec16 = (step == 16 && ox == 0 && oy == 4 && oz == 8 && oi == 12 && ((uintptr_t)d_points % 16) == 0) ? 1 : 0;
+    a.in_mode = input_mode(d_points, step, ox, oy, oz, oi);
     a.pts = h->pts[cur]; a.spts = h->spts[cur]; a.cid = h->cid[cur]; a.cl_root = h->cl_root[cur]; a.cl_size = h->cl_size[cur];
     a.cl_centroid = h->cl_centroid[cur]; a.cl_flags = h->cl_flags[cur]; a.cl_bbox = h->cl_bbox[cur]; a.counts = h->counts[cur];
     a.p_pts = h->pts[prev]; a.p_spts = h->spts[prev]; a.p_cid = h->cid[prev]; a.p_cl_root = h->cl_root[prev]; a.p_cl_size = h->cl_size[prev];
@@ -354,63 +363,48 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
     std::memcpy(a.M.m, h->M, sizeof(h->M));
 }
 
+template <int PH>
+int launch_phase(mor_handle* h, const FramePtrs& a) {
+    prof_begin(h, KID_PHASE0 + PH);
+    const size_t smem = (PH == PH_LINK || PH == PH_SELECT) ? h->frame_smem : 0;
+    cudaError_t e = launch_coop(k_phase<PH>, (unsigned)h->frame_ctas, smem, h->stream, a);
+    prof_end(h);
+    h->launches++;
+    if (e != cudaSuccess) { h->last_error = std::string("k_phase: ") + cudaGetErrorString(e); return MOR_ERR_CUDA; }
+    return MOR_OK;
+}
+
 int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
     cudaStream_t st = h->stream;
     fill_frame(h, d_points, n, step, ox, oy, oz, oi);
     FramePtrs& a = h->frame;
     const unsigned gb = blocks_for(n);
     if (h->cfg.ground_mode != MOR_GROUND_CROP) {
-        // voxel-covariance ground removal (reference cpp:90-200, repaired): 8 launches, then the common pipeline
+        // voxel-covariance ground removal (reference cpp:90-200, repaired): 9 launches, then the frame kernel takes over
         const GroundPtrs& g = h->ground;
         FramePtrs ag = a;
         ag.dgrid = g.ggrid;  // the cell scan of this stage runs over the ball-query grid
         MOR_KLAUNCH(KID_G_INGEST, k_ingest_raw, gb, kBlock, 0, a, g);
         MOR_KLAUNCH(KID_G_KEYS, k_ground_keys, gb, kBlock, 0, a, g);
-        MOR_KLAUNCH(KID_SCAN_CELLS, k_scan_cells, h->num_sms * 8, kBlock, 0, ag);
+        MOR_KLAUNCH(KID_G_SCAN_CELLS, k_scan_cells, h->num_sms * 8, kBlock, 0, ag);
         MOR_KLAUNCH(KID_G_SCAN_VOX, k_scan_voxels, h->num_sms * 8, kBlock, 0, a, g);
         MOR_KLAUNCH(KID_G_SCATTER, k_ground_scatter, gb, kBlock, 0, a, g);
         MOR_KLAUNCH(KID_G_EVAL, k_voxel_eval, h->num_sms * 8, kBlock, 0, a, g);  // warps stride over the voxels
-        MOR_KLAUNCH(KID_G_MODE, k_ground_mode, 1, kSingle, 0, a, g);
+        MOR_KLAUNCH(KID_G_MODE, k_ground_mode, 1, 1024, 0, a, g);
         MOR_KLAUNCH(KID_G_MARK, k_ground_mark, h->num_sms * 8, kBlock, 0, a, g);
         MOR_KLAUNCH(KID_G_PARTITION, k_ground_partition, gb, kBlock, 0, a, g);
+    }
+    if (h->profiling) {  // one launch per phase, each between a pair of events
+        int s;
+        if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_SCATTER>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) ||
+            (s = launch_phase<PH_FLATTEN>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || (s = launch_phase<PH_MATCH>(h, a)) ||
+            (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_CHAIN>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
+            return s;
     } else {
-        MOR_KLAUNCH(KID_INGEST, k_ingest, n ? (n + kIngestTile - 1) / kIngestTile : 1, kIngestBlock, 0, a);
-    }
-    // The transform of the previous frame's clusters needs only the previous frame, the pose delta and the neutral
-    // boxes written by the ingest kernel: it runs on a side stream beside the clustering chain and is joined before
-    // k_match. (With per-kernel profiling on it stays in line so that its events bracket it alone.)
-    const bool fork = h->two_frames && !h->profiling;
-    if (fork) {
-        MOR_CUDA(cudaEventRecord(h->ev_fork, st));
-        MOR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, h->side>>>(a);
+        cudaError_t e = launch_coop(k_frame, (unsigned)h->frame_ctas, h->frame_smem, st, a);
         h->launches++;
-        MOR_CUDA(cudaEventRecord(h->ev_join, h->side));
+        if (e != cudaSuccess) { h->last_error = std::string("k_frame: ") + cudaGetErrorString(e); return MOR_ERR_CUDA; }
     }
-    if (h->dynamic_grid) MOR_KLAUNCH(KID_KEYS, k_keys, gb, kBlock, 0, a);
-    {
-        const int tiles = (h->grid.ncells + kScanTile - 1) / kScanTile;
-        const int scan_blocks = h->dynamic_grid ? h->num_sms * 8 : (tiles < h->num_sms * 8 ? tiles : h->num_sms * 8);
-        MOR_KLAUNCH(KID_SCAN_CELLS, k_scan_cells, scan_blocks, kBlock, 0, a);
-    }
-    MOR_KLAUNCH(KID_SCATTER, k_scatter, gb, kBlock, 0, a);
-    MOR_KLAUNCH(KID_NEIGHBORS, k_link_cells, dim3((n + kLinkBlock - 1) / kLinkBlock + (n ? 0 : 1), 18), kLinkBlock, 0, a);  // near pass (5 rows) + far pass (13 rows)
-    const unsigned g1k = n ? (n + kSingle - 1) / kSingle : 1;
-    MOR_KLAUNCH(KID_FLATTEN, k_flatten, g1k, kSingle, h->select_smem, a);  // + cluster selection in its last block
-    if (fork) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));  // k_cluster_stats' last block runs the correspondences
-    else if (h->two_frames) MOR_LAUNCH(KID_TRANSFORM_PREV, (k_transform_prev<<<(h->n_prev_input + kStatBlock - 1) / kStatBlock + (h->n_prev_input ? 0 : 1), kStatBlock, 0, st>>>(a)));
-    MOR_KLAUNCH(KID_STATS, k_cluster_stats, (n + kStatBlock - 1) / kStatBlock + (n ? 0 : 1), kStatBlock, 0, a);
-    if (h->two_frames) {
-        const unsigned gp = blocks_for(h->n_prev_input);
-        if (h->cfg.method_choice == 2) {
-            MOR_KLAUNCH(KID_LATTICE_INSERT, k_lattice_insert, gp, kBlock, 0, a);
-            MOR_KLAUNCH(KID_LATTICE_COUNT, k_lattice_count, g1k, kSingle, 0, a);  // + flags and consistency chain in its last block
-        } else {
-            const unsigned gp1k = h->n_prev_input ? (h->n_prev_input + kSingle - 1) / kSingle : 1;
-            MOR_KLAUNCH(KID_PDE, k_pde_count, gp1k, kSingle, 0, a);
-        }
-    }
-    MOR_CUDA(cudaGetLastError());
     return MOR_OK;
 }
 
@@ -437,8 +431,7 @@ int join_foreign_stream(mor_handle* h) {
 
 int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi, const double pose7[7]) {
     if (!h || (!data && n) || !pose7) return MOR_ERR_ARG;
-    if (step < 12 || step % 4 || ox % 4 || oy % 4 || oz % 4 || (oi != 0xFFFFFFFFu && oi % 4)) return MOR_ERR_ARG;
-    if (ox + 4 > step || oy + 4 > step || oz + 4 > step || (oi != 0xFFFFFFFFu && oi + 4 > step)) return MOR_ERR_ARG;
+    if (validate_layout(step, ox, oy, oz, oi) != MOR_OK) { h->last_error = "point_step / field offsets do not describe a record with float32 x, y, z"; return MOR_ERR_ARG; }
     if (n > h->nmax) { h->last_error = "frame larger than mor_limits.max_points"; return MOR_ERR_CAPACITY; }
     MOR_CUDA(cudaSetDevice(h->device));
     { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
@@ -458,6 +451,11 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
     return MOR_OK;
 }
 
+// filterCloud. The frame kernel has already run the filter phase on the frame (tracking update into the spare half of
+// the mo_vec double buffer, output cloud into the handle's buffer): the first filterCloud on a frame COMMITS that
+// result (flips the double buffer) and delivers the cloud; a frame that is never filtered leaves mo_vec untouched,
+// as in the reference. A further filterCloud on the same frame runs the filter phase again (k_filter_again) on the
+// updated mo_vec, which is what the reference does when the call is repeated.
 int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uint32_t* n_out) {
     if (!h) return MOR_ERR_ARG;
     if (!h->have_cur) return MOR_ERR_STATE;
@@ -466,17 +464,22 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     cudaStream_t st = h->stream;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[2], st));
     FramePtrs& a = h->frame;
-    if (on_device && out) a.out = (float4*)out;  // write the records straight into the caller's device buffer
-    else a.out = h->base.out;
     if (on_device && out && cap_points < h->n_input) { h->last_error = "device output buffer must hold n_input points"; return MOR_ERR_CAPACITY; }
-    a.mo_parity = h->mo_parity;
-    MOR_KLAUNCH(KID_OUTPUT, k_filter_output, h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kOutBlock, 0, a);
-    h->mo_parity ^= 1;  // the kernel wrote the updated mo_vec into the other half
-    a.mo_parity = h->mo_parity;
-    MOR_CUDA(cudaGetLastError());
-    h->filtered = true;
+    if (h->filtered) {  // repeated call: the tracking update runs once more
+        a.mo_parity = h->mo_parity;
+        prof_begin(h, KID_FILTER_AGAIN);
+        k_filter_again<<<h->n_input ? (h->n_input + kOutTile - 1) / kOutTile : 1, kT, 0, st>>>(a);
+        prof_end(h);
+        h->launches++;
+        MOR_CUDA(cudaGetLastError());
+        h->filtered = false;  // committed below like a first call
+    }
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[3], st));
-    if (on_device && !n_out && !h->profiling) return MOR_OK;  // fully asynchronous device-resident mode
+    if (on_device && !n_out && !h->profiling) {  // fully asynchronous device-resident mode
+        if (out && h->n_input) MOR_CUDA(cudaMemcpyAsync(out, a.out, (size_t)h->n_input * 32, cudaMemcpyDeviceToDevice, st));
+        h->mo_parity ^= 1; a.mo_parity = h->mo_parity; h->filtered = true;
+        return MOR_OK;
+    }
     MOR_CUDA(cudaMemcpyAsync(h->h_counts, a.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, st));
     // The size of the output is only known on the device. Instead of a second round trip (sync on the count, then
     // copy), the cloud copy is issued speculatively with the previous frame's size plus a margin and topped up in
@@ -490,33 +493,31 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     }
     MOR_CUDA(cudaStreamSynchronize(st));
     if (h->profiling) prof_harvest(h);
-    const uint32_t no = (uint32_t)h->h_counts[MOR_CNT_NOUT];
+    const uint32_t no = (uint32_t)h->h_counts[CNT_SPEC_NOUT];
     if (n_out) *n_out = no;
     h->spec_out = no;
     if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
-        char msg[160];
-        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice 8=ground grid 16=grid cells)", h->h_counts[MOR_CNT_ERRFLAGS]);
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice range 8=ground grid 16=coordinate beyond the grid's range)",
+                      h->h_counts[MOR_CNT_ERRFLAGS]);
         h->last_error = msg;
         return MOR_ERR_CAPACITY;
     }
-    if (!on_device) {
-        if (no > cap_points) return MOR_ERR_CAPACITY;
-        if (no > spec) {
-            MOR_CUDA(cudaMemcpyAsync((uint8_t*)out + (size_t)spec * 32, (const uint8_t*)a.out + (size_t)spec * 32, (size_t)(no - spec) * 32, cudaMemcpyDeviceToHost, st));
-            MOR_CUDA(cudaStreamSynchronize(st));
-        }
+    if (no > cap_points && out) return MOR_ERR_CAPACITY;  // not committed: the call can be repeated with a larger buffer
+    if (!on_device && out && no > spec) {
+        MOR_CUDA(cudaMemcpyAsync((uint8_t*)out + (size_t)spec * 32, (const uint8_t*)a.out + (size_t)spec * 32, (size_t)(no - spec) * 32, cudaMemcpyDeviceToHost, st));
+        MOR_CUDA(cudaStreamSynchronize(st));
     }
+    if (on_device && out && no) MOR_CUDA(cudaMemcpyAsync(out, a.out, (size_t)no * 32, cudaMemcpyDeviceToDevice, st));
+    h->mo_parity ^= 1; a.mo_parity = h->mo_parity; h->filtered = true;  // commit
     return MOR_OK;
 }
 
-// The state of a handle that has seen no frame: all device tables zero, the grid descriptor in place, no tracked
-// objects, empty buffers (the reference's freshly constructed object, cpp:368-391). Ordered on the handle's stream.
+// The state of a handle that has seen no frame: all device tables zero, no tracked objects, empty buffers (the
+// reference's freshly constructed object, cpp:368-391). Ordered on the handle's stream.
 int reset_state(mor_handle* h) {
     MOR_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
-    GridDesc g0 = h->grid;
-    if (h->dynamic_grid) { g0.nx = g0.ny = g0.nz = kGridPad + 1; g0.ncells = g0.nx * g0.ny * g0.nz; }
-    MOR_CUDA(cudaMemcpyAsync(h->base.dgrid, &g0, sizeof(g0), cudaMemcpyHostToDevice, h->stream));
-    MOR_CUDA(cudaStreamSynchronize(h->stream));  // g0 is on this stack frame
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->have_cur = h->have_prev = h->filtered = h->two_frames = false;
     h->mo_parity = 0; h->n_input = h->n_prev_input = 0; h->spec_out = 0;
     h->last_stream = h->stream;
@@ -531,34 +532,32 @@ extern "C" {
 int mor_create_ex(const char* config_path, int n_bad, int n_good, int device, const mor_limits* limits, mor_handle** out) {
     if (!out || !config_path) return MOR_ERR_ARG;
     *out = nullptr;
+    // moving_confidence / static_confidence are compared as unsigned sizes in the reference (cpp:489; .h:88-93): a
+    // negative value never confirms anything there. Rejected here instead of imitated.
+    if (n_bad < 0 || n_good < 0) return MOR_ERR_ARG;
     mor_config cfg;
     int st = mor_parse_config(config_path, &cfg);
     if (st != MOR_OK) return st;
     cfg.n_bad = n_bad; cfg.n_good = n_good;
     if (cfg.ground_mode != MOR_GROUND_CROP && !(cfg.gp_leaf > 0.f)) return MOR_ERR_CONFIG_VALUE;
+    if (limits && limits->max_points >= (1u << 25)) return MOR_ERR_ARG;  // packed 31-bit partition counters, 2 x N table slots
     mor_handle* h = new mor_handle();
     h->cfg = cfg; h->device = device;
     h->nmax = limits && limits->max_points ? limits->max_points : 300000u;
     h->kmax = limits && limits->max_clusters ? limits->max_clusters : 8192u;
     h->momax = limits && limits->max_moving ? limits->max_moving : 1024u;
-    h->static_cell_cap = limits ? limits->max_cells : 0u;
-    if (h->kmax > 16384u) h->kmax = 16384u;  // k_select_clusters sorts the clusters of a frame in shared memory (128 KB of keys)
+    h->max_cells = limits && limits->max_cells ? (int)(limits->max_cells > 0x40000000u ? 0x40000000u : limits->max_cells) : (1 << 24);
+    if (h->kmax > 16384u) h->kmax = 16384u;  // the select phase sorts the clusters of a frame in shared memory (128 KB of keys)
     h->ring_depth = (n_bad > 1 ? n_bad : 1) + 2;
     st = build_grid(h);
     if (st != MOR_OK) { delete h; return st; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaGetLastError(); mor_destroy(h); return MOR_ERR_CUDA; }  // mor_destroy releases whatever exists
     st = allocate(h);
+    if (st == MOR_OK) st = configure_kernels(h);
     if (st != MOR_OK) { cudaGetLastError(); mor_destroy(h); return st; }
     fill_static(h);
-    {
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
-    }
     st = reset_state(h);
     if (st != MOR_OK) { mor_destroy(h); return st; }
     *out = h;
@@ -580,9 +579,6 @@ int mor_destroy(mor_handle* h) {
     if (!h) return MOR_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->slot_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->prof_pool) cudaEventDestroy(e);
@@ -625,18 +621,27 @@ int mor_filter_cloud(mor_handle* h, void* out, uint32_t cap_points, uint32_t* n_
 }
 int mor_filter_cloud_device(mor_handle* h, void* d_out, uint32_t cap_points, uint32_t* n_out) { return do_filter(h, d_out, true, cap_points, n_out); }
 
-// One pushRawCloudAndPose + filterCloud for S independent sequences in one set of launches (BASELINE config 5).
+int mor_get_output_device(mor_handle* h, const void** d_records) {
+    if (!h || !d_records) return MOR_ERR_ARG;
+    if (!h->have_cur || !h->filtered) return MOR_ERR_STATE;
+    *d_records = h->frame.out;
+    return MOR_OK;
+}
+
+// One pushRawCloudAndPose + filterCloud for S independent sequences in one launch (BASELINE config 5).
 int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* d_data, const uint32_t* n, uint32_t point_step, uint32_t off_x,
                           uint32_t off_y, uint32_t off_z, uint32_t off_i, const double* poses7, void* const* d_out) {
     if (!hs || !S || !d_data || !n || !poses7 || !d_out || !hs[0]) return MOR_ERR_ARG;
     mor_handle* h = hs[0];  // leader: owns the stream and the argument array of the batch
-    if (point_step < 12 || point_step % 4 || off_x % 4 || off_y % 4 || off_z % 4 || (off_i != 0xFFFFFFFFu && off_i % 4)) return MOR_ERR_ARG;
-    uint32_t n_max = 0, np_max = 0;
+    if (validate_layout(point_step, off_x, off_y, off_z, off_i) != MOR_OK) return MOR_ERR_ARG;
     for (uint32_t s = 0; s < S; s++) {
         mor_handle* g = hs[s];
-        if (!g || g->device != h->device || g->nmax != h->nmax || g->kmax != h->kmax || g->cfg.method_choice != h->cfg.method_choice ||
-            g->dynamic_grid != h->dynamic_grid || g->grid.ncells != h->grid.ncells || g->have_prev != h->have_prev || g->have_cur != h->have_cur ||
-            g->profiling) { h->last_error = "batched handles must share device, limits, config and frame count"; return MOR_ERR_ARG; }
+        // same device, limits, frame count and configuration (every key that reaches the kernels)
+        if (!g || g->device != h->device || g->nmax != h->nmax || g->kmax != h->kmax || g->momax != h->momax || g->have_prev != h->have_prev ||
+            g->have_cur != h->have_cur || g->profiling || std::memcmp(&g->cfg, &h->cfg, offsetof(mor_config, output_topic)) != 0) {
+            h->last_error = "batched handles must share device, limits, config and frame count";
+            return MOR_ERR_ARG;
+        }
         if (g->cfg.ground_mode != MOR_GROUND_CROP) { h->last_error = "batched stepping supports ground_mode 0 only"; return MOR_ERR_ARG; }
         if (n[s] > g->nmax || (!d_data[s] && n[s]) || !d_out[s]) return n[s] > g->nmax ? MOR_ERR_CAPACITY : MOR_ERR_ARG;
         for (uint32_t t = 0; t < s; t++) if (hs[t] == g) return MOR_ERR_ARG;
@@ -670,48 +675,23 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
         fill_frame(g, (const uint8_t*)d_data[s], n[s], point_step, off_x, off_y, off_z, off_i);
         g->frame.out = (float4*)d_out[s];
         hp[s] = g->frame;
-        n_max = n[s] > n_max ? n[s] : n_max;
-        np_max = g->n_prev_input > np_max ? g->n_prev_input : np_max;
         g->last_stream = st;
     }
     MOR_CUDA(cudaMemcpyAsync(dp, hp, sizeof(FramePtrs) * S, cudaMemcpyHostToDevice, st));
     MOR_CUDA(cudaEventRecord(h->batch_ev[slot], st));
-    const bool two = h->two_frames;
-    const unsigned gb = blocks_for(n_max), g1k = n_max ? (n_max + kSingle - 1) / kSingle : 1;
-    launch_pdl(k_ingest_batch, dim3(n_max ? (n_max + kIngestTile - 1) / kIngestTile : 1, 1, S), dim3(kIngestBlock), 0, st, (const FramePtrs*)dp);
-    if (two) {  // the transform of the previous clusters runs beside the clustering chain (see enqueue_push)
-        MOR_CUDA(cudaEventRecord(h->ev_fork, st));
-        MOR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        k_transform_prev_batch<<<dim3(np_max ? (np_max + kStatBlock - 1) / kStatBlock : 1, 1, S), kStatBlock, 0, h->side>>>(dp);
-        MOR_CUDA(cudaEventRecord(h->ev_join, h->side));
-    }
-    if (h->dynamic_grid) launch_pdl(k_keys_batch, dim3(gb, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+    // G CTAs per sequence; the groups run side by side, a group that has more than one sequence steps them in turn
+    int G = h->frame_ctas / (int)S;
+    if (const char* env = std::getenv("MOR_BATCH_G")) { const int v = std::atoi(env); if (v > 0) G = v; }
+    if (G < 1) G = 1;
+    if (G > h->frame_ctas) G = h->frame_ctas;
+    int groups = h->frame_ctas / G;
+    if (groups > (int)S) groups = (int)S;
     {
-        const int tiles = (h->grid.ncells + kScanTileBatch - 1) / kScanTileBatch;
-        const int per_seq = h->num_sms * 8 / (int)S > 8 ? h->num_sms * 8 / (int)S : 8;
-        const int scan_blocks = h->dynamic_grid ? per_seq : (tiles < per_seq ? tiles : per_seq);
-        launch_pdl(k_scan_cells_batch, dim3(scan_blocks, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
+        cudaError_t e = launch_coop(k_frame_batch, (unsigned)(groups * G), h->frame_smem, st, (const FramePtrs*)dp, (int)S, G);
+        h->launches++;
+        if (e != cudaSuccess) { h->last_error = std::string("k_frame_batch: ") + cudaGetErrorString(e); return MOR_ERR_CUDA; }
     }
-    launch_pdl(k_scatter_batch, dim3(gb, 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
-    launch_pdl(k_link_cells_batch, dim3((n_max + kLinkBlockBatch - 1) / kLinkBlockBatch + (n_max ? 0 : 1), 18, S), dim3(kLinkBlockBatch), 0, st, (const FramePtrs*)dp);
-    launch_pdl(k_flatten_batch, dim3(g1k, 1, S), dim3(kSingle), h->select_smem, st, (const FramePtrs*)dp);
-    if (two) MOR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-    launch_pdl(k_cluster_stats_batch, dim3(g1k, 1, S), dim3(kStatBlock), 0, st, (const FramePtrs*)dp);
-    h->launches += 6 + (h->dynamic_grid ? 1 : 0);
-    if (two) {
-        if (h->cfg.method_choice == 2) {
-            launch_pdl(k_lattice_insert_batch, dim3(blocks_for(np_max), 1, S), dim3(kBlock), 0, st, (const FramePtrs*)dp);
-            launch_pdl(k_lattice_count_batch, dim3(g1k, 1, S), dim3(kSingle), 0, st, (const FramePtrs*)dp);
-            h->launches += 3;
-        } else {
-            launch_pdl(k_pde_count_batch, dim3(np_max ? (np_max + kSingle - 1) / kSingle : 1, 1, S), dim3(kSingle), 0, st, (const FramePtrs*)dp);
-            h->launches += 2;
-        }
-    }
-    launch_pdl(k_filter_output_batch, dim3(n_max ? (n_max + kOutTile - 1) / kOutTile : 1, 1, S), dim3(kOutBlock), 0, st, (const FramePtrs*)dp);
-    h->launches += 1;
-    MOR_CUDA(cudaGetLastError());
-    for (uint32_t s = 0; s < S; s++) {
+    for (uint32_t s = 0; s < S; s++) {  // push + filter in one call: the frame is committed
         hs[s]->mo_parity ^= 1;
         hs[s]->frame.mo_parity = hs[s]->mo_parity;
         hs[s]->filtered = true;
@@ -805,13 +785,16 @@ int mor_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_bytes
     const FramePtrs& a = h->frame;
     int32_t c[MOR_NCOUNTS];
     MOR_CUDA(cudaMemcpy(c, a.counts, sizeof(c), cudaMemcpyDeviceToHost));
+    // the filter phase parks its results in spare slots until filterCloud commits the frame (do_filter)
+    if (h->filtered) { c[MOR_CNT_NOUT] = c[CNT_SPEC_NOUT]; c[MOR_CNT_NMO] = c[CNT_SPEC_NMO]; c[MOR_CNT_EXTRACT_OVERFLOW] = c[CNT_SPEC_OVERFLOW]; }
+    c[CNT_SPEC_NOUT] = c[CNT_SPEC_NMO] = c[CNT_SPEC_OVERFLOW] = 0;
     const void* src = nullptr;
     size_t bytes = 0;
     std::vector<uint8_t> host;  // for taps assembled on the host
     const size_t N = c[MOR_CNT_N], NC = c[MOR_CNT_NC], K = c[MOR_CNT_K], KP = c[MOR_CNT_KPREV], M = c[MOR_CNT_M], MU = c[MOR_CNT_MU], NMO = c[MOR_CNT_NMO],
                  NCP = c[MOR_CNT_NCPREV];
     switch (tap) {
-        case MOR_TAP_COUNTS: host.assign((uint8_t*)c, (uint8_t*)c + sizeof(c)); break;
+        case MOR_TAP_COUNTS: host.assign((uint8_t*)c, (uint8_t*)c + sizeof(c)); break;  // (after the merge of the filter phase's results below)
         case MOR_TAP_POINT_CLASS: src = a.point_class; bytes = N; break;
         case MOR_TAP_LABELS: src = a.label; bytes = NC * 4; break;
         case MOR_TAP_CLUSTER_ID: src = a.cid; bytes = NC * 4; break;
@@ -889,7 +872,7 @@ int mor_get_cluster_collection(mor_handle* h, void* out, uint32_t cap_points, ui
     const FramePtrs& a = h->frame;
     CollectionPtrs c;
     c.cid = a.cid; c.pts = a.pts; c.cl_size = a.cl_size; c.counts = a.counts; c.cursor = h->coll_cursor; c.turn = h->coll_turn;
-    c.out = h->base.out;  // free between calls: mor_filter_cloud has copied its result out before it returns
+    c.out = h->coll_out;  // not base.out: that holds the frame's filtered cloud until filterCloud has delivered it
     k_collection_offsets<<<1, kCollBlock, 0, h->stream>>>(c);
     k_cluster_collection<<<h->n_input ? (h->n_input + kCollBlock - 1) / kCollBlock : 1, kCollBlock, 0, h->stream>>>(c);
     h->launches += 2;

@@ -47,26 +47,16 @@ __global__ void __launch_bounds__(kBlock) k_ingest_raw(FramePtrs a, GroundPtrs g
     const uint32_t i = (uint32_t)tile * kBlock + threadIdx.x;
     const uint32_t stride = gridDim.x * kBlock;
     for (uint32_t t = i; t < 65536u; t += stride) gp.bin_hist[t] = 0;
-    if (a.two_frames) {
-        if (a.method == 2) {
-            uint4* lat = reinterpret_cast<uint4*>(a.lattice);
-            for (uint32_t t = i; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        }
-        const uint32_t kp6 = (uint32_t)a.p_counts[MOR_CNT_K] * 6u;
-        for (uint32_t t = i; t < kp6; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
-    }
     float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
     bool in = false;
     if (i < a.n) {
         const uint8_t* p = a.in + (size_t)i * a.step;
-        if (a.vec16) {
+        if (a.in_mode == 0) {
             float4 v = __ldg(reinterpret_cast<const float4*>(p));
             x = v.x; y = v.y; z = v.z; w = v.w;
         } else {
-            x = __ldg(reinterpret_cast<const float*>(p + a.off_x));
-            y = __ldg(reinterpret_cast<const float*>(p + a.off_y));
-            z = __ldg(reinterpret_cast<const float*>(p + a.off_z));
-            w = a.off_i != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float*>(p + a.off_i)) : 0.f;
+            x = load_f32(p + a.off_x, a.in_mode); y = load_f32(p + a.off_y, a.in_mode); z = load_f32(p + a.off_z, a.in_mode);
+            w = a.off_i != 0xFFFFFFFFu ? load_f32(p + a.off_i, a.in_mode) : 0.f;
         }
         in = isfinite(x) && isfinite(y) && isfinite(z) && !(x < -a.trim_x || x > a.trim_x) && !(y < -a.trim_y || y > a.trim_y);
         a.point_class[i] = 0;
@@ -155,6 +145,44 @@ __global__ void __launch_bounds__(kBlock) k_ground_keys(FramePtrs a, GroundPtrs 
     const int vk = (int)(i0 + i1 * v.div[0] + i2 * (long long)v.div[0] * v.div[1]);
     gp.vkey[r] = vk;
     atomicAdd(&gp.vox_count[vk], 1);
+}
+
+// ===================================================================================== G2b
+// Exclusive scan of the ball grid's per-cell histogram (counting sort of the cell keys) -> cell_start[0..ncells]. The
+// histogram itself is left in place: k_ground_scatter counts it back down to zero (rank = atomicSub - 1), which both
+// hands out the slots of a cell and leaves the table clean for the next frame. Persistent blocks pull tiles by ticket,
+// so the launch does not depend on the (device-side) cell count.
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kBlock * kScanItems;
+__global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) {
+    pdl_prologue();
+    __shared__ int s_tile;
+    const int ncells = a.dgrid->ncells;
+    const int ntiles = (ncells + kScanTile - 1) / kScanTile;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_cells, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) return;
+        const int base = tile * kScanTile + threadIdx.x * kScanItems;
+        int v[kScanItems];
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) sum += v[k];
+        int total;
+        const int in_block = block_exclusive_scan<int>(sum, &total);
+        const int before = (int)tile_exclusive_prefix(a.st_cells, tile, (unsigned long long)total);
+        int run = before + in_block;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if (base + k < ncells) a.cell_start[base + k] = run;
+            run += v[k];
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) a.cell_start[ncells] = before + total;
+    }
 }
 
 // ===================================================================================== G3
@@ -430,8 +458,8 @@ __global__ void __launch_bounds__(kBlock) k_ground_mark(FramePtrs a, GroundPtrs 
 }
 
 // ===================================================================================== G8
-// ExtractIndices(negative) (cpp:194-198): stable partition of raw_cloud into cloud / gp_indices, fused with
-// the clustering-grid key + histogram (static grid) or the cloud bounding box (dynamic grid).
+// ExtractIndices(negative) (cpp:194-198): stable partition of raw_cloud into cloud / gp_indices. The frame kernel
+// takes over from here (phase_bin_cloud).
 __global__ void __launch_bounds__(kBlock) k_ground_partition(FramePtrs a, GroundPtrs gp) {
     pdl_prologue();
     __shared__ int s_tile;
@@ -460,30 +488,10 @@ __global__ void __launch_bounds__(kBlock) k_ground_partition(FramePtrs a, Ground
         const int c = (int)(mine & 0x7FFFFFFFull);
         a.pts[c] = p;
         a.cloud_src[c] = src;
-        a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
-        a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
-        if (!a.dynamic_grid) {
-            const GridDesc& g = a.grid;
-            int cx = (int)floor(((double)p.x - g.ox) * g.inv_h), cy = (int)floor(((double)p.y - g.oy) * g.inv_h), cz = (int)floor(((double)p.z - g.oz) * g.inv_h);
-            cx = min(max(cx, kGridPad), g.nx - 1); cy = min(max(cy, kGridPad), g.ny - 1); cz = min(max(cz, kGridPad), g.nz - 1);
-            const int key = (cz * g.ny + cy) * g.nx + cx;
-            a.cell_key[c] = key;
-            atomicAdd(&a.cell_count[key], 1);
-        }
     } else if (cls == 2) {
         const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
         a.gpts[gi] = p;
         a.gsrc[gi] = src;
-    }
-    if (a.dynamic_grid) {
-        const bool v = cls == 1;
-        const unsigned kx = fkey(p.x), ky = fkey(p.y), kz = fkey(p.z);
-        const unsigned ix = __reduce_max_sync(kFull, v ? ~kx : 0u), iy = __reduce_max_sync(kFull, v ? ~ky : 0u), iz = __reduce_max_sync(kFull, v ? ~kz : 0u);
-        const unsigned mx = __reduce_max_sync(kFull, v ? kx : 0u), my = __reduce_max_sync(kFull, v ? ky : 0u), mz = __reduce_max_sync(kFull, v ? kz : 0u);
-        if ((threadIdx.x & 31) == 0 && (ix | mx)) {
-            atomicMax(&a.scratch->box_inv_min[0], ix); atomicMax(&a.scratch->box_inv_min[1], iy); atomicMax(&a.scratch->box_inv_min[2], iz);
-            atomicMax(&a.scratch->box_max[0], mx); atomicMax(&a.scratch->box_max[1], my); atomicMax(&a.scratch->box_max[2], mz);
-        }
     }
     if (tile == last_tile && threadIdx.x == 0) {
         const unsigned long long all = before + total;

@@ -1,43 +1,60 @@
-// mor_kernels.cuh — the per-frame MOR kernels (sm_100a), crop ground mode + clustering + matching +
-// moving tests + tracking + output. Launched by mor_b200.cu. Every kernel cites the reference lines
-// (src/MovingObjectRemoval.cpp unless noted) whose behaviour it reproduces; DESIGN.md has the data
+// mor_kernels.cuh — the per-frame MOR pipeline as ONE persistent cooperative kernel (sm_100a): crop ground mode,
+// clustering, matching, moving tests, tracking and the output cloud. Launched by mor_b200.cu. Every phase cites the
+// reference lines (src/MovingObjectRemoval.cpp unless noted) whose behaviour it reproduces; DESIGN.md has the data
 // layout and the roofline of each.
-// Every kernel exists twice: NAME(FramePtrs) for one sequence (arguments in the constant bank) and
-// NAME_batch(const FramePtrs*) for S sequences in one launch (blockIdx.z selects the sequence; the per-sequence
-// state - scratch, tickets, tables - is disjoint, so the bodies are identical).
+//
+// Execution model. A frame is a chain of ~12 dependent phases, each a few microseconds of L2-resident work. As
+// separate launches every boundary costs ~3 us on B200 plus the ramp and tail of a grid; a barrier between the CTAs of
+// one resident grid costs 1.2-1.8 us (profiles/r02_ubench_barrier.txt). So the frame is one kernel, k_frame: a group of
+// G CTAs (kT threads each, one CTA per SM) owns one sequence, runs phase after phase over "virtual blocks" (tiles of
+// points, cells or clusters, strided over the group: sized from the device-side counts, so no CTA is launched for work
+// that does not exist) and meets at a group barrier in between. One sequence takes the whole GPU (G = #SMs); S
+// sequences per launch (mor_batch_step_device) take G = #SMs / S CTAs each and run independently side by side.
+// The same phase functions can be launched one kernel per phase (k_phase<>, per-phase timing for bench.py).
 #pragma once
-#ifndef LINK_BLOCK_SINGLE
-#define LINK_BLOCK_SINGLE 128
-#endif
 #include "mor_device.cuh"
 #include "../../include/mor_b200.h"
 
 namespace mor {
 
-constexpr int kSingle = 1024;  // threads of the single-block bookkeeping kernels
+constexpr int kT = 1024;         // threads per CTA of the frame kernel: one CTA per SM, up to 64 registers per thread
+constexpr int kSingle = kT;      // single-CTA bookkeeping phases use the whole CTA
+constexpr int kWarps = kT / 32;
 constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
-constexpr int kGridPad = 2;  // empty cells on the low side of every axis: backward neighbour look-ups need no bounds checks
-constexpr int kRootCheckCount = 48;  // far pass: cells above this size are first checked for a common root
+constexpr int kHeavyPair = 1024; // a cell pair with more point pairs than this is examined by the whole warp
+constexpr int kLinkTilePts = 2048;  // points of one link round (32 cells) staged in shared memory by one bulk copy (32 KB)
 
-enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_CAP = 16 };
+enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16 };
+// counts[] slots in which the filter phase parks its results until filterCloud commits the frame (mor_b200.cu, do_filter)
+enum { CNT_SPEC_NOUT = 21, CNT_SPEC_NMO = 22, CNT_SPEC_OVERFLOW = 23 };
 
-struct GridDesc {  // uniform grid over `cloud`; cell edge h = r/sqrt(3)*(1-2^-10): two points of one cell are always
-                   // within r (one union-find node per cell) and d<r => |dcell| <= 2 per axis. The origin lies kGridPad
-                   // cells below the data on every axis, so every real cell has coordinates >= kGridPad
+// One occupied cell of the clustering grid: open-addressing hash table keyed by the packed cell coordinates.
+// key == 0 is "empty" (every real key has bit 63 set), so a zeroed table is a clean table.
+struct __align__(16) Cell {
+    unsigned long long key;
+    int start;  // first sorted position of the cell's points (= the cell's union-find node)
+    int cnt;
+};
+
+struct GridDesc {  // dense grid of the voxel ground modes' ball query (mor_ground.cuh); the clustering grid is sparse
     double ox, oy, oz, inv_h;
     int nx, ny, nz, ncells;
 };
 
-struct Scratch {  // zeroed at the start of every frame (one memset, together with cell_count)
-    int ticket_ingest, ticket_cells, ticket_out, n_roots;
-    int moving_total, stats_blocks_done, out_blocks_done, flatten_blocks_done;
-    int moving_blocks_done, pad5, pad6, pad7;
-    unsigned box_inv_min[3], box_max[3];  // dynamic grid: bbox of `cloud` (ordered keys; mins stored inverted so 0 is neutral)
-    int pad3, pad4;
+struct Scratch {  // all zero between frames: every counter is put back by the frame that used it
+    unsigned bar;            // group barrier of k_frame (monotonic within a launch)
+    int blocks_done;         // CTAs that have finished the frame
+    int n_cells, n_roots;
+    int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
+    int err_early;           // error bits raised before the frame's counts exist
+    int pad0;
+    // voxel ground modes only
+    int ticket_ingest, ticket_cells;
+    unsigned box_inv_min[3], box_max[3];  // bbox of raw_cloud (ordered keys; mins stored inverted so 0 is neutral)
 };
 
 struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:109-128)
-    int n_mo[2];      // mo_vec.size(), double-buffered like mo_centroid / mo_conf (see k_filter_output)
+    int n_mo[2];      // mo_vec.size(), double-buffered like mo_centroid / mo_conf (see filter phase)
     int res_count, res_head;    // res_vec deque
     int corr_count, corr_head;  // corrs_vec deque
     int frames;
@@ -45,29 +62,31 @@ struct TrackState {  // persists across frames (MovingObjectRemoval members, .h:
     int n_markers;    // mo_vec entries the last filterCloud looked up (one bounding-box marker each, cpp:640-642)
 };
 
-// Everything a kernel needs, passed by value (fits the 4 KB parameter space comfortably).
+// Everything a phase needs; one per sequence, read from device memory (P[seq]).
 struct FramePtrs {
     // ---- input
-    const uint8_t* in; uint32_t n, step, off_x, off_y, off_z, off_i; int vec16;
+    const uint8_t* in; uint32_t n, step, off_x, off_y, off_z, off_i; int in_mode;  // 0: float4 records, 1: aligned fields, 2: byte-assembled
     // ---- config
     float trim_x, trim_y, trim_z, gp_limit, r2, volume_constraint, pde_lb, pde_ub, pde_thr, leave_off, catch_up;
     long long min_cluster, max_cluster;
     int method, opc_factor, moving_confidence, static_confidence;
     int kmax, momax, ring_depth;
-    GridDesc grid;            // static mode: the config crop box (known at create)
-    GridDesc* dgrid;          // the grid every kernel after k_ingest/k_keys reads (device copy; rewritten per frame in dynamic mode)
-    int dynamic_grid;         // 1: the config box would need too many cells -> per-frame grid over the bounding box of `cloud`
-    int max_cells; double cell_h;
+    double inv_h, cell_h;      // clustering cell edge h = r/sqrt(3)*(1-2^-10): two points of one cell are always within r
+    int skip_ingest;           // voxel ground modes: `cloud` / gp_indices were produced by mor_ground.cuh
+    // ---- clustering grid (sparse)
+    Cell* table; unsigned table_mask;
+    int* cell_list;            // [n_cells] table slot of every occupied cell, in creation order
+    unsigned long long* ckey; int* cstart;  // [n_cells(+1)] compact copies: key, first sorted position
+    int2* pslot;               // [N_c] (table slot, rank inside the cell) of every cloud point
+    int* slead;                // [N_c] leader position (cell start) of every sorted position
     // ---- per-frame scratch
-    Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cells; unsigned long long* st_out;
-    int* cell_count; int* cell_start;
+    Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cscan; unsigned long long* st_out;
     uint8_t* point_class; uint8_t* removed_mask;
     int* cloud_src; float4* gpts; int* gsrc;
-    int* cell_key; int* skey;
     int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
-    int* comp; int* minidx; unsigned long long* done;  // indexed by sorted position (cell leaders)
-    int* scid;        // cluster id per sorted position (coalesced companion of spts for the method-1 search)
-    uint4* cell_box;  // [2*N] per leader position: {min x,y,z keys, count}, {max x,y,z keys, 0}
+    int* comp; int* minidx;    // indexed by sorted position (cell leaders)
+    int* scid;                 // cluster id per sorted position
+    uint4* cell_box;           // [2*N] per leader position: {min x,y,z keys, -}, {max x,y,z keys, -}
     unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
     unsigned* acc_box;            // [kmax*6] min xyz, max xyz keys
     unsigned* pacc_box;           // [kmax*6] transformed prev clusters
@@ -75,7 +94,7 @@ struct FramePtrs {
     float* pct;                   // [kmax*3] transformed prev centroids
     float* pbbox;                 // [kmax*6] decoded
     int* recip_q; int* recip_m; int* match_q; int* match_m; float* match_dist; double* match_score;
-    int* match_of_prev; int* mid_of_prev; int* mid_of_cur; double* anchor; int* newcount;
+    int* match_of_prev; int* mid_of_prev; int* mid_of_cur; double* anchorp; int* newcount;
     unsigned long long* lattice; unsigned lattice_mask;
     uint8_t* cluster_removed; int* found;
     int* marker_cluster;          // [momax] cluster each mo_vec entry was matched to by the last filterCloud
@@ -90,465 +109,609 @@ struct FramePtrs {
     Affine12 M; int two_frames;
     int mo_parity;  // which half of the mo_vec double buffer is current
     int pde_ring;   // method 1: search reach in cells, ceil(sqrt(pde_ub)/h)
-    int tiles_pts, tiles_cells;  // sizes of the scan status arrays
-    unsigned lattice_words16;    // lattice size in 16-byte units (cleared by k_ingest)
+    int tiles_pts;  // size of the scan status arrays
+    unsigned lattice_words16;    // lattice size in 16-byte units
+    // ---- voxel ground modes only (mor_ground.cuh): dense ball-query grid
+    int* cell_count; int* cell_start; int* cell_key; int* skey; GridDesc* dgrid; unsigned long long* st_cells; int tiles_cells; int max_cells;
 };
 
-// ===================================================================================== K1
-// pcl::fromPCLPointCloud2 (cpp:523) + PassThrough x, y (cpp:66-74, A1) + CropBox with removed indices
-// (cpp:78-86, A2), fused with the stable two-way partition into `cloud` / gp_indices order, the grid
-// cell key of every cloud point and the per-cell histogram. kIngestItems consecutive points per thread
-// (tile = 1024 points): the decoupled look-back chain has n/1024 links instead of n/256.
-#ifndef INGEST_BLOCK
-#define INGEST_BLOCK 256
-#endif
-constexpr int kIngestBlock = INGEST_BLOCK;
-constexpr int kIngestTile = 1024;
-constexpr int kIngestItems = kIngestTile / kIngestBlock;
-
-__device__ __forceinline__ void k_ingest_body(const FramePtrs& a) {
-    pdl_prologue();
-    __shared__ int s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_ingest, 1);
-    if (a.two_frames) {
-        // housekeeping for the two-frame stages, spread over the grid and overlapped with the ticket's round
-        // trip: empty octree-lattice hash set, neutral bounding boxes for the transformed previous clusters
-        const uint32_t gtid = blockIdx.x * kIngestBlock + threadIdx.x, stride = gridDim.x * kIngestBlock;
-        if (a.method == 2) {
-            uint4* lat = reinterpret_cast<uint4*>(a.lattice);
-            for (uint32_t t = gtid; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        }
-        const uint32_t kp6 = (uint32_t)a.p_counts[MOR_CNT_K] * 6u;
-        for (uint32_t t = gtid; t < kp6; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
-    }
-    __syncthreads();
-    const int tile = s_tile;
-    const uint32_t i0 = (uint32_t)tile * kIngestTile + threadIdx.x * kIngestItems;
-    float4 v[kIngestItems];
-    int cls[kIngestItems];
-    unsigned long long packed = 0ull;
-#pragma unroll
-    for (int k = 0; k < kIngestItems; k++) {
-        const uint32_t i = i0 + k;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cls[k] = 0;
-        if (i < a.n) {
-            const uint8_t* p = a.in + (size_t)i * a.step;
-            if (a.vec16) {
-                v[k] = __ldg(reinterpret_cast<const float4*>(p));
-            } else {
-                v[k].x = __ldg(reinterpret_cast<const float*>(p + a.off_x));
-                v[k].y = __ldg(reinterpret_cast<const float*>(p + a.off_y));
-                v[k].z = __ldg(reinterpret_cast<const float*>(p + a.off_z));
-                v[k].w = a.off_i != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float*>(p + a.off_i)) : 0.f;
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kIngestItems; k++) {
-        const uint32_t i = i0 + k;
-        if (i < a.n) {
-            const float x = v[k].x, y = v[k].y, z = v[k].z;
-            const bool fin = isfinite(x) && isfinite(y) && isfinite(z);
-            const bool in_xy = fin && !(x < -a.trim_x || x > a.trim_x) && !(y < -a.trim_y || y > a.trim_y);
-            if (in_xy) cls[k] = (z < a.gp_limit || z > a.trim_z) ? 2 : 1;  // x,y box tests of CropBox are implied by the trim
-            a.point_class[i] = (uint8_t)cls[k];
-            a.removed_mask[i] = cls[k] ? 1 : 0;
-            packed += (cls[k] == 1 ? 1ull : 0ull) | (cls[k] == 2 ? (1ull << 31) : 0ull);
-        }
-    }
-    unsigned long long total;
-    const unsigned long long in_block = block_exclusive_scan<unsigned long long, kIngestBlock>(packed, &total);
-    const unsigned long long before = tile_exclusive_prefix(a.st_ingest, tile, total);
-    unsigned long long mine = before + in_block;
-#pragma unroll
-    for (int k = 0; k < kIngestItems; k++) {
-        int key = -1;
-        if (cls[k] == 1 && !a.dynamic_grid) {
-            const GridDesc& g = a.grid;
-            int cx = (int)floor(((double)v[k].x - g.ox) * g.inv_h);
-            int cy = (int)floor(((double)v[k].y - g.oy) * g.inv_h);
-            int cz = (int)floor(((double)v[k].z - g.oz) * g.inv_h);
-            cx = min(max(cx, kGridPad), g.nx - 1); cy = min(max(cy, kGridPad), g.ny - 1); cz = min(max(cz, kGridPad), g.nz - 1);
-            key = (cz * g.ny + cy) * g.nx + cx;
-            atomicAdd(&a.cell_count[key], 1);  // result unused: a fire-and-forget RED, no round trip on the critical path
-        }
-        if (cls[k] == 1) {
-            const int c = (int)(mine & 0x7FFFFFFFull);
-            mine += 1ull;
-            a.pts[c] = v[k];
-            a.cloud_src[c] = (int)(i0 + k);
-            a.cell_box[2 * c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // slot c doubles as a sorted position
-            a.cell_box[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
-            if (!a.dynamic_grid) a.cell_key[c] = key;
-        } else if (cls[k] == 2) {
-            const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
-            mine += 1ull << 31;
-            a.gpts[gi] = v[k];
-            a.gsrc[gi] = (int)(i0 + k);
-        }
-    }
-    if (a.dynamic_grid) {  // bounding box of `cloud`: warp redux, then one set of atomics per warp
-        unsigned ix = 0u, iy = 0u, iz = 0u, mx = 0u, my = 0u, mz = 0u;
-#pragma unroll
-        for (int k = 0; k < kIngestItems; k++)
-            if (cls[k] == 1) {
-                const unsigned kx = fkey(v[k].x), ky = fkey(v[k].y), kz = fkey(v[k].z);
-                ix = max(ix, ~kx); iy = max(iy, ~ky); iz = max(iz, ~kz); mx = max(mx, kx); my = max(my, ky); mz = max(mz, kz);
-            }
-        ix = __reduce_max_sync(kFull, ix); iy = __reduce_max_sync(kFull, iy); iz = __reduce_max_sync(kFull, iz);
-        mx = __reduce_max_sync(kFull, mx); my = __reduce_max_sync(kFull, my); mz = __reduce_max_sync(kFull, mz);
-        if ((threadIdx.x & 31) == 0 && (ix | mx)) {
-            atomicMax(&a.scratch->box_inv_min[0], ix); atomicMax(&a.scratch->box_inv_min[1], iy); atomicMax(&a.scratch->box_inv_min[2], iz);
-            atomicMax(&a.scratch->box_max[0], mx); atomicMax(&a.scratch->box_max[1], my); atomicMax(&a.scratch->box_max[2], mz);
-        }
-    }
-    const int last_tile = a.n ? (int)((a.n - 1) / kIngestTile) : 0;
-    if (tile == last_tile && threadIdx.x == 0) {
-        const unsigned long long all = before + total;
-        const int nc = (int)(all & 0x7FFFFFFFull), ng = (int)((all >> 31) & 0x7FFFFFFFull);
-        int* c = a.counts;
-        for (int k = 0; k < MOR_NCOUNTS; k++) c[k] = 0;
-        c[MOR_CNT_N] = (int)a.n; c[MOR_CNT_NT] = nc + ng; c[MOR_CNT_NC] = nc; c[MOR_CNT_NG] = ng;
-        c[MOR_CNT_TWO_FRAMES] = a.two_frames;
-        if (a.two_frames) { c[MOR_CNT_KPREV] = a.p_counts[MOR_CNT_K]; c[MOR_CNT_NCPREV] = a.p_counts[MOR_CNT_NC]; }
-        c[MOR_CNT_FRAME] = a.track->frames + 1;
-        a.track->frames += 1;
-    }
+// ------------------------------------------------------------------------------------------------ group barrier
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__global__ void __launch_bounds__(kIngestBlock) k_ingest(FramePtrs a) { k_ingest_body(a); }
-__global__ void __launch_bounds__(kIngestBlock) k_ingest_batch(const FramePtrs* __restrict__ P) { k_ingest_body(P[blockIdx.z]); }
-
-
-// ===================================================================================== K1b (dynamic grid only)
-// When the config crop box would need more cells than the table holds (e.g. trim "disabled" with huge
-// values), the grid is laid over the bounding box of this frame's `cloud` instead. Every block derives
-// the same GridDesc from the reduced box; block 0 publishes it for the later kernels.
-__device__ __forceinline__ GridDesc grid_from_box(const FramePtrs& a, bool* too_big) {
-    GridDesc g;
-    const Scratch* sc = a.scratch;
-    const double inv_h = 1.0 / a.cell_h;
-    double lo[3], hi[3];
-#pragma unroll
-    for (int q = 0; q < 3; q++) { lo[q] = (double)fkey_inv(~sc->box_inv_min[q]); hi[q] = (double)fkey_inv(sc->box_max[q]); }
-    if (a.counts[MOR_CNT_NC] == 0) { lo[0] = lo[1] = lo[2] = 0; hi[0] = hi[1] = hi[2] = 0; }
-    const double pad = (double)kGridPad * a.cell_h;
-    g.ox = lo[0] - pad; g.oy = lo[1] - pad; g.oz = lo[2] - pad; g.inv_h = inv_h;
-    const double fx = floor((hi[0] - g.ox) * inv_h) + 1.0, fy = floor((hi[1] - g.oy) * inv_h) + 1.0, fz = floor((hi[2] - g.oz) * inv_h) + 1.0;
-    *too_big = fx * fy * fz > (double)a.max_cells;
-    if (*too_big) { g.nx = g.ny = g.nz = kGridPad + 1; }  // memory-safe degenerate grid (one real cell); the frame is flagged
-    else { g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; }
-    g.ncells = g.nx * g.ny * g.nz;
-    return g;
-}
-
-__device__ __forceinline__ void k_keys_body(const FramePtrs& a) {
-    pdl_prologue();
-    __shared__ GridDesc s_g;
-    if (threadIdx.x == 0) {
-        bool too_big;
-        s_g = grid_from_box(a, &too_big);
-        if (blockIdx.x == 0) {
-            *a.dgrid = s_g;
-            if (too_big) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_GRID_CAP);
-        }
-    }
-    __syncthreads();
-    const int c = blockIdx.x * kBlock + threadIdx.x;
-    if (c >= a.counts[MOR_CNT_NC]) return;
-    const GridDesc& g = s_g;
-    const float4 p = a.pts[c];
-    int cx = (int)floor(((double)p.x - g.ox) * g.inv_h);
-    int cy = (int)floor(((double)p.y - g.oy) * g.inv_h);
-    int cz = (int)floor(((double)p.z - g.oz) * g.inv_h);
-    cx = min(max(cx, kGridPad), g.nx - 1); cy = min(max(cy, kGridPad), g.ny - 1); cz = min(max(cz, kGridPad), g.nz - 1);
-    const int key = (cz * g.ny + cy) * g.nx + cx;
-    a.cell_key[c] = key;
-    atomicAdd(&a.cell_count[key], 1);
-}
-__global__ void __launch_bounds__(kBlock) k_keys(FramePtrs a) { k_keys_body(a); }
-__global__ void __launch_bounds__(kBlock) k_keys_batch(const FramePtrs* __restrict__ P) { k_keys_body(P[blockIdx.z]); }
-
-
-// ===================================================================================== K2
-// Exclusive scan of the per-cell histogram (counting sort of the cell keys) -> cell_start[0..ncells]. The histogram
-// itself is left in place: k_scatter counts it back down to zero (rank = atomicSub - 1), which both hands out the
-// slots of a cell and leaves the table clean for the next frame - the dense table is read once and written once.
-// Persistent blocks pull tiles by ticket, so the launch does not depend on the (possibly device-side)
-// cell count.
-// Tile size: 2048 cells for one sequence (more, shorter tiles overlap better with the neighbouring kernels of the
-// chain: +5 % frame rate), 4096 in batches (fewer look-back hops per byte: +3 %). Arrays are sized for the smaller.
-constexpr int kScanItems = 8, kScanItemsBatch = 16;
-constexpr int kScanTile = kBlock * kScanItems, kScanTileBatch = kBlock * kScanItemsBatch;
-
-template <int ITEMS>
-__device__ __forceinline__ void k_scan_cells_body(const FramePtrs& a) {
-    pdl_prologue();
-    __shared__ int s_tile;
-    const int ncells = a.dgrid->ncells;
-    const int ntiles = (ncells + (kBlock * ITEMS) - 1) / (kBlock * ITEMS);
-    while (true) {
+// All CTAs of a group (co-resident: cooperative launch) meet here; writes before it are visible after it.
+struct GroupBarrier {
+    unsigned* ctr; unsigned target, G;
+    __device__ __forceinline__ void sync() {
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_cells, 1);
+        if (G > 1 && threadIdx.x == 0) {
+            target += G;
+            __threadfence();
+            atomicAdd(ctr, 1u);
+            while (ld_acquire_u32(ctr) < target) {}
+            __threadfence();
+        }
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= ntiles) return;
-        const int base = tile * (kBlock * ITEMS) + threadIdx.x * ITEMS;
-        int v[ITEMS];
-        if (base + ITEMS <= ncells) {
-            const int4* src = reinterpret_cast<const int4*>(a.cell_count + base);
-#pragma unroll
-            for (int k = 0; k < ITEMS / 4; k++) {
-                const int4 t = src[k];
-                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < ITEMS; k++) v[k] = (base + k < ncells) ? a.cell_count[base + k] : 0;
-        }
-        int sum = 0;
-#pragma unroll
-        for (int k = 0; k < ITEMS; k++) sum += v[k];
-        int total;
-        const int in_block = block_exclusive_scan<int>(sum, &total);
-        const int before = (int)tile_exclusive_prefix(a.st_cells, tile, (unsigned long long)total);
-        int run = before + in_block;
-        if (base + ITEMS <= ncells) {
-            int4* d0 = reinterpret_cast<int4*>(a.cell_start + base);
-#pragma unroll
-            for (int k = 0; k < ITEMS / 4; k++) {
-                int4 t;
-                t.x = run; run += v[4 * k];
-                t.y = run; run += v[4 * k + 1];
-                t.z = run; run += v[4 * k + 2];
-                t.w = run; run += v[4 * k + 3];
-                d0[k] = t;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < ITEMS; k++) {
-                if (base + k < ncells) a.cell_start[base + k] = run;
-                run += v[k];
-            }
-        }
-        if (tile == ntiles - 1 && threadIdx.x == 0) a.cell_start[ncells] = before + total;
     }
+};
+
+// ------------------------------------------------------------------------------------------------ 1-D bulk copy (TMA)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__global__ void __launch_bounds__(kBlock) k_scan_cells(FramePtrs a) { k_scan_cells_body<kScanItems>(a); }
-__global__ void __launch_bounds__(kBlock, 8) k_scan_cells_batch(const FramePtrs* __restrict__ P) { k_scan_cells_body<kScanItemsBatch>(P[blockIdx.z]); }
-
-
-// ===================================================================================== K3
-// Scatter cloud points into cell-sorted order (float4 xyz + cloud index) for the neighbour search and
-// reset the per-position union-find state. The first point of a cell (its "leader" position
-// cell_start[key]) is the union-find node of the whole cell.
-__device__ __forceinline__ void k_scatter_body(const FramePtrs& a) {
-    pdl_prologue();
-    const int c = blockIdx.x * kBlock + threadIdx.x;
-    if (c >= a.counts[MOR_CNT_NC]) return;
-    const int key = a.cell_key[c];
-    const int pos = a.cell_start[key] + atomicSub(&a.cell_count[key], 1) - 1;  // slots of a cell are handed out last to first
-    float4 p = a.pts[c];
-    p.w = __int_as_float(c);
-    a.spts[pos] = p;
-    a.skey[pos] = key;
-    a.parent[c] = c;  // c doubles as a sorted position here: both index spaces are [0, N_c)
-    a.comp_size[c] = 0;
-    a.minidx[c] = 0x7FFFFFFF;
-    a.done[c] = 0ull;
-    // tight bounding box of every crowded cell (prunes the point-vs-cell scans of k_link_cells);
-    // lanes of a warp that fall into the same cell are combined with redux before the atomics
-    const int cnt = a.cell_start[key + 1] - a.cell_start[key];
-    if (cnt > kBoxMinCount) {
-        const unsigned grp = __match_any_sync(__activemask(), key);
-        const unsigned kx = fkey(p.x), ky = fkey(p.y), kz = fkey(p.z);
-        const unsigned mnx = __reduce_min_sync(grp, kx), mny = __reduce_min_sync(grp, ky), mnz = __reduce_min_sync(grp, kz);
-        const unsigned mxx = __reduce_max_sync(grp, kx), mxy = __reduce_max_sync(grp, ky), mxz = __reduce_max_sync(grp, kz);
-        if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
-            unsigned* b = reinterpret_cast<unsigned*>(a.cell_box + 2 * a.cell_start[key]);
-            atomicMin(b + 0, mnx); atomicMin(b + 1, mny); atomicMin(b + 2, mnz);
-            atomicMax(b + 4, mxx); atomicMax(b + 5, mxy); atomicMax(b + 6, mxz);
-        }
-    }
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of dst are done (WAR across proxies)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__global__ void __launch_bounds__(kBlock) k_scatter(FramePtrs a) { k_scatter_body(a); }
-__global__ void __launch_bounds__(kBlock) k_scatter_batch(const FramePtrs* __restrict__ P) { k_scatter_body(P[blockIdx.z]); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
-
-// ===================================================================================== K4
-// pcl::EuclideanClusterExtraction radius graph (cpp:213-218; A5-A7) on cell granularity. Every point q
-// looks at the 62 "backward" cells of its 5x5x5 neighbourhood (13 x-rows, each a contiguous run of the
-// sorted array); the first point of such a cell with L2_Simple distance < r2 (strict) connects the two
-// cells. A 62-bit mask per cell records the pairs already united, so each connected cell pair costs
-// one atomicOr + one union, however many point pairs realise it.
-__device__ __forceinline__ unsigned long long ld_done(const unsigned long long* p) {
+// ------------------------------------------------------------------------------------------------ clustering grid
+constexpr int kCellBias = 1 << 20;  // cell coordinates are stored biased, 21 bits per axis
+__device__ __forceinline__ unsigned long long cell_pack(int cx, int cy, int cz) {
+    return (1ull << 63) | ((unsigned long long)(unsigned)(cz + kCellBias) << 42) | ((unsigned long long)(unsigned)(cy + kCellBias) << 21) |
+           (unsigned long long)(unsigned)(cx + kCellBias);
+}
+__device__ __forceinline__ void cell_unpack(unsigned long long key, int& cx, int& cy, int& cz) {
+    cx = (int)(key & 0x1FFFFFull) - kCellBias; cy = (int)((key >> 21) & 0x1FFFFFull) - kCellBias; cz = (int)((key >> 42) & 0x1FFFFFull) - kCellBias;
+}
+// Cell coordinate of one float coordinate (double arithmetic; identical wherever a point is binned). Range-limited so
+// that the +-2 neighbourhood never leaves the 21-bit field; *oob is set for coordinates beyond (|x| > ~2^20 cells).
+__device__ __forceinline__ int cell_coord(float v, double inv_h, bool* oob) {
+    const double c = floor((double)v * inv_h);
+    const double lim = (double)(kCellBias - 8);
+    if (c < -lim || c > lim) { *oob = true; return c < 0 ? -(kCellBias - 8) : (kCellBias - 8); }
+    return (int)c;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
-
-// Examines the sorted positions j..e-1 (the cells of one x-run of a neighbour row) for point q; see k_link_cells.
-// `rowkey` is the key of the cell straight "above" q's cell in that row: the pair bit of cell kj is row*5 + (kj - rowkey + 2).
-template <int PHASE>
-__device__ __forceinline__ void link_scan_range(const FramePtrs& a, const float4 q, int lead, int row, int rowkey, int j, const int e,
-                                                unsigned long long& dmask) {
-    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
-    while (j < e) {
-        const int kj = a.skey[j];
-        const int cell_end = a.cell_start[kj + 1];
-        const int bit = row * 5 + (kj - rowkey + 2);
-        bool skip = (dmask >> bit) & 1ull;
-        if (!skip && cell_end - j > kBoxMinCount) {
-            // conservative point-to-box distance: no point of the cell can be closer than this
-            const uint4 lo = a.cell_box[2 * j], hi = a.cell_box[2 * j + 1];
-            const float ex = fmaxf(fmaxf(fkey_inv(lo.x) - q.x, q.x - fkey_inv(hi.x)), 0.f);
-            const float ey = fmaxf(fmaxf(fkey_inv(lo.y) - q.y, q.y - fkey_inv(hi.y)), 0.f);
-            const float ez = fmaxf(fmaxf(fkey_inv(lo.z) - q.z, q.z - fkey_inv(hi.z)), 0.f);
-            skip = ex * ex + ey * ey + ez * ez > r2_prune;
-            if (PHASE == 2 && !skip && cell_end - j > kRootCheckCount) {
-                // far pass: the near pass has already merged most of a dense surface; two cells of one
-                // component need no point tests (the pair is marked done, which is all the mask means)
-                // one lane per (cell pair) of the converged lanes walks the two paths and shares the verdict
-                const unsigned grp = __match_any_sync(__activemask(), (lead << 6) | bit);
-                const int leader_lane = __ffs(grp) - 1;
-                int same = 0;
-                if ((int)(threadIdx.x & 31) == leader_lane) {
-                    same = uf_find(a.parent, lead) == uf_find(a.parent, j) ? 1 : 0;
-                    if (same) atomicOr(a.done + lead, 1ull << bit);
-                }
-                same = __shfl_sync(grp, same, leader_lane);
-                if (same) { dmask |= 1ull << bit; skip = true; }
-            }
+__device__ __forceinline__ int grid_find_or_insert(const FramePtrs& a, unsigned long long key, bool* created) {
+    unsigned slot = hash64(key) & a.table_mask;
+    while (true) {
+        const unsigned long long cur = ld_relaxed_u64(&a.table[slot].key);
+        if (cur == key) { *created = false; return (int)slot; }
+        if (cur == 0ull) {
+            const unsigned long long old = atomicCAS(&a.table[slot].key, 0ull, key);
+            if (old == 0ull) { *created = true; return (int)slot; }
+            if (old == key) { *created = false; return (int)slot; }
         }
-        if (!skip) {
-            bool hit = false;
-            const int other = j;  // leader position of the neighbour cell
-            const int last = cell_end - 1;
-            for (int it = 0; j < cell_end && !hit; j += 4) {  // always 4 independent loads in flight (indices clamped)
-                const float4 p0 = a.spts[j], p1 = a.spts[min(j + 1, last)], p2 = a.spts[min(j + 2, last)], p3 = a.spts[min(j + 3, last)];
-                const float d0 = sqdist3(q.x, q.y, q.z, p0.x, p0.y, p0.z), d1 = sqdist3(q.x, q.y, q.z, p1.x, p1.y, p1.z);
-                const float d2 = sqdist3(q.x, q.y, q.z, p2.x, p2.y, p2.z), d3 = sqdist3(q.x, q.y, q.z, p3.x, p3.y, p3.z);
-                hit = fminf(fminf(d0, d1), fminf(d2, d3)) < r2;
-                if (((++it) & 63) == 63 && !hit) {  // somebody else of my cell may have connected this pair meanwhile
-                    dmask |= ld_done(a.done + lead);
-                    if ((dmask >> bit) & 1ull) break;
-                }
-            }
-            if (hit) {
-                // lanes of the warp that found the same cell pair at the same time elect one publisher: the
-                // done word of a crowded cell would otherwise take thousands of same-address atomics
-                const unsigned grp = __match_any_sync(__activemask(), (lead << 6) | bit);
-                if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
-                    dmask |= ld_done(a.done + lead);
-                    if (!((dmask >> bit) & 1ull)) {
-                        const unsigned long long old = atomicOr(a.done + lead, 1ull << bit);
-                        if (!((old >> bit) & 1ull)) uf_union(a.parent, lead, other);
-                    }
-                }
-                dmask |= 1ull << bit;
-            }
-        }
-        j = cell_end;
+        slot = (slot + 1) & a.table_mask;
     }
 }
-
-// grid = (point tiles, rows): one thread per (point q, x-row of the backward neighbourhood), so the serial
-// chain of a thread is a handful of cells and a warp walks the same cells for neighbouring q.
-// PHASE 1 = the 13 backward cells of the 3x3x3 block (5 rows); PHASE 2 = the 49 cells at offset 2 (13 rows).
-// Neighbour rows are addressed linearly from the point's own key (key + dy*nx + dz*nx*ny +- 2): the grid carries
-// kGridPad empty cells on the low side of every axis, so a backward offset never leaves the table and an offset
-// that runs over the high end of a row / layer lands in the next row's / layer's padding, which is always empty.
-// Block size: at 32 registers an SM holds 64 warps either way; one sequence alone is a latency chain in which a
-// block should retire as soon as its slowest warp does (small blocks), a batch of sequences keeps the SMs full and
-// pays per block (large blocks).
-constexpr int kLinkBlock = LINK_BLOCK_SINGLE, kLinkBlockBatch = 256;
-template <int PHASE, int BLOCK>
-__device__ __forceinline__ void k_link_cells_body(const FramePtrs& a, int row_index) {
-    pdl_prologue();
-    const int s = blockIdx.x * BLOCK + threadIdx.x;
-    const int nc = a.counts[MOR_CNT_NC];
-    if (s >= nc) return;
-    // canonical row ids (they fix the bit layout): 0-4: dz=-2, 5-9: dz=-1, 10-12: dz=0 with dy=-2,-1,0
-    int row = row_index;
-    if (PHASE == 1) row = row_index == 0 ? 12 : (row_index == 1 ? 11 : 4 + row_index);  // near rows: 12, 11, 6, 7, 8
-    const int dz = row < 5 ? -2 : (row < 10 ? -1 : 0);
-    const int dy = row < 10 ? (row % 5) - 2 : row - 12;
-    const bool near_row = dz >= -1 && dy >= -1 && dy <= 1;
-    const int key = a.skey[s];
-    const int nx = a.dgrid->nx, ny = a.dgrid->ny;
-    const int rowkey = key + dy * nx + dz * nx * ny;
-    // the x-runs of this (point, row): most of them are empty, so their bounds are fetched before anything else
-    int ka, kb, kc = 0, kd = -1;
-    if (PHASE == 1) { ka = rowkey - 1; kb = row == 12 ? rowkey - 1 : rowkey + 1; }
-    else if (!near_row) { ka = rowkey - 2; kb = rowkey + 2; }
-    else { ka = kb = rowkey - 2; if (row != 12) { kc = kd = rowkey + 2; } }
-    const int j0 = a.cell_start[ka], e0 = a.cell_start[kb + 1];
-    int j1 = 0, e1 = 0;
-    if (kd >= kc) { j1 = a.cell_start[kc]; e1 = a.cell_start[kd + 1]; }
-    if (j0 >= e0 && j1 >= e1) return;
-    const float4 q = a.spts[s];
-    const int lead = a.cell_start[key];
-    unsigned long long dmask = ld_done(a.done + lead);
-    if (j0 < e0) link_scan_range<PHASE>(a, q, lead, row, rowkey, j0, e0, dmask);
-    if (j1 < e1) link_scan_range<PHASE>(a, q, lead, row, rowkey, j1, e1, dmask);
+// Read-only look-up (the table is complete: after the barrier that follows the insert phase).
+__device__ __forceinline__ bool grid_lookup(const FramePtrs& a, unsigned long long key, Cell* out) {
+    unsigned slot = hash64(key) & a.table_mask;
+    while (true) {
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(a.table + slot));
+        const unsigned long long cur = ((unsigned long long)raw.y << 32) | raw.x;
+        if (cur == key) { out->key = cur; out->start = (int)raw.z; out->cnt = (int)raw.w; return true; }
+        if (cur == 0ull) return false;
+        slot = (slot + 1) & a.table_mask;
+    }
 }
-// One launch for both passes: blockIdx.y 0..4 = near pass, 5..17 = far pass. Blocks are dispatched y-major, so the
-// near rows start first and most of their unions are in place when the far rows run their root checks; the two
-// passes' tails overlap instead of adding up (the far pass is correct with any amount of near-pass progress: its
-// root check is only a shortcut).
-__global__ void __launch_bounds__(kLinkBlock, 2048 / kLinkBlock) k_link_cells(FramePtrs a) {
-    if (blockIdx.y < 5) k_link_cells_body<1, kLinkBlock>(a, blockIdx.y); else k_link_cells_body<2, kLinkBlock>(a, blockIdx.y - 5);
-}
-__global__ void __launch_bounds__(kLinkBlockBatch, 2048 / kLinkBlockBatch) k_link_cells_batch(const FramePtrs* __restrict__ P) {
-    if (blockIdx.y < 5) k_link_cells_body<1, kLinkBlockBatch>(P[blockIdx.z], blockIdx.y); else k_link_cells_body<2, kLinkBlockBatch>(P[blockIdx.z], blockIdx.y - 5);
-}
-
-// ===================================================================================== K5
-// Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud
-// index of every component (the canonical label) with warp-aggregated atomics, collect the roots.
-__device__ void select_block(const FramePtrs& a);
-
-__device__ __forceinline__ void k_flatten_body(const FramePtrs& a) {
-    pdl_prologue();
-    const int s = blockIdx.x * kSingle + threadIdx.x;
+// Whole warp: the lanes with `valid` bin their point. Lanes that fall into the same cell (neighbouring beams usually
+// do) elect one lane that walks the table and takes one ticket block for the group. Returns (slot, rank in the cell).
+__device__ __forceinline__ int2 grid_insert_warp(const FramePtrs& a, bool valid, unsigned long long key) {
     const int lane = threadIdx.x & 31;
-    const int nc = a.counts[MOR_CNT_NC];
-    const bool act = s < nc;
-    int c = 0, r = -1 - lane;
-    if (act) {
-        c = __float_as_int(a.spts[s].w);
-        const int lead = a.cell_start[a.skey[s]];
-        r = uf_find(a.parent, lead);
-        a.comp[s] = r;
-        if (r == s) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s;
+    const unsigned grp = __match_any_sync(kFull, valid ? key : (unsigned long long)lane);  // real keys have bit 63 set
+    const int leader = __ffs(grp) - 1;
+    int slot = 0, base = 0;
+    bool created = false;
+    if (valid && lane == leader) {
+        slot = grid_find_or_insert(a, key, &created);
+        base = atomicAdd(&a.table[slot].cnt, __popc(grp));
     }
-    const unsigned same = __match_any_sync(kFull, r);
-    const int mn = __reduce_min_sync(same, c);
-    if (act && (int)(__ffs(same) - 1) == lane) {
-        atomicAdd(&a.comp_size[r], __popc(same));
-        atomicMin(&a.minidx[r], mn);
+    const unsigned cmask = __ballot_sync(kFull, created);
+    if (cmask) {  // one ticket block of the cell list per warp
+        int lbase = 0;
+        if (lane == __ffs(cmask) - 1) lbase = atomicAdd(&a.scratch->n_cells, __popc(cmask));
+        lbase = __shfl_sync(kFull, lbase, __ffs(cmask) - 1);
+        if (created) a.cell_list[lbase + __popc(cmask & ((1u << lane) - 1u))] = slot;
     }
-    // the last block to finish selects and orders the clusters (K6) - no separate single-block launch
-    __shared__ int s_last;
-    __threadfence();  // root_list entries are plain stores of arbitrary threads
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(&a.scratch->flatten_blocks_done, 1) == (int)gridDim.x - 1;
-        __threadfence();
-    }
-    __syncthreads();
-    if (s_last) select_block(a);
+    slot = __shfl_sync(kFull, slot, leader);
+    base = __shfl_sync(kFull, base, leader);
+    return make_int2(slot, base + __popc(grp & ((1u << lane) - 1u)));
 }
-__global__ void __launch_bounds__(kSingle) k_flatten(FramePtrs a) { k_flatten_body(a); }
-__global__ void __launch_bounds__(kSingle) k_flatten_batch(const FramePtrs* __restrict__ P) { k_flatten_body(P[blockIdx.z]); }
 
+// ------------------------------------------------------------------------------------------------ octree-leaf lattice
+// pcl::octree::OctreePointCloudChangeDetector (cpp:319-330, A13): the leaf lattice of a previous cluster is
+// floor((p - anchor)/res) in double, anchored at its first point (PCL 1.8 adoptBoundingBoxToPoint + getKeyBitSize, see
+// DESIGN.md); the occupied leaves of every transformed previous cluster go into one global hash set keyed
+// (prev cluster, ix, iy, iz).
+__device__ __forceinline__ bool lattice_key(const double* anchor3, int k, float x, float y, float z, unsigned long long* key) {
+    const double res = (double)0.1f;
+    const long long ix = (long long)floor(((double)x - anchor3[0]) / res);
+    const long long iy = (long long)floor(((double)y - anchor3[1]) / res);
+    const long long iz = (long long)floor(((double)z - anchor3[2]) / res);
+    const bool ok = ix >= -32768 && ix < 32768 && iy >= -32768 && iy < 32768 && iz >= -32768 && iz < 32768;
+    *key = ((unsigned long long)(unsigned)k << 48) | ((unsigned long long)(ix + 32768) << 32) | ((unsigned long long)(iy + 32768) << 16) |
+           (unsigned long long)(iz + 32768);
+    return ok;
+}
 
-// ===================================================================================== K6
-// Size filter min <= size <= max (cpp:215-216), cluster order = size descending then min index
-// ascending (A9 canonical rule) by a shared-memory bitonic sort of (~size, root) keys.
-__device__ void select_block(const FramePtrs& a) {
-    extern __shared__ unsigned long long keys[];
+// ===================================================================================== phase A: ingest
+// pcl::fromPCLPointCloud2 (cpp:523) + PassThrough x, y (cpp:66-74, A1) + CropBox with removed indices (cpp:78-86, A2),
+// fused with the stable two-way partition into `cloud` / gp_indices order (one packed decoupled look-back scan over
+// 1024-point tiles) and the binning of every cloud point into the clustering grid.
+constexpr int kIngestTile = kT;
+
+__device__ __forceinline__ float load_f32(const uint8_t* p, int mode) {
+    if (mode != 2) return __ldg(reinterpret_cast<const float*>(p));
+    // records whose stride or field offsets are not multiples of 4 (e.g. the 22-byte velodyne XYZIRT layout)
+    const unsigned b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+    return __uint_as_float(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+}
+
+__device__ __forceinline__ void frame_housekeeping(const FramePtrs& a, int cta, int G) {
+    // work for the two-frame stages that depends on the previous frame only, spread over the group: empty octree-leaf
+    // hash set, neutral boxes and lattice anchors of the transformed previous clusters
+    if (!a.two_frames) return;
+    const uint32_t gtid = (uint32_t)cta * kT + threadIdx.x, stride = (uint32_t)G * kT;
+    if (a.method == 2) {
+        uint4* lat = reinterpret_cast<uint4*>(a.lattice);
+        for (uint32_t t = gtid; t < a.lattice_words16; t += stride) lat[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+    const uint32_t kp = (uint32_t)a.p_counts[MOR_CNT_K];
+    for (uint32_t t = gtid; t < kp * 6u; t += stride) a.pacc_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
+    if (a.method == 2) {
+        for (uint32_t t = gtid; t < kp; t += stride) {
+            // the first point added to the octree is the previous cluster's first (= minimum cloud index) point, transformed
+            const float4 p = a.p_pts[a.p_cl_root[t]];
+            const float3 f = xform(a.M, p.x, p.y, p.z);
+            const double res = (double)0.1f, eps = (double)1.1920928955078125e-07f;
+            const double fv[3] = {(double)f.x, (double)f.y, (double)f.z};
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const double lo = fv[q] - res / 2, hi = fv[q] + res / 2;
+                const double side = 2.0 * res - eps;
+                const double over = (side - (hi - lo)) / 2.0;
+                a.anchorp[t * 3 + q] = lo - over;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long bin_point(const FramePtrs& a, const float4& v, bool* oob) {
+    const int cx = cell_coord(v.x, a.inv_h, oob), cy = cell_coord(v.y, a.inv_h, oob), cz = cell_coord(v.z, a.inv_h, oob);
+    return cell_pack(cx, cy, cz);
+}
+
+__device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G) {
+    frame_housekeeping(a, cta, G);
+    const int ntiles = a.n ? (int)((a.n + kIngestTile - 1) / kIngestTile) : 1;
+    for (int tile = cta; tile < ntiles; tile += G) {
+        const uint32_t i = (uint32_t)tile * kIngestTile + threadIdx.x;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cls = 0;
+        if (i < a.n) {
+            const uint8_t* p = a.in + (size_t)i * a.step;
+            if (a.in_mode == 0) {
+                v = __ldg(reinterpret_cast<const float4*>(p));
+            } else {
+                v.x = load_f32(p + a.off_x, a.in_mode); v.y = load_f32(p + a.off_y, a.in_mode); v.z = load_f32(p + a.off_z, a.in_mode);
+                v.w = a.off_i != 0xFFFFFFFFu ? load_f32(p + a.off_i, a.in_mode) : 0.f;
+            }
+            const bool fin = isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
+            const bool in_xy = fin && !(v.x < -a.trim_x || v.x > a.trim_x) && !(v.y < -a.trim_y || v.y > a.trim_y);
+            if (in_xy) cls = (v.z < a.gp_limit || v.z > a.trim_z) ? 2 : 1;  // x,y box tests of CropBox are implied by the trim
+            a.point_class[i] = (uint8_t)cls;
+            a.removed_mask[i] = cls ? 1 : 0;
+        }
+        // binning first: its table walk and ticket overlap with the look-back of the partition below
+        bool oob = false;
+        const unsigned long long key = cls == 1 ? bin_point(a, v, &oob) : 0ull;
+        const int2 sr = grid_insert_warp(a, cls == 1, key);
+        if (oob) atomicOr(&a.scratch->err_early, ERR_GRID_RANGE);
+        const unsigned long long packed = (cls == 1 ? 1ull : 0ull) | (cls == 2 ? (1ull << 31) : 0ull);
+        unsigned long long total;
+        const unsigned long long in_block = block_exclusive_scan<unsigned long long, kT>(packed, &total);
+        const unsigned long long before = tile_exclusive_prefix(a.st_ingest, tile, total);
+        const unsigned long long mine = before + in_block;
+        if (cls == 1) {
+            const int c = (int)(mine & 0x7FFFFFFFull);
+            a.pts[c] = v;
+            a.cloud_src[c] = (int)i;
+            a.pslot[c] = sr;
+        } else if (cls == 2) {
+            const int gi = (int)((mine >> 31) & 0x7FFFFFFFull);
+            a.gpts[gi] = v;
+            a.gsrc[gi] = (int)i;
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            const unsigned long long all = before + total;
+            const int nc = (int)(all & 0x7FFFFFFFull), ng = (int)((all >> 31) & 0x7FFFFFFFull);
+            int* c = a.counts;
+            for (int k = 0; k < MOR_NCOUNTS; k++) c[k] = 0;
+            c[MOR_CNT_N] = (int)a.n; c[MOR_CNT_NT] = nc + ng; c[MOR_CNT_NC] = nc; c[MOR_CNT_NG] = ng;
+            c[MOR_CNT_TWO_FRAMES] = a.two_frames;
+            if (a.two_frames) { c[MOR_CNT_KPREV] = a.p_counts[MOR_CNT_K]; c[MOR_CNT_NCPREV] = a.p_counts[MOR_CNT_NC]; }
+            c[MOR_CNT_FRAME] = a.track->frames + 1;
+            a.track->frames += 1;
+        }
+    }
+}
+
+// Voxel ground modes: `cloud` already exists (k_ground_partition); only the binning is left to do.
+__device__ __forceinline__ void phase_bin_cloud(const FramePtrs& a, int cta, int G) {
+    frame_housekeeping(a, cta, G);
+    const int nc = a.counts[MOR_CNT_NC];
+    for (int base = cta * kT; base < nc; base += G * kT) {
+        const int c = base + threadIdx.x;
+        bool oob = false;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nc) v = a.pts[c];
+        const unsigned long long key = c < nc ? bin_point(a, v, &oob) : 0ull;
+        const int2 sr = grid_insert_warp(a, c < nc, key);
+        if (oob) atomicOr(&a.scratch->err_early, ERR_GRID_RANGE);
+        if (c < nc) a.pslot[c] = sr;
+    }
+}
+
+// ===================================================================================== phase B: cell scan + transform
+// (1) Exclusive scan of the cell populations in cell-list order -> first sorted position of every cell; the cell's
+//     union-find node, its compact descriptors and (crowded cells) its neutral bounding box are set up on the way.
+// (2) Beside it, on the CTAs the scan does not need: pcl_ros::transformPointCloud of every previous-frame cluster
+//     (cpp:544-551, A12), the bounding box of the transformed points (getMinMax3D runs after the transform, cpp:272)
+//     and, for method 2, their octree leaves (cpp:319-324).
+__device__ __forceinline__ void cell_scan_tile(const FramePtrs& a, int tile, int n_cells, int ntiles) {
+    const int i = tile * kT + threadIdx.x;
+    int slot = 0, cnt = 0;
+    unsigned long long key = 0ull;
+    if (i < n_cells) {
+        slot = a.cell_list[i];
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(a.table + slot));
+        key = ((unsigned long long)raw.y << 32) | raw.x;
+        cnt = (int)raw.w;
+    }
+    int total;
+    const int in_block = block_exclusive_scan<int, kT>(cnt, &total);
+    const int before = (int)tile_exclusive_prefix(a.st_cscan, tile, (unsigned long long)total);
+    const int start = before + in_block;
+    if (i < n_cells) {
+        a.table[slot].start = start;
+        a.ckey[i] = key; a.cstart[i] = start;
+        a.parent[start] = start; a.comp_size[start] = 0; a.minidx[start] = 0x7FFFFFFF;
+        if (cnt > kBoxMinCount) {
+            a.cell_box[2 * start] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+            a.cell_box[2 * start + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) a.cstart[n_cells] = before + total;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// Per-cluster accumulation of coordinate sums (optional) and bounding boxes with two levels of aggregation before the
+// global atomics: warp (match.any + redux) and block (shared memory). In sorted order a tile of kT consecutive points
+// lies inside one cluster most of the time, so a 30k-point cluster costs ~30 sets of atomics instead of 30k. Every
+// thread of the block must call.
+template <bool WITH_SUMS>
+__device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc_sum, unsigned* acc_box, int k, bool valid, float x, float y, float z) {
+    __shared__ int s_k[kWarps];                       // cluster of the warp, -1 = no valid lane, -2 = mixed
+    __shared__ unsigned long long s_sum[kWarps][6];
+    __shared__ unsigned s_box[kWarps][6];
+    __shared__ int s_mode;                            // >= 0: the whole block is cluster s_mode; -1: per-warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned vmask = __ballot_sync(kFull, valid);
+    const unsigned grp = __match_any_sync(kFull, valid ? k : -1);
+    const bool leader = valid && (int)(__ffs(grp) - 1) == lane;
+    const bool uniform = vmask != 0 && (grp & vmask) == vmask && valid;  // true in the valid lanes of a one-cluster warp
+    const bool warp_uniform = __any_sync(kFull, uniform);
+    unsigned bx[6];
+    {
+        const unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
+        bx[0] = __reduce_min_sync(grp, kx); bx[1] = __reduce_min_sync(grp, ky); bx[2] = __reduce_min_sync(grp, kz);
+        bx[3] = __reduce_max_sync(grp, kx); bx[4] = __reduce_max_sync(grp, ky); bx[5] = __reduce_max_sync(grp, kz);
+    }
+    unsigned long long sm[6] = {0, 0, 0, 0, 0, 0};
+    if (WITH_SUMS) {
+        const float v[3] = {x, y, z};
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            long long h, l;
+            split_fixed(v[q], h, l);  // h in [-2^31, 2^31), l in [0, 2^30): summed in 16/15-bit pieces so redux.add (32-bit) cannot overflow
+            const long long sh = ((long long)__reduce_add_sync(grp, (int)(h >> 16)) << 16) + (long long)__reduce_add_sync(grp, (int)(h & 0xFFFF));
+            const long long sl = ((long long)__reduce_add_sync(grp, (int)(l >> 15)) << 15) + (long long)__reduce_add_sync(grp, (int)(l & 0x7FFF));
+            sm[q * 2] = (unsigned long long)sh; sm[q * 2 + 1] = (unsigned long long)sl;
+        }
+    }
+    __syncthreads();  // the previous tile's readers of s_k / s_sum / s_box are done
+    if (warp_uniform && leader) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) { s_box[warp][q] = bx[q]; if (WITH_SUMS) s_sum[warp][q] = sm[q]; }
+    }
+    const int k_first = __shfl_sync(kFull, k, vmask ? __ffs(vmask) - 1 : 0);
+    if (lane == 0) s_k[warp] = !vmask ? -1 : (warp_uniform ? k_first : -2);
+    __syncthreads();
+    if (warp == 0) {
+        const int wk = lane < kWarps ? s_k[lane] : -1;
+        const unsigned has = __ballot_sync(kFull, wk != -1);
+        const int first = has ? __shfl_sync(kFull, wk, __ffs(has) - 1) : -1;
+        const bool same = __all_sync(kFull, wk == -1 || (wk == first && wk >= 0));
+        if (lane == 0) s_mode = (has && same) ? first : -1;
+    }
+    __syncthreads();
+    const int mode = s_mode;
+    if (mode >= 0) {  // the whole block is one cluster: one set of atomics
+        if (threadIdx.x < 6) {
+            unsigned v = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+            for (int w = 0; w < kWarps; w++)
+                if (s_k[w] >= 0) v = threadIdx.x < 3 ? min(v, s_box[w][threadIdx.x]) : max(v, s_box[w][threadIdx.x]);
+            if (threadIdx.x < 3) atomicMin(acc_box + mode * 6 + threadIdx.x, v); else atomicMax(acc_box + mode * 6 + threadIdx.x, v);
+        } else if (WITH_SUMS && threadIdx.x >= 32 && threadIdx.x < 38) {
+            const int q = threadIdx.x - 32;
+            unsigned long long v = 0;
+            for (int w = 0; w < kWarps; w++)
+                if (s_k[w] >= 0) v += s_sum[w][q];
+            atomicAdd(acc_sum + mode * 6 + q, v);
+        }
+    } else if (leader) {  // one set of atomics per (warp, cluster) group
+        unsigned* b = acc_box + k * 6;
+        atomicMin(b + 0, bx[0]); atomicMin(b + 1, bx[1]); atomicMin(b + 2, bx[2]);
+        atomicMax(b + 3, bx[3]); atomicMax(b + 4, bx[4]); atomicMax(b + 5, bx[5]);
+        if (WITH_SUMS) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) atomicAdd(acc_sum + k * 6 + q, sm[q]);
+        }
+    }
+}
+
+__device__ __forceinline__ void transform_tile(const FramePtrs& a, int tile) {
+    const int s = tile * kT + threadIdx.x;
+    const int ncp = a.p_counts[MOR_CNT_NC];
+    int k = -1;
+    float3 t = make_float3(0, 0, 0);
+    if (s < ncp) {
+        const float4 p = a.p_spts[s];
+        const int c = __float_as_int(p.w);
+        k = a.p_cid[c];
+        if (k >= 0) {
+            t = xform(a.M, p.x, p.y, p.z);
+            a.tpts[c] = make_float4(t.x, t.y, t.z, __int_as_float(k));
+            if (a.method == 2) {
+                unsigned long long key;
+                if (lattice_key(a.anchorp + (size_t)k * 3, k, t.x, t.y, t.z, &key)) hset_insert(a.lattice, a.lattice_mask, key);
+                else atomicOr(&a.scratch->err_early, ERR_LATTICE_RANGE);
+            }
+        } else {
+            a.tpts[c] = make_float4(0, 0, 0, __int_as_float(-1));
+        }
+    }
+    block_cluster_accumulate<false>(nullptr, a.pacc_box, k, k >= 0, t.x, t.y, t.z);
+}
+
+__device__ __forceinline__ void phase_cells_and_transform(const FramePtrs& a, int cta, int G) {
+    const int n_cells = __ldcg(&a.scratch->n_cells);
+    const int ctiles = n_cells ? (n_cells + kT - 1) / kT : 1;
+    const int ncp = a.two_frames ? a.p_counts[MOR_CNT_NC] : 0;
+    const int ttiles = (ncp + kT - 1) / kT;
+    for (int vb = cta; vb < ctiles + ttiles; vb += G) {
+        if (vb < ctiles) cell_scan_tile(a, vb, n_cells, ctiles);
+        else transform_tile(a, vb - ctiles);
+    }
+}
+
+// ===================================================================================== phase C: scatter
+// Cloud points into cell order (float4 xyz + cloud index): slot = cell start + the rank taken at binning time. Tight
+// bounding boxes of the crowded cells (they prune the point tests of the link phase).
+__device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G) {
+    const int nc = a.counts[MOR_CNT_NC];
+    for (int base = cta * kT; base < nc; base += G * kT) {
+        const int c = base + threadIdx.x;
+        const int lane = threadIdx.x & 31;
+        bool crowded = false;
+        int start = -1 - lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nc) {
+            const int2 sr = a.pslot[c];
+            const int2 sc = __ldcg(reinterpret_cast<const int2*>(&a.table[sr.x].start));  // (start, cnt)
+            p = a.pts[c];
+            p.w = __int_as_float(c);
+            a.spts[sc.x + sr.y] = p;
+            a.slead[sc.x + sr.y] = sc.x;
+            crowded = sc.y > kBoxMinCount;
+            if (crowded) start = sc.x;
+        }
+        if (__any_sync(kFull, crowded)) {
+            // lanes of a warp that fall into the same crowded cell are combined with redux before the atomics
+            const unsigned grp = __match_any_sync(kFull, start);
+            const unsigned kx = fkey(p.x), ky = fkey(p.y), kz = fkey(p.z);
+            const unsigned mnx = __reduce_min_sync(grp, kx), mny = __reduce_min_sync(grp, ky), mnz = __reduce_min_sync(grp, kz);
+            const unsigned mxx = __reduce_max_sync(grp, kx), mxy = __reduce_max_sync(grp, ky), mxz = __reduce_max_sync(grp, kz);
+            if (crowded && (int)(__ffs(grp) - 1) == lane) {
+                unsigned* b = reinterpret_cast<unsigned*>(a.cell_box + 2 * start);
+                atomicMin(b + 0, mnx); atomicMin(b + 1, mny); atomicMin(b + 2, mnz);
+                atomicMax(b + 4, mxx); atomicMax(b + 5, mxy); atomicMax(b + 6, mxz);
+            }
+        }
+    }
+}
+
+// ===================================================================================== phase D: link
+// pcl::EuclideanClusterExtraction's radius graph (cpp:213-218; A5-A7) on cell granularity. Any two points of one cell
+// are neighbours (cell diagonal < r), so a cell is one union-find node, and a neighbour lies at most 2 cells away per
+// axis: cell A must be tested against the 62 cells of its 5x5x5 block that precede it in (dz,dy,dx) order (the other 62
+// test A from their side). Two cells are linked iff some point pair has L2_Simple distance < r2 (strict).
+// One WARP per cell; a link round takes 32 consecutive cells of the cell list, whose points are one contiguous range of
+// the sorted array: it is staged in shared memory by a single bulk copy (TMA) while the lanes walk the hash table -
+// lane l looks up neighbours l and l+32. Every lane then tests its neighbour cells' points (read from L2) against A's
+// points (shared memory) and unites on the first hit; cell pairs with many point pairs are left to the whole warp
+// (lanes across B's points, bounding-box pruning on both sides, root check first).
+struct BoxF { float lx, ly, lz, hx, hy, hz; };
+__device__ __forceinline__ BoxF load_box(const FramePtrs& a, int start) {
+    const uint4 lo = __ldcg(a.cell_box + 2 * start), hi = __ldcg(a.cell_box + 2 * start + 1);
+    BoxF b;
+    b.lx = fkey_inv(lo.x); b.ly = fkey_inv(lo.y); b.lz = fkey_inv(lo.z); b.hx = fkey_inv(hi.x); b.hy = fkey_inv(hi.y); b.hz = fkey_inv(hi.z);
+    return b;
+}
+// conservative squared distance from a point to a box: no point of the box can be closer
+__device__ __forceinline__ float box_point_d2(const BoxF& b, float x, float y, float z) {
+    const float ex = fmaxf(fmaxf(b.lx - x, x - b.hx), 0.f), ey = fmaxf(fmaxf(b.ly - y, y - b.hy), 0.f), ez = fmaxf(fmaxf(b.lz - z, z - b.hz), 0.f);
+    return ex * ex + ey * ey + ez * ez;
+}
+__device__ __forceinline__ float box_box_d2(const BoxF& p, const BoxF& q) {
+    const float ex = fmaxf(fmaxf(p.lx - q.hx, q.lx - p.hx), 0.f), ey = fmaxf(fmaxf(p.ly - q.hy, q.ly - p.hy), 0.f), ez = fmaxf(fmaxf(p.lz - q.hz, q.lz - p.hz), 0.f);
+    return ex * ex + ey * ey + ez * ez;
+}
+
+// Whole warp on one crowded cell pair (A: cntA points at A[], B: cB points at sorted positions sB..).
+__device__ __forceinline__ void link_heavy_pair(const FramePtrs& a, const float4* A, int startA, int cntA, bool hasBoxA, const BoxF& boxA, int sB, int cB, int lane) {
+    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
+    // dense surfaces are mostly merged through their nearer cells already: two cells of one component need no point tests
+    int same = 0;
+    if (lane == 0) same = uf_find(a.parent, startA) == uf_find(a.parent, sB) ? 1 : 0;
+    if (__shfl_sync(kFull, same, 0)) return;
+    const bool hasBoxB = cB > kBoxMinCount;
+    BoxF boxB = boxA;
+    if (hasBoxB) {
+        boxB = load_box(a, sB);
+        if (hasBoxA && box_box_d2(boxA, boxB) > r2_prune) return;
+    }
+    bool hit = false;
+    for (int b0 = 0; b0 < cB && !hit; b0 += 32) {
+        const int b = b0 + lane;
+        bool valid = b < cB;
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            pb = a.spts[sB + b];
+            if (hasBoxA) valid = box_point_d2(boxA, pb.x, pb.y, pb.z) <= r2_prune;
+        }
+        if (!__any_sync(kFull, valid)) continue;
+        for (int a0 = 0; a0 < cntA && !hit; a0 += 4) {
+            bool h = false;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float4 pa = A[min(a0 + u, cntA - 1)];
+                if (hasBoxB && box_point_d2(boxB, pa.x, pa.y, pa.z) > r2_prune) continue;  // uniform over the warp
+                h |= valid && sqdist3(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < r2;
+            }
+            hit = __any_sync(kFull, h);
+        }
+    }
+    if (hit && lane == 0) uf_union(a.parent, startA, sB);
+}
+
+__device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float4* A, int lane) {
+    const unsigned long long key = a.ckey[i];
+    const int startA = a.cstart[i], cntA = a.cstart[i + 1] - startA;
+    int cx, cy, cz;
+    cell_unpack(key, cx, cy, cz);
+    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
+    // the 62 preceding cells of the 5x5x5 block: offset index n = (dz+2)*25 + (dy+2)*5 + (dx+2) < 62
+    Cell nb[2];
+    bool has[2], heavy[2] = {false, false};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int n = lane + 32 * q;
+        has[q] = false;
+        if (n < 62) {
+            const int dz = n / 25 - 2, dy = (n / 5) % 5 - 2, dx = n % 5 - 2;
+            has[q] = grid_lookup(a, cell_pack(cx + dx, cy + dy, cz + dz), &nb[q]);
+        }
+    }
+    const bool hasBoxA = cntA > kBoxMinCount;
+    BoxF boxA = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (hasBoxA) boxA = load_box(a, startA);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (!has[q]) continue;
+        const int sB = nb[q].start, cB = nb[q].cnt;
+        if ((long long)cntA * cB > kHeavyPair) { heavy[q] = true; continue; }
+        if (hasBoxA && cB > kBoxMinCount && box_box_d2(boxA, load_box(a, sB)) > r2_prune) continue;
+        bool hit = false;
+        for (int b = 0; b < cB && !hit; b += 2) {  // two independent loads in flight (index clamped)
+            const float4 p0 = a.spts[sB + b], p1 = a.spts[sB + min(b + 1, cB - 1)];
+            if (hasBoxA && box_point_d2(boxA, p0.x, p0.y, p0.z) > r2_prune && box_point_d2(boxA, p1.x, p1.y, p1.z) > r2_prune) continue;
+            for (int k = 0; k < cntA; k++) {
+                const float4 pa = A[k];
+                if (fminf(sqdist3(pa.x, pa.y, pa.z, p0.x, p0.y, p0.z), sqdist3(pa.x, pa.y, pa.z, p1.x, p1.y, p1.z)) < r2) { hit = true; break; }
+            }
+        }
+        if (hit) uf_union(a.parent, startA, sB);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        unsigned todo = __ballot_sync(kFull, heavy[q]);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int sB = __shfl_sync(kFull, nb[q].start, src), cB = __shfl_sync(kFull, nb[q].cnt, src);
+            link_heavy_pair(a, A, startA, cntA, hasBoxA, boxA, sB, cB, lane);
+        }
+    }
+}
+
+__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, float4* tile, unsigned long long* mbar, unsigned& parity) {
+    __shared__ int s_base, s_n;
+    const int n_cells = __ldcg(&a.scratch->n_cells);
+    const int rounds = (n_cells + kWarps - 1) / kWarps;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int round = cta; round < rounds; round += G) {
+        const int i0 = round * kWarps, i1 = min(i0 + kWarps, n_cells);
+        __syncthreads();  // the previous round's readers of the tile are done
+        if (threadIdx.x == 0) {
+            const int s0 = a.cstart[i0], s1 = a.cstart[i1];
+            s_base = s0;
+            s_n = (s1 - s0 <= kLinkTilePts) ? s1 - s0 : 0;  // a round of very crowded cells reads A from L2 instead
+            if (s_n) bulk_load(tile, a.spts + s0, (unsigned)s_n * 16u, mbar);
+        }
+        __syncthreads();
+        const int base = s_base, staged = s_n;
+        const int i = i0 + warp;
+        if (staged) { mbar_wait(mbar, parity); parity ^= 1u; }
+        if (i < i1) link_cell(a, i, staged ? tile + (a.cstart[i] - base) : a.spts + a.cstart[i], lane);
+    }
+}
+
+// ===================================================================================== phase E: flatten
+// Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud index of every
+// component (the canonical label) with warp-aggregated atomics, collect the roots.
+__device__ __forceinline__ void phase_flatten(const FramePtrs& a, int cta, int G) {
+    const int nc = a.counts[MOR_CNT_NC];
+    const int lane = threadIdx.x & 31;
+    for (int base = cta * kT; base < nc; base += G * kT) {
+        const int s = base + threadIdx.x;
+        const bool act = s < nc;
+        int c = 0, r = -1 - lane;
+        if (act) {
+            c = __float_as_int(a.spts[s].w);
+            r = uf_find(a.parent, a.slead[s]);
+            a.comp[s] = r;
+            if (r == s) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s;
+        }
+        const unsigned same = __match_any_sync(kFull, r);
+        const int mn = __reduce_min_sync(same, c);
+        if (act && (int)(__ffs(same) - 1) == lane) {
+            atomicAdd(&a.comp_size[r], __popc(same));
+            atomicMin(&a.minidx[r], mn);
+        }
+    }
+}
+
+// ===================================================================================== phase F: select (one CTA)
+// Size filter min <= size <= max (cpp:215-216), cluster order = size descending then min index ascending (A9 canonical
+// rule) by a shared-memory bitonic sort of (~size, root) keys.
+__device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long long* keys) {
     __shared__ int s_k;
     if (threadIdx.x == 0) s_k = 0;
     __syncthreads();
@@ -601,193 +764,37 @@ __device__ void select_block(const FramePtrs& a) {
         for (int q = 0; q < 3; q++) { a.acc_box[k * 6 + q] = 0xFFFFFFFFu; a.acc_box[k * 6 + 3 + q] = 0u; }
     }
     atomicAdd(&a.counts[MOR_CNT_NK], nk);
-    if (threadIdx.x == 0) a.counts[MOR_CNT_K] = K;
-    // the ingest / cell scans of this frame are complete: reset their look-back state for the next frame
-    for (int t = threadIdx.x; t < a.tiles_pts; t += kSingle) a.st_ingest[t] = 0ull;
-    for (int t = threadIdx.x; t < a.tiles_cells; t += kSingle) a.st_cells[t] = 0ull;
     if (threadIdx.x == 0) {
-        a.scratch->ticket_ingest = 0; a.scratch->ticket_cells = 0; a.scratch->n_roots = 0; a.scratch->stats_blocks_done = 0;
-        a.scratch->flatten_blocks_done = 0; a.scratch->moving_blocks_done = 0;
+        a.counts[MOR_CNT_K] = K;
+        const int e = __ldcg(&a.scratch->err_early);
+        if (e) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], e);
     }
-    if (threadIdx.x < 3) { a.scratch->box_inv_min[threadIdx.x] = 0u; a.scratch->box_max[threadIdx.x] = 0u; }
 }
 
-// ===================================================================================== K7
+// ===================================================================================== phase G: cluster statistics
 // Per-cluster statistics (cpp:221-244): cluster id of every point, exact coordinate sums for
-// compute3DCentroid<double> (A10) and getMinMax3D bounding boxes (cpp:272-275), warp-aggregated.
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
-__device__ __forceinline__ unsigned warp_min_u(unsigned v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(kFull, v, o));
-    return v;
-}
-__device__ __forceinline__ unsigned warp_max_u(unsigned v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFull, v, o));
-    return v;
-}
-
-// Per-cluster accumulation of coordinate sums (optional) and bounding boxes with two levels of
-// aggregation before the global atomics: warp (shuffles) and block (shared memory). In sorted order a
-// block of kStatBlock consecutive points lies inside one cluster most of the time, so a 30k-point
-// cluster costs ~30 sets of atomics instead of 30k. Every thread of the block must call.
-constexpr int kStatBlock = 1024;
-
-template <bool WITH_SUMS>
-__device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc_sum, unsigned* acc_box, int k, bool valid, float x, float y, float z) {
-    __shared__ int s_k[kStatBlock / 32];                       // cluster of the warp, -1 = no valid lane, -2 = mixed
-    __shared__ unsigned long long s_sum[kStatBlock / 32][6];
-    __shared__ unsigned s_box[kStatBlock / 32][6];
-    __shared__ int s_mode;                                     // >= 0: the whole block is cluster s_mode; -1: per-warp
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // warp level: lanes are grouped by cluster (match.any) and every group is reduced with redux
-    const unsigned vmask = __ballot_sync(kFull, valid);
-    const unsigned grp = __match_any_sync(kFull, valid ? k : -1);
-    const bool leader = valid && (int)(__ffs(grp) - 1) == lane;
-    const bool uniform = vmask != 0 && (grp & vmask) == vmask && valid;  // true in the valid lanes of a one-cluster warp
-    const bool warp_uniform = __any_sync(kFull, uniform);
-    unsigned bx[6];
-    {
-        const unsigned kx = fkey(x), ky = fkey(y), kz = fkey(z);
-        bx[0] = __reduce_min_sync(grp, kx); bx[1] = __reduce_min_sync(grp, ky); bx[2] = __reduce_min_sync(grp, kz);
-        bx[3] = __reduce_max_sync(grp, kx); bx[4] = __reduce_max_sync(grp, ky); bx[5] = __reduce_max_sync(grp, kz);
-    }
-    unsigned long long sm[6] = {0, 0, 0, 0, 0, 0};
-    if (WITH_SUMS) {
-        const float v[3] = {x, y, z};
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            long long h, l;
-            split_fixed(v[q], h, l);  // h in [-2^31, 2^31), l in [0, 2^30): summed in 16/15-bit pieces so redux.add (32-bit) cannot overflow
-            const long long sh = ((long long)__reduce_add_sync(grp, (int)(h >> 16)) << 16) + (long long)__reduce_add_sync(grp, (int)(h & 0xFFFF));
-            const long long sl = ((long long)__reduce_add_sync(grp, (int)(l >> 15)) << 15) + (long long)__reduce_add_sync(grp, (int)(l & 0x7FFF));
-            sm[q * 2] = (unsigned long long)sh; sm[q * 2 + 1] = (unsigned long long)sl;
-        }
-    }
-    if (warp_uniform && leader) {
-#pragma unroll
-        for (int q = 0; q < 6; q++) { s_box[warp][q] = bx[q]; if (WITH_SUMS) s_sum[warp][q] = sm[q]; }
-    }
-    const int k_first = __shfl_sync(kFull, k, vmask ? __ffs(vmask) - 1 : 0);
-    if (lane == 0) s_k[warp] = !vmask ? -1 : (warp_uniform ? k_first : -2);
-    __syncthreads();
-    if (warp == 0) {
-        const int nw = blockDim.x >> 5;
-        const int wk = lane < nw ? s_k[lane] : -1;
-        const unsigned has = __ballot_sync(kFull, wk != -1);
-        const int first = has ? __shfl_sync(kFull, wk, __ffs(has) - 1) : -1;
-        const bool same = __all_sync(kFull, wk == -1 || (wk == first && wk >= 0));
-        if (lane == 0) s_mode = (has && same) ? first : -1;
-    }
-    __syncthreads();
-    const int mode = s_mode;
-    if (mode >= 0) {  // the whole block is one cluster: one set of atomics
-        const int nw = blockDim.x >> 5;
-        if (threadIdx.x < 6) {
-            unsigned v = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
-            for (int w = 0; w < nw; w++)
-                if (s_k[w] >= 0) v = threadIdx.x < 3 ? min(v, s_box[w][threadIdx.x]) : max(v, s_box[w][threadIdx.x]);
-            if (threadIdx.x < 3) atomicMin(acc_box + mode * 6 + threadIdx.x, v); else atomicMax(acc_box + mode * 6 + threadIdx.x, v);
-        } else if (WITH_SUMS && threadIdx.x >= 32 && threadIdx.x < 38) {
-            const int q = threadIdx.x - 32;
-            unsigned long long v = 0;
-            for (int w = 0; w < nw; w++)
-                if (s_k[w] >= 0) v += s_sum[w][q];
-            atomicAdd(acc_sum + mode * 6 + q, v);
-        }
-    } else if (leader) {  // one set of atomics per (warp, cluster) group
-        unsigned* b = acc_box + k * 6;
-        atomicMin(b + 0, bx[0]); atomicMin(b + 1, bx[1]); atomicMin(b + 2, bx[2]);
-        atomicMax(b + 3, bx[3]); atomicMax(b + 4, bx[4]); atomicMax(b + 5, bx[5]);
-        if (WITH_SUMS) {
-#pragma unroll
-            for (int q = 0; q < 6; q++) atomicAdd(acc_sum + k * 6 + q, sm[q]);
-        }
-    }
-}
-
-__device__ void match_block(const FramePtrs& a);
-
-__device__ __forceinline__ void k_cluster_stats_body(const FramePtrs& a) {
-    pdl_prologue();
-    const int s = blockIdx.x * kStatBlock + threadIdx.x;
+// compute3DCentroid<double> (A10) and getMinMax3D bounding boxes (cpp:272-275).
+__device__ __forceinline__ void phase_stats(const FramePtrs& a, int cta, int G) {
     const int nc = a.counts[MOR_CNT_NC];
-    if (blockIdx.x * kStatBlock >= nc && !(nc == 0 && blockIdx.x == 0)) return;  // whole blocks stay alive for the barriers
-    float4 p = make_float4(0, 0, 0, 0);
-    int k = -1;
-    if (s < nc) {
-        p = a.spts[s];
-        const int c = __float_as_int(p.w);
-        const int lab = a.minidx[a.comp[s]];
-        a.label[c] = lab;
-        k = a.cid_of_root[lab];
-        a.cid[c] = k;
-        a.scid[s] = k;
-    }
-    block_cluster_accumulate<true>(a.acc_sum, a.acc_box, k, k >= 0, p.x, p.y, p.z);
-    // the last block to finish turns the accumulators into centroids (compute3DCentroid<double>, A10)
-    // and bounding boxes
-    __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();  // the block's accumulator atomics are ordered before the ticket
-        s_last = atomicAdd(&a.scratch->stats_blocks_done, 1) == max((nc + kStatBlock - 1) / kStatBlock, 1) - 1;
-        __threadfence();
-    }
-    __syncthreads();
-    if (!s_last) return;
-    const int K = a.counts[MOR_CNT_K];
-    for (int c = threadIdx.x; c < K; c += kStatBlock) {
-        const double n = (double)a.cl_size[c];
-#pragma unroll
-        for (int q = 0; q < 3; q++)
-            a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
-#pragma unroll
-        for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
-    }
-    // ... and, with two frames, goes straight on to the cluster correspondences (K9)
-    if (a.two_frames) {
-        __syncthreads();
-        match_block(a);
-    }
-}
-__global__ void __launch_bounds__(kStatBlock) k_cluster_stats(FramePtrs a) { k_cluster_stats_body(a); }
-__global__ void __launch_bounds__(kStatBlock, 2) k_cluster_stats_batch(const FramePtrs* __restrict__ P) { k_cluster_stats_body(P[blockIdx.z]); }
-
-
-// ===================================================================================== K8
-// pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12) and the bounding box
-// of the transformed points (getMinMax3D runs after the transform, cpp:272).
-__device__ __forceinline__ void k_transform_prev_body(const FramePtrs& a) {
-    pdl_prologue();
-    const int s = blockIdx.x * kStatBlock + threadIdx.x;
-    const int ncp = a.p_counts[MOR_CNT_NC];
-    if (blockIdx.x * kStatBlock >= ncp) return;
-    int k = -1;
-    float3 t = make_float3(0, 0, 0);
-    if (s < ncp) {
-        const float4 p = a.p_spts[s];
-        const int c = __float_as_int(p.w);
-        k = a.p_cid[c];
-        if (k >= 0) {
-            t = xform(a.M, p.x, p.y, p.z);
-            a.tpts[c] = make_float4(t.x, t.y, t.z, __int_as_float(k));
-        } else {
-            a.tpts[c] = make_float4(0, 0, 0, __int_as_float(-1));
+    for (int base = cta * kT; base < nc; base += G * kT) {
+        const int s = base + threadIdx.x;
+        float4 p = make_float4(0, 0, 0, 0);
+        int k = -1;
+        if (s < nc) {
+            p = a.spts[s];
+            const int c = __float_as_int(p.w);
+            const int lab = a.minidx[a.comp[s]];
+            a.label[c] = lab;
+            k = a.cid_of_root[lab];
+            a.cid[c] = k;
+            a.scid[s] = k;
         }
+        block_cluster_accumulate<true>(a.acc_sum, a.acc_box, k, k >= 0, p.x, p.y, p.z);
     }
-    block_cluster_accumulate<false>(nullptr, a.pacc_box, k, k >= 0, t.x, t.y, t.z);
 }
-__global__ void __launch_bounds__(kStatBlock) k_transform_prev(FramePtrs a) { k_transform_prev_body(a); }
-__global__ void __launch_bounds__(kStatBlock) k_transform_prev_batch(const FramePtrs* __restrict__ P) { k_transform_prev_body(P[blockIdx.z]); }
 
-
-// Block-wide ordered compaction helper for the single-block kernels: returns the exclusive rank of
-// `flag` among all threads, *total = number of set flags. kSingle threads.
+// Block-wide ordered compaction helper for the single-CTA phases: returns the exclusive rank of `flag` among all
+// threads, *total = number of set flags. kSingle threads.
 __device__ __forceinline__ int single_block_rank(bool flag, int* total) {
     __shared__ int s_w[kSingle / 32];
     __shared__ int s_tot;
@@ -812,9 +819,9 @@ __device__ __forceinline__ int single_block_rank(bool flag, int* total) {
     return r;
 }
 
-// ===================================================================================== K9
-// Finalise centroids/boxes, transform the previous centroids (cpp:540-541), reciprocal 1-NN between
-// centroid sets (cpp:291-294, A16), volume constraint (cpp:264-283, A17), per-match octree anchors.
+// ===================================================================================== phase H: match (one CTA)
+// Finalise centroids/boxes, transform the previous centroids (cpp:540-541), reciprocal 1-NN between centroid sets
+// (cpp:291-294, A16), volume constraint (cpp:264-283, A17).
 __device__ __forceinline__ int nn_brute(const float* pts, int n, float qx, float qy, float qz, float* out_d) {
     int best = -1;
     float bd = 3.402823466e+38f;
@@ -826,8 +833,18 @@ __device__ __forceinline__ int nn_brute(const float* pts, int n, float qx, float
     return best;
 }
 
-__device__ void match_block(const FramePtrs& a) {
-    const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K];
+__device__ __forceinline__ void phase_match(const FramePtrs& a) {
+    const int K = a.counts[MOR_CNT_K];
+    for (int c = threadIdx.x; c < K; c += kSingle) {
+        const double n = (double)a.cl_size[c];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
+    }
+    if (!a.two_frames) return;
+    const int Kp = a.p_counts[MOR_CNT_K];
     // previous centroids and boxes into the current frame
     for (int i = threadIdx.x; i < Kp; i += kSingle) {
         const float3 t = xform(a.M, a.p_cl_centroid[i * 3], a.p_cl_centroid[i * 3 + 1], a.p_cl_centroid[i * 3 + 2]);
@@ -856,7 +873,7 @@ __device__ void match_block(const FramePtrs& a) {
     }
     __syncthreads();
     // volume constraint; match_dist is rewritten in place (rank <= index, chunked with barriers)
-    int n_match = 0, p1 = 0, p2 = 0;
+    int n_match = 0;
     for (int base = 0; base < n_recip; base += kSingle) {
         const int u = base + threadIdx.x;
         bool ok = false; int i = -1, j = -1; float d = 0.f;
@@ -874,169 +891,94 @@ __device__ void match_block(const FramePtrs& a) {
             a.match_q[m] = i; a.match_m[m] = j; a.match_dist[m] = d;
             a.match_of_prev[i] = j; a.mid_of_prev[i] = m; a.mid_of_cur[j] = m;
             a.newcount[m] = 0; a.match_score[m] = 0.0;
-            // OctreePointCloudChangeDetector lattice anchor from the first point of the previous cluster
-            // (its min-index point) - PCL 1.8 adoptBoundingBoxToPoint + getKeyBitSize (A13)
-            const float4 f = a.tpts[a.p_cl_root[i]];
-            const double res = (double)0.1f, eps = (double)1.1920928955078125e-07f;
-            const double fv[3] = {(double)f.x, (double)f.y, (double)f.z};
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                const double lo = fv[q] - res / 2, hi = fv[q] + res / 2;
-                const double side = 2.0 * res - eps;
-                const double over = (side - (hi - lo)) / 2.0;
-                a.anchor[m * 3 + q] = lo - over;
-            }
             atomicAdd(&a.counts[MOR_CNT_P1], a.p_cl_size[i]);
             atomicAdd(&a.counts[MOR_CNT_P2], a.cl_size[j]);
         }
         n_match += tot;
     }
-    (void)p1; (void)p2;
     if (threadIdx.x == 0) {
         a.counts[MOR_CNT_MU] = n_recip; a.counts[MOR_CNT_M] = n_match;
         a.counts[MOR_CNT_NKPREV] = a.p_counts[MOR_CNT_NK];
     }
 }
 
-// ===================================================================================== K10 / K11 (method 2)
-// pcl::octree::OctreePointCloudChangeDetector (cpp:319-330, A13): the leaf lattice of every matched
-// pair is floor((p - anchor)/res) in double; the occupied leaves of the transformed previous cluster
-// go into one global hash set keyed (match, ix, iy, iz); the score is the number of points of the
-// current cluster whose leaf is absent.
-__device__ __forceinline__ bool lattice_key(const FramePtrs& a, int m, float x, float y, float z, unsigned long long* key) {
-    const double res = (double)0.1f;
-    const long long ix = (long long)floor(((double)x - a.anchor[m * 3]) / res);
-    const long long iy = (long long)floor(((double)y - a.anchor[m * 3 + 1]) / res);
-    const long long iz = (long long)floor(((double)z - a.anchor[m * 3 + 2]) / res);
-    const bool ok = ix >= -32768 && ix < 32768 && iy >= -32768 && iy < 32768 && iz >= -32768 && iz < 32768;
-    *key = ((unsigned long long)(unsigned)m << 48) | ((unsigned long long)(ix + 32768) << 32) | ((unsigned long long)(iy + 32768) << 16) |
-           (unsigned long long)(iz + 32768);
-    return ok;
-}
-
-__device__ __forceinline__ void k_lattice_insert_body(const FramePtrs& a) {
-    pdl_prologue();
-    const int c = blockIdx.x * kBlock + threadIdx.x;
-    if (c >= a.p_counts[MOR_CNT_NC]) return;
-    const float4 t = a.tpts[c];
-    const int k = __float_as_int(t.w);
-    if (k < 0) return;
-    const int m = a.mid_of_prev[k];
-    if (m < 0) return;
-    unsigned long long key;
-    if (!lattice_key(a, m, t.x, t.y, t.z, &key)) { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); return; }
-    hset_insert(a.lattice, a.lattice_mask, key);
-}
-__global__ void __launch_bounds__(kBlock) k_lattice_insert(FramePtrs a) { k_lattice_insert_body(a); }
-__global__ void __launch_bounds__(kBlock) k_lattice_insert_batch(const FramePtrs* __restrict__ P) { k_lattice_insert_body(P[blockIdx.z]); }
-
-
-__device__ void chain_block(const FramePtrs& a);
-
-// Shared tail of the two moving-test kernels: the last block to finish turns the scores into flags and runs the
-// consistency chain (K12).
-__device__ __forceinline__ void moving_test_epilogue(const FramePtrs& a) {
-    __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(&a.scratch->moving_blocks_done, 1) == (int)gridDim.x - 1;
-        __threadfence();
-    }
-    __syncthreads();
-    if (s_last) chain_block(a);
-}
-
-__device__ __forceinline__ void k_lattice_count_body(const FramePtrs& a) {
-    pdl_prologue();
-    const int s = blockIdx.x * kSingle + threadIdx.x;
-    int m = -1;
-    bool is_new = false;
-    if (s < a.counts[MOR_CNT_NC]) {
-        const float4 p = a.spts[s];
-        const int c = __float_as_int(p.w);
-        const int k = a.cid[c];
-        m = k >= 0 ? a.mid_of_cur[k] : -1;
-        if (m >= 0) {
-            unsigned long long key;
-            if (lattice_key(a, m, p.x, p.y, p.z, &key)) is_new = !hset_contains(a.lattice, a.lattice_mask, key);
-            else { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); is_new = true; }
+// ===================================================================================== phase I: moving test
+// Method 2 (default): the score of a matched pair is the number of points of the current cluster whose octree leaf
+// holds no point of the transformed previous cluster (cpp:325-330).
+__device__ __forceinline__ void phase_lattice_count(const FramePtrs& a, int cta, int G) {
+    const int nc = a.counts[MOR_CNT_NC];
+    const int lane = threadIdx.x & 31;
+    for (int base = cta * kT; base < nc; base += G * kT) {
+        const int s = base + threadIdx.x;
+        int m = -1;
+        bool is_new = false;
+        if (s < nc) {
+            const int k = a.scid[s];
+            m = k >= 0 ? a.mid_of_cur[k] : -1;
+            if (m >= 0) {
+                const float4 p = a.spts[s];
+                const int kp = a.match_q[m];
+                unsigned long long key;
+                if (lattice_key(a.anchorp + (size_t)kp * 3, kp, p.x, p.y, p.z, &key)) is_new = !hset_contains(a.lattice, a.lattice_mask, key);
+                else { atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_LATTICE_RANGE); is_new = true; }
+            }
         }
+        const unsigned same = __match_any_sync(kFull, is_new ? m : -1 - lane);
+        if (is_new && (int)(__ffs(same) - 1) == lane) atomicAdd(&a.newcount[m], __popc(same));
     }
-    const unsigned same = __match_any_sync(kFull, is_new ? m : -1 - (int)(threadIdx.x & 31));
-    if (is_new && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.newcount[m], __popc(same));
-    moving_test_epilogue(a);
 }
-__global__ void __launch_bounds__(kSingle) k_lattice_count(FramePtrs a) { k_lattice_count_body(a); }
-__global__ void __launch_bounds__(kSingle, 2) k_lattice_count_batch(const FramePtrs* __restrict__ P) { k_lattice_count_body(P[blockIdx.z]); }
 
-
-// ===================================================================================== K10' (method 1)
-// CorrespondenceEstimation::determineCorrespondences (cpp:343-361): for every point of the transformed
-// previous cluster the nearest point of the matched current cluster; only squared distances inside
-// (pde_lb, pde_ub) count, so the search is bounded by sqrt(pde_ub) on the clustering grid.
-__device__ __forceinline__ void k_pde_count_body(const FramePtrs& a) {
-    pdl_prologue();
+// Method 1: CorrespondenceEstimation::determineCorrespondences (cpp:343-361): for every point of the transformed
+// previous cluster the nearest point of the matched current cluster; only squared distances inside (pde_lb, pde_ub)
+// count, so the search is bounded by sqrt(pde_ub) on the clustering grid. Shells of growing Chebyshev distance around
+// the query's cell: a point in shell r is at least (r-1)*h away, so the search stops as soon as that bound exceeds the
+// best distance (or pde_ub: farther neighbours never count), and a neighbour at d2 <= pde_lb settles the answer.
+__device__ __forceinline__ void phase_pde_count(const FramePtrs& a, int cta, int G) {
+    const int ncp = a.p_counts[MOR_CNT_NC];
     const int ring = a.pde_ring;
-    const int c = blockIdx.x * kSingle + threadIdx.x;
-    if (c < a.p_counts[MOR_CNT_NC]) {
+    const float h = (float)a.cell_h;
+    for (int base = cta * kT; base < ncp; base += G * kT) {
+        const int c = base + threadIdx.x;
+        if (c >= ncp) continue;
         const float4 t = a.tpts[c];
         const int kp = __float_as_int(t.w);
         const int m = kp >= 0 ? a.mid_of_prev[kp] : -1;
-        if (m >= 0) {
-            const int target = a.match_m[m];
-            const GridDesc g = *a.dgrid;
-            const int cx = (int)floor(((double)t.x - g.ox) * g.inv_h), cy = (int)floor(((double)t.y - g.oy) * g.inv_h), cz = (int)floor(((double)t.z - g.oz) * g.inv_h);
-            const float h = (float)(1.0 / g.inv_h);
-            float best = 3.402823466e+38f;
-            // Shells of growing Chebyshev distance r around the query's cell. A point in shell r is at least (r-1)*h away,
-            // so the search stops as soon as that bound exceeds the best distance (or pde_ub: farther neighbours never
-            // count), and a neighbour at d2 <= pde_lb settles the answer (the nearest one is then <= pde_lb: not counted).
-            bool settled = false;
-            for (int r = 0; r <= ring && !settled; r++) {
-                if (r > 1) {
-                    const float lb = (float)(r - 1) * h * 0.99999f;
-                    if (lb * lb >= fminf(best, a.pde_ub)) break;
-                }
-                for (int dz = -r; dz <= r && !settled; dz++) {
-                    const int zz = cz + dz;
-                    if (zz < 0 || zz >= g.nz) continue;
-                    for (int dy = -r; dy <= r && !settled; dy++) {
-                        const int yy = cy + dy;
-                        if (yy < 0 || yy >= g.ny) continue;
-                        const int base = (zz * g.ny + yy) * g.nx;
-                        const bool full = (dz == -r || dz == r || dy == -r || dy == r);  // rows on the shell's faces: whole x-run
-                        // otherwise only the two end cells x = cx -+ r belong to the shell
-                        for (int part = 0; part < (full || r == 0 ? 1 : 2); part++) {
-                            int xa, xb;
-                            if (full || r == 0) { xa = cx - r; xb = cx + r; } else if (part == 0) { xa = xb = cx - r; } else { xa = xb = cx + r; }
-                            xa = max(xa, 0); xb = min(xb, g.nx - 1);
-                            if (xa > xb) continue;
-                            const int b = a.cell_start[base + xa], e = a.cell_start[base + xb + 1];
-                            for (int j = b; j < e; j++) {
-                                if (a.scid[j] != target) continue;
-                                const float4 q = a.spts[j];
-                                best = fminf(best, sqdist3(t.x, t.y, t.z, q.x, q.y, q.z));
-                            }
-                            if (best <= a.pde_lb) { settled = true; break; }
+        if (m < 0) continue;
+        const int target = a.match_m[m];
+        bool oob = false;
+        const int cx = cell_coord(t.x, a.inv_h, &oob), cy = cell_coord(t.y, a.inv_h, &oob), cz = cell_coord(t.z, a.inv_h, &oob);
+        float best = 3.402823466e+38f;
+        bool settled = oob;  // a query outside the grid's range has no neighbour within sqrt(pde_ub)
+        for (int r = 0; r <= ring && !settled; r++) {
+            if (r > 1) {
+                const float lb = (float)(r - 1) * h * 0.99999f;
+                if (lb * lb >= fminf(best, a.pde_ub)) break;
+            }
+            for (int dz = -r; dz <= r && !settled; dz++)
+                for (int dy = -r; dy <= r && !settled; dy++) {
+                    const bool face = (dz == -r || dz == r || dy == -r || dy == r);  // rows on the shell's faces: whole x-run
+                    const int step = (face || r == 0) ? 1 : 2 * r;                    // otherwise only the two end cells
+                    for (int dx = -r; dx <= r; dx += step) {
+                        Cell e;
+                        if (!grid_lookup(a, cell_pack(cx + dx, cy + dy, cz + dz), &e)) continue;
+                        for (int j = e.start; j < e.start + e.cnt; j++) {
+                            if (a.scid[j] != target) continue;
+                            const float4 q = a.spts[j];
+                            best = fminf(best, sqdist3(t.x, t.y, t.z, q.x, q.y, q.z));
                         }
+                        if (best <= a.pde_lb) { settled = true; break; }
                     }
                 }
-            }
-            if (best > a.pde_lb && best < a.pde_ub) atomicAdd(&a.newcount[m], 1);
         }
+        if (best > a.pde_lb && best < a.pde_ub) atomicAdd(&a.newcount[m], 1);
     }
-    moving_test_epilogue(a);
 }
-__global__ void __launch_bounds__(kSingle) k_pde_count(FramePtrs a) { k_pde_count_body(a); }
-__global__ void __launch_bounds__(kSingle) k_pde_count_batch(const FramePtrs* __restrict__ P) { k_pde_count_body(P[blockIdx.z]); }
 
-
-// ===================================================================================== K12
-// Detection flags (cpp:580-606) and the N-frame consistency chain: checkMovingClusterChain
-// (cpp:478-514), recurseFindClusterChain (cpp:415-453), pushCentroid (cpp:455-476). corrs_vec /
-// res_vec are device-resident ring buffers; a correspondence map is stored as match_of_prev[].
-__device__ void chain_block(const FramePtrs& a) {
+// ===================================================================================== phase J: chain (one CTA) + cleanup
+// Detection flags (cpp:580-606) and the N-frame consistency chain: checkMovingClusterChain (cpp:478-514),
+// recurseFindClusterChain (cpp:415-453), pushCentroid (cpp:455-476). corrs_vec / res_vec are device-resident ring
+// buffers; a correspondence map is stored as match_of_prev[].
+__device__ __forceinline__ void phase_chain(const FramePtrs& a) {
     const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K], M = a.counts[MOR_CNT_M];
     const int D = a.ring_depth, kmax = a.kmax;
     TrackState* ts = a.track;
@@ -1146,47 +1088,60 @@ __device__ void chain_block(const FramePtrs& a) {
             ts->corr_count = corr_count; ts->res_count = res_count; ts->res_head = res_head % D;
         }
         ts->n_mo[a.mo_parity] = n_mo;
-        a.counts[MOR_CNT_NMO] = n_mo;
     }
 }
 
-// ===================================================================================== K13 + K14
-// filterCloud (cpp:613-696) in one kernel.
-//  Tracking part (cpp:630-671): 1-NN of every confirmed mover among the current centroids, unconditional
-//  selection of that cluster (cpp:644-648), confidence update and erase. It is tiny (|mo_vec| x K distance
-//  evaluations), so EVERY block recomputes the selection into shared memory instead of waiting for a separate
-//  single-block kernel; block 0 alone writes the updated mo_vec into the other half of a double buffer.
-//  Output part: ExtractIndices(negative) of the moving points + append of the ground points (cpp:673-684),
-//  written as pcl::PointXYZI wire records (cpp:690); stable single-pass compaction over [cloud | ground],
-//  kOutItems consecutive points per thread.
-#ifndef OUT_BLOCK
-#define OUT_BLOCK 256
-#endif
-constexpr int kOutBlock = OUT_BLOCK;
-constexpr int kOutTile = 1024;
-constexpr int kOutItems = kOutTile / kOutBlock;
+// The clustering grid and the scan states go back to "all zero" for the next frame; CTA 0 meanwhile runs the chain.
+__device__ __forceinline__ void phase_chain_and_cleanup(const FramePtrs& a, int cta, int G) {
+    const int n_cells = __ldcg(&a.scratch->n_cells);
+    const int first = G > 1 ? 1 : 0;          // with more than one CTA, CTA 0 is busy with the chain
+    const int workers = G > 1 ? G - 1 : 1;
+    if (cta >= first) {
+        const int w = cta - first;
+        for (int i = w * kT + threadIdx.x; i < n_cells; i += workers * kT)
+            *reinterpret_cast<uint4*>(a.table + a.cell_list[i]) = make_uint4(0u, 0u, 0u, 0u);
+        for (int t = w * kT + threadIdx.x; t < a.tiles_pts; t += workers * kT) { a.st_ingest[t] = 0ull; a.st_cscan[t] = 0ull; }
+    }
+    if (cta == 0) {
+        if (a.two_frames) phase_chain(a);
+        __syncthreads();
+        if (threadIdx.x == 0) a.counts[MOR_CNT_NMO] = a.track->n_mo[a.mo_parity];
+    }
+}
+
+// ===================================================================================== phase K: filterCloud
+// filterCloud (cpp:613-696).
+//  Tracking part (cpp:630-671): 1-NN of every confirmed mover among the current centroids, unconditional selection of
+//  that cluster (cpp:644-648), confidence update and erase. It is tiny (|mo_vec| x K distance evaluations), so EVERY
+//  CTA recomputes the selection into shared memory; one CTA alone (`writer`) writes the updated mo_vec into the other
+//  half of a double buffer - the host makes it current when filterCloud is called, so the phase can run at the end of
+//  the frame kernel (a frame that is never filtered leaves mo_vec untouched, as in the reference).
+//  Output part: ExtractIndices(negative) of the moving points + append of the ground points (cpp:673-684), written as
+//  pcl::PointXYZI wire records (cpp:690); stable single-pass compaction over [cloud | ground].
+constexpr int kOutTile = kT;
 constexpr int kRemovedBits = 16384;  // = max kmax
 
-__device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
-    pdl_prologue();
+struct FilterShared {
+    unsigned removed[kRemovedBits / 32];
+    int total, keep_base;
+};
+
+__device__ __forceinline__ int filter_tracking(const FramePtrs& a, FilterShared& sh, bool writer) {
     const int mo_parity = a.mo_parity;
-    __shared__ unsigned s_removed[kRemovedBits / 32];
-    __shared__ int s_tile, s_total, s_keep_base;
     const int K = a.counts[MOR_CNT_K];
-    const int nc = a.counts[MOR_CNT_NC], ng = a.counts[MOR_CNT_NG];
+    const int nc = a.counts[MOR_CNT_NC];
     TrackState* ts = a.track;
     const int n_mo = ts->n_mo[mo_parity];
     const float* mo_c_in = a.mo_centroid + (size_t)mo_parity * a.momax * 3;
     const int* mo_f_in = a.mo_conf + (size_t)mo_parity * a.momax;
     float* mo_c_out = a.mo_centroid + (size_t)(mo_parity ^ 1) * a.momax * 3;
     int* mo_f_out = a.mo_conf + (size_t)(mo_parity ^ 1) * a.momax;
-    if (threadIdx.x == 0) { s_tile = atomicAdd(&a.scratch->ticket_out, 1); s_total = 0; s_keep_base = 0; }
-    for (int t = threadIdx.x; t < (K + 31) / 32; t += kOutBlock) s_removed[t] = 0u;
     __syncthreads();
-    const int tile = s_tile;
-    const bool writer = tile == 0;  // the first block to start also owns the mo_vec update
-    // ---- tracking (redundant in every block; K == 0: un-built kd-tree in the reference (UB) -> entries untouched)
-    for (int base = 0; base < n_mo && K > 0; base += kOutBlock) {
+    if (threadIdx.x == 0) { sh.total = 0; sh.keep_base = 0; }
+    for (int t = threadIdx.x; t < (K + 31) / 32; t += kT) sh.removed[t] = 0u;
+    __syncthreads();
+    // K == 0: un-built kd-tree in the reference (UB) -> entries untouched
+    for (int base = 0; base < n_mo && K > 0; base += kT) {
         const int t = base + threadIdx.x;
         bool keep = false;
         float cx = 0, cy = 0, cz = 0; int conf = 0;
@@ -1196,8 +1151,8 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
             float d;
             const int k = nn_brute(a.cl_centroid, K, cx, cy, cz, &d);
             if (writer) a.marker_cluster[t] = k;
-            atomicOr(&s_removed[k >> 5], 1u << (k & 31));
-            atomicAdd(&s_total, a.cl_size[k]);
+            atomicOr(&sh.removed[k >> 5], 1u << (k & 31));
+            atomicAdd(&sh.total, a.cl_size[k]);
             if (!a.cl_flags[k] || d > a.leave_off) {  // cpp:650
                 conf--;
                 keep = conf != 0;
@@ -1209,87 +1164,187 @@ __device__ __forceinline__ void k_filter_output_body(const FramePtrs& a) {
         }
         if (writer) {  // ordered erase (cpp:655-660): survivors keep their relative order
             int tot;
-            const int r = block_exclusive_scan<int, kOutBlock>(keep ? 1 : 0, &tot);
+            const int r = block_exclusive_scan<int, kT>(keep ? 1 : 0, &tot);
             if (keep) {
-                const int o = s_keep_base + r;
+                const int o = sh.keep_base + r;
                 mo_c_out[o * 3] = cx; mo_c_out[o * 3 + 1] = cy; mo_c_out[o * 3 + 2] = cz;
                 mo_f_out[o] = conf;
             }
             __syncthreads();
-            if (threadIdx.x == 0) s_keep_base += tot;
+            if (threadIdx.x == 0) sh.keep_base += tot;
         }
         __syncthreads();
     }
     __syncthreads();
-    const int overflow = s_total > nc ? 1 : 0;  // ExtractIndices: more indices than points => error, empty output (A18)
+    const int overflow = sh.total > nc ? 1 : 0;  // ExtractIndices: more indices than points => error, empty output (A18)
     if (writer) {
         if (K == 0) {  // entries untouched: copy through
-            for (int t = threadIdx.x; t < n_mo; t += kOutBlock) {
+            for (int t = threadIdx.x; t < n_mo; t += kT) {
                 mo_c_out[t * 3] = mo_c_in[t * 3]; mo_c_out[t * 3 + 1] = mo_c_in[t * 3 + 1]; mo_c_out[t * 3 + 2] = mo_c_in[t * 3 + 2];
                 mo_f_out[t] = mo_f_in[t];
             }
         }
-        for (int k = threadIdx.x; k < K; k += kOutBlock) a.cluster_removed[k] = (s_removed[k >> 5] >> (k & 31)) & 1u;
+        for (int k = threadIdx.x; k < K; k += kT) a.cluster_removed[k] = (sh.removed[k >> 5] >> (k & 31)) & 1u;
         if (threadIdx.x == 0) {
-            const int kept = K > 0 ? s_keep_base : n_mo;
-            ts->n_mo[mo_parity ^ 1] = kept;  // the host flips the parity after this launch
-            a.counts[MOR_CNT_NMO] = kept;
+            const int kept = K > 0 ? sh.keep_base : n_mo;
+            ts->n_mo[mo_parity ^ 1] = kept;  // the host flips the parity when filterCloud commits the frame
             ts->extract_overflow = overflow;
             ts->n_markers = K > 0 ? n_mo : 0;
-            a.counts[MOR_CNT_EXTRACT_OVERFLOW] = overflow;
+            a.counts[CNT_SPEC_NMO] = kept;
+            a.counts[CNT_SPEC_OVERFLOW] = overflow;
         }
     }
-    // ---- output compaction
-    const int total_items = nc + ng;
-    const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
-    if (tile <= last_tile) {
-    const int t0 = tile * kOutTile + threadIdx.x * kOutItems;
-    float4 p[kOutItems];
-    bool keep[kOutItems];
-    int nkeep = 0;
-#pragma unroll
-    for (int k = 0; k < kOutItems; k++) {
-        const int t = t0 + k;
-        keep[k] = false;
-        p[k] = make_float4(0, 0, 0, 0);
-        if (t < nc) {
-            p[k] = a.pts[t];
-            const int c = a.cid[t];
-            const bool removed = overflow || (c >= 0 && ((s_removed[c >> 5] >> (c & 31)) & 1u));
-            keep[k] = !removed;
-            if (removed) a.removed_mask[a.cloud_src[t]] = 2;
-        } else if (t < total_items) {
-            p[k] = a.gpts[t - nc];
-            keep[k] = true;
-        }
-        nkeep += keep[k] ? 1 : 0;
+    return overflow;
+}
+
+__device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShared& sh, int overflow, int tile, int last_tile) {
+    const int nc = a.counts[MOR_CNT_NC], ng = a.counts[MOR_CNT_NG];
+    const int t = tile * kOutTile + threadIdx.x;
+    bool keep = false;
+    float4 p = make_float4(0, 0, 0, 0);
+    if (t < nc) {
+        p = a.pts[t];
+        const int c = a.cid[t];
+        const bool removed = overflow || (c >= 0 && ((sh.removed[c >> 5] >> (c & 31)) & 1u));
+        keep = !removed;
+        if (removed) a.removed_mask[a.cloud_src[t]] = 2;
+    } else if (t < nc + ng) {
+        p = a.gpts[t - nc];
+        keep = true;
     }
     int tot;
-    const int in_block = block_exclusive_scan<int, kOutBlock>(nkeep, &tot);
+    const int in_block = block_exclusive_scan<int, kT>(keep ? 1 : 0, &tot);
     const int before = (int)tile_exclusive_prefix(a.st_out, tile, (unsigned long long)tot);
-    int o = before + in_block;
-#pragma unroll
-    for (int k = 0; k < kOutItems; k++) {
-        if (keep[k]) {
-            a.out[2 * o] = make_float4(p[k].x, p[k].y, p[k].z, 1.0f);
-            a.out[2 * o + 1] = make_float4(p[k].w, 0.f, 0.f, 0.f);
-            o++;
-        }
+    if (keep) {
+        const int o = before + in_block;
+        a.out[2 * o] = make_float4(p.x, p.y, p.z, 1.0f);
+        a.out[2 * o + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
     }
-    if (tile == last_tile && threadIdx.x == 0) a.counts[MOR_CNT_NOUT] = before + tot;
-    }
-    // the last block to finish resets the look-back state, so filterCloud may be called again at any time
+    if (tile == last_tile && threadIdx.x == 0) a.counts[CNT_SPEC_NOUT] = before + tot;
+}
+
+__device__ __forceinline__ void phase_filter(const FramePtrs& a, int cta, int G, FilterShared& sh) {
+    const int total_items = a.counts[MOR_CNT_NC] + a.counts[MOR_CNT_NG];
+    const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
+    if (cta > last_tile) return;  // nothing to compact here (CTA 0 always has tile 0: it owns the mo_vec update)
+    const int overflow = filter_tracking(a, sh, cta == 0);
+    for (int tile = cta; tile <= last_tile; tile += G) filter_tile(a, sh, overflow, tile, last_tile);
+}
+
+// Last CTA out: every counter of the frame back to zero.
+__device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.scratch->blocks_done, 1) == G - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
+    if (threadIdx.x == 0) {
+        Scratch* sc = a.scratch;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->err_early = 0;
+        sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
+        for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
+    }
+}
+
+// ===================================================================================== the frame kernel
+enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_FLATTEN, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
+
+struct FrameShared {
+    unsigned long long mbar;
+    FilterShared filter;
+};
+
+template <int PH>
+__device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
+    if (PH == PH_INGEST) { if (a.skip_ingest) phase_bin_cloud(a, cta, G); else phase_ingest(a, cta, G); }
+    if (PH == PH_CELLS) phase_cells_and_transform(a, cta, G);
+    if (PH == PH_SCATTER) phase_scatter(a, cta, G);
+    if (PH == PH_LINK) phase_link(a, cta, G, reinterpret_cast<float4*>(dyn), &sh.mbar, parity);
+    if (PH == PH_FLATTEN) phase_flatten(a, cta, G);
+    if (PH == PH_SELECT) { if (cta == 0) phase_select(a, dyn); }
+    if (PH == PH_STATS) phase_stats(a, cta, G);
+    if (PH == PH_MATCH) { if (cta == 0) phase_match(a); }
+    if (PH == PH_MOVING) { if (a.two_frames) { if (a.method == 2) phase_lattice_count(a, cta, G); else phase_pde_count(a, cta, G); } }
+    if (PH == PH_CHAIN) phase_chain_and_cleanup(a, cta, G);
+    if (PH == PH_FILTER) phase_filter(a, cta, G, sh.filter);
+}
+
+__device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
+    GroupBarrier bar{&a.scratch->bar, 0u, (unsigned)G};
+    run_phase<PH_INGEST>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_CELLS>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_SCATTER>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_LINK>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_FLATTEN>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_SELECT>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_STATS>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_MATCH>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_MOVING>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_CHAIN>(a, cta, G, sh, dyn, parity); bar.sync();
+    run_phase<PH_FILTER>(a, cta, G, sh, dyn, parity);
+    frame_epilogue(a, G);
+}
+
+// One sequence, the whole grid is its group; the frame's arguments travel in the constant bank.
+__global__ void __launch_bounds__(kT, 1) k_frame(const __grid_constant__ FramePtrs a) {
+    extern __shared__ __align__(128) unsigned long long dyn[];
+    __shared__ FrameShared sh;
+    if (threadIdx.x == 0) mbar_init(&sh.mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    frame_body(a, blockIdx.x, gridDim.x, sh, dyn, parity);
+}
+
+// S sequences per launch: grid = groups x G CTAs; group g steps sequences g, g + groups, ... (each through all
+// phases, independently of the other groups), G CTAs per sequence.
+__global__ void __launch_bounds__(kT, 1) k_frame_batch(const FramePtrs* __restrict__ P, int S, int G) {
+    extern __shared__ __align__(128) unsigned long long dyn[];
+    __shared__ FrameShared sh;
+    const int group = blockIdx.x / G, cta = blockIdx.x % G, groups = gridDim.x / G;
+    if (threadIdx.x == 0) mbar_init(&sh.mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    for (int seq = group; seq < S; seq += groups) frame_body(P[seq], cta, G, sh, dyn, parity);
+}
+
+// One phase per launch (per-phase timing; the kernel boundary is the barrier). Same grid, same striding.
+template <int PH>
+__global__ void __launch_bounds__(kT, 1) k_phase(const __grid_constant__ FramePtrs a) {
+    extern __shared__ __align__(128) unsigned long long dyn[];
+    __shared__ FrameShared sh;
+    if (threadIdx.x == 0) mbar_init(&sh.mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    run_phase<PH>(a, blockIdx.x, gridDim.x, sh, dyn, parity);
+    if (PH == PH_FILTER) frame_epilogue(a, gridDim.x);
+}
+
+// filterCloud called again on a frame that was already filtered (the reference then runs the tracking update once
+// more on the updated mo_vec): the filter phase alone. Tiles by ticket, so a plain launch suffices.
+__global__ void __launch_bounds__(kT, 1) k_filter_again(const __grid_constant__ FramePtrs a) {
+    __shared__ FilterShared sh;
+    __shared__ int s_tile, s_last;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_out, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int total_items = a.counts[MOR_CNT_NC] + a.counts[MOR_CNT_NG];
+    const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
+    if (tile <= last_tile) {
+        const int overflow = filter_tracking(a, sh, tile == 0);
+        filter_tile(a, sh, overflow, tile, last_tile);
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&a.scratch->out_blocks_done, 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (s_last) {
-        for (int t = threadIdx.x; t < a.tiles_pts; t += kOutBlock) a.st_out[t] = 0ull;
+        for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
         if (threadIdx.x == 0) { a.scratch->ticket_out = 0; a.scratch->out_blocks_done = 0; }
     }
 }
-__global__ void __launch_bounds__(kOutBlock) k_filter_output(FramePtrs a) { k_filter_output_body(a); }
-__global__ void __launch_bounds__(kOutBlock, 2048 / kOutBlock) k_filter_output_batch(const FramePtrs* __restrict__ P) { k_filter_output_body(P[blockIdx.z]); }
-
 
 }  // namespace mor

@@ -123,6 +123,9 @@ int mor_push_raw_cloud_and_pose_device(mor_handle* h, const void* d_data, uint32
                                        uint32_t point_step, uint32_t off_x, uint32_t off_y,
                                        uint32_t off_z, uint32_t off_i, const double pose7[7]);
 int mor_filter_cloud_device(mor_handle* h, void* d_out, uint32_t cap_points, uint32_t* n_out);
+/* Zero-copy: mor_filter_cloud_device(h, NULL, 0, n_out or NULL) leaves the records in the handle's own device buffer;
+ * this returns its address (valid until the next push on the handle). */
+int mor_get_output_device(mor_handle* h, const void** d_records);
 int mor_sync(mor_handle* h);
 
 /* Batched device-resident step (BASELINE config 5: many independent sequences per GPU): one pushRawCloudAndPose +

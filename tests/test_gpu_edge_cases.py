@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from dynamicslamtool_b200 import MovingObjectRemoval
+from dynamicslamtool_b200.binding import NO_FIELD
 from helpers import IDENTITY_POSE, OPEN_CFG, blob, components_min_label, f32_sqdist_matrix, with_intensity, write_cfg
 from parity import ParityStats, compare_frame
 
@@ -319,25 +320,58 @@ def test_run_to_run_determinism(product, cfg_dir):
     assert a == b == c
 
 
-@pytest.mark.parametrize("max_cells", [0, 1 << 20])
-def test_small_radius_over_a_large_crop_box(product, oracle, cfg_dir, tmp_path, max_cells):
-    """Outdoor trim with the indoor clustering radius: 80 m x 80 m x 4.4 m at r = 0.11 m needs 1.1e8 cells. With the default
-    limits that is one big static table; with a small max_cells the grid follows each frame's bounding box instead
-    (which here is still too large => MOR_ERR_CAPACITY, reported, never a wrong answer)."""
-    from dynamicslamtool_b200 import MorError, Synth
-    cfg = write_cfg(tmp_path, base=cfg_dir / "MOR_config_hdl64.txt", ec_distance_threshold=0.11, min_cluster_size=20)
+@pytest.mark.parametrize("r", [0.11, 0.03])
+def test_small_radius_over_a_large_crop_box(product, oracle, cfg_dir, tmp_path, r):
+    """Outdoor trim with the indoor clustering radius (and a quarter of it): 80 m x 80 m x 4.4 m at r = 0.11 m is
+    1.1e8 cells of edge r/sqrt(3), at r = 0.03 m 5e9. The clustering grid is a hash table of the occupied cells, so
+    neither the crop box nor the radius bounds anything: no capacity error exists on this path."""
+    from dynamicslamtool_b200 import Synth
+    cfg = write_cfg(tmp_path, base=cfg_dir / "MOR_config_hdl64.txt", ec_distance_threshold=r, min_cluster_size=20 if r > 0.1 else 3)
     s = Synth(2, 2)
-    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=s.max_points, max_cells=max_cells)
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=s.max_points)
     orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
-    if max_cells == 0:
-        for f in range(3):
-            step(gpu, orc, *s.frame(f))
-    else:
-        pts, pose = s.frame(0)
-        gpu.push_raw_cloud_and_pose(pts, pose)
-        with pytest.raises(MorError) as e:
-            gpu.filter_cloud()
-        assert e.value.status == 6 and "16" in str(e.value)
+    for f in range(3):
+        step(gpu, orc, *s.frame(f))
+
+
+def test_trimming_disabled_with_huge_limits(product, oracle, tmp_path):
+    """trim_* = 1e6 m ("disabled"): the grid follows no box at all. Points kilometres apart still cluster exactly."""
+    rng = np.random.default_rng(77)
+    cfg = write_cfg(tmp_path, trim_x=1e6, trim_y=1e6, trim_z=1e6, gp_limit=-1e6, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000)
+    gpu = MovingObjectRemoval(cfg, 4, 3, binding=product)
+    orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    far = [blob(rng, c, 200, 0.1) for c in ((0, 0, 0), (3000, -2500, 40), (-9000.5, 8000.25, -3), (20000, 20000, 100))]
+    for f in range(6):
+        pts = with_intensity(np.concatenate([b + np.float32([0.12 * f * (i % 2), 0, 0]) for i, b in enumerate(far)]))
+        step(gpu, orc, pts)
+    assert gpu.counts()["K"] == 4
+
+
+def test_unaligned_point_step(product, oracle, tmp_path):
+    """pcl::fromPCLPointCloud2 maps fields by name whatever the record layout (cpp:523): the 22-byte XYZIRT record of
+    the stock velodyne driver (x@0 y@4 z@8 intensity@12 ring@16 time@18) has no 4-byte alignment from the second
+    point on; a packed 13-byte record with odd offsets even less."""
+    rng = np.random.default_rng(5)
+    cfg = write_cfg(tmp_path, ec_distance_threshold=0.3, min_cluster_size=50, max_cluster_size=5000, **OPEN_CFG)
+    for step_b, offs in ((22, (0, 4, 8, 12)), (13, (1, 5, 9, NO_FIELD)), (19, (3, 7, 11, 15))):
+        gpu = MovingObjectRemoval(cfg, 4, 3, binding=product)
+        orc = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+        ref = MovingObjectRemoval(cfg, 4, 3, binding=product)
+        a, b = blob(rng, (2, 0, 0), 300, 0.12), blob(rng, (-2, 1, 0), 300, 0.12)
+        for f in range(7):
+            pts = with_intensity(np.concatenate([a, b + np.float32([0.12 * f, 0, 0])]), 0.25)
+            rec = np.full((len(pts), step_b), 0xA5, np.uint8)
+            for col, off in enumerate(offs):
+                if off != NO_FIELD:
+                    rec[:, off:off + 4] = pts[:, col:col + 1].copy().view(np.uint8)
+            rec = np.ascontiguousarray(rec)
+            gpu.push_raw_cloud_and_pose(rec, IDENTITY_POSE, point_step=step_b, offsets=offs)
+            orc.push_raw_cloud_and_pose(rec, IDENTITY_POSE, point_step=step_b, offsets=offs)
+            og, oo = gpu.filter_cloud().copy(), orc.filter_cloud().copy()
+            assert not compare_frame(gpu, orc, og, oo)
+            plain = pts if offs[3] != NO_FIELD else np.ascontiguousarray(pts[:, :3])
+            ref.push_raw_cloud_and_pose(plain, IDENTITY_POSE)
+            assert ref.filter_cloud().tobytes() == og.tobytes()
 
 
 @pytest.mark.parametrize("seed", range(18))
