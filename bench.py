@@ -26,6 +26,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 from pathlib import Path
 
 import numpy as np
@@ -125,12 +126,20 @@ def _oracle_worker(orc, frames, maxp, steps, warmup, sample, out, slot, barrier)
         barrier.wait()
 
 
+def bench_config(world, frames_in_pool=None, frame_bytes=None):
+    """The `config` object of the JSON line: identical for the GPU arm and the CPU arm (same workload, same parameters)."""
+    return {"workload": WORKLOAD, "sequences_per_gpu": 1, "parallelism": f"replicas x{world} (independent sequences, no collective)",
+            "l2": "no input is ever re-read: every step reads a frame no earlier step has read (K+W distinct frames staged in HBM / pinned host memory); "
+                  "intermediates (~10 MB per frame) are L2-resident by design",
+            "n_bad": 4, "n_good": 3, "mor_config": "config/MOR_config_hdl64.txt"}
+
+
 def run_reference(args, rank, world):
     """CPU arm. The reference (ROS + PCL 1.8 + FLANN + Eigen) cannot be built offline, so this times the oracle port
     (kind "port"). The workload is ONE sensor sequence, as on the GPU arm, and the reference is strictly
     single-threaded per sequence (no threads / OpenMP anywhere in src/): `value` is therefore one thread on one
     sequence. The all-cores aggregate (one independent sequence per host thread - the C5-style workload) is
-    reported beside it in `all_cores`, to be compared with the GPU arm's `multi_sequence` figure."""
+    reported beside it in `all_cores`, to be compared with the GPU arm's `multi_sequence` / `c5` figures."""
     if rank != 0:
         return
     orc = MorBinding(C.CDLL(str(ROOT / "oracle" / "libmor_oracle.so")), "oracle_")
@@ -160,8 +169,8 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_single[0] / K_eff, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sequences": 1, "timed_steps": K_eff,
-                   "note": "one sequence, one thread: the reference path is single-threaded per sensor stream"},
+        "config": bench_config(world),
+        "reference_arm": {"timed_steps": K_eff, "note": "one sequence, one thread: the reference path is single-threaded per sensor stream"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "port",
                          "sample": f"{K_eff} frames replaying the first {sample} frames of C2, CPU oracle (PCL-semantics restatement, g++ -O2)",
                          "host_cpus": os.cpu_count()},
@@ -172,10 +181,26 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cores(local_rank, world):
+    """Each rank keeps to its own share of the host cores (rank r -> cores [r*c/w, (r+1)*c/w)): eight processes that
+    share one host otherwise migrate over all cores and NUMA nodes while they feed their GPUs."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // world)
+        mine = cpus[local_rank * per:(local_rank + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        return [mine[0], mine[-1]]
+    except OSError:
+        return None
+
+
 def run_product(args, rank, local_rank, world):
     import torch  # device plumbing + torch.distributed only
     import torch.distributed as dist
 
+    cores = bind_to_gpu_cores(local_rank, world)
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -244,18 +269,18 @@ def run_product(args, rank, local_rank, world):
     e2e_ms = m.event_elapsed_ms(0, 1)
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
+    crc_e2e_last = zlib.crc32(out_host[: n_out.value].tobytes())
     m.close()
 
     # ------------------------------------------------------------------ device-resident: value
-    d_frames, d_out = C.c_void_p(), C.c_void_p()
+    d_frames = C.c_void_p()
     frame_bytes = maxp * 16
     assert b.device_alloc(local_rank, F * frame_bytes, C.byref(d_frames)) == 0
-    assert b.device_alloc(local_rank, maxp * 32, C.byref(d_out)) == 0
     assert b.device_upload(local_rank, d_frames, pts.ctypes.data_as(C.c_void_p), F * frame_bytes) == 0
     m = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
     for f in range(W):
         m.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-        m.filter_device(d_out.value, maxp, want_count=False)
+        m.filter_device(None, 0, want_count=False)
     m.sync()
     barrier()
     l0 = m.launch_count()
@@ -263,7 +288,7 @@ def run_product(args, rank, local_rank, world):
     for i in range(K):
         f = W + i
         m.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-        m.filter_device(d_out.value, maxp, want_count=False)
+        m.filter_device(None, 0, want_count=False)  # the filtered cloud stays in the handle's device buffer
     m.event_record(1)
     dev_ms = m.event_elapsed_ms(0, 1)
     barrier()
@@ -273,8 +298,15 @@ def run_product(args, rank, local_rank, world):
     counts_last = m.counts()
     if counts_last["ERRFLAGS"]:
         raise RuntimeError(f"device capacity flags {counts_last['ERRFLAGS']}")
+    # the timed run did the work: its last output equals the last output of the (independent) end-to-end run, byte for byte
+    last = np.empty((counts_last["NOUT"], 8), np.float32)
+    if last.size:
+        assert b.device_download(local_rank, last.ctypes.data_as(C.c_void_p), C.c_void_p(m.output_device()), last.nbytes) == 0
+    crc_dev_last = zlib.crc32(last.tobytes())
+    m.close()
 
     # ------------------------------------------------------------------ multi-sequence (C5-style): S independent sequences per GPU
+    from dynamicslamtool_b200 import SequenceBatch
     multi = None
     S = args.sequences
     if S > 1:
@@ -285,8 +317,6 @@ def run_product(args, rank, local_rank, world):
             assert b.device_alloc(local_rank, maxp * 32, C.byref(p)) == 0
             d_outs.append(p)
         offs = [(si * F) // S for si in range(S)]  # every sequence starts at its own frame of the pool and wraps around once
-
-        from dynamicslamtool_b200 import SequenceBatch
         batch = SequenceBatch(hs)
         outs = [p.value for p in d_outs]
 
@@ -306,15 +336,28 @@ def run_product(args, rank, local_rank, world):
         multi_ms = hs[0].event_elapsed_ms(0, 1)
         barrier()
         multi_ms = max_over_ranks(multi_ms)
-        T = 1
         multi_launches = hs[0].launch_count() - l0m
+        alg = 0.0
+        for hh2 in hs:
+            hh2.sync()
+            alg += algorithmic_bytes(hh2.counts())
+        peak_m, which_m = measured_peak_gbs()
+        step_us = 1e3 * multi_ms / K
         multi = {"sequences_per_gpu": S, "value": world * S * K / (multi_ms * 1e-3), "unit": "frames/s", "ms_per_round": multi_ms / K,
                  "launches": multi_launches,
-                 "note": "device-resident, mor_batch_step_device: S sequences per set of launches (blockIdx.z = sequence); aggregate over all sequences and GPUs"}
-        for hh in hs:
-            hh.close()
+                 "roofline": {"bound": "hbm", "kernel": "k_frame_batch", "achieved": alg / (step_us * 1e-6) / 1e9, "peak": peak_m, "unit": "GB/s",
+                              "frac": alg / (step_us * 1e-6) / 1e9 / peak_m, "peak_source": which_m, "algorithmic_bytes_per_launch": alg,
+                              "kernel_avg_us": step_us, "note": "one launch per step: the step time is the kernel's duration (CUDA events on its stream)"},
+                 "note": "device-resident, mor_batch_step_device: S sequences per launch of the frame kernel (a group of CTAs per sequence); aggregate over all sequences and GPUs"}
+        for hh2 in hs:
+            hh2.close()
         for p in d_outs:
             b.device_free(local_rank, p)
+
+    # ------------------------------------------------------------------ C5: 128 sequences per GPU (1024 on 8 GPUs), 32 frames each, seeds 1000 + s
+    c5 = None
+    if args.c5_sequences > 0:
+        c5 = run_c5(b, local_rank, rank, world, args.c5_sequences, 32, args.sequences if args.sequences > 1 else 16, maxp, max_over_ranks, sum_over_ranks, barrier)
 
     # ------------------------------------------------------------------ multi-sequence, end to end: one host thread per sequence through
     # the host C ABI (pinned input, H2D, kernels, D2H): copies of one sequence overlap the kernels of the others
@@ -328,14 +371,14 @@ def run_product(args, rank, local_rank, world):
         gate = threading.Barrier(Se + 1)
 
         def drive(si):
-            hh, outp = hs2[si].h, C.c_void_p(outs2[si][0].ctypes.data)
+            hh3, outp = hs2[si].h, C.c_void_p(outs2[si][0].ctypes.data)
             no = C.c_uint32(0)
             for phase, cnt in (("warm", 5), ("timed", Ke)):
                 if phase == "timed":
                     gate.wait()
                 for t in range(cnt):
                     f = (offs2[si] + (t if phase == "warm" else 5 + t)) % F
-                    if b.push(hh, in_ptrs[f], ns[f], 16, 0, 4, 8, 12, pose_arrs[f]) or b.filter(hh, outp, maxp, C.byref(no)):
+                    if b.push(hh3, in_ptrs[f], ns[f], 16, 0, 4, 8, 12, pose_arrs[f]) or b.filter(hh3, outp, maxp, C.byref(no)):
                         raise RuntimeError("C ABI error in the multi-sequence e2e leg")
             gate.wait()
 
@@ -351,76 +394,108 @@ def run_product(args, rank, local_rank, world):
         dt = max_over_ranks(dt)
         multi_e2e = {"sequences_per_gpu": Se, "value": world * Se * Ke / dt, "unit": "frames/s",
                      "note": "host C ABI, one host thread + stream per sequence, pinned buffers, H2D and D2H inside; wall clock over all sequences"}
-        for hh in hs2:
-            hh.close()
+        for hh3 in hs2:
+            hh3.close()
 
     clocks = sampler.stop() if rank == 0 else None
 
-    # ------------------------------------------------------------------ per-kernel profile (rank 0; outside the timed regions)
+    # ------------------------------------------------------------------ the frame kernel's duration and its phases (rank 0; outside the timed regions)
     roofline = None
-    per_kernel = {}
+    phases = {}
     frame_bytes_alg = 0.0
     if rank == 0:
-        m2 = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+        peak, which = measured_peak_gbs()
         prof_frames = min(F, 64)
-        for f in range(min(W, prof_frames)):
+        w0 = min(W, prof_frames)
+        # pass 1: the fused kernel, one pair of CUDA events around every launch
+        m2 = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+        m2.set_timing(True)
+        kern_ms, alg_sum, nc_sum, nprof = 0.0, 0, 0, 0
+        timeline = {}
+        for f in range(prof_frames):
             m2.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-            m2.filter_device(d_out.value, maxp, want_count=True)
+            m2.filter_device(None, 0, want_count=True)
+            if f >= w0:
+                kern_ms += m2.last_device_ms()[0]
+                for k, v in m2.phase_times().items():
+                    timeline[k] = timeline.get(k, 0.0) + v
+                c = m2.counts()
+                alg_sum += algorithmic_bytes(c)
+                nc_sum += c["NC"]
+                nprof += 1
+        m2.close()
+        nprof = max(nprof, 1)
+        frame_bytes_alg = alg_sum / nprof
+        kern_us = 1e3 * kern_ms / nprof
+        traffic, traffic_note = None, None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            tj = json.loads(tp.read_text())
+            traffic, traffic_note = tj.get("k_frame"), tj.get("note")
+        roofline = {"bound": "hbm", "kernel": "k_frame", "achieved": frame_bytes_alg / (kern_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": frame_bytes_alg / (kern_us * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": which,
+                    "algorithmic_bytes_per_launch": frame_bytes_alg, "units_per_launch": 1, "bytes_per_unit": frame_bytes_alg,
+                    "unit_note": "one launch = one frame; SURVEY 8(d): 16N + 17Nt + 104Nc + 24Nk' + 32(P1+P2) + 20Nt + 16Nout from the frame's device-side counts",
+                    "kernel_avg_us": kern_us, "kernel_share_of_frame": kern_us / (1e3 * dev_ms / K), "mean_cloud_points": nc_sum / nprof}
+        # pass 2: one launch per phase (the same device functions), each between events
+        m2 = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+        for f in range(w0):
+            m2.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
+            m2.filter_device(None, 0, want_count=True)
         m2.set_kernel_profiling(True)
-        nc_sum, alg_sum, nprof = 0, 0, 0
-        for f in range(min(W, prof_frames), prof_frames):
+        for f in range(w0, prof_frames):
             m2.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-            m2.filter_device(d_out.value, maxp, want_count=True)
-            c = m2.counts()
-            nc_sum += c["NC"]
-            alg_sum += algorithmic_bytes(c)
-            nprof += 1
+            m2.filter_device(None, 0, want_count=True)
         prof = m2.kernel_profile()
         m2.set_kernel_profiling(False)
         m2.close()
-        per_kernel = {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1], "share": 0.0} for k, v in prof.items() if v[1]}
-        tot = sum(v[0] for v in prof.values())
-        for k, v in prof.items():
-            if v[1]:
-                per_kernel[k]["share"] = v[0] / tot
-        dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_us"] * per_kernel[k]["launches"])
-        peak, which = measured_peak_gbs()
-        # SURVEY §8(d) per-unit figures (bytes per cloud point of the stage the kernel implements)
-        per_unit = {"k_link_cells": 20, "k_ingest": 33, "k_scatter": 40, "k_flatten": 8, "k_cluster_stats": 16, "k_filter_output": 36,
-                    "k_lattice_insert": 16, "k_lattice_count": 16, "k_transform_prev": 24, "k_scan_cells": 8}
-        unit_bytes = per_unit.get(dom, 20)
-        mean_nc = nc_sum / max(nprof, 1)
-        alg = unit_bytes * mean_nc
-        achieved = alg / (per_kernel[dom]["avg_us"] * 1e-6) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get(dom)
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": which, "algorithmic_bytes_per_launch": alg, "units_per_launch": mean_nc, "bytes_per_unit": unit_bytes,
-                    "kernel_avg_us": per_kernel[dom]["avg_us"], "kernel_share_of_frame": per_kernel[dom]["share"]}
-        frame_bytes_alg = alg_sum / max(nprof, 1)
+        tot = sum(v[0] for v in prof.values()) or 1.0
+        phases = {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1], "share": v[0] / tot, "in_frame_kernel_us": timeline.get(k, 0.0) / nprof}
+                  for k, v in prof.items() if v[1]}
+        if "ph_link" in phases:
+            mean_nc = nc_sum / nprof
+            phases["ph_link"]["roofline"] = {"bytes_per_unit": 20, "units": mean_nc, "achieved_gbs": 20 * mean_nc / (phases["ph_link"]["avg_us"] * 1e-6) / 1e9,
+                                             "frac": 20 * mean_nc / (phases["ph_link"]["avg_us"] * 1e-6) / 1e9 / peak}
 
-    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
-    cpu = None
+    # ------------------------------------------------------------------ CPU baseline + parity spot check (rank 0, N = 1 only)
+    cpu, spot = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
         orc = MorBinding(C.CDLL(str(ROOT / "oracle" / "libmor_oracle.so")), "oracle_")
         mo = MovingObjectRemoval(CFG, 4, 3, binding=orc)
         out_o = np.empty((maxp, 8), np.float32)
         budget, t_used, nf = 20.0, 0.0, 0
+        crcs_o = []
         for f in range(F):
             t0 = time.perf_counter()
             mo.push_raw_cloud_and_pose(pts[f, : npts[f]], poses[f])
-            mo.filter_cloud(out_o)
+            oo = mo.filter_cloud(out_o)
             t_used += time.perf_counter() - t0
+            crcs_o.append((zlib.crc32(oo.tobytes()), zlib.crc32(mo.tap("removed_mask").tobytes())))
             nf += 1
             if t_used > budget:
                 break
         cpu = {"value": nf / t_used, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": f"first {nf} frames of the same C2 sequence, single thread, CPU oracle (PCL-semantics restatement, -O2)", "host_cpus": os.cpu_count()}
+        # the same frames through the product, untimed: output cloud and removal mask of every frame against the oracle's
+        mg = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+        equal = 0
+        first_bad = None
+        for f in range(nf):
+            mg.push_raw_cloud_and_pose(pts[f, : npts[f]], poses[f])
+            og = mg.filter_cloud(out_host)
+            ok = (zlib.crc32(og.tobytes()), zlib.crc32(mg.tap("removed_mask").tobytes())) == crcs_o[f]
+            equal += 1 if ok else 0
+            if not ok and first_bad is None:
+                first_bad = f
+        spot = {"frames": nf, "crc_equal": equal == nf, "frames_equal": equal, "first_mismatch": first_bad,
+                "what": "crc32 of the filtered cloud bytes and of the removed-point mask, product vs oracle, frame by frame from the start of the timed sequence",
+                "timed_run_last_frame_crc_equal": crc_dev_last == crc_e2e_last,
+                "timed_run_note": "last output of the device-resident timed run == last output of the end-to-end timed run (two independent full passes)"}
+        if nf == F:
+            spot["timed_run_last_frame_equals_oracle"] = crcs_o[-1][0] == crc_dev_last
+        mg.close()
 
     b.device_free(local_rank, d_frames)
-    b.device_free(local_rank, d_out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,14 +504,11 @@ def run_product(args, rank, local_rank, world):
     value = world * K / (dev_ms * 1e-3)
     e2e_value = world * K / (e2e_ms * 1e-3)
     peak, which = measured_peak_gbs()
+    cfg = bench_config(world)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sequences_per_gpu": 1, "parallelism": f"replicas x{world} (independent sequences, no collective)",
-                   "l2": (("inputs larger than L2: " if F * frame_bytes > 126e6 else "no input is ever re-read: ") +
-                          f"{F} distinct frames = {F * frame_bytes / 1e6:.0f} MB staged in HBM (L2 is 126 MB), every step reads a frame "
-                          "no earlier step has read; intermediates (~10 MB per frame) are L2-resident by design"),
-                   "n_bad": 4, "n_good": 3},
+        "config": cfg,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(np.mean(npts[W:]) * 16 + 56), "d2h_bytes_per_step": int(d2h / K),
                 "ms_per_step": e2e_ms / K, "latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3),
@@ -445,12 +517,85 @@ def run_product(args, rank, local_rank, world):
         "roofline": roofline,
         "frame_roofline": {"algorithmic_bytes_per_frame": frame_bytes_alg, "achieved_gbs": frame_bytes_alg * (K / (dev_ms * 1e-3)) / 1e9,
                            "frac": frame_bytes_alg * (K / (dev_ms * 1e-3)) / 1e9 / peak, "peak": peak, "peak_source": which},
-        "kernels": per_kernel,
+        "phases": phases,
         "multi_sequence": multi,
+        "c5": c5,
         "multi_sequence_e2e": multi_e2e,
         "cpu_baseline": cpu,
+        "parity_spot_check": spot,
+        "host": {"staged_frames": F, "staged_mb": F * frame_bytes / 1e6, "rank_cores": cores},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_c5(b, local_rank, rank, world, per_gpu, T, S, maxp, max_over_ranks, sum_over_ranks, barrier):
+    """BASELINE config 5 as SURVEY 8(d) words it: independent C2-shaped sequences with seeds 1000 + s, 32 frames each,
+    sequence s -> rank s mod world; `per_gpu` sequences per GPU (128 => the full 1024 on 8 GPUs: weak scaling). The
+    sequences of a rank are taken S at a time: generated on the host and staged in HBM (untimed: the generator is not
+    the subject), handles reset, then T batched steps timed with CUDA events on the launching stream."""
+    from concurrent.futures import ThreadPoolExecutor
+    from dynamicslamtool_b200 import SequenceBatch
+    total = per_gpu * world
+    mine = [s for s in range(total) if s % world == rank]
+    frame_bytes = maxp * 16
+    d_in = C.c_void_p()
+    assert b.device_alloc(local_rank, S * T * frame_bytes, C.byref(d_in)) == 0
+    d_outs = []
+    for _ in range(S):
+        p = C.c_void_p()
+        assert b.device_alloc(local_rank, maxp * 32, C.byref(p)) == 0
+        d_outs.append(p)
+    hs = [MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp) for _ in range(S)]
+    threads = max(1, (os.cpu_count() or 8) // max(1, min(world, 8)))
+
+    def generate(seq):
+        syn = Synth(SCENARIO, 1000 + seq)
+        syn.threads = 1  # the pool below already runs one sequence per host thread
+        return [syn.frame(f) for f in range(T)]
+
+    timed_ms, frames_done, launches, gen_s, out_pts = 0.0, 0, 0, 0.0, 0
+    for b0 in range(0, len(mine), S):
+        seqs = mine[b0:b0 + S]
+        t0 = time.time()
+        with ThreadPoolExecutor(threads) as ex:
+            data = list(ex.map(generate, seqs))
+        gen_s += time.time() - t0
+        for si, frames in enumerate(data):
+            for f, (p, _) in enumerate(frames):
+                assert b.device_upload(local_rank, C.c_void_p(d_in.value + (si * T + f) * frame_bytes), p.ctypes.data_as(C.c_void_p), p.nbytes) == 0
+        group = hs[:len(seqs)]
+        for h in group:
+            h.reset()
+        batch = SequenceBatch(group)
+        lead = group[0]
+        l0 = lead.launch_count()
+        lead.event_record(0)
+        for f in range(T):
+            batch.step_device([d_in.value + (si * T + f) * frame_bytes for si in range(len(seqs))], [int(data[si][f][0].shape[0]) for si in range(len(seqs))],
+                              [data[si][f][1] for si in range(len(seqs))], [p.value for p in d_outs[:len(seqs)]])
+        lead.event_record(1)
+        lead.sync()
+        timed_ms += lead.event_elapsed_ms(0, 1)
+        launches += lead.launch_count() - l0
+        frames_done += len(seqs) * T
+        for h in group:
+            h.sync()
+            c = h.counts()
+            if c["ERRFLAGS"]:
+                raise RuntimeError(f"C5: device capacity flags {c['ERRFLAGS']}")
+            out_pts += c["NOUT"]
+    for h in hs:
+        h.close()
+    for p in d_outs:
+        b.device_free(local_rank, p)
+    b.device_free(local_rank, d_in)
+    barrier()
+    worst = max_over_ranks(timed_ms)
+    frames_all = sum_over_ranks(frames_done)
+    return {"workload": f"C5: {total} independent C2-shaped sequences (seeds 1000..{1000 + total - 1}), {T} frames each, sequence s -> rank s mod {world}, "
+                        f"{S} sequences per launch", "sequences": total, "sequences_per_gpu": per_gpu, "frames": int(frames_all),
+            "value": frames_all / (worst * 1e-3), "unit": "frames/s", "timed_ms_max_over_ranks": worst, "launches_rank0": launches,
+            "generator_seconds_rank0": gen_s, "output_points_last_frames_rank0": out_pts, "data": "synthetic, staged in HBM before the timed region"}
 
 
 def main():
@@ -462,6 +607,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-sequences", type=int, default=8, help="sequences (= host threads) of the multi-sequence end-to-end figure (1 = skip)")
     ap.add_argument("--sequences", type=int, default=16, help="independent sequences per GPU for the extra multi_sequence figure (1 = skip)")
+    ap.add_argument("--c5-sequences", type=int, default=128, help="BASELINE config 5: sequences per GPU (128 x 8 GPUs = the full 1024), 32 frames each (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

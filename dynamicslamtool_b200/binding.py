@@ -128,6 +128,8 @@ class MorBinding:
         self.event_elapsed_ms = f("event_elapsed_ms", [vp, C.c_int, C.c_int, C.POINTER(C.c_float)], True)
         self.set_kernel_profiling = f("set_kernel_profiling", [vp, C.c_int], True)
         self.get_kernel_profile = f("get_kernel_profile", [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], True)
+        self.get_phase_times = f("get_phase_times", [vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)], True)
+        self.phase_name = f("phase_name", [C.c_int], True, C.c_char_p)
 
     def _fn(self, name, argtypes, optional=False, restype=C.c_int):
         try:
@@ -318,6 +320,13 @@ class MovingObjectRemoval:
             out[name.value.decode()] = (ms.value, n.value)
             i += 1
         return out
+
+    def phase_times(self) -> dict:
+        """{phase name: microseconds} of the last frame kernel (its own %globaltimer timeline, barriers included)."""
+        us = (C.c_float * 32)()
+        n = C.c_int(0)
+        self._check(self.b.get_phase_times(self.h, us, 32, C.byref(n)), "get_phase_times")
+        return {self.b.phase_name(i).decode(): float(us[i]) for i in range(n.value)}
 
     def set_timing(self, enabled: bool):
         self._check(self.b.set_timing(self.h, 1 if enabled else 0), "set_timing")

@@ -139,7 +139,7 @@ namespace {
 
 enum KernelId { KID_PHASE0 = 0, KID_FRAME = PH__COUNT, KID_FILTER_AGAIN,
                 KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_CELLS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells+transform", "ph_scatter", "ph_link", "ph_flatten", "ph_select", "ph_stats", "ph_match",
+const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells+transform", "ph_scatter", "ph_link", "ph_link_heavy", "ph_flatten", "ph_select", "ph_stats", "ph_match",
                                               "ph_moving_test", "ph_chain+cleanup", "ph_filter", "k_frame", "k_filter_again",
                                               "k_ingest_raw", "k_ground_keys", "k_scan_cells", "k_scan_voxels", "k_ground_scatter",
                                               "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
@@ -237,7 +237,7 @@ int allocate(mor_handle* h) {
         b.st_out = carve<unsigned long long>(p, tiles_pts);
         b.table = carve<Cell>(p, tab);
         b.cell_list = carve<int>(p, N); b.ckey = carve<unsigned long long>(p, N + 1); b.cstart = carve<int>(p, N + 1);
-        b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N);
+        b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N); b.heavy = carve<int4>(p, 4 * N);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
         b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
@@ -250,7 +250,7 @@ int allocate(mor_handle* h) {
         b.anchorp = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
         b.lattice = carve<unsigned long long>(p, lat);
         b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
-        b.marker_cluster = carve<int>(p, MO); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
+        b.marker_cluster = carve<int>(p, MO); b.phase_ts = carve<unsigned long long>(p, PH__COUNT + 1); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
         b.out = carve<float4>(p, N * 2); h->coll_out = carve<float4>(p, N * 2);
         for (int f = 0; f < 2; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
@@ -281,7 +281,7 @@ int allocate(mor_handle* h) {
     int P = 1;
     while (P < (int)K) P <<= 1;
     h->frame_smem = (size_t)P * sizeof(unsigned long long);
-    if (h->frame_smem < (size_t)kLinkTilePts * 16) h->frame_smem = (size_t)kLinkTilePts * 16;
+    if (h->frame_smem < kLinkSmem) h->frame_smem = kLinkSmem;
     return MOR_OK;
 }
 
@@ -318,6 +318,7 @@ void fill_static(mor_handle* h) {
     b.cell_h = h->cell_h; b.inv_h = 1.0 / h->cell_h;
     b.skip_ingest = c.ground_mode != MOR_GROUND_CROP ? 1 : 0;
     b.table_mask = (unsigned)(h->table_cap - 1);
+    b.heavy_cap = (int)(4 * h->nmax);
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
     b.pde_ring = h->pde_ring;
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
@@ -396,7 +397,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     }
     if (h->profiling) {  // one launch per phase, each between a pair of events
         int s;
-        if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_SCATTER>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) ||
+        if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_SCATTER>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) || (s = launch_phase<PH_LINK_HEAVY>(h, a)) ||
             (s = launch_phase<PH_FLATTEN>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || (s = launch_phase<PH_MATCH>(h, a)) ||
             (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_CHAIN>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
             return s;
@@ -709,6 +710,17 @@ int mor_sync(mor_handle* h) {
 
 int mor_alloc_pinned(size_t bytes, void** out) { return cudaMallocHost(out, bytes) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA; }
 int mor_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA; }
+int mor_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return MOR_ERR_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) return MOR_OK;
+    cudaGetLastError();
+    return MOR_ERR_CUDA;
+}
+int mor_host_unregister(void* p) {
+    if (cudaHostUnregister(p) == cudaSuccess) return MOR_OK;
+    cudaGetLastError();
+    return MOR_ERR_CUDA;
+}
 int mor_device_alloc(int device, size_t bytes, void** out) {
     if (cudaSetDevice(device) != cudaSuccess) return MOR_ERR_CUDA;
     return cudaMalloc(out, bytes) == cudaSuccess ? MOR_OK : MOR_ERR_CUDA;
@@ -767,6 +779,28 @@ int mor_set_kernel_profiling(mor_handle* h, int enabled) {
     if (enabled) { std::memset(h->prof_ms, 0, sizeof(h->prof_ms)); std::memset(h->prof_n, 0, sizeof(h->prof_n)); }
     return MOR_OK;
 }
+// The last frame kernel's own timeline: microseconds CTA 0 spent in each phase (barrier included), from %globaltimer.
+int mor_get_phase_times(mor_handle* h, float* us, int cap, int* n_phases) {
+    if (!h || !us || !n_phases) return MOR_ERR_ARG;
+    if (!h->have_cur) return MOR_ERR_STATE;
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned long long ts[PH__COUNT + 1];
+    MOR_CUDA(cudaMemcpy(ts, h->base.phase_ts, sizeof ts, cudaMemcpyDeviceToHost));
+    *n_phases = PH__COUNT;
+    for (int i = 0; i < PH__COUNT && i < cap; i++) us[i] = (float)((double)(ts[i + 1] - ts[i]) * 1e-3);
+    return MOR_OK;
+}
+#ifdef MOR_LINK_STATS
+int mor_debug_link_stats(unsigned long long* out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, g_link_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return MOR_ERR_CUDA;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_link_stats, z, sizeof z); }
+    return MOR_OK;
+}
+#endif
+const char* mor_phase_name(int index) { return index >= 0 && index < PH__COUNT ? kKernelNames[index] : ""; }
+
 int mor_get_kernel_profile(mor_handle* h, int index, char name[32], double* total_ms, uint64_t* launches) {
     if (!h || index < 0 || index >= KID__COUNT || !name || !total_ms || !launches) return MOR_ERR_ARG;
     std::snprintf(name, 32, "%s", kKernelNames[index]);

@@ -21,8 +21,10 @@ constexpr int kT = 1024;         // threads per CTA of the frame kernel: one CTA
 constexpr int kSingle = kT;      // single-CTA bookkeeping phases use the whole CTA
 constexpr int kWarps = kT / 32;
 constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
-constexpr int kHeavyPair = 1024; // a cell pair with more point pairs than this is examined by the whole warp
+constexpr int kLightPair = 256;  // a cell pair with more point pairs than this is queued for a whole warp (phase_link_heavy)
 constexpr int kLinkTilePts = 2048;  // points of one link round (32 cells) staged in shared memory by one bulk copy (32 KB)
+constexpr int kLinkListCap = 256;   // per warp: neighbour points dealt out to the lanes per pass (1 KB of shared memory)
+constexpr size_t kLinkSmem = (size_t)kLinkTilePts * 16 + (size_t)kWarps * kLinkListCap * 4;
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16 };
 // counts[] slots in which the filter phase parks its results until filterCloud commits the frame (mor_b200.cu, do_filter)
@@ -44,7 +46,7 @@ struct GridDesc {  // dense grid of the voxel ground modes' ball query (mor_grou
 struct Scratch {  // all zero between frames: every counter is put back by the frame that used it
     unsigned bar;            // group barrier of k_frame (monotonic within a launch)
     int blocks_done;         // CTAs that have finished the frame
-    int n_cells, n_roots;
+    int n_cells, n_roots, n_heavy, pad1;
     int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
     int err_early;           // error bits raised before the frame's counts exist
     int pad0;
@@ -79,6 +81,7 @@ struct FramePtrs {
     unsigned long long* ckey; int* cstart;  // [n_cells(+1)] compact copies: key, first sorted position
     int2* pslot;               // [N_c] (table slot, rank inside the cell) of every cloud point
     int* slead;                // [N_c] leader position (cell start) of every sorted position
+    int4* heavy; int heavy_cap; // work list of the heavy cell pairs: (start A, count A, start B, count B)
     // ---- per-frame scratch
     Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cscan; unsigned long long* st_out;
     uint8_t* point_class; uint8_t* removed_mask;
@@ -98,6 +101,7 @@ struct FramePtrs {
     unsigned long long* lattice; unsigned lattice_mask;
     uint8_t* cluster_removed; int* found;
     int* marker_cluster;          // [momax] cluster each mo_vec entry was matched to by the last filterCloud
+    unsigned long long* phase_ts; // [PH__COUNT + 1] %globaltimer at the start of the frame kernel and after every phase (CTA 0)
     float4* out;
     // ---- ping-pong frame state: cur / prev
     float4* pts; float4* spts; int* cid; int* cl_root; int* cl_size; float* cl_centroid; uint8_t* cl_flags; float* cl_bbox; int* counts;
@@ -387,10 +391,6 @@ __device__ __forceinline__ void cell_scan_tile(const FramePtrs& a, int tile, int
         a.table[slot].start = start;
         a.ckey[i] = key; a.cstart[i] = start;
         a.parent[start] = start; a.comp_size[start] = 0; a.minidx[start] = 0x7FFFFFFF;
-        if (cnt > kBoxMinCount) {
-            a.cell_box[2 * start] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
-            a.cell_box[2 * start + 1] = make_uint4(0u, 0u, 0u, 0u);
-        }
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) a.cstart[n_cells] = before + total;
 }
@@ -512,37 +512,18 @@ __device__ __forceinline__ void phase_cells_and_transform(const FramePtrs& a, in
 }
 
 // ===================================================================================== phase C: scatter
-// Cloud points into cell order (float4 xyz + cloud index): slot = cell start + the rank taken at binning time. Tight
-// bounding boxes of the crowded cells (they prune the point tests of the link phase).
+// Cloud points into cell order (float4 xyz + cloud index): slot = cell start + the rank taken at binning time.
 __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G) {
     const int nc = a.counts[MOR_CNT_NC];
     for (int base = cta * kT; base < nc; base += G * kT) {
         const int c = base + threadIdx.x;
-        const int lane = threadIdx.x & 31;
-        bool crowded = false;
-        int start = -1 - lane;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < nc) {
             const int2 sr = a.pslot[c];
-            const int2 sc = __ldcg(reinterpret_cast<const int2*>(&a.table[sr.x].start));  // (start, cnt)
-            p = a.pts[c];
+            const int start = __ldcg(&a.table[sr.x].start);
+            float4 p = a.pts[c];
             p.w = __int_as_float(c);
-            a.spts[sc.x + sr.y] = p;
-            a.slead[sc.x + sr.y] = sc.x;
-            crowded = sc.y > kBoxMinCount;
-            if (crowded) start = sc.x;
-        }
-        if (__any_sync(kFull, crowded)) {
-            // lanes of a warp that fall into the same crowded cell are combined with redux before the atomics
-            const unsigned grp = __match_any_sync(kFull, start);
-            const unsigned kx = fkey(p.x), ky = fkey(p.y), kz = fkey(p.z);
-            const unsigned mnx = __reduce_min_sync(grp, kx), mny = __reduce_min_sync(grp, ky), mnz = __reduce_min_sync(grp, kz);
-            const unsigned mxx = __reduce_max_sync(grp, kx), mxy = __reduce_max_sync(grp, ky), mxz = __reduce_max_sync(grp, kz);
-            if (crowded && (int)(__ffs(grp) - 1) == lane) {
-                unsigned* b = reinterpret_cast<unsigned*>(a.cell_box + 2 * start);
-                atomicMin(b + 0, mnx); atomicMin(b + 1, mny); atomicMin(b + 2, mnz);
-                atomicMax(b + 4, mxx); atomicMax(b + 5, mxy); atomicMax(b + 6, mxz);
-            }
+            a.spts[start + sr.y] = p;
+            a.slead[start + sr.y] = start;
         }
     }
 }
@@ -552,11 +533,21 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
 // are neighbours (cell diagonal < r), so a cell is one union-find node, and a neighbour lies at most 2 cells away per
 // axis: cell A must be tested against the 62 cells of its 5x5x5 block that precede it in (dz,dy,dx) order (the other 62
 // test A from their side). Two cells are linked iff some point pair has L2_Simple distance < r2 (strict).
-// One WARP per cell; a link round takes 32 consecutive cells of the cell list, whose points are one contiguous range of
-// the sorted array: it is staged in shared memory by a single bulk copy (TMA) while the lanes walk the hash table -
-// lane l looks up neighbours l and l+32. Every lane then tests its neighbour cells' points (read from L2) against A's
-// points (shared memory) and unites on the first hit; cell pairs with many point pairs are left to the whole warp
-// (lanes across B's points, bounding-box pruning on both sides, root check first).
+//
+// D1, light pairs: one WARP per cell. A link round takes 32 consecutive cells of the cell list, whose points are one
+// contiguous range of the sorted array: it is staged in shared memory by a single bulk copy (TMA) while the lanes walk
+// the hash table - lane l looks up neighbours l and l+32, both probes in flight together. The points of all light
+// neighbour cells are then flattened into one list (shared memory) and dealt out to the lanes, one neighbour point per
+// lane and step: a single round of independent loads, each tested against A's points in shared memory; the lanes that
+// hit unite (one lane per neighbour cell).
+// D2, heavy pairs (more than kLightPair point pairs): queued by D1 and dealt out to all warps of the group, a whole warp
+// per pair: root check first (dense surfaces are mostly merged through their light neighbours already), bounding-box
+// pruning on both sides, lanes across B's points, early exit.
+#ifdef MOR_LINK_STATS
+#define MOR_CLOCK(v) const long long v = clock64()
+#else
+#define MOR_CLOCK(v)
+#endif
 struct BoxF { float lx, ly, lz, hx, hy, hz; };
 __device__ __forceinline__ BoxF load_box(const FramePtrs& a, int start) {
     const uint4 lo = __ldcg(a.cell_box + 2 * start), hi = __ldcg(a.cell_box + 2 * start + 1);
@@ -574,19 +565,21 @@ __device__ __forceinline__ float box_box_d2(const BoxF& p, const BoxF& q) {
     return ex * ex + ey * ey + ez * ez;
 }
 
-// Whole warp on one crowded cell pair (A: cntA points at A[], B: cB points at sorted positions sB..).
-__device__ __forceinline__ void link_heavy_pair(const FramePtrs& a, const float4* A, int startA, int cntA, bool hasBoxA, const BoxF& boxA, int sB, int cB, int lane) {
+// Whole warp on one heavy cell pair (A: cntA points at A[], B: cB points at sorted positions sB..).
+template <bool BOXES>
+__device__ __forceinline__ void link_heavy_pair(const FramePtrs& a, const float4* A, int startA, int cntA, int sB, int cB, int lane) {
     const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
-    // dense surfaces are mostly merged through their nearer cells already: two cells of one component need no point tests
+    MOR_CLOCK(h0);
     int same = 0;
     if (lane == 0) same = uf_find(a.parent, startA) == uf_find(a.parent, sB) ? 1 : 0;
-    if (__shfl_sync(kFull, same, 0)) return;
-    const bool hasBoxB = cB > kBoxMinCount;
-    BoxF boxB = boxA;
-    if (hasBoxB) {
-        boxB = load_box(a, sB);
-        if (hasBoxA && box_box_d2(boxA, boxB) > r2_prune) return;
-    }
+    MOR_CLOCK(h1);
+    if (lane == 0) { MOR_STAT2_ADD(7, 1); if (same) MOR_STAT2_ADD(9, 1); MOR_STAT2_ADD(3, h1 - h0); MOR_STAT2_MAX(4, h1 - h0); }
+    if (__shfl_sync(kFull, same, 0)) return;  // two cells of one component need no point tests
+    const bool hasBoxA = BOXES && cntA > kBoxMinCount, hasBoxB = BOXES && cB > kBoxMinCount;  // (the boxes are complete after the light phase)
+    BoxF boxA = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, boxB = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (hasBoxA) boxA = load_box(a, startA);
+    if (hasBoxB) boxB = load_box(a, sB);
+    if (hasBoxA && hasBoxB && box_box_d2(boxA, boxB) > r2_prune) return;
     bool hit = false;
     for (int b0 = 0; b0 < cB && !hit; b0 += 32) {
         const int b = b0 + lane;
@@ -597,71 +590,154 @@ __device__ __forceinline__ void link_heavy_pair(const FramePtrs& a, const float4
             if (hasBoxA) valid = box_point_d2(boxA, pb.x, pb.y, pb.z) <= r2_prune;
         }
         if (!__any_sync(kFull, valid)) continue;
-        for (int a0 = 0; a0 < cntA && !hit; a0 += 4) {
+        // A in blocks of 32: one coalesced load, then every candidate point (inside r of B's box) is broadcast by shuffle
+        // to all lanes: 32 x 32 point pairs per round trip to memory
+        for (int a0 = 0; a0 < cntA && !hit; a0 += 32) {
+            const float4 pa = A[min(a0 + lane, cntA - 1)];
+            const bool av = a0 + lane < cntA && (!hasBoxB || box_point_d2(boxB, pa.x, pa.y, pa.z) <= r2_prune);
             bool h = false;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const float4 pa = A[min(a0 + u, cntA - 1)];
-                if (hasBoxB && box_point_d2(boxB, pa.x, pa.y, pa.z) > r2_prune) continue;  // uniform over the warp
-                h |= valid && sqdist3(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < r2;
+            for (unsigned m = __ballot_sync(kFull, av); m; m &= m - 1) {
+                const int u = __ffs(m) - 1;
+                const float ax = __shfl_sync(kFull, pa.x, u), ay = __shfl_sync(kFull, pa.y, u), az = __shfl_sync(kFull, pa.z, u);
+                h |= sqdist3(ax, ay, az, pb.x, pb.y, pb.z) < r2;
             }
-            hit = __any_sync(kFull, h);
+            hit = __any_sync(kFull, h && valid);
         }
     }
+    MOR_CLOCK(h2);
     if (hit && lane == 0) uf_union(a.parent, startA, sB);
+    MOR_CLOCK(h3);
+    if (lane == 0) { if (hit) MOR_STAT2_ADD(10, 1); else MOR_STAT2_ADD(11, 1); MOR_STAT2_ADD(5, h2 - h1); MOR_STAT2_ADD(6, h3 - h2); MOR_STAT2_MAX(8, h3 - h0); }
 }
 
-__device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float4* A, int lane) {
+// Both neighbours of a lane are looked up with their first probes in flight together.
+__device__ __forceinline__ void grid_lookup2(const FramePtrs& a, bool v0, unsigned long long k0, bool v1, unsigned long long k1, int2* sc0, int2* sc1) {
+    unsigned s0 = hash64(k0) & a.table_mask, s1 = hash64(k1) & a.table_mask;
+    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+    if (v0) r0 = __ldcg(reinterpret_cast<const uint4*>(a.table + s0));
+    if (v1) r1 = __ldcg(reinterpret_cast<const uint4*>(a.table + s1));
+    *sc0 = make_int2(0, 0); *sc1 = make_int2(0, 0);
+    while (v0) {
+        const unsigned long long cur = ((unsigned long long)r0.y << 32) | r0.x;
+        if (cur == k0) { *sc0 = make_int2((int)r0.z, (int)r0.w); break; }
+        if (cur == 0ull) break;
+        s0 = (s0 + 1) & a.table_mask;
+        r0 = __ldcg(reinterpret_cast<const uint4*>(a.table + s0));
+    }
+    while (v1) {
+        const unsigned long long cur = ((unsigned long long)r1.y << 32) | r1.x;
+        if (cur == k1) { *sc1 = make_int2((int)r1.z, (int)r1.w); break; }
+        if (cur == 0ull) break;
+        s1 = (s1 + 1) & a.table_mask;
+        r1 = __ldcg(reinterpret_cast<const uint4*>(a.table + s1));
+    }
+}
+
+__device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float4* A, int* list, int lane) {
+    MOR_CLOCK(t0);
     const unsigned long long key = a.ckey[i];
     const int startA = a.cstart[i], cntA = a.cstart[i + 1] - startA;
     int cx, cy, cz;
     cell_unpack(key, cx, cy, cz);
-    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
+    const float r2 = a.r2;
     // the 62 preceding cells of the 5x5x5 block: offset index n = (dz+2)*25 + (dy+2)*5 + (dx+2) < 62
-    Cell nb[2];
-    bool has[2], heavy[2] = {false, false};
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int n = lane + 32 * q;
-        has[q] = false;
-        if (n < 62) {
-            const int dz = n / 25 - 2, dy = (n / 5) % 5 - 2, dx = n % 5 - 2;
-            has[q] = grid_lookup(a, cell_pack(cx + dx, cy + dy, cz + dz), &nb[q]);
-        }
+    int2 nb[2];  // (start, cnt) of the lane's two neighbour cells, cnt 0 = empty
+    {
+        const int n0 = lane, n1 = lane + 32;
+        const unsigned long long k0 = cell_pack(cx + n0 % 5 - 2, cy + (n0 / 5) % 5 - 2, cz + n0 / 25 - 2);
+        const unsigned long long k1 = cell_pack(cx + n1 % 5 - 2, cy + (n1 / 5) % 5 - 2, cz + n1 / 25 - 2);
+        grid_lookup2(a, true, k0, n1 < 62, k1, &nb[0], &nb[1]);
     }
-    const bool hasBoxA = cntA > kBoxMinCount;
-    BoxF boxA = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (hasBoxA) boxA = load_box(a, startA);
+    MOR_CLOCK(t1);
+    if (cntA > kBoxMinCount) {  // tight bounding box of a crowded cell (prunes the point tests of the heavy pairs)
+        unsigned mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0u, mxy = 0u, mxz = 0u;
+        for (int k = lane; k < cntA; k += 32) {
+            const float4 pa = A[k];
+            const unsigned kx = fkey(pa.x), ky = fkey(pa.y), kz = fkey(pa.z);
+            mnx = min(mnx, kx); mny = min(mny, ky); mnz = min(mnz, kz); mxx = max(mxx, kx); mxy = max(mxy, ky); mxz = max(mxz, kz);
+        }
+        mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny); mnz = __reduce_min_sync(kFull, mnz);
+        mxx = __reduce_max_sync(kFull, mxx); mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
+        if (lane == 0) { a.cell_box[2 * startA] = make_uint4(mnx, mny, mnz, 0u); a.cell_box[2 * startA + 1] = make_uint4(mxx, mxy, mxz, 0u); }
+    }
+    // heavy pairs go to the group's work list (whole warps pick them up in the next phase)
+    bool heavy[2];
+    heavy[0] = (long long)cntA * nb[0].y > kLightPair; heavy[1] = (long long)cntA * nb[1].y > kLightPair;
+    const unsigned hm0 = __ballot_sync(kFull, heavy[0]), hm1 = __ballot_sync(kFull, heavy[1]);
+    unsigned over0 = 0u, over1 = 0u;
+    if (hm0 | hm1) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&a.scratch->n_heavy, __popc(hm0) + __popc(hm1));
+        base = __shfl_sync(kFull, base, 0);
+        const int w0 = base + __popc(hm0 & ((1u << lane) - 1u)), w1 = base + __popc(hm0) + __popc(hm1 & ((1u << lane) - 1u));
+        const bool o0 = heavy[0] && w0 >= a.heavy_cap, o1 = heavy[1] && w1 >= a.heavy_cap;
+        if (heavy[0] && !o0) a.heavy[w0] = make_int4(startA, cntA, nb[0].x, nb[0].y);
+        if (heavy[1] && !o1) a.heavy[w1] = make_int4(startA, cntA, nb[1].x, nb[1].y);
+        over0 = __ballot_sync(kFull, o0); over1 = __ballot_sync(kFull, o1);
+    }
+    MOR_CLOCK(t2);
+    // Light neighbours. Their points are flattened into one list and dealt out to the lanes, one neighbour point per lane
+    // and step (a single round of independent loads per step), each tested against A's points in shared memory. In
+    // rounds of growing depth: the first round takes 4 points of every neighbour cell - a connected neighbour nearly
+    // always shows a hit there - and only the cells without a hit go on with 16, 64, 256 more.
+    int c[2] = {heavy[0] ? 0 : nb[0].y, heavy[1] ? 0 : nb[1].y}, off[2] = {0, 0};
+    for (int chunk = 4; ; chunk *= 4) {
+        const int r0 = min(chunk, c[0] - off[0]), r1 = min(chunk, c[1] - off[1]);
+        int incl = r0 + r1;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        if (!has[q]) continue;
-        const int sB = nb[q].start, cB = nb[q].cnt;
-        if ((long long)cntA * cB > kHeavyPair) { heavy[q] = true; continue; }
-        if (hasBoxA && cB > kBoxMinCount && box_box_d2(boxA, load_box(a, sB)) > r2_prune) continue;
-        bool hit = false;
-        for (int b = 0; b < cB && !hit; b += 2) {  // two independent loads in flight (index clamped)
-            const float4 p0 = a.spts[sB + b], p1 = a.spts[sB + min(b + 1, cB - 1)];
-            if (hasBoxA && box_point_d2(boxA, p0.x, p0.y, p0.z) > r2_prune && box_point_d2(boxA, p1.x, p1.y, p1.z) > r2_prune) continue;
-            for (int k = 0; k < cntA; k++) {
-                const float4 pa = A[k];
-                if (fminf(sqdist3(pa.x, pa.y, pa.z, p0.x, p0.y, p0.z), sqdist3(pa.x, pa.y, pa.z, p1.x, p1.y, p1.z)) < r2) { hit = true; break; }
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+        const int M = __shfl_sync(kFull, incl, 31), base = incl - (r0 + r1);
+        if (M == 0) break;
+        unsigned hit_lo = 0u, hit_hi = 0u;  // neighbour slots (lane, lane + 32) with a hit in this round
+        for (int w0 = 0; w0 < M; w0 += kLinkListCap) {
+            // entry = sorted position | owner slot << 25
+            for (int k = max(0, w0 - base); k < r0 && base + k < w0 + kLinkListCap; k++) list[base + k - w0] = (nb[0].x + off[0] + k) | (lane << 25);
+            for (int k = max(0, w0 - base - r0); k < r1 && base + r0 + k < w0 + kLinkListCap; k++) list[base + r0 + k - w0] = (nb[1].x + off[1] + k) | ((lane + 32) << 25);
+            __syncwarp();
+            const int wn = min(kLinkListCap, M - w0);
+            for (int j0 = 0; j0 < wn; j0 += 32) {
+                const int j = j0 + lane;
+                bool hit = false;
+                int slot = 0;
+                if (j < wn) {
+                    const int e = list[j];
+                    slot = e >> 25;
+                    const float4 p = a.spts[e & 0x1FFFFFF];
+                    for (int k = 0; k < cntA; k++) {
+                        const float4 pa = A[k];
+                        if (sqdist3(pa.x, pa.y, pa.z, p.x, p.y, p.z) < r2) { hit = true; break; }
+                    }
+                }
+                hit_lo |= __reduce_or_sync(kFull, hit && slot < 32 ? 1u << slot : 0u);
+                hit_hi |= __reduce_or_sync(kFull, hit && slot >= 32 ? 1u << (slot - 32) : 0u);
             }
+            __syncwarp();
         }
-        if (hit) uf_union(a.parent, startA, sB);
-    }
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        unsigned todo = __ballot_sync(kFull, heavy[q]);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int sB = __shfl_sync(kFull, nb[q].start, src), cB = __shfl_sync(kFull, nb[q].cnt, src);
-            link_heavy_pair(a, A, startA, cntA, hasBoxA, boxA, sB, cB, lane);
+        MOR_CLOCK(t3);
+        // the owner lane of a neighbour cell with a hit unites - unless the cell hangs directly under A's root already
+        // (the usual case inside an existing component: one read of its own parent word settles it)
+        const bool u0 = (hit_lo >> lane) & 1u, u1 = (hit_hi >> lane) & 1u;
+        if (hit_lo | hit_hi) {
+            int rootA = 0;
+            if (lane == 0) rootA = uf_find(a.parent, startA);
+            rootA = __shfl_sync(kFull, rootA, 0);
+            if (u0 && nb[0].x != rootA && ld_parent_cached(a.parent + nb[0].x) != rootA) uf_union(a.parent, rootA, nb[0].x);
+            if (u1 && nb[1].x != rootA && ld_parent_cached(a.parent + nb[1].x) != rootA) uf_union(a.parent, rootA, nb[1].x);
         }
+        __syncwarp();
+        MOR_CLOCK(t4);
+        if (lane == 0) { MOR_STAT2_ADD(15, t4 - t3); }
+        off[0] = u0 ? c[0] : off[0] + r0;  // a cell with a hit is finished
+        off[1] = u1 ? c[1] : off[1] + r1;
     }
+    MOR_CLOCK(t5);
+    if (lane == 0) { MOR_STAT2_ADD(12, t1 - t0); MOR_STAT2_ADD(13, t2 - t1); MOR_STAT2_ADD(14, t5 - t2); MOR_STAT2_MAX(2, t5 - t0); MOR_STAT2_ADD(0, 1); }
+    // work list full (never at sane capacities): the pair is examined right here
+    while (over0) { const int src = __ffs(over0) - 1; over0 &= over0 - 1; link_heavy_pair<false>(a, A, startA, cntA, __shfl_sync(kFull, nb[0].x, src), __shfl_sync(kFull, nb[0].y, src), lane); }
+    while (over1) { const int src = __ffs(over1) - 1; over1 &= over1 - 1; link_heavy_pair<false>(a, A, startA, cntA, __shfl_sync(kFull, nb[1].x, src), __shfl_sync(kFull, nb[1].y, src), lane); }
 }
 
-__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, float4* tile, unsigned long long* mbar, unsigned& parity) {
+__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, float4* tile, int* lists, unsigned long long* mbar, unsigned& parity) {
     __shared__ int s_base, s_n;
     const int n_cells = __ldcg(&a.scratch->n_cells);
     const int rounds = (n_cells + kWarps - 1) / kWarps;
@@ -679,7 +755,16 @@ __device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, f
         const int base = s_base, staged = s_n;
         const int i = i0 + warp;
         if (staged) { mbar_wait(mbar, parity); parity ^= 1u; }
-        if (i < i1) link_cell(a, i, staged ? tile + (a.cstart[i] - base) : a.spts + a.cstart[i], lane);
+        if (i < i1) link_cell(a, i, staged ? tile + (a.cstart[i] - base) : a.spts + a.cstart[i], lists + warp * kLinkListCap, lane);
+    }
+}
+
+__device__ __forceinline__ void phase_link_heavy(const FramePtrs& a, int cta, int G) {
+    const int n = min(__ldcg(&a.scratch->n_heavy), a.heavy_cap);
+    const int lane = threadIdx.x & 31;
+    for (int w = cta * kWarps + (threadIdx.x >> 5); w < n; w += G * kWarps) {
+        const int4 hp = __ldcg(a.heavy + w);
+        link_heavy_pair<true>(a, a.spts + hp.x, hp.x, hp.y, hp.z, hp.w, lane);
     }
 }
 
@@ -1245,14 +1330,14 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
     if (threadIdx.x == 0) {
         Scratch* sc = a.scratch;
-        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->err_early = 0;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_heavy = 0; sc->err_early = 0;
         sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
         for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
     }
 }
 
 // ===================================================================================== the frame kernel
-enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_FLATTEN, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
+enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_LINK_HEAVY, PH_FLATTEN, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
 
 struct FrameShared {
     unsigned long long mbar;
@@ -1264,7 +1349,8 @@ __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, Fr
     if (PH == PH_INGEST) { if (a.skip_ingest) phase_bin_cloud(a, cta, G); else phase_ingest(a, cta, G); }
     if (PH == PH_CELLS) phase_cells_and_transform(a, cta, G);
     if (PH == PH_SCATTER) phase_scatter(a, cta, G);
-    if (PH == PH_LINK) phase_link(a, cta, G, reinterpret_cast<float4*>(dyn), &sh.mbar, parity);
+    if (PH == PH_LINK) phase_link(a, cta, G, reinterpret_cast<float4*>(dyn), reinterpret_cast<int*>(dyn) + kLinkTilePts * 4, &sh.mbar, parity);
+    if (PH == PH_LINK_HEAVY) phase_link_heavy(a, cta, G);
     if (PH == PH_FLATTEN) phase_flatten(a, cta, G);
     if (PH == PH_SELECT) { if (cta == 0) phase_select(a, dyn); }
     if (PH == PH_STATS) phase_stats(a, cta, G);
@@ -1274,19 +1360,34 @@ __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, Fr
     if (PH == PH_FILTER) phase_filter(a, cta, G, sh.filter);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int PH>
+__device__ __forceinline__ void frame_step(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity, GroupBarrier& bar) {
+    run_phase<PH>(a, cta, G, sh, dyn, parity);
+    if (PH != PH_FILTER) bar.sync();
+    if (cta == 0 && threadIdx.x == 0) a.phase_ts[PH + 1] = global_ns();  // a dozen stores per frame: the frame's own timeline
+}
+
 __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
     GroupBarrier bar{&a.scratch->bar, 0u, (unsigned)G};
-    run_phase<PH_INGEST>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_CELLS>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_SCATTER>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_LINK>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_FLATTEN>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_SELECT>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_STATS>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_MATCH>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_MOVING>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_CHAIN>(a, cta, G, sh, dyn, parity); bar.sync();
-    run_phase<PH_FILTER>(a, cta, G, sh, dyn, parity);
+    if (cta == 0 && threadIdx.x == 0) a.phase_ts[0] = global_ns();
+    frame_step<PH_INGEST>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_CELLS>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_SCATTER>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_LINK>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_LINK_HEAVY>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_FLATTEN>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_SELECT>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_STATS>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_MATCH>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_MOVING>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_CHAIN>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_FILTER>(a, cta, G, sh, dyn, parity, bar);
     frame_epilogue(a, G);
 }
 

@@ -9,7 +9,11 @@
 //   mov_harness <MOR_config.txt> --replay <dir> [frames] [n_bad=4] [n_good=3] [--quiet] [--out <dir>]
 //       (either form: --debug also fetches the VISUALIZE debug cloud and bounding-box markers of every frame)
 //       recorded data: KITTI-style .bin clouds + poses.txt (+ calib.txt), see replay_io.h; --out writes the filtered clouds
+//       unsynchronised recording: <dir>/times.txt (one stamp in seconds per cloud) + <dir>/odometry.txt (t tx ty tz qx qy qz qw,
+//       its own stamps and rate) instead of poses.txt: cloud and odometry are paired like the reference node pairs its two
+//       topics, message_filters ApproximateTime with queue 10 (src/external_sync_test.cpp:31-35; approx_time.h)
 //   mov_harness --inspect <dir>                 the frames and poses --replay would feed (host only)
+//   mov_harness --pair <stamps A> <stamps B> [queue=10]   the pairs ApproximateTime selects for two stamp files (host only)
 //   mov_harness --pose-of <12 numbers>          the pose7 the replay front end derives from a 3x4 matrix (host only)
 #include <malloc.h>
 
@@ -23,6 +27,7 @@
 
 #include "../dynamicslamtool_b200/csrc/mor_synth.h"
 #include "../include/MOR/MovingObjectRemoval.h"
+#include "approx_time.h"
 #include "replay_io.h"
 
 static uint32_t crc32_buf(const uint8_t* p, size_t n) {
@@ -57,8 +62,23 @@ struct FrameSource {
         if (bins.empty()) { err = "no .bin clouds in " + dir; return false; }
         replay::Mat34 tr;
         const bool have_calib = replay::read_calib(dir + "/calib.txt", tr);
-        if (!replay::read_poses(dir + "/poses.txt", have_calib ? &tr : nullptr, poses, err)) return false;
-        if (poses.size() < bins.size()) bins.resize(poses.size());  // a cloud without a pose cannot be processed
+        std::vector<double> cloud_t, odom_t;
+        if (replay::read_stamps(dir + "/times.txt", 0, cloud_t) && replay::read_stamps(dir + "/odometry.txt", 8, odom_t)) {
+            // independently stamped streams: pair them like the reference node does (ApproximateTime, queue 10)
+            std::vector<std::array<double, 7>> odom;
+            if (!replay::read_poses(dir + "/odometry.txt", nullptr, odom, err)) return false;
+            if (cloud_t.size() < bins.size()) bins.resize(cloud_t.size());
+            std::vector<std::string> paired_bins;
+            replay::ApproximateTime<2> sync(10, [&](const replay::ApproximateTime<2>::Msg (&m)[2]) {
+                paired_bins.push_back(bins[m[0].index]);
+                poses.push_back(odom[m[1].index]);
+            });
+            replay::feed_in_arrival_order(sync, cloud_t, bins.size(), odom_t, odom.size());
+            bins.swap(paired_bins);
+        } else {
+            if (!replay::read_poses(dir + "/poses.txt", have_calib ? &tr : nullptr, poses, err)) return false;
+            if (poses.size() < bins.size()) bins.resize(poses.size());  // a cloud without a pose cannot be processed
+        }
         for (const std::string& b : bins) {
             FILE* f = std::fopen(b.c_str(), "rb");
             if (!f) { err = "cannot open " + b; return false; }
@@ -94,6 +114,15 @@ int main(int argc, char** argv) {
         double p7[7];
         replay::to_pose7(m, p7);
         std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p7[0], p7[1], p7[2], p7[3], p7[4], p7[5], p7[6]);
+        return 0;
+    }
+    if (argc >= 4 && !std::strcmp(argv[1], "--pair")) {
+        std::vector<double> ta, tb;
+        if (!replay::read_stamps(argv[2], 0, ta) || !replay::read_stamps(argv[3], 0, tb)) { std::fprintf(stderr, "cannot read the stamp files\n"); return 2; }
+        replay::ApproximateTime<2> sync(argc > 4 ? (uint32_t)std::atoi(argv[4]) : 10u, [&](const replay::ApproximateTime<2>::Msg (&m)[2]) {
+            std::printf("pair %d %d\n", m[0].index, m[1].index);
+        });
+        replay::feed_in_arrival_order(sync, ta, ta.size(), tb, tb.size());
         return 0;
     }
     if (argc >= 3 && !std::strcmp(argv[1], "--inspect")) {  // what --replay would feed, without touching a GPU

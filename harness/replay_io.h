@@ -108,6 +108,31 @@ inline bool read_poses(const std::string& path, const Mat34* calib, std::vector<
     return true;
 }
 
+// First number of every data line (seconds); with `columns` > 0 only lines of exactly that many numbers count.
+inline bool read_stamps(const std::string& path, size_t columns, std::vector<double>& out) {
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        const std::vector<double> v = numbers_of(line);
+        if (v.empty() || (columns && v.size() != columns)) return false;
+        out.push_back(v[0]);
+    }
+    return !out.empty();
+}
+
+// Feeds two stamped streams to a synchroniser in the order a bag player would deliver them (by stamp; topic 0 first on ties).
+template <class Sync>
+inline void feed_in_arrival_order(Sync& sync, const std::vector<double>& ta, size_t na, const std::vector<double>& tb, size_t nb) {
+    size_t i = 0, j = 0;
+    auto ns = [](double t) { return (int64_t)std::llround(t * 1e9); };
+    while (i < na || j < nb) {
+        if (j >= nb || (i < na && ta[i] <= tb[j])) { sync.add(0, ns(ta[i]), (int)i); i++; }
+        else { sync.add(1, ns(tb[j]), (int)j); j++; }
+    }
+}
+
 inline bool read_calib(const std::string& path, Mat34& tr) {
     std::ifstream f(path);
     std::string line;

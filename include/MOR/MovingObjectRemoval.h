@@ -16,7 +16,10 @@
 //
 // Differences from the reference, all on error paths:
 //   * a bad config throws std::runtime_error instead of calling exit(0) (cpp:703-707, :856-860);
-//   * filterCloud returns false if the device reported an error (the reference always returns true, cpp:695);
+//   * filterCloud returns false if the device reported an error or if the preceding pushRawCloudAndPose was rejected
+//     (missing x/y/z field, frame larger than the handle's capacity ...): a node that publishes `output` whenever
+//     filterCloud returns true (external_sync_test.cpp:15-18) then skips the frame instead of re-publishing the previous
+//     one (the reference always returns true, cpp:695);
 //   * the VISUALIZE side effects (debug cloud published and copied over the caller's input cloud at cpp:553-558,
 //     bounding-box markers published at cpp:640-642) are not performed behind the caller's back: the same data is
 //     available on request (clusterCollection, movingMarkers) for the node to publish; the input cloud is never
@@ -98,8 +101,11 @@ private:
     mor_config cfg_{};
     int status_ = MOR_OK;
     uint32_t n_in_ = 0;
-    void* pinned_out_ = nullptr;  // page-locked staging for the D2H copy of the filtered cloud
+    bool push_failed_ = false;    // the last pushRawCloudAndPose did not reach the device: filterCloud must not publish the frame before it
+    void* pinned_out_ = nullptr;  // page-locked staging (clusterCollection)
     size_t pinned_cap_ = 0;
+    void* registered_ = nullptr;  // storage of output.data, page-locked in place: the D2H copy of filterCloud lands in the message itself
+    void pin_output();
     void init(const std::string& path, int n_bad, int n_good, int device, const mor_limits* limits);
 };
 

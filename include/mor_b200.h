@@ -140,6 +140,10 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
 /* cudaMallocHost / cudaFreeHost passthroughs so callers can stage frames in pinned memory. */
 int mor_alloc_pinned(size_t bytes, void** out);
 int mor_free_pinned(void* p);
+/* cudaHostRegister / cudaHostUnregister passthroughs: page-lock memory the caller already owns (e.g. the storage of the
+ * message a ROS node publishes), so that mor_filter_cloud copies straight into it at full PCIe rate. */
+int mor_host_register(void* p, size_t bytes);
+int mor_host_unregister(void* p);
 /* Plain device buffer helpers for harnesses that keep frames resident (cudaMalloc/Memcpy/Free). */
 int mor_device_alloc(int device, size_t bytes, void** out);
 int mor_device_free(int device, void* p);
@@ -162,6 +166,10 @@ int mor_event_elapsed_ms(mor_handle* h, int slot_a, int slot_b, float* ms);
  * Forces a stream synchronisation per frame; never enable it inside a throughput measurement. */
 int mor_set_kernel_profiling(mor_handle* h, int enabled);
 int mor_get_kernel_profile(mor_handle* h, int index, char name[32], double* total_ms, uint64_t* launches);
+/* The frame kernel's own timeline (always recorded: one %globaltimer store per phase): microseconds the last frame spent
+ * in each of its phases, group barrier included. *n_phases receives the number of phases; names by mor_phase_name. */
+int mor_get_phase_times(mor_handle* h, float* us, int cap, int* n_phases);
+const char* mor_phase_name(int index);
 
 /* ---- the reference's VISUALIZE outputs (IncludeAll.h:32), on request ---------------------- */
 /* cb->cluster_collection as published on the debug topic (cpp:226-229, :553-558): the points of all size-valid
