@@ -106,7 +106,7 @@ struct mor_handle {
     size_t arena_bytes = 0;
     uint8_t* d_in = nullptr;
     size_t d_in_bytes = 0;
-    size_t lattice_cap = 0, table_cap = 0;
+    size_t lattice_cap = 0, table_cap = 0, edge_cap = 0, heavy_cap = 0;
     FramePtrs base;  // pointers that do not change from frame to frame
     int* coll_cursor = nullptr; int* coll_turn = nullptr; float4* coll_out = nullptr;  // mor_get_cluster_collection scratch
     GroundPtrs ground;  // voxel-covariance ground removal state (ground_mode 1/2 only)
@@ -139,7 +139,7 @@ namespace {
 
 enum KernelId { KID_PHASE0 = 0, KID_FRAME = PH__COUNT, KID_FILTER_AGAIN,
                 KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_CELLS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells+transform", "ph_scatter", "ph_link", "ph_link_heavy", "ph_flatten", "ph_select", "ph_stats", "ph_match",
+const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells+transform", "ph_scatter", "ph_link", "ph_link_heavy", "ph_jump", "ph_cross", "ph_roots", "ph_select", "ph_stats", "ph_match",
                                               "ph_moving_test", "ph_chain+cleanup", "ph_filter", "k_frame", "k_filter_again",
                                               "k_ingest_raw", "k_ground_keys", "k_scan_cells", "k_scan_voxels", "k_ground_scatter",
                                               "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
@@ -225,6 +225,7 @@ int allocate(mor_handle* h) {
     while (tab < 2 * N) tab <<= 1;  // load factor <= 1/2 even if every point had a cell of its own
     h->table_cap = tab;
     h->d_in_bytes = N * 32;
+    h->edge_cap = 24 * N + 65536; h->heavy_cap = 6 * N + 16384;  // split into per-CTA segments at launch (a cell has at most 62 edges; ~8 is typical)
     const bool ground = h->cfg.ground_mode != MOR_GROUND_CROP;
     // ---- size pass (mirror of the carve pass below)
     auto plan = [&](uint8_t* p0) -> uint8_t* {
@@ -237,11 +238,13 @@ int allocate(mor_handle* h) {
         b.st_out = carve<unsigned long long>(p, tiles_pts);
         b.table = carve<Cell>(p, tab);
         b.cell_list = carve<int>(p, N); b.ckey = carve<unsigned long long>(p, N + 1); b.cstart = carve<int>(p, N + 1);
-        b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N); b.heavy = carve<int4>(p, 4 * N);
+        b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N);
+        b.edges = carve<int2>(p, h->edge_cap); b.heavy = carve<int2>(p, h->heavy_cap); b.edge_cnt = carve<int>(p, 256); b.heavy_cnt = carve<int>(p, 256);
+        b.cmin = carve<int>(p, N); b.cell_of_lead = carve<int>(p, N); b.scell = carve<int>(p, N); b.hook = carve<int>(p, N); b.rsize = carve<int>(p, N); b.rmin = carve<int>(p, N);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
-        b.parent = carve<int>(p, N); b.label = carve<int>(p, N); b.comp_size = carve<int>(p, N); b.root_list = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
-        b.comp = carve<int>(p, N); b.scid = carve<int>(p, N); b.minidx = carve<int>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
+        b.label = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
+        b.scid = carve<int>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
         b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
         b.recip_q = carve<int>(p, K); b.recip_m = carve<int>(p, K); b.match_q = carve<int>(p, K); b.match_m = carve<int>(p, K);
@@ -250,7 +253,7 @@ int allocate(mor_handle* h) {
         b.anchorp = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
         b.lattice = carve<unsigned long long>(p, lat);
         b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
-        b.marker_cluster = carve<int>(p, MO); b.phase_ts = carve<unsigned long long>(p, PH__COUNT + 1); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
+        b.marker_cluster = carve<int>(p, MO); b.phase_ts = carve<unsigned long long>(p, 32); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
         b.out = carve<float4>(p, N * 2); h->coll_out = carve<float4>(p, N * 2);
         for (int f = 0; f < 2; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
@@ -277,7 +280,8 @@ int allocate(mor_handle* h) {
     plan(h->arena);
     MOR_CUDA(cudaMallocHost(&h->h_counts, sizeof(int32_t) * MOR_NCOUNTS));
     for (int i = 0; i < 4; i++) MOR_CUDA(cudaEventCreate(&h->ev[i]));
-    // dynamic shared memory of the frame kernel: the cluster sort keys of the select phase / the link phase's point tile
+    // dynamic shared memory of the frame kernel: the link phase's point tile + neighbour lists, or the cluster sort keys
+    // of the select phase
     int P = 1;
     while (P < (int)K) P <<= 1;
     h->frame_smem = (size_t)P * sizeof(unsigned long long);
@@ -318,7 +322,6 @@ void fill_static(mor_handle* h) {
     b.cell_h = h->cell_h; b.inv_h = 1.0 / h->cell_h;
     b.skip_ingest = c.ground_mode != MOR_GROUND_CROP ? 1 : 0;
     b.table_mask = (unsigned)(h->table_cap - 1);
-    b.heavy_cap = (int)(4 * h->nmax);
     b.lattice_mask = (unsigned)(h->lattice_cap - 1);
     b.pde_ring = h->pde_ring;
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
@@ -348,6 +351,12 @@ int input_mode(const void* d_points, uint32_t step, uint32_t ox, uint32_t oy, ui
     return 2;
 }
 
+// The link phases write their results into one segment per CTA of the group that runs the frame.
+void set_segments(mor_handle* h, FramePtrs& a, int group_ctas) {
+    a.edge_seg = (int)(h->edge_cap / (size_t)group_ctas);
+    a.heavy_seg = (int)(h->heavy_cap / (size_t)group_ctas);
+}
+
 // Arguments of the current frame (everything the kernels read) from the handle's host-side state.
 void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
     FramePtrs& a = h->frame;
@@ -362,6 +371,7 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
     a.two_frames = h->two_frames ? 1 : 0;
     a.mo_parity = h->mo_parity;
     std::memcpy(a.M.m, h->M, sizeof(h->M));
+    set_segments(h, a, h->frame_ctas);
 }
 
 template <int PH>
@@ -398,7 +408,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     if (h->profiling) {  // one launch per phase, each between a pair of events
         int s;
         if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_SCATTER>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) || (s = launch_phase<PH_LINK_HEAVY>(h, a)) ||
-            (s = launch_phase<PH_FLATTEN>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || (s = launch_phase<PH_MATCH>(h, a)) ||
+            (s = launch_phase<PH_JUMP>(h, a)) || (s = launch_phase<PH_CROSS>(h, a)) || (s = launch_phase<PH_ROOTS>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || (s = launch_phase<PH_MATCH>(h, a)) ||
             (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_CHAIN>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
             return s;
     } else {
@@ -666,6 +676,13 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
     MOR_CUDA(cudaEventSynchronize(h->batch_ev[slot]));
     FramePtrs* hp = h->h_batch + (size_t)slot * h->batch_cap;
     FramePtrs* dp = h->d_batch + (size_t)slot * h->batch_cap;
+    // G CTAs per sequence; the groups run side by side, a group that has more than one sequence steps them in turn
+    int G = h->frame_ctas / (int)S;
+    if (const char* env = std::getenv("MOR_BATCH_G")) { const int v = std::atoi(env); if (v > 0) G = v; }
+    if (G < 1) G = 1;
+    if (G > h->frame_ctas) G = h->frame_ctas;
+    int groups = h->frame_ctas / G;
+    if (groups > (int)S) groups = (int)S;
     for (uint32_t s = 0; s < S; s++) {
         mor_handle* g = hs[s];
         if (g->last_stream != st) {  // earlier work of this handle ran elsewhere (its own stream or another batch): wait for it once
@@ -675,18 +692,12 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
         advance_frame(g, n[s], poses7 + 7 * s);
         fill_frame(g, (const uint8_t*)d_data[s], n[s], point_step, off_x, off_y, off_z, off_i);
         g->frame.out = (float4*)d_out[s];
+        set_segments(g, g->frame, G);
         hp[s] = g->frame;
         g->last_stream = st;
     }
     MOR_CUDA(cudaMemcpyAsync(dp, hp, sizeof(FramePtrs) * S, cudaMemcpyHostToDevice, st));
     MOR_CUDA(cudaEventRecord(h->batch_ev[slot], st));
-    // G CTAs per sequence; the groups run side by side, a group that has more than one sequence steps them in turn
-    int G = h->frame_ctas / (int)S;
-    if (const char* env = std::getenv("MOR_BATCH_G")) { const int v = std::atoi(env); if (v > 0) G = v; }
-    if (G < 1) G = 1;
-    if (G > h->frame_ctas) G = h->frame_ctas;
-    int groups = h->frame_ctas / G;
-    if (groups > (int)S) groups = (int)S;
     {
         cudaError_t e = launch_coop(k_frame_batch, (unsigned)(groups * G), h->frame_smem, st, (const FramePtrs*)dp, (int)S, G);
         h->launches++;
@@ -799,6 +810,13 @@ int mor_debug_link_stats(unsigned long long* out16, int reset) {
     return MOR_OK;
 }
 #endif
+int mor_debug_phase_ts(mor_handle* h, unsigned long long* out32) {  // raw timeline words incl. the sub-steps some phases record
+    if (!h || !out32) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    MOR_CUDA(cudaMemcpy(out32, h->base.phase_ts, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost));
+    return MOR_OK;
+}
 const char* mor_phase_name(int index) { return index >= 0 && index < PH__COUNT ? kKernelNames[index] : ""; }
 
 int mor_get_kernel_profile(mor_handle* h, int index, char name[32], double* total_ms, uint64_t* launches) {

@@ -79,94 +79,44 @@ __device__ __forceinline__ double join_fixed_mean(long long hi, long long lo, do
 }
 
 // ----------------------------------------------------------------------------- union-find
-// parent[] is read and written concurrently by the whole group. Every pointer leads to a node that is HIGHER in a fixed
-// total order (uf_before) and belongs to what is, or is about to become, the same set; pointers only ever move further
-// up. Two consequences carry the whole design:
-//  * any value a parent word has ever held is still a valid ancestor-or-relative to climb through, so the climbing reads
-//    may be served by the SM's L1 (ld.global.ca), however stale. That matters: every find of a big component ends at the
-//    same few root words, and tens of thousands of reads of ONE address are served by one L2 slice one after the other
-//    (measured: the link phases spent most of their time there) - from L1 they cost nothing;
-//  * only the hook of a root needs the truth, and gets it from its atomicCAS (whose result also refreshes a stale view).
-__device__ __forceinline__ int ld_parent(const int* p) {  // coherent (L2) read
+// parent[] over cell indices, read and written concurrently by the whole group: all accesses are relaxed gpu-scope
+// (served by L2, never by a stale L1 line), hooks are atomicCAS on roots only. Every pointer leads to a SMALLER index,
+// so the forest is acyclic whatever the interleaving, and the root of a set is its smallest index.
+__device__ __forceinline__ int ld_parent(const int* p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ld_parent_cached(const int* p) {  // possibly stale (L1) read: good enough to climb
-    int v;
-    asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_parent(int* p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v));
 }
-#ifdef MOR_LINK_STATS
-__device__ unsigned long long g_link_stats[16];  // debug build only, see tools/link_stats.py
-#define MOR_STAT2_ADD(i, v) atomicAdd(&g_link_stats[i], (unsigned long long)(v))
-#define MOR_STAT2_MAX(i, v) atomicMax(&g_link_stats[i], (unsigned long long)(v))
-#if MOR_LINK_STATS >= 2  // also inside find / union (distorts the timing)
-#define MOR_STAT_ADD(i, v) MOR_STAT2_ADD(i, v)
-#define MOR_STAT_MAX(i, v) MOR_STAT2_MAX(i, v)
-#else
-#define MOR_STAT_ADD(i, v)
-#define MOR_STAT_MAX(i, v)
-#endif
-#else
-#define MOR_STAT_ADD(i, v)
-#define MOR_STAT_MAX(i, v)
-#define MOR_STAT2_ADD(i, v)
-#define MOR_STAT2_MAX(i, v)
-#endif
-// Root of x as far as this SM can tell (path halving on the way). After a group barrier the view is exact.
 __device__ __forceinline__ int uf_find(int* parent, int x) {
-    int p = ld_parent_cached(parent + x);
-    int hops = 0;
+    int p = ld_parent(parent + x);
     while (p != x) {  // path halving; only non-roots are rewritten, always to an ancestor
-        int gp = ld_parent_cached(parent + p);
+        int gp = ld_parent(parent + p);
         if (gp != p) st_parent(parent + x, gp);
         x = p;
         p = gp;
-        hops++;
     }
-    MOR_STAT_ADD(0, 1); MOR_STAT_ADD(1, hops);
-    (void)hops;
     return x;
 }
-// Roots are ordered by a hashed priority (ties by index) and the lower root is hooked under the higher
-// one. Any strict total order keeps the forest acyclic; a pseudo-random one keeps it shallow (sorted
-// positions would chain hundreds of cells of a wall along an x-row). The canonical label of a
-// component (its minimum cloud index) is reduced separately in k_flatten, so root identity is free.
-__device__ __forceinline__ bool uf_before(int a, int b) {
-    const unsigned ha = (unsigned)a * 0x9E3779B1u, hb = (unsigned)b * 0x9E3779B1u;
-    return ha < hb || (ha == hb && a < b);
+// Read-only find: for a pass that stores each node's root itself (a concurrent path-halving store of another thread could
+// land after that store and replace the root by an intermediate ancestor).
+__device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
+    int p = ld_parent(parent + x);
+    while (p != x) { x = p; p = ld_parent(parent + x); }
+    return x;
 }
-// Union by Rem's algorithm with splicing (the fastest concurrent variant in practice): both paths are climbed together,
-// always from the node whose parent is lower in the root order, and the walk stops as soon as the two nodes share a
-// parent - for an edge inside an existing component (most edges of a dense surface) that is after one or two steps, not
-// after two full finds. On the way every visited node is re-pointed at the other path's (higher) parent, which compresses
-// both paths. Parents only ever move to higher nodes of what is or is about to become the same set, so concurrent
-// unions and finds stay consistent: a find may see two nodes of one final component under different roots for a
-// moment, never the reverse.
-__device__ __forceinline__ void uf_union(int* parent, int u, int v) {
-    int pu = ld_parent_cached(parent + u), pv = ld_parent_cached(parent + v);
-    int steps = 0;
-    MOR_STAT_ADD(3, 1);
-    while (pu != pv) {
-        steps++;
-        MOR_STAT_ADD(4, 1); MOR_STAT_MAX(5, steps);
-        if (uf_before(pv, pu)) { int t = u; u = v; v = t; t = pu; pu = pv; pv = t; }  // pu is the lower parent
-        if (u == pu) {  // u is a root below pv: hook it
-            const int old = atomicCAS(&parent[u], u, pv);
-            if (old == u) return;
-            pu = old;  // somebody else hooked u first
-            MOR_STAT_ADD(6, 1);
-            continue;
-        }
-        st_parent(parent + u, pv);  // splice: pv is above pu, which is above u
-        u = pu;
-        pu = ld_parent_cached(parent + u);
+// Returns the root of the merged set.
+__device__ __forceinline__ int uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return a;
+        if (a < b) { int t = a; a = b; b = t; }  // a is the larger root: it goes under b
+        const int old = atomicCAS(&parent[a], a, b);
+        if (old == a) return b;
     }
-    (void)steps;
 }
 
 // ----------------------------------------------------------------------------- look-back tile prefix

@@ -12,6 +12,7 @@
 // sequences per launch (mor_batch_step_device) take G = #SMs / S CTAs each and run independently side by side.
 // The same phase functions can be launched one kernel per phase (k_phase<>, per-phase timing for bench.py).
 #pragma once
+#include <cstdio>
 #include "mor_device.cuh"
 #include "../../include/mor_b200.h"
 
@@ -26,7 +27,7 @@ constexpr int kLinkTilePts = 2048;  // points of one link round (32 cells) stage
 constexpr int kLinkListCap = 256;   // per warp: neighbour points dealt out to the lanes per pass (1 KB of shared memory)
 constexpr size_t kLinkSmem = (size_t)kLinkTilePts * 16 + (size_t)kWarps * kLinkListCap * 4;
 
-enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16 };
+enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16, ERR_EDGE_CAP = 32 };
 // counts[] slots in which the filter phase parks its results until filterCloud commits the frame (mor_b200.cu, do_filter)
 enum { CNT_SPEC_NOUT = 21, CNT_SPEC_NMO = 22, CNT_SPEC_OVERFLOW = 23 };
 
@@ -46,7 +47,7 @@ struct GridDesc {  // dense grid of the voxel ground modes' ball query (mor_grou
 struct Scratch {  // all zero between frames: every counter is put back by the frame that used it
     unsigned bar;            // group barrier of k_frame (monotonic within a launch)
     int blocks_done;         // CTAs that have finished the frame
-    int n_cells, n_roots, n_heavy, pad1;
+    int n_cells, pad1, pad2, pad3;
     int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
     int err_early;           // error bits raised before the frame's counts exist
     int pad0;
@@ -81,13 +82,19 @@ struct FramePtrs {
     unsigned long long* ckey; int* cstart;  // [n_cells(+1)] compact copies: key, first sorted position
     int2* pslot;               // [N_c] (table slot, rank inside the cell) of every cloud point
     int* slead;                // [N_c] leader position (cell start) of every sorted position
-    int4* heavy; int heavy_cap; // work list of the heavy cell pairs: (start A, count A, start B, count B)
+    // link results, one segment per CTA of the group (no shared counters): connected cell pairs and the heavy pairs still to test
+    int2* edges; int edge_seg; int* edge_cnt;   // (cell index A, cell index B)
+    int2* heavy; int heavy_seg; int* heavy_cnt;
+    int* cmin;                 // [n_cells] minimum cloud index of the cell's points
+    int* cell_of_lead;         // [N_c] cell index of a leader position
+    int* scell;                // [N_c] cell index of every sorted position
+    int* hook;                 // [n_cells] union-find over cell indices: parent word (pointers lead to smaller indices)
+    int* rsize; int* rmin;     // [n_cells] per root: points and minimum cloud index (= canonical label) of its component
     // ---- per-frame scratch
     Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cscan; unsigned long long* st_out;
     uint8_t* point_class; uint8_t* removed_mask;
     int* cloud_src; float4* gpts; int* gsrc;
-    int* parent; int* label; int* comp_size; int* root_list; int* cid_of_root;
-    int* comp; int* minidx;    // indexed by sorted position (cell leaders)
+    int* label; int* cid_of_root;
     int* scid;                 // cluster id per sorted position
     uint4* cell_box;           // [2*N] per leader position: {min x,y,z keys, -}, {max x,y,z keys, -}
     unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
@@ -390,7 +397,8 @@ __device__ __forceinline__ void cell_scan_tile(const FramePtrs& a, int tile, int
     if (i < n_cells) {
         a.table[slot].start = start;
         a.ckey[i] = key; a.cstart[i] = start;
-        a.parent[start] = start; a.comp_size[start] = 0; a.minidx[start] = 0x7FFFFFFF;
+        a.cell_of_lead[start] = i;
+        a.hook[i] = i; a.rsize[i] = 0; a.rmin[i] = 0x7FFFFFFF;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) a.cstart[n_cells] = before + total;
 }
@@ -524,25 +532,32 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
             p.w = __int_as_float(c);
             a.spts[start + sr.y] = p;
             a.slead[start + sr.y] = start;
+            a.scell[start + sr.y] = a.cell_of_lead[start];
         }
     }
 }
 
 // ===================================================================================== phase D: link
 // pcl::EuclideanClusterExtraction's radius graph (cpp:213-218; A5-A7) on cell granularity. Any two points of one cell
-// are neighbours (cell diagonal < r), so a cell is one union-find node, and a neighbour lies at most 2 cells away per
-// axis: cell A must be tested against the 62 cells of its 5x5x5 block that precede it in (dz,dy,dx) order (the other 62
-// test A from their side). Two cells are linked iff some point pair has L2_Simple distance < r2 (strict).
+// are neighbours (cell diagonal < r), so a cell is one node, and a neighbour lies at most 2 cells away per axis: cell A
+// must be tested against the 62 cells of its 5x5x5 block that precede it in (dz,dy,dx) order (the other 62 test A from
+// their side). Two cells are connected iff some point pair has L2_Simple distance < r2 (strict).
 //
 // D1, light pairs: one WARP per cell. A link round takes 32 consecutive cells of the cell list, whose points are one
 // contiguous range of the sorted array: it is staged in shared memory by a single bulk copy (TMA) while the lanes walk
 // the hash table - lane l looks up neighbours l and l+32, both probes in flight together. The points of all light
 // neighbour cells are then flattened into one list (shared memory) and dealt out to the lanes, one neighbour point per
-// lane and step: a single round of independent loads, each tested against A's points in shared memory; the lanes that
-// hit unite (one lane per neighbour cell).
+// lane and step, each tested against A's points in shared memory; rounds of growing depth (4, 16, 64, 256 points per
+// neighbour cell) stop at a cell's first hit.
 // D2, heavy pairs (more than kLightPair point pairs): queued by D1 and dealt out to all warps of the group, a whole warp
-// per pair: root check first (dense surfaces are mostly merged through their light neighbours already), bounding-box
-// pruning on both sides, lanes across B's points, early exit.
+// per pair: bounding-box pruning on both sides, lanes across B's points, A broadcast by shuffle, early exit.
+// Both RECORD the connected pairs (edges, in per-CTA segments: no shared counter) and point the larger cell of a pair
+// at the smaller one (atomicMin on the cell's own word); the components are formed from that in phase E.
+#ifdef MOR_DEBUG_BOUNDS
+#define MOR_CHECK(cond, tag, v) do { if (!(cond)) { printf("BOUNDS %s: %d (line %d, cta %d thread %d)\n", tag, (int)(v), __LINE__, (int)blockIdx.x, (int)threadIdx.x); } } while (0)
+#else
+#define MOR_CHECK(cond, tag, v)
+#endif
 #ifdef MOR_LINK_STATS
 #define MOR_CLOCK(v) const long long v = clock64()
 #else
@@ -565,21 +580,16 @@ __device__ __forceinline__ float box_box_d2(const BoxF& p, const BoxF& q) {
     return ex * ex + ey * ey + ez * ez;
 }
 
-// Whole warp on one heavy cell pair (A: cntA points at A[], B: cB points at sorted positions sB..).
+// Whole warp on one heavy cell pair (A: cntA points at A[], B: cB points at sorted positions sB..): is there a point
+// pair within r? BOXES: the cells' bounding boxes are complete (after the light phase).
 template <bool BOXES>
-__device__ __forceinline__ void link_heavy_pair(const FramePtrs& a, const float4* A, int startA, int cntA, int sB, int cB, int lane) {
+__device__ __forceinline__ bool heavy_pair_connected(const FramePtrs& a, const float4* A, int startA, int cntA, int sB, int cB, int lane) {
     const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
-    MOR_CLOCK(h0);
-    int same = 0;
-    if (lane == 0) same = uf_find(a.parent, startA) == uf_find(a.parent, sB) ? 1 : 0;
-    MOR_CLOCK(h1);
-    if (lane == 0) { MOR_STAT2_ADD(7, 1); if (same) MOR_STAT2_ADD(9, 1); MOR_STAT2_ADD(3, h1 - h0); MOR_STAT2_MAX(4, h1 - h0); }
-    if (__shfl_sync(kFull, same, 0)) return;  // two cells of one component need no point tests
-    const bool hasBoxA = BOXES && cntA > kBoxMinCount, hasBoxB = BOXES && cB > kBoxMinCount;  // (the boxes are complete after the light phase)
+    const bool hasBoxA = BOXES && cntA > kBoxMinCount, hasBoxB = BOXES && cB > kBoxMinCount;
     BoxF boxA = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, boxB = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (hasBoxA) boxA = load_box(a, startA);
     if (hasBoxB) boxB = load_box(a, sB);
-    if (hasBoxA && hasBoxB && box_box_d2(boxA, boxB) > r2_prune) return;
+    if (hasBoxA && hasBoxB && box_box_d2(boxA, boxB) > r2_prune) return false;
     bool hit = false;
     for (int b0 = 0; b0 < cB && !hit; b0 += 32) {
         const int b = b0 + lane;
@@ -592,22 +602,24 @@ __device__ __forceinline__ void link_heavy_pair(const FramePtrs& a, const float4
         if (!__any_sync(kFull, valid)) continue;
         // A in blocks of 32: one coalesced load, then every candidate point (inside r of B's box) is broadcast by shuffle
         // to all lanes: 32 x 32 point pairs per round trip to memory
-        for (int a0 = 0; a0 < cntA && !hit; a0 += 32) {
-            const float4 pa = A[min(a0 + lane, cntA - 1)];
-            const bool av = a0 + lane < cntA && (!hasBoxB || box_point_d2(boxB, pa.x, pa.y, pa.z) <= r2_prune);
+        for (int a0 = 0; a0 < cntA && !hit; a0 += 128) {  // four blocks of A in flight
+            float4 pa[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) pa[q] = A[min(a0 + 32 * q + lane, cntA - 1)];
             bool h = false;
-            for (unsigned m = __ballot_sync(kFull, av); m; m &= m - 1) {
-                const int u = __ffs(m) - 1;
-                const float ax = __shfl_sync(kFull, pa.x, u), ay = __shfl_sync(kFull, pa.y, u), az = __shfl_sync(kFull, pa.z, u);
-                h |= sqdist3(ax, ay, az, pb.x, pb.y, pb.z) < r2;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const bool av = a0 + 32 * q + lane < cntA && (!hasBoxB || box_point_d2(boxB, pa[q].x, pa[q].y, pa[q].z) <= r2_prune);
+                for (unsigned m = __ballot_sync(kFull, av); m; m &= m - 1) {
+                    const int u = __ffs(m) - 1;
+                    const float ax = __shfl_sync(kFull, pa[q].x, u), ay = __shfl_sync(kFull, pa[q].y, u), az = __shfl_sync(kFull, pa[q].z, u);
+                    h |= sqdist3(ax, ay, az, pb.x, pb.y, pb.z) < r2;
+                }
             }
             hit = __any_sync(kFull, h && valid);
         }
     }
-    MOR_CLOCK(h2);
-    if (hit && lane == 0) uf_union(a.parent, startA, sB);
-    MOR_CLOCK(h3);
-    if (lane == 0) { if (hit) MOR_STAT2_ADD(10, 1); else MOR_STAT2_ADD(11, 1); MOR_STAT2_ADD(5, h2 - h1); MOR_STAT2_ADD(6, h3 - h2); MOR_STAT2_MAX(8, h3 - h0); }
+    return hit;
 }
 
 // Both neighbours of a lane are looked up with their first probes in flight together.
@@ -633,10 +645,30 @@ __device__ __forceinline__ void grid_lookup2(const FramePtrs& a, bool v0, unsign
     }
 }
 
-__device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float4* A, int* list, int lane) {
-    MOR_CLOCK(t0);
+struct LinkShared { int n_edges, n_heavy, base, staged; };
+
+// The lanes flagged in (m0, m1) append one record each (their slot 0 / slot 1 neighbour) to the CTA's segment.
+// HOOK: the records are connected pairs: the larger cell of each pair is pointed at the smaller one if that lowers its
+// pointer (atomicMin on the cell's own word: a local spanning forest, the seed of the components phase).
+template <bool HOOK>
+__device__ __forceinline__ void append_pairs(const FramePtrs& a, int2* seg, int seg_cap, int* counter, unsigned m0, unsigned m1, bool f0, bool f1, int2 v0, int2 v1, int lane) {
+    if (!(m0 | m1)) return;
+    if (HOOK) {
+        if (f0) atomicMin(&a.hook[max(v0.x, v0.y)], min(v0.x, v0.y));
+        if (f1) atomicMin(&a.hook[max(v1.x, v1.y)], min(v1.x, v1.y));
+    }
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(m0) + __popc(m1));  // shared-memory counter of the CTA
+    base = __shfl_sync(kFull, base, 0);
+    const int w0 = base + __popc(m0 & ((1u << lane) - 1u)), w1 = base + __popc(m0) + __popc(m1 & ((1u << lane) - 1u));
+    if (f0) { if (w0 < seg_cap) seg[w0] = v0; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
+    if (f1) { if (w1 < seg_cap) seg[w1] = v1; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
+}
+
+__device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float4* A, int* list, LinkShared& ls, int2* eseg, int2* hseg, int lane) {
     const unsigned long long key = a.ckey[i];
     const int startA = a.cstart[i], cntA = a.cstart[i + 1] - startA;
+    MOR_CHECK(startA >= 0 && cntA > 0 && startA + cntA <= a.counts[MOR_CNT_NC], "cellA", cntA);
     int cx, cy, cz;
     cell_unpack(key, cx, cy, cz);
     const float r2 = a.r2;
@@ -647,39 +679,39 @@ __device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float
         const unsigned long long k0 = cell_pack(cx + n0 % 5 - 2, cy + (n0 / 5) % 5 - 2, cz + n0 / 25 - 2);
         const unsigned long long k1 = cell_pack(cx + n1 % 5 - 2, cy + (n1 / 5) % 5 - 2, cz + n1 / 25 - 2);
         grid_lookup2(a, true, k0, n1 < 62, k1, &nb[0], &nb[1]);
+        MOR_CHECK(nb[0].y >= 0 && nb[0].x >= 0 && nb[0].x + nb[0].y <= a.counts[MOR_CNT_NC], "nb0", nb[0].y);
+        MOR_CHECK(nb[1].y >= 0 && nb[1].x >= 0 && nb[1].x + nb[1].y <= a.counts[MOR_CNT_NC], "nb1", nb[1].y);
     }
-    MOR_CLOCK(t1);
-    if (cntA > kBoxMinCount) {  // tight bounding box of a crowded cell (prunes the point tests of the heavy pairs)
+    {   // the cell's minimum cloud index (its component's canonical label is the minimum over its cells) and, for a
+        // crowded cell, its tight bounding box (prunes the point tests of the heavy pairs)
+        int mn = 0x7FFFFFFF;
         unsigned mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0u, mxy = 0u, mxz = 0u;
         for (int k = lane; k < cntA; k += 32) {
             const float4 pa = A[k];
+            mn = min(mn, __float_as_int(pa.w));
             const unsigned kx = fkey(pa.x), ky = fkey(pa.y), kz = fkey(pa.z);
             mnx = min(mnx, kx); mny = min(mny, ky); mnz = min(mnz, kz); mxx = max(mxx, kx); mxy = max(mxy, ky); mxz = max(mxz, kz);
         }
-        mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny); mnz = __reduce_min_sync(kFull, mnz);
-        mxx = __reduce_max_sync(kFull, mxx); mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
-        if (lane == 0) { a.cell_box[2 * startA] = make_uint4(mnx, mny, mnz, 0u); a.cell_box[2 * startA + 1] = make_uint4(mxx, mxy, mxz, 0u); }
+        mn = __reduce_min_sync(kFull, mn);
+        if (cntA > kBoxMinCount) {
+            mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny); mnz = __reduce_min_sync(kFull, mnz);
+            mxx = __reduce_max_sync(kFull, mxx); mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
+            if (lane == 0) { a.cell_box[2 * startA] = make_uint4(mnx, mny, mnz, 0u); a.cell_box[2 * startA + 1] = make_uint4(mxx, mxy, mxz, 0u); }
+        }
+        if (lane == 0) a.cmin[i] = mn;
     }
-    // heavy pairs go to the group's work list (whole warps pick them up in the next phase)
+    // heavy pairs go to the CTA's work list (whole warps of the group pick them up in the next phase)
     bool heavy[2];
     heavy[0] = (long long)cntA * nb[0].y > kLightPair; heavy[1] = (long long)cntA * nb[1].y > kLightPair;
-    const unsigned hm0 = __ballot_sync(kFull, heavy[0]), hm1 = __ballot_sync(kFull, heavy[1]);
-    unsigned over0 = 0u, over1 = 0u;
-    if (hm0 | hm1) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&a.scratch->n_heavy, __popc(hm0) + __popc(hm1));
-        base = __shfl_sync(kFull, base, 0);
-        const int w0 = base + __popc(hm0 & ((1u << lane) - 1u)), w1 = base + __popc(hm0) + __popc(hm1 & ((1u << lane) - 1u));
-        const bool o0 = heavy[0] && w0 >= a.heavy_cap, o1 = heavy[1] && w1 >= a.heavy_cap;
-        if (heavy[0] && !o0) a.heavy[w0] = make_int4(startA, cntA, nb[0].x, nb[0].y);
-        if (heavy[1] && !o1) a.heavy[w1] = make_int4(startA, cntA, nb[1].x, nb[1].y);
-        over0 = __ballot_sync(kFull, o0); over1 = __ballot_sync(kFull, o1);
+    {
+        const unsigned hm0 = __ballot_sync(kFull, heavy[0]), hm1 = __ballot_sync(kFull, heavy[1]);
+        if (hm0 | hm1) {
+            const int j0 = heavy[0] ? a.cell_of_lead[nb[0].x] : 0, j1 = heavy[1] ? a.cell_of_lead[nb[1].x] : 0;
+            append_pairs<false>(a, hseg, a.heavy_seg, &ls.n_heavy, hm0, hm1, heavy[0], heavy[1], make_int2(i, j0), make_int2(i, j1), lane);
+        }
     }
-    MOR_CLOCK(t2);
-    // Light neighbours. Their points are flattened into one list and dealt out to the lanes, one neighbour point per lane
-    // and step (a single round of independent loads per step), each tested against A's points in shared memory. In
-    // rounds of growing depth: the first round takes 4 points of every neighbour cell - a connected neighbour nearly
-    // always shows a hit there - and only the cells without a hit go on with 16, 64, 256 more.
+    // Light neighbours, in rounds of growing depth: the first round takes 4 points of every neighbour cell - a connected
+    // neighbour nearly always shows a hit there - and only the cells without a hit go on with 16, 64, 256 more.
     int c[2] = {heavy[0] ? 0 : nb[0].y, heavy[1] ? 0 : nb[1].y}, off[2] = {0, 0};
     for (int chunk = 4; ; chunk *= 4) {
         const int r0 = min(chunk, c[0] - off[0]), r1 = min(chunk, c[1] - off[1]);
@@ -695,138 +727,181 @@ __device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float
             for (int k = max(0, w0 - base - r0); k < r1 && base + r0 + k < w0 + kLinkListCap; k++) list[base + r0 + k - w0] = (nb[1].x + off[1] + k) | ((lane + 32) << 25);
             __syncwarp();
             const int wn = min(kLinkListCap, M - w0);
-            for (int j0 = 0; j0 < wn; j0 += 32) {
-                const int j = j0 + lane;
-                bool hit = false;
-                int slot = 0;
-                if (j < wn) {
-                    const int e = list[j];
-                    slot = e >> 25;
-                    const float4 p = a.spts[e & 0x1FFFFFF];
-                    for (int k = 0; k < cntA; k++) {
-                        const float4 pa = A[k];
-                        if (sqdist3(pa.x, pa.y, pa.z, p.x, p.y, p.z) < r2) { hit = true; break; }
-                    }
+            for (int j0 = 0; j0 < wn; j0 += 64) {  // two independent point loads in flight per lane
+                const int ja = j0 + lane, jb = j0 + 32 + lane;
+                const int ea = ja < wn ? list[ja] : -1, eb = jb < wn ? list[jb] : -1;
+                float4 pa4 = make_float4(0.f, 0.f, 0.f, 0.f), pb4 = pa4;
+                if (ea >= 0) pa4 = a.spts[ea & 0x1FFFFFF];
+                if (eb >= 0) pb4 = a.spts[eb & 0x1FFFFFF];
+                bool hita = false, hitb = false;
+                for (int k = 0; k < cntA; k++) {
+                    const float4 q = A[k];
+                    hita |= sqdist3(q.x, q.y, q.z, pa4.x, pa4.y, pa4.z) < r2;
+                    hitb |= sqdist3(q.x, q.y, q.z, pb4.x, pb4.y, pb4.z) < r2;
                 }
-                hit_lo |= __reduce_or_sync(kFull, hit && slot < 32 ? 1u << slot : 0u);
-                hit_hi |= __reduce_or_sync(kFull, hit && slot >= 32 ? 1u << (slot - 32) : 0u);
+                hita &= ea >= 0; hitb &= eb >= 0;
+                const int sa = ea >> 25, sb = eb >> 25;
+                hit_lo |= __reduce_or_sync(kFull, (hita && sa < 32 ? 1u << sa : 0u) | (hitb && sb < 32 ? 1u << sb : 0u));
+                hit_hi |= __reduce_or_sync(kFull, (hita && sa >= 32 ? 1u << (sa - 32) : 0u) | (hitb && sb >= 32 ? 1u << (sb - 32) : 0u));
             }
             __syncwarp();
         }
-        MOR_CLOCK(t3);
-        // the owner lane of a neighbour cell with a hit unites - unless the cell hangs directly under A's root already
-        // (the usual case inside an existing component: one read of its own parent word settles it)
+        // the owner lane of a neighbour cell with a hit records the edge
         const bool u0 = (hit_lo >> lane) & 1u, u1 = (hit_hi >> lane) & 1u;
         if (hit_lo | hit_hi) {
-            int rootA = 0;
-            if (lane == 0) rootA = uf_find(a.parent, startA);
-            rootA = __shfl_sync(kFull, rootA, 0);
-            if (u0 && nb[0].x != rootA && ld_parent_cached(a.parent + nb[0].x) != rootA) uf_union(a.parent, rootA, nb[0].x);
-            if (u1 && nb[1].x != rootA && ld_parent_cached(a.parent + nb[1].x) != rootA) uf_union(a.parent, rootA, nb[1].x);
+            const int j0 = u0 ? a.cell_of_lead[nb[0].x] : 0, j1 = u1 ? a.cell_of_lead[nb[1].x] : 0;
+            MOR_CHECK(j0 >= 0 && j0 < a.scratch->n_cells && j1 >= 0 && j1 < a.scratch->n_cells, "edge j", j0);
+            append_pairs<true>(a, eseg, a.edge_seg, &ls.n_edges, hit_lo, hit_hi, u0, u1, make_int2(i, j0), make_int2(i, j1), lane);
         }
-        __syncwarp();
-        MOR_CLOCK(t4);
-        if (lane == 0) { MOR_STAT2_ADD(15, t4 - t3); }
         off[0] = u0 ? c[0] : off[0] + r0;  // a cell with a hit is finished
         off[1] = u1 ? c[1] : off[1] + r1;
     }
-    MOR_CLOCK(t5);
-    if (lane == 0) { MOR_STAT2_ADD(12, t1 - t0); MOR_STAT2_ADD(13, t2 - t1); MOR_STAT2_ADD(14, t5 - t2); MOR_STAT2_MAX(2, t5 - t0); MOR_STAT2_ADD(0, 1); }
-    // work list full (never at sane capacities): the pair is examined right here
-    while (over0) { const int src = __ffs(over0) - 1; over0 &= over0 - 1; link_heavy_pair<false>(a, A, startA, cntA, __shfl_sync(kFull, nb[0].x, src), __shfl_sync(kFull, nb[0].y, src), lane); }
-    while (over1) { const int src = __ffs(over1) - 1; over1 &= over1 - 1; link_heavy_pair<false>(a, A, startA, cntA, __shfl_sync(kFull, nb[1].x, src), __shfl_sync(kFull, nb[1].y, src), lane); }
 }
 
 __device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, float4* tile, int* lists, unsigned long long* mbar, unsigned& parity) {
-    __shared__ int s_base, s_n;
+    __shared__ LinkShared ls;
     const int n_cells = __ldcg(&a.scratch->n_cells);
     const int rounds = (n_cells + kWarps - 1) / kWarps;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int2* eseg = a.edges + (size_t)cta * a.edge_seg;
+    int2* hseg = a.heavy + (size_t)cta * a.heavy_seg;
+    if (threadIdx.x == 0) { ls.n_edges = 0; ls.n_heavy = 0; }
     for (int round = cta; round < rounds; round += G) {
         const int i0 = round * kWarps, i1 = min(i0 + kWarps, n_cells);
         __syncthreads();  // the previous round's readers of the tile are done
         if (threadIdx.x == 0) {
             const int s0 = a.cstart[i0], s1 = a.cstart[i1];
-            s_base = s0;
-            s_n = (s1 - s0 <= kLinkTilePts) ? s1 - s0 : 0;  // a round of very crowded cells reads A from L2 instead
-            if (s_n) bulk_load(tile, a.spts + s0, (unsigned)s_n * 16u, mbar);
+            ls.base = s0;
+            ls.staged = (s1 - s0 <= kLinkTilePts) ? s1 - s0 : 0;  // a round of very crowded cells reads A from L2 instead
+            if (ls.staged) bulk_load(tile, a.spts + s0, (unsigned)ls.staged * 16u, mbar);
         }
         __syncthreads();
-        const int base = s_base, staged = s_n;
+        const int base = ls.base, staged = ls.staged;
         const int i = i0 + warp;
         if (staged) { mbar_wait(mbar, parity); parity ^= 1u; }
-        if (i < i1) link_cell(a, i, staged ? tile + (a.cstart[i] - base) : a.spts + a.cstart[i], lists + warp * kLinkListCap, lane);
+        if (i < i1) link_cell(a, i, staged ? tile + (a.cstart[i] - base) : a.spts + a.cstart[i], lists + warp * kLinkListCap, ls, eseg, hseg, lane);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { a.edge_cnt[cta] = min(ls.n_edges, a.edge_seg); a.heavy_cnt[cta] = min(ls.n_heavy, a.heavy_seg); }
 }
 
+// D2: the heavy pairs of all CTAs' lists, dealt out warp by warp over the whole group.
 __device__ __forceinline__ void phase_link_heavy(const FramePtrs& a, int cta, int G) {
-    const int n = min(__ldcg(&a.scratch->n_heavy), a.heavy_cap);
-    const int lane = threadIdx.x & 31;
-    for (int w = cta * kWarps + (threadIdx.x >> 5); w < n; w += G * kWarps) {
-        const int4 hp = __ldcg(a.heavy + w);
-        link_heavy_pair<true>(a, a.spts + hp.x, hp.x, hp.y, hp.z, hp.w, lane);
+    __shared__ int s_pre[257], s_edges;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // running totals of the per-CTA heavy lists (G <= 256)
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < G; c++) { s_pre[c] = run; run += __ldcg(&a.heavy_cnt[c]); }
+        s_pre[G] = run;
+        s_edges = __ldcg(&a.edge_cnt[cta]);
+    }
+    __syncthreads();
+    const int total = s_pre[G];
+    int2* eseg = a.edges + (size_t)cta * a.edge_seg;
+    int seg = 0;
+    for (int w = cta * kWarps + warp; w < total; w += G * kWarps) {
+        while (s_pre[seg + 1] <= w) seg++;
+        const int2 hp = __ldcg(a.heavy + (size_t)seg * a.heavy_seg + (w - s_pre[seg]));
+        MOR_CHECK(hp.x >= 0 && hp.x < a.scratch->n_cells && hp.y >= 0 && hp.y < a.scratch->n_cells, "heavy pair", hp.y);
+        const int sA = a.cstart[hp.x], cA = a.cstart[hp.x + 1] - sA, sB = a.cstart[hp.y], cB = a.cstart[hp.y + 1] - sB;
+        const bool hit = heavy_pair_connected<true>(a, a.spts + sA, sA, cA, sB, cB, lane);
+        if (hit && lane == 0) {
+            const int slot = atomicAdd(&s_edges, 1);
+            if (slot < a.edge_seg) eseg[slot] = hp; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
+            atomicMin(&a.hook[max(hp.x, hp.y)], min(hp.x, hp.y));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.edge_cnt[cta] = min(s_edges, a.edge_seg);
+}
+
+// ===================================================================================== phase E: components
+// Connected components of the cell graph (a few thousand cells, ~8 edges per cell), then min <= size <= max
+// (cpp:215-216) and the cluster order: size descending, min index ascending (A9 canonical rule).
+// A union-find fed with all edges has every SM read and CAS the root words of the few big components: one L2 slice
+// serves them one after the other, and that was most of the frame. Instead:
+//  E1  the link phases left every cell pointing at its smallest connected neighbour: a spanning forest of local trees
+//      (cells are numbered in scan order, so a surface is a handful of trees). Pointer jumping flattens it; the reads
+//      are spread over the cells' own words.
+//  E2  every edge compares the two labels (two scattered reads of non-shared words): all but a few hundred agree. The
+//      rest are real unions between local trees (lock-free, roots ordered by index).
+//  E3  every cell looks up its final root; size and minimum cloud index per root, grouped per warp before the atomics.
+//  E4  one CTA selects and sorts the clusters (bitonic sort of (~size, min index) keys in shared memory).
+__device__ __forceinline__ void phase_jump(const FramePtrs& a, int cta, int G) {
+    const int C = __ldcg(&a.scratch->n_cells);
+    for (int i = cta * kT + threadIdx.x; i < C; i += G * kT) {
+        int p = ld_parent(a.hook + i);
+        MOR_CHECK(p >= 0 && p <= i, "jump p", p);
+        while (true) {  // every cell jumps at the same time, so the distance to the root halves per step
+            const int g = ld_parent(a.hook + p);
+            if (g == p) break;
+            st_parent(a.hook + i, g);
+            p = g;
+        }
     }
 }
 
-// ===================================================================================== phase E: flatten
-// Pointer-jump every cell leader to its root, count component sizes and reduce the minimum cloud index of every
-// component (the canonical label) with warp-aggregated atomics, collect the roots.
-__device__ __forceinline__ void phase_flatten(const FramePtrs& a, int cta, int G) {
-    const int nc = a.counts[MOR_CNT_NC];
-    const int lane = threadIdx.x & 31;
-    for (int base = cta * kT; base < nc; base += G * kT) {
-        const int s = base + threadIdx.x;
-        const bool act = s < nc;
-        int c = 0, r = -1 - lane;
-        if (act) {
-            c = __float_as_int(a.spts[s].w);
-            r = uf_find(a.parent, a.slead[s]);
-            a.comp[s] = r;
-            if (r == s) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s;
-        }
-        const unsigned same = __match_any_sync(kFull, r);
-        const int mn = __reduce_min_sync(same, c);
-        if (act && (int)(__ffs(same) - 1) == lane) {
-            atomicAdd(&a.comp_size[r], __popc(same));
-            atomicMin(&a.minidx[r], mn);
-        }
+__device__ __forceinline__ void phase_cross(const FramePtrs& a, int cta, int G) {
+    const int n = __ldcg(&a.edge_cnt[cta]);
+    const int2* seg = a.edges + (size_t)cta * a.edge_seg;
+    for (int e = threadIdx.x; e < n; e += kT) {
+        const int2 uv = __ldcg(seg + e);
+        MOR_CHECK(uv.x >= 0 && uv.x < a.scratch->n_cells && uv.y >= 0 && uv.y < a.scratch->n_cells, "cross uv", uv.y);
+        const int lu = ld_parent(a.hook + uv.x), lv = ld_parent(a.hook + uv.y);
+        MOR_CHECK(lu >= 0 && lu < a.scratch->n_cells && lv >= 0 && lv < a.scratch->n_cells, "cross label", lu);
+        if (lu != lv) uf_union(a.hook, lu, lv);
     }
 }
 
-// ===================================================================================== phase F: select (one CTA)
-// Size filter min <= size <= max (cpp:215-216), cluster order = size descending then min index ascending (A9 canonical
-// rule) by a shared-memory bitonic sort of (~size, root) keys.
+__device__ __forceinline__ void phase_roots(const FramePtrs& a, int cta, int G) {
+    const int C = __ldcg(&a.scratch->n_cells);
+    const int lane = threadIdx.x & 31;
+    for (int base = cta * kT; base < C; base += G * kT) {
+        const int i = base + threadIdx.x;
+        int r = -1 - lane, cnt = 0, mn = 0x7FFFFFFF;
+        if (i < C) {
+            const int s0 = a.cstart[i], s1 = a.cstart[i + 1];
+            mn = __ldcg(&a.cmin[i]);
+            cnt = s1 - s0;
+            r = uf_find_ro(a.hook, i);  // (no path halving here: nothing but the roots themselves may be stored in this phase)
+            st_parent(a.hook + i, r);   // flat for the per-point look-ups of the statistics phase
+        }
+        const unsigned grp = __match_any_sync(kFull, r);
+        const int gsum = __reduce_add_sync(grp, cnt), gmin = __reduce_min_sync(grp, mn);
+        if (i < C && (int)(__ffs(grp) - 1) == lane) { atomicAdd(&a.rsize[r], gsum); atomicMin(&a.rmin[r], gmin); }
+    }
+}
+
 __device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long long* keys) {
     __shared__ int s_k;
+    const int C = __ldcg(&a.scratch->n_cells);
     if (threadIdx.x == 0) s_k = 0;
     __syncthreads();
-    const int n_roots = __ldcg(&a.scratch->n_roots);
-    for (int t = threadIdx.x; t < n_roots; t += kSingle) {
-        const int rpos = a.root_list[t];
-        const int sz = __ldcg(&a.comp_size[rpos]);
-        const int root = __ldcg(&a.minidx[rpos]);  // min cloud index of the component = canonical label
+    for (int i = threadIdx.x; i < C; i += kT) {
+        if (__ldcg(&a.hook[i]) != i) continue;
+        const int sz = __ldcg(&a.rsize[i]), lab = __ldcg(&a.rmin[i]);
         if ((long long)sz >= a.min_cluster && (long long)sz <= a.max_cluster) {
             const int slot = atomicAdd(&s_k, 1);
-            if (slot < a.kmax) keys[slot] = ((unsigned long long)(0xFFFFFFFFu - (unsigned)sz) << 32) | (unsigned)root;
+            if (slot < a.kmax) keys[slot] = ((unsigned long long)(0xFFFFFFFFu - (unsigned)sz) << 32) | (unsigned)lab;
+            else a.cid_of_root[lab] = -1;
         } else {
-            a.cid_of_root[root] = -1;
+            a.cid_of_root[lab] = -1;
         }
     }
     __syncthreads();
     int K = s_k;
     if (K > a.kmax) {  // capacity exceeded: keep the first kmax found, flag the frame
         if (threadIdx.x == 0) atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_CLUSTER_CAP);
-        // the dropped roots must not keep a stale cluster id
-        for (int t = threadIdx.x; t < n_roots; t += kSingle) a.cid_of_root[__ldcg(&a.minidx[a.root_list[t]])] = -1;
         K = a.kmax;
     }
-    int P = 1;
-    while (P < K) P <<= 1;
-    for (int t = K + threadIdx.x; t < P; t += kSingle) keys[t] = ~0ull;
+    int Pk = 1;
+    while (Pk < K) Pk <<= 1;
+    for (int t = K + threadIdx.x; t < Pk; t += kT) keys[t] = ~0ull;
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
+    for (int size = 2; size <= Pk; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += kSingle) {
+            for (int t = threadIdx.x; t < (Pk >> 1); t += kT) {
                 const int lo = 2 * t - (t & (stride - 1));
                 const int hi = lo + stride;
                 const bool up = ((lo & size) == 0);
@@ -837,7 +912,7 @@ __device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long l
         }
     }
     int nk = 0;
-    for (int k = threadIdx.x; k < K; k += kSingle) {
+    for (int k = threadIdx.x; k < K; k += kT) {
         const unsigned long long kk = keys[k];
         const int root = (int)(unsigned)(kk & 0xFFFFFFFFull);
         const int sz = (int)(0xFFFFFFFFu - (unsigned)(kk >> 32));
@@ -868,7 +943,10 @@ __device__ __forceinline__ void phase_stats(const FramePtrs& a, int cta, int G) 
         if (s < nc) {
             p = a.spts[s];
             const int c = __float_as_int(p.w);
-            const int lab = a.minidx[a.comp[s]];
+            MOR_CHECK(a.scell[s] >= 0 && a.scell[s] < a.scratch->n_cells, "scell", a.scell[s]);
+            MOR_CHECK(a.hook[a.scell[s]] >= 0 && a.hook[a.scell[s]] < a.scratch->n_cells, "hook", a.hook[a.scell[s]]);
+            const int lab = a.rmin[a.hook[a.scell[s]]];  // hook is flat: the cell's root; consecutive points share all three words
+            MOR_CHECK(lab >= 0 && lab < nc, "label", lab);
             a.label[c] = lab;
             k = a.cid_of_root[lab];
             a.cid[c] = k;
@@ -1330,14 +1408,14 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
     if (threadIdx.x == 0) {
         Scratch* sc = a.scratch;
-        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_heavy = 0; sc->err_early = 0;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->err_early = 0;
         sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
         for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
     }
 }
 
 // ===================================================================================== the frame kernel
-enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_LINK_HEAVY, PH_FLATTEN, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
+enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_LINK_HEAVY, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
 
 struct FrameShared {
     unsigned long long mbar;
@@ -1351,7 +1429,9 @@ __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, Fr
     if (PH == PH_SCATTER) phase_scatter(a, cta, G);
     if (PH == PH_LINK) phase_link(a, cta, G, reinterpret_cast<float4*>(dyn), reinterpret_cast<int*>(dyn) + kLinkTilePts * 4, &sh.mbar, parity);
     if (PH == PH_LINK_HEAVY) phase_link_heavy(a, cta, G);
-    if (PH == PH_FLATTEN) phase_flatten(a, cta, G);
+    if (PH == PH_JUMP) phase_jump(a, cta, G);
+    if (PH == PH_CROSS) phase_cross(a, cta, G);
+    if (PH == PH_ROOTS) phase_roots(a, cta, G);
     if (PH == PH_SELECT) { if (cta == 0) phase_select(a, dyn); }
     if (PH == PH_STATS) phase_stats(a, cta, G);
     if (PH == PH_MATCH) { if (cta == 0) phase_match(a); }
@@ -1381,7 +1461,9 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
     frame_step<PH_SCATTER>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_LINK>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_LINK_HEAVY>(a, cta, G, sh, dyn, parity, bar);
-    frame_step<PH_FLATTEN>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_JUMP>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_CROSS>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_ROOTS>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_SELECT>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_STATS>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_MATCH>(a, cta, G, sh, dyn, parity, bar);

@@ -8,9 +8,9 @@ fn = b.lib.mor_debug_link_stats
 fn.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
 s = Synth(2, 2)
 m = MovingObjectRemoval('config/MOR_config_hdl64.txt', 4, 3, binding=b, max_points=s.max_points)
-names = ["cells", "-", "max_cell_cyc", "hv_rootcheck_cyc", "hv_rootcheck_max", "hv_test_cyc", "hv_union_cyc", "heavy_pairs", "hv_pair_max_cyc", "heavy_same_root", "heavy_hit", "heavy_miss",
+names = ["cells", "rounds", "max_cell_cyc", "cyc_findA", "cyc_check", "cyc_unions", "union_rounds", "real_unions", "hit_neighbours", "heavy_same_root", "heavy_hit", "heavy_miss",
          "cyc_probe", "cyc_box_append", "cyc_list_test_union", "cyc_union_only"]
-for f in list(range(0, 3)) + [20, 60, 104]:
+for f in list(range(0, 2)) + [20, 60]:
     pts, pose = s.frame(f)
     m.push_raw_cloud_and_pose(pts, pose); m.filter_cloud()
     out = (C.c_ulonglong * 16)()
