@@ -20,7 +20,7 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-PRODUCT_LIB = PKG_DIR / "libmor_b200.so"
+PRODUCT_LIB = Path(os.environ["MOR_PRODUCT_LIB"]) if os.environ.get("MOR_PRODUCT_LIB") else PKG_DIR / "libmor_b200.so"  # (debug builds)
 SYNTH_LIB = PKG_DIR / "libmor_synth.so"
 
 NO_FIELD = 0xFFFFFFFF
@@ -130,6 +130,9 @@ class MorBinding:
         self.get_kernel_profile = f("get_kernel_profile", [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], True)
         self.get_phase_times = f("get_phase_times", [vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)], True)
         self.phase_name = f("phase_name", [C.c_int], True, C.c_char_p)
+        self.submit_frame = f("submit_frame", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double), vp, u32], True)
+        self.collect_frame = f("collect_frame", [vp, C.POINTER(u32)], True)
+        self.frames_in_flight = f("frames_in_flight", [vp, C.POINTER(u32)], True)
 
     def _fn(self, name, argtypes, optional=False, restype=C.c_int):
         try:
@@ -297,6 +300,41 @@ class MovingObjectRemoval:
         p = C.c_void_p()
         self._check(self.b.get_output_device(self.h, C.byref(p)), "get_output_device")
         return p.value
+
+    # pipelined streaming (product only): copies of neighbouring frames overlap the frame kernel
+    def submit_frame(self, points: np.ndarray, pose7, out: np.ndarray, point_step=None, offsets=None):
+        """push + filter of one frame, enqueued without waiting; `points` and `out` (float32 [cap, 8], both ideally views
+        of pinned memory) must stay untouched until collect_frame() has returned for this frame."""
+        pose = (C.c_double * 7)(*[float(v) for v in pose7])
+        if points.dtype == np.float32 and point_step is None:
+            assert points.ndim == 2 and points.shape[1] >= 3 and points.flags.c_contiguous
+            n, step = points.shape[0], points.shape[1] * 4
+            offs = (0, 4, 8, 12 if points.shape[1] >= 4 else NO_FIELD)
+        else:
+            assert points.flags.c_contiguous and point_step is not None and offsets is not None
+            n, step, offs = points.nbytes // point_step, point_step, offsets
+        assert out.dtype == np.float32 and out.ndim == 2 and out.shape[1] == 8 and out.flags.c_contiguous
+        self.n_input = n
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((points, out))
+        st = self.b.submit_frame(self.h, points.ctypes.data_as(C.c_void_p), n, step, *offs, pose, out.ctypes.data_as(C.c_void_p), out.shape[0])
+        if st:
+            self._inflight.pop()
+        self._check(st, "submit_frame")
+
+    def collect_frame(self) -> np.ndarray:
+        """Waits for the oldest submitted frame; returns the filled part of the `out` it was submitted with."""
+        n_out = C.c_uint32(0)
+        st = self.b.collect_frame(self.h, C.byref(n_out))
+        q = getattr(self, "_inflight", [])
+        out = q.pop(0)[1] if q else None
+        self._check(st, "collect_frame")
+        return out[: n_out.value]
+
+    def frames_in_flight(self) -> int:
+        v = C.c_uint32(0)
+        self._check(self.b.frames_in_flight(self.h, C.byref(v)), "frames_in_flight")
+        return v.value
 
     def event_record(self, slot: int):
         self._check(self.b.event_record(self.h, slot), "event_record")

@@ -106,6 +106,17 @@ struct mor_handle {
     size_t arena_bytes = 0;
     uint8_t* d_in = nullptr;
     size_t d_in_bytes = 0;
+    // pipelined streaming (mor_submit_frame / mor_collect_frame): two slots, each with its own staging buffer, output
+    // buffer, pinned counts and events; copies run on two streams of their own beside the frame kernels
+    struct StreamSlot {
+        uint8_t* d_in = nullptr; float4* d_out = nullptr; int32_t* h_counts = nullptr;
+        cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+        void* out = nullptr; uint32_t cap = 0, spec = 0;
+    } slot[2];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_join = nullptr;
+    int sf_head = 0, inflight = 0;
+    float4* out_cur = nullptr;  // output buffer of the frame being enqueued (slot 0's unless a streaming slot says otherwise)
     size_t lattice_cap = 0, table_cap = 0, edge_cap = 0, heavy_cap = 0;
     FramePtrs base;  // pointers that do not change from frame to frame
     int* coll_cursor = nullptr; int* coll_turn = nullptr; float4* coll_out = nullptr;  // mor_get_cluster_collection scratch
@@ -232,6 +243,7 @@ int allocate(mor_handle* h) {
         uint8_t* p = p0;
         FramePtrs& b = h->base;
         h->d_in = carve<uint8_t>(p, h->d_in_bytes);
+        h->slot[0].d_in = h->d_in; h->slot[1].d_in = carve<uint8_t>(p, h->d_in_bytes);
         b.scratch = carve<Scratch>(p, 1);
         b.st_ingest = carve<unsigned long long>(p, tiles_pts);
         b.st_cscan = carve<unsigned long long>(p, tiles_pts);
@@ -240,7 +252,7 @@ int allocate(mor_handle* h) {
         b.cell_list = carve<int>(p, N); b.ckey = carve<unsigned long long>(p, N + 1); b.cstart = carve<int>(p, N + 1);
         b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N);
         b.edges = carve<int2>(p, h->edge_cap); b.heavy = carve<int2>(p, h->heavy_cap); b.edge_cnt = carve<int>(p, 256); b.heavy_cnt = carve<int>(p, 256);
-        b.cmin = carve<int>(p, N); b.cell_of_lead = carve<int>(p, N); b.scell = carve<int>(p, N); b.hook = carve<int>(p, N); b.rsize = carve<int>(p, N); b.rmin = carve<int>(p, N);
+        b.cmin = carve<int>(p, N); b.cell_of_lead = carve<int>(p, N); b.scell = carve<int>(p, N); b.hook = carve<int>(p, N); b.rsize = carve<int>(p, N); b.rmin = carve<int>(p, N); b.root_list = carve<int>(p, N);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
         b.label = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
@@ -253,8 +265,9 @@ int allocate(mor_handle* h) {
         b.anchorp = carve<double>(p, K * 3); b.newcount = carve<int>(p, K);
         b.lattice = carve<unsigned long long>(p, lat);
         b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
-        b.marker_cluster = carve<int>(p, MO); b.phase_ts = carve<unsigned long long>(p, 32); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
+        b.marker_cluster = carve<int>(p, MO); b.phase_ts = carve<unsigned long long>(p, 32); b.cta_trace = carve<unsigned long long>(p, 32 * 256); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
         b.out = carve<float4>(p, N * 2); h->coll_out = carve<float4>(p, N * 2);
+        h->slot[0].d_out = b.out; h->slot[1].d_out = carve<float4>(p, N * 2); h->out_cur = b.out;
         for (int f = 0; f < 2; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
             h->cl_root[f] = carve<int>(p, K); h->cl_size[f] = carve<int>(p, K); h->cl_centroid[f] = carve<float>(p, K * 3);
@@ -370,6 +383,7 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
     a.p_cl_centroid = h->cl_centroid[prev]; a.p_cl_flags = h->cl_flags[prev]; a.p_counts = h->counts[prev];
     a.two_frames = h->two_frames ? 1 : 0;
     a.mo_parity = h->mo_parity;
+    a.out = h->out_cur;
     std::memcpy(a.M.m, h->M, sizeof(h->M));
     set_segments(h, a, h->frame_ctas);
 }
@@ -444,6 +458,8 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
     if (!h || (!data && n) || !pose7) return MOR_ERR_ARG;
     if (validate_layout(step, ox, oy, oz, oi) != MOR_OK) { h->last_error = "point_step / field offsets do not describe a record with float32 x, y, z"; return MOR_ERR_ARG; }
     if (n > h->nmax) { h->last_error = "frame larger than mor_limits.max_points"; return MOR_ERR_CAPACITY; }
+    if (h->inflight) { h->last_error = "submitted frames are in flight: collect them first"; return MOR_ERR_STATE; }
+    h->out_cur = h->slot[0].d_out;
     MOR_CUDA(cudaSetDevice(h->device));
     { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[0], h->stream));
@@ -470,6 +486,7 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
 int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uint32_t* n_out) {
     if (!h) return MOR_ERR_ARG;
     if (!h->have_cur) return MOR_ERR_STATE;
+    if (h->inflight) { h->last_error = "submitted frames are in flight: collect them first"; return MOR_ERR_STATE; }
     MOR_CUDA(cudaSetDevice(h->device));
     { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     cudaStream_t st = h->stream;
@@ -509,7 +526,7 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     h->spec_out = no;
     if (h->h_counts[MOR_CNT_ERRFLAGS]) {  // a device-side capacity was exceeded: the frame's results are not reference-exact
         char msg[200];
-        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice range 8=ground grid 16=coordinate beyond the grid's range)",
+        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice range 8=ground grid 16=coordinate beyond the grid's range 32=cell pairs)",
                       h->h_counts[MOR_CNT_ERRFLAGS]);
         h->last_error = msg;
         return MOR_ERR_CAPACITY;
@@ -527,6 +544,10 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
 // The state of a handle that has seen no frame: all device tables zero, no tracked objects, empty buffers (the
 // reference's freshly constructed object, cpp:368-391). Ordered on the handle's stream.
 int reset_state(mor_handle* h) {
+    if (h->copy_in) MOR_CUDA(cudaStreamSynchronize(h->copy_in));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->copy_out) MOR_CUDA(cudaStreamSynchronize(h->copy_out));
+    h->inflight = 0; h->sf_head = 0; h->out_cur = h->slot[0].d_out;
     MOR_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->have_cur = h->have_prev = h->filtered = h->two_frames = false;
@@ -594,6 +615,15 @@ int mor_destroy(mor_handle* h) {
     for (auto& e : h->slot_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->prof_pool) cudaEventDestroy(e);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->copy_in) { cudaStreamSynchronize(h->copy_in); cudaStreamDestroy(h->copy_in); }
+    if (h->copy_out) { cudaStreamSynchronize(h->copy_out); cudaStreamDestroy(h->copy_out); }
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (auto& sl : h->slot) {
+        if (sl.h_counts) cudaFreeHost(sl.h_counts);
+        if (sl.h2d) cudaEventDestroy(sl.h2d);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.d2h) cudaEventDestroy(sl.d2h);
+    }
     if (h->d_batch) cudaFree(h->d_batch);
     if (h->h_batch) cudaFreeHost(h->h_batch);
     for (auto& e : h->batch_ev) if (e) cudaEventDestroy(e);
@@ -649,7 +679,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
         mor_handle* g = hs[s];
         // same device, limits, frame count and configuration (every key that reaches the kernels)
         if (!g || g->device != h->device || g->nmax != h->nmax || g->kmax != h->kmax || g->momax != h->momax || g->have_prev != h->have_prev ||
-            g->have_cur != h->have_cur || g->profiling || std::memcmp(&g->cfg, &h->cfg, offsetof(mor_config, output_topic)) != 0) {
+            g->have_cur != h->have_cur || g->profiling || g->inflight || std::memcmp(&g->cfg, &h->cfg, offsetof(mor_config, output_topic)) != 0) {
             h->last_error = "batched handles must share device, limits, config and frame count";
             return MOR_ERR_ARG;
         }
@@ -690,6 +720,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
             if (g->stream != st) MOR_CUDA(cudaStreamSynchronize(g->stream));
         }
         advance_frame(g, n[s], poses7 + 7 * s);
+        g->out_cur = g->slot[0].d_out;
         fill_frame(g, (const uint8_t*)d_data[s], n[s], point_step, off_x, off_y, off_z, off_i);
         g->frame.out = (float4*)d_out[s];
         set_segments(g, g->frame, G);
@@ -716,6 +747,99 @@ int mor_sync(mor_handle* h) {
     MOR_CUDA(cudaSetDevice(h->device));
     { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
     MOR_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->copy_out) MOR_CUDA(cudaStreamSynchronize(h->copy_out));
+    return MOR_OK;
+}
+
+// ---- pipelined streaming ---------------------------------------------------------------------------
+// Frame f lives in slot f & 1. Three streams: copy_in (H2D of the raw records), the handle's stream (frame kernels, in
+// order: the tracker state is a chain through the frames) and copy_out (counts + filtered cloud). A slot is reused by
+// frame f + 2, which cannot be submitted before frame f has been collected, i.e. before its D2H copy - and with it the
+// kernel that read the slot's staging buffer and wrote its output buffer - has completed: no other ordering is needed.
+static int ensure_streaming(mor_handle* h) {
+    if (h->copy_in) return MOR_OK;
+    MOR_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    MOR_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    MOR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    for (auto& sl : h->slot) {
+        MOR_CUDA(cudaMallocHost(&sl.h_counts, sizeof(int32_t) * MOR_NCOUNTS));
+        MOR_CUDA(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+        MOR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        MOR_CUDA(cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming));
+    }
+    return MOR_OK;
+}
+
+int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi,
+                     const double pose7[7], void* out, uint32_t cap_points) {
+    if (!h || (!data && n) || !pose7 || (!out && cap_points)) return MOR_ERR_ARG;
+    if (validate_layout(step, ox, oy, oz, oi) != MOR_OK) { h->last_error = "point_step / field offsets do not describe a record with float32 x, y, z"; return MOR_ERR_ARG; }
+    if (n > h->nmax) { h->last_error = "frame larger than mor_limits.max_points"; return MOR_ERR_CAPACITY; }
+    const size_t bytes = (size_t)n * step;
+    if (bytes > h->d_in_bytes) { h->last_error = "n * point_step exceeds the staging buffer (32 B/point)"; return MOR_ERR_CAPACITY; }
+    if (h->profiling) { h->last_error = "per-phase profiling serialises every frame: not available while streaming"; return MOR_ERR_STATE; }
+    if (h->inflight >= MOR_STREAM_DEPTH) { h->last_error = "MOR_STREAM_DEPTH frames are in flight: collect one first"; return MOR_ERR_STATE; }
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int st = ensure_streaming(h); if (st != MOR_OK) return st; }
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    const int si = (h->sf_head + h->inflight) & 1;
+    mor_handle::StreamSlot& sl = h->slot[si];
+    if (!h->inflight) {  // the pipeline starts: earlier work of the synchronous calls may still use slot 0's buffers
+        MOR_CUDA(cudaEventRecord(h->ev_join, h->stream));
+        MOR_CUDA(cudaStreamWaitEvent(h->copy_in, h->ev_join, 0));
+    }
+    if (bytes) MOR_CUDA(cudaMemcpyAsync(sl.d_in, data, bytes, cudaMemcpyHostToDevice, h->copy_in));
+    MOR_CUDA(cudaEventRecord(sl.h2d, h->copy_in));
+    MOR_CUDA(cudaStreamWaitEvent(h->stream, sl.h2d, 0));
+    advance_frame(h, n, pose7);
+    h->out_cur = sl.d_out;
+    int st = enqueue_push(h, sl.d_in, n, step, ox, oy, oz, oi);
+    if (st != MOR_OK) return st;
+    MOR_CUDA(cudaEventRecord(sl.done, h->stream));
+    MOR_CUDA(cudaStreamWaitEvent(h->copy_out, sl.done, 0));
+    MOR_CUDA(cudaMemcpyAsync(sl.h_counts, h->frame.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, h->copy_out));
+    // the size of the output is known on the device only: the copy is sized from the last collected frame plus a margin
+    // and topped up at collection in the rare case the frame turned out larger
+    uint32_t spec = h->spec_out ? h->spec_out + h->spec_out / 32 + 1024 : n;
+    if (spec > n) spec = n;
+    if (spec > cap_points) spec = cap_points;
+    if (spec) MOR_CUDA(cudaMemcpyAsync(out, sl.d_out, (size_t)spec * 32, cudaMemcpyDeviceToHost, h->copy_out));
+    MOR_CUDA(cudaEventRecord(sl.d2h, h->copy_out));
+    sl.out = out; sl.cap = cap_points; sl.spec = spec;
+    h->mo_parity ^= 1; h->frame.mo_parity = h->mo_parity; h->filtered = true;  // committed like push + one filterCloud
+    h->inflight++;
+    return MOR_OK;
+}
+
+int mor_collect_frame(mor_handle* h, uint32_t* n_out) {
+    if (!h) return MOR_ERR_ARG;
+    if (!h->inflight) { h->last_error = "no frame in flight"; return MOR_ERR_STATE; }
+    MOR_CUDA(cudaSetDevice(h->device));
+    mor_handle::StreamSlot& sl = h->slot[h->sf_head];
+    MOR_CUDA(cudaEventSynchronize(sl.d2h));
+    h->sf_head ^= 1; h->inflight--;
+    const uint32_t no = (uint32_t)sl.h_counts[CNT_SPEC_NOUT];
+    if (n_out) *n_out = no;
+    h->spec_out = no;
+    if (sl.h_counts[MOR_CNT_ERRFLAGS]) {
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "device capacity exceeded (error bits 0x%x: 1=clusters 2=moving 4=lattice range 8=ground grid 16=coordinate beyond the grid's range 32=cell pairs)",
+                      sl.h_counts[MOR_CNT_ERRFLAGS]);
+        h->last_error = msg;
+        return MOR_ERR_CAPACITY;
+    }
+    if (no > sl.cap) { h->last_error = "output buffer of the submitted frame too small"; return MOR_ERR_CAPACITY; }
+    if (no > sl.spec) {  // (the slot's device buffer is not rewritten before the frame after next is submitted)
+        MOR_CUDA(cudaMemcpyAsync((uint8_t*)sl.out + (size_t)sl.spec * 32, (const uint8_t*)sl.d_out + (size_t)sl.spec * 32, (size_t)(no - sl.spec) * 32,
+                                 cudaMemcpyDeviceToHost, h->copy_out));
+        MOR_CUDA(cudaStreamSynchronize(h->copy_out));
+    }
+    return MOR_OK;
+}
+
+int mor_frames_in_flight(const mor_handle* h, uint32_t* out) {
+    if (!h || !out) return MOR_ERR_ARG;
+    *out = (uint32_t)h->inflight;
     return MOR_OK;
 }
 
@@ -815,6 +939,13 @@ int mor_debug_phase_ts(mor_handle* h, unsigned long long* out32) {  // raw timel
     MOR_CUDA(cudaSetDevice(h->device));
     MOR_CUDA(cudaStreamSynchronize(h->stream));
     MOR_CUDA(cudaMemcpy(out32, h->base.phase_ts, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost));
+    return MOR_OK;
+}
+int mor_debug_cta_trace(mor_handle* h, unsigned long long* out, int n_words) {  // MOR_CTA_TRACE builds: [phase][cta] arrival times
+    if (!h || !out || n_words > 32 * 256) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    MOR_CUDA(cudaMemcpy(out, h->base.cta_trace, sizeof(unsigned long long) * n_words, cudaMemcpyDeviceToHost));
     return MOR_OK;
 }
 const char* mor_phase_name(int index) { return index >= 0 && index < PH__COUNT ? kKernelNames[index] : ""; }

@@ -47,7 +47,7 @@ struct GridDesc {  // dense grid of the voxel ground modes' ball query (mor_grou
 struct Scratch {  // all zero between frames: every counter is put back by the frame that used it
     unsigned bar;            // group barrier of k_frame (monotonic within a launch)
     int blocks_done;         // CTAs that have finished the frame
-    int n_cells, pad1, pad2, pad3;
+    int n_cells, n_roots, pad2, pad3;
     int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
     int err_early;           // error bits raised before the frame's counts exist
     int pad0;
@@ -90,6 +90,7 @@ struct FramePtrs {
     int* scell;                // [N_c] cell index of every sorted position
     int* hook;                 // [n_cells] union-find over cell indices: parent word (pointers lead to smaller indices)
     int* rsize; int* rmin;     // [n_cells] per root: points and minimum cloud index (= canonical label) of its component
+    int* root_list;            // [n_roots] the roots, in no particular order
     // ---- per-frame scratch
     Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cscan; unsigned long long* st_out;
     uint8_t* point_class; uint8_t* removed_mask;
@@ -109,6 +110,7 @@ struct FramePtrs {
     uint8_t* cluster_removed; int* found;
     int* marker_cluster;          // [momax] cluster each mo_vec entry was matched to by the last filterCloud
     unsigned long long* phase_ts; // [PH__COUNT + 1] %globaltimer at the start of the frame kernel and after every phase (CTA 0)
+    unsigned long long* cta_trace; // [32][256] debug builds (MOR_CTA_TRACE): when every CTA reached the barrier of every phase
     float4* out;
     // ---- ping-pong frame state: cur / prev
     float4* pts; float4* spts; int* cid; int* cl_root; int* cl_size; float* cl_centroid; uint8_t* cl_flags; float* cl_bbox; int* counts;
@@ -519,21 +521,27 @@ __device__ __forceinline__ void phase_cells_and_transform(const FramePtrs& a, in
     }
 }
 
+// Work over [0, n) that needs no CTA-wide cooperation is cut into one contiguous slice per CTA (warp granular): a phase
+// is short, so what counts is that all SMs take part, not that a CTA's threads are all busy.
+__device__ __forceinline__ void cta_slice(int n, int cta, int G, int* lo, int* hi) {
+    const int per = ((n + G - 1) / G + 31) & ~31;
+    *lo = min(n, cta * per);
+    *hi = min(n, *lo + per);
+}
+
 // ===================================================================================== phase C: scatter
 // Cloud points into cell order (float4 xyz + cloud index): slot = cell start + the rank taken at binning time.
 __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G) {
-    const int nc = a.counts[MOR_CNT_NC];
-    for (int base = cta * kT; base < nc; base += G * kT) {
-        const int c = base + threadIdx.x;
-        if (c < nc) {
-            const int2 sr = a.pslot[c];
-            const int start = __ldcg(&a.table[sr.x].start);
-            float4 p = a.pts[c];
-            p.w = __int_as_float(c);
-            a.spts[start + sr.y] = p;
-            a.slead[start + sr.y] = start;
-            a.scell[start + sr.y] = a.cell_of_lead[start];
-        }
+    int lo, hi;
+    cta_slice(a.counts[MOR_CNT_NC], cta, G, &lo, &hi);
+    for (int c = lo + threadIdx.x; c < hi; c += kT) {
+        const int2 sr = a.pslot[c];
+        const int start = __ldcg(&a.table[sr.x].start);
+        float4 p = a.pts[c];
+        p.w = __int_as_float(c);
+        a.spts[start + sr.y] = p;
+        a.slead[start + sr.y] = start;
+        a.scell[start + sr.y] = a.cell_of_lead[start];
     }
 }
 
@@ -829,8 +837,9 @@ __device__ __forceinline__ void phase_link_heavy(const FramePtrs& a, int cta, in
 //  E3  every cell looks up its final root; size and minimum cloud index per root, grouped per warp before the atomics.
 //  E4  one CTA selects and sorts the clusters (bitonic sort of (~size, min index) keys in shared memory).
 __device__ __forceinline__ void phase_jump(const FramePtrs& a, int cta, int G) {
-    const int C = __ldcg(&a.scratch->n_cells);
-    for (int i = cta * kT + threadIdx.x; i < C; i += G * kT) {
+    int lo, hi;
+    cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
+    for (int i = lo + threadIdx.x; i < hi; i += kT) {
         int p = ld_parent(a.hook + i);
         MOR_CHECK(p >= 0 && p <= i, "jump p", p);
         while (true) {  // every cell jumps at the same time, so the distance to the root halves per step
@@ -855,31 +864,34 @@ __device__ __forceinline__ void phase_cross(const FramePtrs& a, int cta, int G) 
 }
 
 __device__ __forceinline__ void phase_roots(const FramePtrs& a, int cta, int G) {
-    const int C = __ldcg(&a.scratch->n_cells);
+    int lo, hi;
+    cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
     const int lane = threadIdx.x & 31;
-    for (int base = cta * kT; base < C; base += G * kT) {
+    for (int base = lo; base < hi; base += kT) {
         const int i = base + threadIdx.x;
+        const bool act = i < hi;
         int r = -1 - lane, cnt = 0, mn = 0x7FFFFFFF;
-        if (i < C) {
+        if (act) {
             const int s0 = a.cstart[i], s1 = a.cstart[i + 1];
             mn = __ldcg(&a.cmin[i]);
             cnt = s1 - s0;
             r = uf_find_ro(a.hook, i);  // (no path halving here: nothing but the roots themselves may be stored in this phase)
             st_parent(a.hook + i, r);   // flat for the per-point look-ups of the statistics phase
+            if (r == i) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = i;
         }
         const unsigned grp = __match_any_sync(kFull, r);
         const int gsum = __reduce_add_sync(grp, cnt), gmin = __reduce_min_sync(grp, mn);
-        if (i < C && (int)(__ffs(grp) - 1) == lane) { atomicAdd(&a.rsize[r], gsum); atomicMin(&a.rmin[r], gmin); }
+        if (act && (int)(__ffs(grp) - 1) == lane) { atomicAdd(&a.rsize[r], gsum); atomicMin(&a.rmin[r], gmin); }
     }
 }
 
 __device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long long* keys) {
     __shared__ int s_k;
-    const int C = __ldcg(&a.scratch->n_cells);
+    const int n_roots = __ldcg(&a.scratch->n_roots);
     if (threadIdx.x == 0) s_k = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += kT) {
-        if (__ldcg(&a.hook[i]) != i) continue;
+    for (int t = threadIdx.x; t < n_roots; t += kT) {
+        const int i = a.root_list[t];
         const int sz = __ldcg(&a.rsize[i]), lab = __ldcg(&a.rmin[i]);
         if ((long long)sz >= a.min_cluster && (long long)sz <= a.max_cluster) {
             const int slot = atomicAdd(&s_k, 1);
@@ -936,15 +948,16 @@ __device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long l
 // compute3DCentroid<double> (A10) and getMinMax3D bounding boxes (cpp:272-275).
 __device__ __forceinline__ void phase_stats(const FramePtrs& a, int cta, int G) {
     const int nc = a.counts[MOR_CNT_NC];
-    for (int base = cta * kT; base < nc; base += G * kT) {
+    int lo, hi;
+    cta_slice(nc, cta, G, &lo, &hi);
+    for (int base = lo; base < hi; base += kT) {
         const int s = base + threadIdx.x;
         float4 p = make_float4(0, 0, 0, 0);
         int k = -1;
-        if (s < nc) {
+        if (s < hi) {
             p = a.spts[s];
             const int c = __float_as_int(p.w);
             MOR_CHECK(a.scell[s] >= 0 && a.scell[s] < a.scratch->n_cells, "scell", a.scell[s]);
-            MOR_CHECK(a.hook[a.scell[s]] >= 0 && a.hook[a.scell[s]] < a.scratch->n_cells, "hook", a.hook[a.scell[s]]);
             const int lab = a.rmin[a.hook[a.scell[s]]];  // hook is flat: the cell's root; consecutive points share all three words
             MOR_CHECK(lab >= 0 && lab < nc, "label", lab);
             a.label[c] = lab;
@@ -1069,13 +1082,14 @@ __device__ __forceinline__ void phase_match(const FramePtrs& a) {
 // Method 2 (default): the score of a matched pair is the number of points of the current cluster whose octree leaf
 // holds no point of the transformed previous cluster (cpp:325-330).
 __device__ __forceinline__ void phase_lattice_count(const FramePtrs& a, int cta, int G) {
-    const int nc = a.counts[MOR_CNT_NC];
+    int lo, hi;
+    cta_slice(a.counts[MOR_CNT_NC], cta, G, &lo, &hi);
     const int lane = threadIdx.x & 31;
-    for (int base = cta * kT; base < nc; base += G * kT) {
+    for (int base = lo; base < hi; base += kT) {
         const int s = base + threadIdx.x;
         int m = -1;
         bool is_new = false;
-        if (s < nc) {
+        if (s < hi) {
             const int k = a.scid[s];
             m = k >= 0 ? a.mid_of_cur[k] : -1;
             if (m >= 0) {
@@ -1408,7 +1422,7 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
     if (threadIdx.x == 0) {
         Scratch* sc = a.scratch;
-        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->err_early = 0;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->err_early = 0;
         sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
         for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
     }
@@ -1449,6 +1463,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 template <int PH>
 __device__ __forceinline__ void frame_step(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity, GroupBarrier& bar) {
     run_phase<PH>(a, cta, G, sh, dyn, parity);
+#ifdef MOR_CTA_TRACE
+    __syncthreads();
+    if (threadIdx.x == 0 && cta < 256) a.cta_trace[PH * 256 + cta] = global_ns();
+#endif
     if (PH != PH_FILTER) bar.sync();
     if (cta == 0 && threadIdx.x == 0) a.phase_ts[PH + 1] = global_ns();  // a dozen stores per frame: the frame's own timeline
 }
