@@ -170,6 +170,36 @@ __device__ __forceinline__ unsigned long long tile_exclusive_prefix(unsigned lon
     return s_prefix;
 }
 
+// The same prefix for the frame kernel, where all tiles of a scan are in flight at once (a tile per CTA and round, every
+// CTA resident): instead of a chained look-back - up to tile/32 dependent round trips - the whole CTA reads the
+// aggregates of ALL predecessor tiles at the same time and sums them: one round trip. A tile posts its aggregate before
+// it waits, so the wait cannot deadlock. `aggregate` must be valid in thread 0. BLOCK = blockDim.x.
+template <int BLOCK>
+__device__ __forceinline__ unsigned long long tile_prefix_wide(unsigned long long* status, int tile, unsigned long long aggregate) {
+    __shared__ unsigned long long s_part[BLOCK / 32];
+    __shared__ unsigned long long s_prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) st_status(&status[tile], kStAgg | aggregate);
+    unsigned long long sum = 0;
+    for (int idx = threadIdx.x; idx < tile; idx += BLOCK) {
+        unsigned long long v;
+        do { v = ld_status(&status[idx]); } while ((v >> 62) == 0);
+        sum += v & kStMask;
+    }
+    sum = warp_sum_u64(sum);
+    if (lane == 0) s_part[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < BLOCK / 32 ? s_part[lane] : 0ull;
+        v = warp_sum_u64(v);
+        if (lane == 0) s_prefix = v;
+    }
+    __syncthreads();
+    const unsigned long long r = s_prefix;
+    __syncthreads();  // s_part / s_prefix may be reused by a following call
+    return r;
+}
+
 // Block-wide exclusive scan of one value per thread (kBlock threads). Returns exclusive prefix within
 // the block; *total (valid in all threads) = block sum.
 template <typename T, int BLOCK = kBlock>

@@ -22,10 +22,8 @@ constexpr int kT = 1024;         // threads per CTA of the frame kernel: one CTA
 constexpr int kSingle = kT;      // single-CTA bookkeeping phases use the whole CTA
 constexpr int kWarps = kT / 32;
 constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
-constexpr int kLightPair = 256;  // a cell pair with more point pairs than this is queued for a whole warp (phase_link_heavy)
-constexpr int kLinkTilePts = 2048;  // points of one link round (32 cells) staged in shared memory by one bulk copy (32 KB)
-constexpr int kLinkListCap = 256;   // per warp: neighbour points dealt out to the lanes per pass (1 KB of shared memory)
-constexpr size_t kLinkSmem = (size_t)kLinkTilePts * 16 + (size_t)kWarps * kLinkListCap * 4;
+constexpr int kLightPair = 256;  // a cell pair with at most this many point pairs is tested by one thread, a larger one by a warp
+constexpr int kLightCnt = 128;   // ... and with at most this many points in either cell (7 bits in the packed record)
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16, ERR_EDGE_CAP = 32 };
 // counts[] slots in which the filter phase parks its results until filterCloud commits the frame (mor_b200.cu, do_filter)
@@ -81,15 +79,15 @@ struct FramePtrs {
     int* cell_list;            // [n_cells] table slot of every occupied cell, in creation order
     unsigned long long* ckey; int* cstart;  // [n_cells(+1)] compact copies: key, first sorted position
     int2* pslot;               // [N_c] (table slot, rank inside the cell) of every cloud point
-    int* slead;                // [N_c] leader position (cell start) of every sorted position
-    // link results, one segment per CTA of the group (no shared counters): connected cell pairs and the heavy pairs still to test
-    int2* edges; int edge_seg; int* edge_cnt;   // (cell index A, cell index B)
-    int2* heavy; int heavy_seg; int* heavy_cnt;
+    int* slead;                // [N_c] leader position (cell start = the cell's node) of every sorted position
+    // link lists, one segment per CTA of the group (no shared counters): cell pairs to test (light: one thread, heavy: one
+    // warp) and the connected pairs found (node A, node B)
+    int2* light; int light_seg; int* light_cnt;
+    int4* heavy; int heavy_seg; int* heavy_cnt;
+    int2* edges; int edge_seg; int* edge_cnt;
     int* cmin;                 // [n_cells] minimum cloud index of the cell's points
-    int* cell_of_lead;         // [N_c] cell index of a leader position
-    int* scell;                // [N_c] cell index of every sorted position
-    int* hook;                 // [n_cells] union-find over cell indices: parent word (pointers lead to smaller indices)
-    int* rsize; int* rmin;     // [n_cells] per root: points and minimum cloud index (= canonical label) of its component
+    int* hook;                 // [N_c, at leader positions] union-find over the nodes: parent word (pointers lead to smaller positions)
+    int* rsize; int* rmin;     // [N_c, at root positions] per root: points and minimum cloud index (= canonical label) of its component
     int* root_list;            // [n_roots] the roots, in no particular order
     // ---- per-frame scratch
     Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cscan; unsigned long long* st_out;
@@ -127,6 +125,17 @@ struct FramePtrs {
     // ---- voxel ground modes only (mor_ground.cuh): dense ball-query grid
     int* cell_count; int* cell_start; int* cell_key; int* skey; GridDesc* dgrid; unsigned long long* st_cells; int tiles_cells; int max_cells;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#ifdef MOR_CTA_TRACE  // debug builds: when did this CTA get here? (rows 16.. of the trace are sub-steps of phases; tools/cta_trace.py)
+#define MOR_TRACE(row) do { __syncthreads(); if (threadIdx.x == 0 && cta < 256) a.cta_trace[(row) * 256 + cta] = global_ns(); } while (0)
+#else
+#define MOR_TRACE(row)
+#endif
 
 // ------------------------------------------------------------------------------------------------ group barrier
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -196,14 +205,10 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 __device__ __forceinline__ int grid_find_or_insert(const FramePtrs& a, unsigned long long key, bool* created) {
     unsigned slot = hash64(key) & a.table_mask;
-    while (true) {
-        const unsigned long long cur = ld_relaxed_u64(&a.table[slot].key);
-        if (cur == key) { *created = false; return (int)slot; }
-        if (cur == 0ull) {
-            const unsigned long long old = atomicCAS(&a.table[slot].key, 0ull, key);
-            if (old == 0ull) { *created = true; return (int)slot; }
-            if (old == key) { *created = false; return (int)slot; }
-        }
+    while (true) {  // the CAS is the probe: one round trip whether the cell exists or not
+        const unsigned long long old = atomicCAS(&a.table[slot].key, 0ull, key);
+        if (old == 0ull) { *created = true; return (int)slot; }
+        if (old == key) { *created = false; return (int)slot; }
         slot = (slot + 1) & a.table_mask;
     }
 }
@@ -219,27 +224,31 @@ __device__ __forceinline__ bool grid_lookup(const FramePtrs& a, unsigned long lo
     }
 }
 // Whole warp: the lanes with `valid` bin their point. Lanes that fall into the same cell (neighbouring beams usually
-// do) elect one lane that walks the table and takes one ticket block for the group. Returns (slot, rank in the cell).
-__device__ __forceinline__ int2 grid_insert_warp(const FramePtrs& a, bool valid, unsigned long long key) {
+// do) elect one lane that walks the table and takes one ticket block for the group. Returns (slot, rank in the cell);
+// *created is set in the lane that created its cell: the caller enters the new cells into the cell list.
+__device__ __forceinline__ int2 grid_insert_warp(const FramePtrs& a, bool valid, unsigned long long key, bool* created) {
     const int lane = threadIdx.x & 31;
     const unsigned grp = __match_any_sync(kFull, valid ? key : (unsigned long long)lane);  // real keys have bit 63 set
     const int leader = __ffs(grp) - 1;
     int slot = 0, base = 0;
-    bool created = false;
+    *created = false;
     if (valid && lane == leader) {
-        slot = grid_find_or_insert(a, key, &created);
+        slot = grid_find_or_insert(a, key, created);
         base = atomicAdd(&a.table[slot].cnt, __popc(grp));
-    }
-    const unsigned cmask = __ballot_sync(kFull, created);
-    if (cmask) {  // one ticket block of the cell list per warp
-        int lbase = 0;
-        if (lane == __ffs(cmask) - 1) lbase = atomicAdd(&a.scratch->n_cells, __popc(cmask));
-        lbase = __shfl_sync(kFull, lbase, __ffs(cmask) - 1);
-        if (created) a.cell_list[lbase + __popc(cmask & ((1u << lane) - 1u))] = slot;
     }
     slot = __shfl_sync(kFull, slot, leader);
     base = __shfl_sync(kFull, base, leader);
     return make_int2(slot, base + __popc(grp & ((1u << lane) - 1u)));
+}
+// Cell-list entries of the cells a warp created, one ticket block of the list per warp.
+__device__ __forceinline__ void cell_list_append_warp(const FramePtrs& a, bool created, int slot) {
+    const int lane = threadIdx.x & 31;
+    const unsigned cmask = __ballot_sync(kFull, created);
+    if (!cmask) return;
+    int lbase = 0;
+    if (lane == __ffs(cmask) - 1) lbase = atomicAdd(&a.scratch->n_cells, __popc(cmask));
+    lbase = __shfl_sync(kFull, lbase, __ffs(cmask) - 1);
+    if (created) a.cell_list[lbase + __popc(cmask & ((1u << lane) - 1u))] = slot;
 }
 
 // ------------------------------------------------------------------------------------------------ octree-leaf lattice
@@ -308,10 +317,13 @@ __device__ __forceinline__ unsigned long long bin_point(const FramePtrs& a, cons
 __device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G) {
     frame_housekeeping(a, cta, G);
     const int ntiles = a.n ? (int)((a.n + kIngestTile - 1) / kIngestTile) : 1;
+    __shared__ int s_created, s_cbase;
     for (int tile = cta; tile < ntiles; tile += G) {
         const uint32_t i = (uint32_t)tile * kIngestTile + threadIdx.x;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int cls = 0;
+        if (threadIdx.x == 0) s_created = 0;
+        __syncthreads();  // (also: the previous tile's readers of s_cbase are done)
         if (i < a.n) {
             const uint8_t* p = a.in + (size_t)i * a.step;
             if (a.in_mode == 0) {
@@ -326,16 +338,25 @@ __device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G)
             a.point_class[i] = (uint8_t)cls;
             a.removed_mask[i] = cls ? 1 : 0;
         }
-        // binning first: its table walk and ticket overlap with the look-back of the partition below
-        bool oob = false;
+        // binning first: its table walk overlaps with the scan of the partition below. The new cells of the whole tile take
+        // ONE ticket block of the cell list (a ticket per warp would queue some 4000 atomics of a frame on one word)
+        bool oob = false, created = false;
         const unsigned long long key = cls == 1 ? bin_point(a, v, &oob) : 0ull;
-        const int2 sr = grid_insert_warp(a, cls == 1, key);
+        const int2 sr = grid_insert_warp(a, cls == 1, key, &created);
         if (oob) atomicOr(&a.scratch->err_early, ERR_GRID_RANGE);
+        const unsigned cmask = __ballot_sync(kFull, created);
+        int cslot = 0;
+        if (cmask) {
+            if ((threadIdx.x & 31) == __ffs(cmask) - 1) cslot = atomicAdd(&s_created, __popc(cmask));
+            cslot = __shfl_sync(kFull, cslot, __ffs(cmask) - 1) + __popc(cmask & ((1u << (threadIdx.x & 31)) - 1u));
+        }
         const unsigned long long packed = (cls == 1 ? 1ull : 0ull) | (cls == 2 ? (1ull << 31) : 0ull);
         unsigned long long total;
-        const unsigned long long in_block = block_exclusive_scan<unsigned long long, kT>(packed, &total);
-        const unsigned long long before = tile_exclusive_prefix(a.st_ingest, tile, total);
+        const unsigned long long in_block = block_exclusive_scan<unsigned long long, kT>(packed, &total);  // (barriers: s_created is complete)
+        if (threadIdx.x == kT - 1) { const int nc_new = s_created; s_cbase = nc_new ? atomicAdd(&a.scratch->n_cells, nc_new) : 0; }  // its round trip hides behind the prefix
+        const unsigned long long before = tile_prefix_wide<kT>(a.st_ingest, tile, total);
         const unsigned long long mine = before + in_block;
+        if (created) a.cell_list[s_cbase + cslot] = sr.x;
         if (cls == 1) {
             const int c = (int)(mine & 0x7FFFFFFFull);
             a.pts[c] = v;
@@ -370,18 +391,17 @@ __device__ __forceinline__ void phase_bin_cloud(const FramePtrs& a, int cta, int
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < nc) v = a.pts[c];
         const unsigned long long key = c < nc ? bin_point(a, v, &oob) : 0ull;
-        const int2 sr = grid_insert_warp(a, c < nc, key);
+        bool created = false;
+        const int2 sr = grid_insert_warp(a, c < nc, key, &created);
+        cell_list_append_warp(a, created, sr.x);
         if (oob) atomicOr(&a.scratch->err_early, ERR_GRID_RANGE);
         if (c < nc) a.pslot[c] = sr;
     }
 }
 
-// ===================================================================================== phase B: cell scan + transform
-// (1) Exclusive scan of the cell populations in cell-list order -> first sorted position of every cell; the cell's
-//     union-find node, its compact descriptors and (crowded cells) its neutral bounding box are set up on the way.
-// (2) Beside it, on the CTAs the scan does not need: pcl_ros::transformPointCloud of every previous-frame cluster
-//     (cpp:544-551, A12), the bounding box of the transformed points (getMinMax3D runs after the transform, cpp:272)
-//     and, for method 2, their octree leaves (cpp:319-324).
+// ===================================================================================== phase B: cell scan
+// Exclusive scan of the cell populations in cell-list order -> first sorted position of every cell (= the cell's
+// union-find node); its compact descriptors are set up on the way.
 __device__ __forceinline__ void cell_scan_tile(const FramePtrs& a, int tile, int n_cells, int ntiles) {
     const int i = tile * kT + threadIdx.x;
     int slot = 0, cnt = 0;
@@ -394,13 +414,12 @@ __device__ __forceinline__ void cell_scan_tile(const FramePtrs& a, int tile, int
     }
     int total;
     const int in_block = block_exclusive_scan<int, kT>(cnt, &total);
-    const int before = (int)tile_exclusive_prefix(a.st_cscan, tile, (unsigned long long)total);
+    const int before = (int)tile_prefix_wide<kT>(a.st_cscan, tile, (unsigned long long)total);
     const int start = before + in_block;
     if (i < n_cells) {
         a.table[slot].start = start;
         a.ckey[i] = key; a.cstart[i] = start;
-        a.cell_of_lead[start] = i;
-        a.hook[i] = i; a.rsize[i] = 0; a.rmin[i] = 0x7FFFFFFF;
+        a.hook[start] = start; a.rsize[start] = 0; a.rmin[start] = 0x7FFFFFFF;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) a.cstart[n_cells] = before + total;
 }
@@ -486,47 +505,52 @@ __device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc
     }
 }
 
-__device__ __forceinline__ void transform_tile(const FramePtrs& a, int tile) {
-    const int s = tile * kT + threadIdx.x;
-    const int ncp = a.p_counts[MOR_CNT_NC];
-    int k = -1;
-    float3 t = make_float3(0, 0, 0);
-    if (s < ncp) {
-        const float4 p = a.p_spts[s];
-        const int c = __float_as_int(p.w);
-        k = a.p_cid[c];
-        if (k >= 0) {
-            t = xform(a.M, p.x, p.y, p.z);
-            a.tpts[c] = make_float4(t.x, t.y, t.z, __int_as_float(k));
-            if (a.method == 2) {
-                unsigned long long key;
-                if (lattice_key(a.anchorp + (size_t)k * 3, k, t.x, t.y, t.z, &key)) hset_insert(a.lattice, a.lattice_mask, key);
-                else atomicOr(&a.scratch->err_early, ERR_LATTICE_RANGE);
-            }
-        } else {
-            a.tpts[c] = make_float4(0, 0, 0, __int_as_float(-1));
-        }
-    }
-    block_cluster_accumulate<false>(nullptr, a.pacc_box, k, k >= 0, t.x, t.y, t.z);
-}
-
-__device__ __forceinline__ void phase_cells_and_transform(const FramePtrs& a, int cta, int G) {
-    const int n_cells = __ldcg(&a.scratch->n_cells);
-    const int ctiles = n_cells ? (n_cells + kT - 1) / kT : 1;
-    const int ncp = a.two_frames ? a.p_counts[MOR_CNT_NC] : 0;
-    const int ttiles = (ncp + kT - 1) / kT;
-    for (int vb = cta; vb < ctiles + ttiles; vb += G) {
-        if (vb < ctiles) cell_scan_tile(a, vb, n_cells, ctiles);
-        else transform_tile(a, vb - ctiles);
-    }
-}
-
 // Work over [0, n) that needs no CTA-wide cooperation is cut into one contiguous slice per CTA (warp granular): a phase
 // is short, so what counts is that all SMs take part, not that a CTA's threads are all busy.
 __device__ __forceinline__ void cta_slice(int n, int cta, int G, int* lo, int* hi) {
     const int per = ((n + G - 1) / G + 31) & ~31;
     *lo = min(n, cta * per);
     *hi = min(n, *lo + per);
+}
+
+// pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12), the bounding box of the transformed
+// points (getMinMax3D runs after the transform, cpp:272) and, for method 2, their octree leaves (cpp:319-324). Depends
+// on the previous frame only: it runs beside the single-CTA cluster selection, on the CTAs that one does not need.
+__device__ __forceinline__ void transform_range(const FramePtrs& a, int lo, int hi) {
+    for (int base = lo; base < hi; base += kT) {
+        const int s = base + threadIdx.x;
+        int k = -1;
+        float3 t = make_float3(0, 0, 0);
+        if (s < hi) {
+            const float4 p = a.p_spts[s];
+            const int c = __float_as_int(p.w);
+            k = a.p_cid[c];
+            if (k >= 0) {
+                t = xform(a.M, p.x, p.y, p.z);
+                a.tpts[c] = make_float4(t.x, t.y, t.z, __int_as_float(k));
+                if (a.method == 2) {
+                    unsigned long long key;
+                    if (lattice_key(a.anchorp + (size_t)k * 3, k, t.x, t.y, t.z, &key)) hset_insert(a.lattice, a.lattice_mask, key);
+                    else atomicOr(&a.scratch->err_early, ERR_LATTICE_RANGE);
+                }
+            } else {
+                a.tpts[c] = make_float4(0, 0, 0, __int_as_float(-1));
+            }
+        }
+        block_cluster_accumulate<false>(nullptr, a.pacc_box, k, k >= 0, t.x, t.y, t.z);
+    }
+}
+__device__ __forceinline__ void phase_transform(const FramePtrs& a, int cta, int G) {
+    if (!a.two_frames || (G > 1 && cta == 0)) return;  // CTA 0 selects the clusters meanwhile
+    int lo, hi;
+    cta_slice(a.p_counts[MOR_CNT_NC], G > 1 ? cta - 1 : 0, G > 1 ? G - 1 : 1, &lo, &hi);
+    transform_range(a, lo, hi);
+}
+
+__device__ __forceinline__ void phase_cells(const FramePtrs& a, int cta, int G) {
+    const int n_cells = __ldcg(&a.scratch->n_cells);
+    const int ctiles = n_cells ? (n_cells + kT - 1) / kT : 1;
+    for (int vb = cta; vb < ctiles; vb += G) cell_scan_tile(a, vb, n_cells, ctiles);
 }
 
 // ===================================================================================== phase C: scatter
@@ -541,35 +565,29 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
         p.w = __int_as_float(c);
         a.spts[start + sr.y] = p;
         a.slead[start + sr.y] = start;
-        a.scell[start + sr.y] = a.cell_of_lead[start];
     }
 }
 
 // ===================================================================================== phase D: link
 // pcl::EuclideanClusterExtraction's radius graph (cpp:213-218; A5-A7) on cell granularity. Any two points of one cell
-// are neighbours (cell diagonal < r), so a cell is one node, and a neighbour lies at most 2 cells away per axis: cell A
-// must be tested against the 62 cells of its 5x5x5 block that precede it in (dz,dy,dx) order (the other 62 test A from
-// their side). Two cells are connected iff some point pair has L2_Simple distance < r2 (strict).
+// are neighbours (cell diagonal < r), so a cell is one node (named by the first sorted position of its points), and a
+// neighbour lies at most 2 cells away per axis: cell A must be tested against the 62 cells of its 5x5x5 block that
+// precede it in (dz,dy,dx) order (the other 62 test A from their side). Two cells are connected iff some point pair has
+// L2_Simple distance < r2 (strict).
 //
-// D1, light pairs: one WARP per cell. A link round takes 32 consecutive cells of the cell list, whose points are one
-// contiguous range of the sorted array: it is staged in shared memory by a single bulk copy (TMA) while the lanes walk
-// the hash table - lane l looks up neighbours l and l+32, both probes in flight together. The points of all light
-// neighbour cells are then flattened into one list (shared memory) and dealt out to the lanes, one neighbour point per
-// lane and step, each tested against A's points in shared memory; rounds of growing depth (4, 16, 64, 256 points per
-// neighbour cell) stop at a cell's first hit.
-// D2, heavy pairs (more than kLightPair point pairs): queued by D1 and dealt out to all warps of the group, a whole warp
-// per pair: bounding-box pruning on both sides, lanes across B's points, A broadcast by shuffle, early exit.
-// Both RECORD the connected pairs (edges, in per-CTA segments: no shared counter) and point the larger cell of a pair
-// at the smaller one (atomicMin on the cell's own word); the components are formed from that in phase E.
+// D1, enumerate: one warp per cell; lane l looks up neighbours l and l+32 in the hash table, both probes in flight
+// together. Every occupied neighbour becomes one record of the group's pair lists (per-CTA segments, no shared
+// counter): a LIGHT pair (at most kLightPair point pairs) or a HEAVY pair. The warp also leaves the cell's minimum
+// cloud index and, for crowded cells, its tight bounding box.
+// D2, test: the lists are dealt out evenly over the whole group. A light pair takes one THREAD (a few dozen distance
+// tests with early exit; ~60k pairs keep every thread of the GPU busy for one pass), a heavy pair one WARP: a probe of
+// samples first (a heavy pair is nearly always connected and nearly any sample shows it), bounding-box pruning and the
+// full scan only when the probe finds nothing. Connected pairs are RECORDED (edges, per-CTA segments) and the larger
+// node of a pair is pointed at the smaller one (atomicMin on its own word): the forest phase E starts from.
 #ifdef MOR_DEBUG_BOUNDS
 #define MOR_CHECK(cond, tag, v) do { if (!(cond)) { printf("BOUNDS %s: %d (line %d, cta %d thread %d)\n", tag, (int)(v), __LINE__, (int)blockIdx.x, (int)threadIdx.x); } } while (0)
 #else
 #define MOR_CHECK(cond, tag, v)
-#endif
-#ifdef MOR_LINK_STATS
-#define MOR_CLOCK(v) const long long v = clock64()
-#else
-#define MOR_CLOCK(v)
 #endif
 struct BoxF { float lx, ly, lz, hx, hy, hz; };
 __device__ __forceinline__ BoxF load_box(const FramePtrs& a, int start) {
@@ -588,46 +606,61 @@ __device__ __forceinline__ float box_box_d2(const BoxF& p, const BoxF& q) {
     return ex * ex + ey * ey + ez * ez;
 }
 
-// Whole warp on one heavy cell pair (A: cntA points at A[], B: cB points at sorted positions sB..): is there a point
-// pair within r? BOXES: the cells' bounding boxes are complete (after the light phase).
-template <bool BOXES>
-__device__ __forceinline__ bool heavy_pair_connected(const FramePtrs& a, const float4* A, int startA, int cntA, int sB, int cB, int lane) {
-    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
-    const bool hasBoxA = BOXES && cntA > kBoxMinCount, hasBoxB = BOXES && cB > kBoxMinCount;
-    BoxF boxA = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, boxB = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (hasBoxA) boxA = load_box(a, startA);
-    if (hasBoxB) boxB = load_box(a, sB);
-    if (hasBoxA && hasBoxB && box_box_d2(boxA, boxB) > r2_prune) return false;
-    bool hit = false;
-    for (int b0 = 0; b0 < cB && !hit; b0 += 32) {
-        const int b = b0 + lane;
-        bool valid = b < cB;
-        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            pb = a.spts[sB + b];
-            if (hasBoxA) valid = box_point_d2(boxA, pb.x, pb.y, pb.z) <= r2_prune;
-        }
-        if (!__any_sync(kFull, valid)) continue;
-        // A in blocks of 32: one coalesced load, then every candidate point (inside r of B's box) is broadcast by shuffle
-        // to all lanes: 32 x 32 point pairs per round trip to memory
-        for (int a0 = 0; a0 < cntA && !hit; a0 += 128) {  // four blocks of A in flight
-            float4 pa[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) pa[q] = A[min(a0 + 32 * q + lane, cntA - 1)];
-            bool h = false;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const bool av = a0 + 32 * q + lane < cntA && (!hasBoxB || box_point_d2(boxB, pa[q].x, pa[q].y, pa[q].z) <= r2_prune);
-                for (unsigned m = __ballot_sync(kFull, av); m; m &= m - 1) {
-                    const int u = __ffs(m) - 1;
-                    const float ax = __shfl_sync(kFull, pa[q].x, u), ay = __shfl_sync(kFull, pa[q].y, u), az = __shfl_sync(kFull, pa[q].z, u);
-                    h |= sqdist3(ax, ay, az, pb.x, pb.y, pb.z) < r2;
-                }
-            }
-            hit = __any_sync(kFull, h && valid);
-        }
+// Whole warp on one heavy cell pair (A: cntA points from sorted position sA, B: cB points from sB): is there a point
+// pair within r? Three steps of growing cost.
+// (1) Probe: 32 samples of B (one per lane) against up to 32 samples of A, spread over the cells, a vote after every
+// sample of A. In LiDAR data a crowded cell is connected to every crowded cell around it, and the first or second
+// sample shows it (C2: 6400 of 6470 connected heavy pairs per frame).
+__device__ __forceinline__ bool heavy_probe(const FramePtrs& a, int sA, int cntA, int sB, int cB, int lane) {
+    const float r2 = a.r2;
+    const float4 qb = a.spts[sB + (int)(((long long)lane * cB) >> 5)];
+    const float4 qa = a.spts[sA + (int)(((long long)lane * cntA) >> 5)];
+    for (int t = 0; t < 32; t++) {
+        const int u = (int)(__brev((unsigned)t) >> 27);  // 0, 16, 8, 24, ...: far apart first
+        const float ax = __shfl_sync(kFull, qa.x, u), ay = __shfl_sync(kFull, qa.y, u), az = __shfl_sync(kFull, qa.z, u);
+        if (__any_sync(kFull, sqdist3(ax, ay, az, qb.x, qb.y, qb.z) < r2)) return true;
     }
-    return hit;
+    return false;
+}
+// (2) The cells' bounding boxes (complete since the enumerate phase): most unconnected pairs end here.
+struct HeavyBoxes { BoxF A, B; bool hasA, hasB; };
+__device__ __forceinline__ bool heavy_boxes_apart(const FramePtrs& a, int sA, int cntA, int sB, int cB, HeavyBoxes* hb) {
+    hb->hasA = cntA > kBoxMinCount; hb->hasB = cB > kBoxMinCount;
+    hb->A = BoxF{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; hb->B = hb->A;
+    if (hb->hasA) hb->A = load_box(a, sA);
+    if (hb->hasB) hb->B = load_box(a, sB);
+    return hb->hasA && hb->hasB && box_box_d2(hb->A, hb->B) > a.r2 * 1.00001f;
+}
+// (3) Full scan of one chunk of 32 points of B (from b0) against all of A, both pruned by the other cell's box: A in
+// blocks of 32 per coalesced load, four blocks in flight, every candidate point broadcast by shuffle to all lanes.
+__device__ __forceinline__ bool heavy_scan_chunk(const FramePtrs& a, const HeavyBoxes& hb, int sA, int cntA, int sB, int cB, int b0, int lane) {
+    const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
+    const float4* A = a.spts + sA;
+    const int b = b0 + lane;
+    bool valid = b < cB;
+    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        pb = a.spts[sB + b];
+        if (hb.hasA) valid = box_point_d2(hb.A, pb.x, pb.y, pb.z) <= r2_prune;
+    }
+    if (!__any_sync(kFull, valid)) return false;
+    for (int a0 = 0; a0 < cntA; a0 += 128) {
+        float4 pa[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) pa[q] = A[min(a0 + 32 * q + lane, cntA - 1)];
+        bool h = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool av = a0 + 32 * q + lane < cntA && (!hb.hasB || box_point_d2(hb.B, pa[q].x, pa[q].y, pa[q].z) <= r2_prune);
+            for (unsigned m = __ballot_sync(kFull, av); m; m &= m - 1) {
+                const int u = __ffs(m) - 1;
+                const float ax = __shfl_sync(kFull, pa[q].x, u), ay = __shfl_sync(kFull, pa[q].y, u), az = __shfl_sync(kFull, pa[q].z, u);
+                h |= sqdist3(ax, ay, az, pb.x, pb.y, pb.z) < r2;
+            }
+        }
+        if (__any_sync(kFull, h && valid)) return true;
+    }
+    return false;
 }
 
 // Both neighbours of a lane are looked up with their first probes in flight together.
@@ -653,33 +686,28 @@ __device__ __forceinline__ void grid_lookup2(const FramePtrs& a, bool v0, unsign
     }
 }
 
-struct LinkShared { int n_edges, n_heavy, base, staged; };
-
-// The lanes flagged in (m0, m1) append one record each (their slot 0 / slot 1 neighbour) to the CTA's segment.
-// HOOK: the records are connected pairs: the larger cell of each pair is pointed at the smaller one if that lowers its
-// pointer (atomicMin on the cell's own word: a local spanning forest, the seed of the components phase).
-template <bool HOOK>
-__device__ __forceinline__ void append_pairs(const FramePtrs& a, int2* seg, int seg_cap, int* counter, unsigned m0, unsigned m1, bool f0, bool f1, int2 v0, int2 v1, int lane) {
+// The lanes with f0 / f1 append one record each to the CTA's segment (counter in shared memory).
+template <typename T>
+__device__ __forceinline__ void warp_append2(const FramePtrs& a, T* seg, int seg_cap, int* counter, bool f0, bool f1, const T& v0, const T& v1, int lane) {
+    const unsigned m0 = __ballot_sync(kFull, f0), m1 = __ballot_sync(kFull, f1);
     if (!(m0 | m1)) return;
-    if (HOOK) {
-        if (f0) atomicMin(&a.hook[max(v0.x, v0.y)], min(v0.x, v0.y));
-        if (f1) atomicMin(&a.hook[max(v1.x, v1.y)], min(v1.x, v1.y));
-    }
     int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(m0) + __popc(m1));  // shared-memory counter of the CTA
+    if (lane == 0) base = atomicAdd(counter, __popc(m0) + __popc(m1));
     base = __shfl_sync(kFull, base, 0);
     const int w0 = base + __popc(m0 & ((1u << lane) - 1u)), w1 = base + __popc(m0) + __popc(m1 & ((1u << lane) - 1u));
     if (f0) { if (w0 < seg_cap) seg[w0] = v0; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
     if (f1) { if (w1 < seg_cap) seg[w1] = v1; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
 }
 
-__device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float4* A, int* list, LinkShared& ls, int2* eseg, int2* hseg, int lane) {
+struct LinkShared { int n_light, n_heavy; };
+
+// light record: (start | (count - 1) << 25) of both cells; heavy record: (start A, count A, start B, count B)
+__device__ __forceinline__ void enumerate_cell(const FramePtrs& a, int i, LinkShared& ls, int2* lseg, int4* hseg, int lane) {
     const unsigned long long key = a.ckey[i];
     const int startA = a.cstart[i], cntA = a.cstart[i + 1] - startA;
     MOR_CHECK(startA >= 0 && cntA > 0 && startA + cntA <= a.counts[MOR_CNT_NC], "cellA", cntA);
     int cx, cy, cz;
     cell_unpack(key, cx, cy, cz);
-    const float r2 = a.r2;
     // the 62 preceding cells of the 5x5x5 block: offset index n = (dz+2)*25 + (dy+2)*5 + (dx+2) < 62
     int2 nb[2];  // (start, cnt) of the lane's two neighbour cells, cnt 0 = empty
     {
@@ -692,6 +720,7 @@ __device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float
     }
     {   // the cell's minimum cloud index (its component's canonical label is the minimum over its cells) and, for a
         // crowded cell, its tight bounding box (prunes the point tests of the heavy pairs)
+        const float4* A = a.spts + startA;
         int mn = 0x7FFFFFFF;
         unsigned mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0u, mxy = 0u, mxz = 0u;
         for (int k = lane; k < cntA; k += 32) {
@@ -708,116 +737,179 @@ __device__ __forceinline__ void link_cell(const FramePtrs& a, int i, const float
         }
         if (lane == 0) a.cmin[i] = mn;
     }
-    // heavy pairs go to the CTA's work list (whole warps of the group pick them up in the next phase)
-    bool heavy[2];
-    heavy[0] = (long long)cntA * nb[0].y > kLightPair; heavy[1] = (long long)cntA * nb[1].y > kLightPair;
-    {
-        const unsigned hm0 = __ballot_sync(kFull, heavy[0]), hm1 = __ballot_sync(kFull, heavy[1]);
-        if (hm0 | hm1) {
-            const int j0 = heavy[0] ? a.cell_of_lead[nb[0].x] : 0, j1 = heavy[1] ? a.cell_of_lead[nb[1].x] : 0;
-            append_pairs<false>(a, hseg, a.heavy_seg, &ls.n_heavy, hm0, hm1, heavy[0], heavy[1], make_int2(i, j0), make_int2(i, j1), lane);
-        }
-    }
-    // Light neighbours, in rounds of growing depth: the first round takes 4 points of every neighbour cell - a connected
-    // neighbour nearly always shows a hit there - and only the cells without a hit go on with 16, 64, 256 more.
-    int c[2] = {heavy[0] ? 0 : nb[0].y, heavy[1] ? 0 : nb[1].y}, off[2] = {0, 0};
-    for (int chunk = 4; ; chunk *= 4) {
-        const int r0 = min(chunk, c[0] - off[0]), r1 = min(chunk, c[1] - off[1]);
-        int incl = r0 + r1;
+    bool light[2], heavy[2];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-        const int M = __shfl_sync(kFull, incl, 31), base = incl - (r0 + r1);
-        if (M == 0) break;
-        unsigned hit_lo = 0u, hit_hi = 0u;  // neighbour slots (lane, lane + 32) with a hit in this round
-        for (int w0 = 0; w0 < M; w0 += kLinkListCap) {
-            // entry = sorted position | owner slot << 25
-            for (int k = max(0, w0 - base); k < r0 && base + k < w0 + kLinkListCap; k++) list[base + k - w0] = (nb[0].x + off[0] + k) | (lane << 25);
-            for (int k = max(0, w0 - base - r0); k < r1 && base + r0 + k < w0 + kLinkListCap; k++) list[base + r0 + k - w0] = (nb[1].x + off[1] + k) | ((lane + 32) << 25);
-            __syncwarp();
-            const int wn = min(kLinkListCap, M - w0);
-            for (int j0 = 0; j0 < wn; j0 += 64) {  // two independent point loads in flight per lane
-                const int ja = j0 + lane, jb = j0 + 32 + lane;
-                const int ea = ja < wn ? list[ja] : -1, eb = jb < wn ? list[jb] : -1;
-                float4 pa4 = make_float4(0.f, 0.f, 0.f, 0.f), pb4 = pa4;
-                if (ea >= 0) pa4 = a.spts[ea & 0x1FFFFFF];
-                if (eb >= 0) pb4 = a.spts[eb & 0x1FFFFFF];
-                bool hita = false, hitb = false;
-                for (int k = 0; k < cntA; k++) {
-                    const float4 q = A[k];
-                    hita |= sqdist3(q.x, q.y, q.z, pa4.x, pa4.y, pa4.z) < r2;
-                    hitb |= sqdist3(q.x, q.y, q.z, pb4.x, pb4.y, pb4.z) < r2;
-                }
-                hita &= ea >= 0; hitb &= eb >= 0;
-                const int sa = ea >> 25, sb = eb >> 25;
-                hit_lo |= __reduce_or_sync(kFull, (hita && sa < 32 ? 1u << sa : 0u) | (hitb && sb < 32 ? 1u << sb : 0u));
-                hit_hi |= __reduce_or_sync(kFull, (hita && sa >= 32 ? 1u << (sa - 32) : 0u) | (hitb && sb >= 32 ? 1u << (sb - 32) : 0u));
-            }
-            __syncwarp();
-        }
-        // the owner lane of a neighbour cell with a hit records the edge
-        const bool u0 = (hit_lo >> lane) & 1u, u1 = (hit_hi >> lane) & 1u;
-        if (hit_lo | hit_hi) {
-            const int j0 = u0 ? a.cell_of_lead[nb[0].x] : 0, j1 = u1 ? a.cell_of_lead[nb[1].x] : 0;
-            MOR_CHECK(j0 >= 0 && j0 < a.scratch->n_cells && j1 >= 0 && j1 < a.scratch->n_cells, "edge j", j0);
-            append_pairs<true>(a, eseg, a.edge_seg, &ls.n_edges, hit_lo, hit_hi, u0, u1, make_int2(i, j0), make_int2(i, j1), lane);
-        }
-        off[0] = u0 ? c[0] : off[0] + r0;  // a cell with a hit is finished
-        off[1] = u1 ? c[1] : off[1] + r1;
+    for (int q = 0; q < 2; q++) {
+        const bool occ = nb[q].y > 0;
+        light[q] = occ && cntA <= kLightCnt && nb[q].y <= kLightCnt && cntA * nb[q].y <= kLightPair;
+        heavy[q] = occ && !light[q];
     }
+    const int wa = startA | ((cntA - 1) << 25);
+    warp_append2<int2>(a, lseg, a.light_seg, &ls.n_light, light[0], light[1], make_int2(wa, nb[0].x | ((nb[0].y - 1) << 25)), make_int2(wa, nb[1].x | ((nb[1].y - 1) << 25)), lane);
+    warp_append2<int4>(a, hseg, a.heavy_seg, &ls.n_heavy, heavy[0], heavy[1], make_int4(startA, cntA, nb[0].x, nb[0].y), make_int4(startA, cntA, nb[1].x, nb[1].y), lane);
 }
 
-__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, float4* tile, int* lists, unsigned long long* mbar, unsigned& parity) {
+__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G) {
     __shared__ LinkShared ls;
     const int n_cells = __ldcg(&a.scratch->n_cells);
-    const int rounds = (n_cells + kWarps - 1) / kWarps;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int2* eseg = a.edges + (size_t)cta * a.edge_seg;
-    int2* hseg = a.heavy + (size_t)cta * a.heavy_seg;
-    if (threadIdx.x == 0) { ls.n_edges = 0; ls.n_heavy = 0; }
-    for (int round = cta; round < rounds; round += G) {
-        const int i0 = round * kWarps, i1 = min(i0 + kWarps, n_cells);
-        __syncthreads();  // the previous round's readers of the tile are done
-        if (threadIdx.x == 0) {
-            const int s0 = a.cstart[i0], s1 = a.cstart[i1];
-            ls.base = s0;
-            ls.staged = (s1 - s0 <= kLinkTilePts) ? s1 - s0 : 0;  // a round of very crowded cells reads A from L2 instead
-            if (ls.staged) bulk_load(tile, a.spts + s0, (unsigned)ls.staged * 16u, mbar);
-        }
-        __syncthreads();
-        const int base = ls.base, staged = ls.staged;
-        const int i = i0 + warp;
-        if (staged) { mbar_wait(mbar, parity); parity ^= 1u; }
-        if (i < i1) link_cell(a, i, staged ? tile + (a.cstart[i] - base) : a.spts + a.cstart[i], lists + warp * kLinkListCap, ls, eseg, hseg, lane);
-    }
+    int2* lseg = a.light + (size_t)cta * a.light_seg;
+    int4* hseg = a.heavy + (size_t)cta * a.heavy_seg;
+    if (threadIdx.x == 0) { ls.n_light = 0; ls.n_heavy = 0; }
     __syncthreads();
-    if (threadIdx.x == 0) { a.edge_cnt[cta] = min(ls.n_edges, a.edge_seg); a.heavy_cnt[cta] = min(ls.n_heavy, a.heavy_seg); }
+    // an equal share of the cells for every CTA, a warp per cell
+    const int lo = (int)(((long long)n_cells * cta) / G), hi = (int)(((long long)n_cells * (cta + 1)) / G);
+    for (int i = lo + warp; i < hi; i += kWarps) enumerate_cell(a, i, ls, lseg, hseg, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) { a.light_cnt[cta] = min(ls.n_light, a.light_seg); a.heavy_cnt[cta] = min(ls.n_heavy, a.heavy_seg); a.edge_cnt[cta] = 0; }
 }
 
-// D2: the heavy pairs of all CTAs' lists, dealt out warp by warp over the whole group.
-__device__ __forceinline__ void phase_link_heavy(const FramePtrs& a, int cta, int G) {
-    __shared__ int s_pre[257], s_edges;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // running totals of the per-CTA heavy lists (G <= 256)
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int c = 0; c < G; c++) { s_pre[c] = run; run += __ldcg(&a.heavy_cnt[c]); }
-        s_pre[G] = run;
-        s_edges = __ldcg(&a.edge_cnt[cta]);
+// Running totals of the per-CTA list lengths (G <= 256) into pre[0..G], by one warp.
+__device__ __forceinline__ void warp_prefix_counts(const int* cnt, int G, int* pre, int lane) {
+    const int per = (G + 31) / 32;  // <= 8
+    int v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int c = lane * per + q;
+        v[q] = (q < per && c < G) ? __ldcg(cnt + c) : 0;
+        sum += v[q];
     }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    int run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int c = lane * per + q;
+        if (q < per && c < G) pre[c] = run;
+        run += v[q];
+    }
+    if (lane == 31) pre[G] = incl;
+}
+// largest s in [0, G) with pre[s] <= w (w < pre[G])
+__device__ __forceinline__ int segment_of(const int* pre, int G, int w) {
+    int lo = 0, hi = G;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= w) lo = mid; else hi = mid; }
+    return lo;
+}
+
+template <int BLK>
+__device__ __forceinline__ bool light_pair_connected(const float4* S, int cS, const float4* L, int cL, float r2) {
+    for (int k0 = 0; k0 < cS; k0 += BLK) {
+        float sx[BLK], sy[BLK], sz[BLK];
+#pragma unroll
+        for (int q = 0; q < BLK; q++) { const float4 p = S[min(k0 + q, cS - 1)]; sx[q] = p.x; sy[q] = p.y; sz[q] = p.z; }  // (the last block may repeat a point)
+        for (int j = 0; j < cL; j++) {
+            const float4 pl = L[j];
+            bool h = false;
+#pragma unroll
+            for (int q = 0; q < BLK; q++) h |= sqdist3(sx[q], sy[q], sz[q], pl.x, pl.y, pl.z) < r2;
+            if (h) return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
+    constexpr int kHardCap = 96;
+    __shared__ int s_lpre[257], s_hpre[257], s_edges, s_nhard, s_hard_hit[kHardCap];
+    __shared__ int4 s_hard[kHardCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) warp_prefix_counts(a.light_cnt, G, s_lpre, lane);
+    if (warp == 1) warp_prefix_counts(a.heavy_cnt, G, s_hpre, lane);
+    if (threadIdx.x == 64) { s_edges = 0; s_nhard = 0; }
     __syncthreads();
-    const int total = s_pre[G];
+    const float r2 = a.r2;
     int2* eseg = a.edges + (size_t)cta * a.edge_seg;
-    int seg = 0;
-    for (int w = cta * kWarps + warp; w < total; w += G * kWarps) {
-        while (s_pre[seg + 1] <= w) seg++;
-        const int2 hp = __ldcg(a.heavy + (size_t)seg * a.heavy_seg + (w - s_pre[seg]));
-        MOR_CHECK(hp.x >= 0 && hp.x < a.scratch->n_cells && hp.y >= 0 && hp.y < a.scratch->n_cells, "heavy pair", hp.y);
-        const int sA = a.cstart[hp.x], cA = a.cstart[hp.x + 1] - sA, sB = a.cstart[hp.y], cB = a.cstart[hp.y + 1] - sB;
-        const bool hit = heavy_pair_connected<true>(a, a.spts + sA, sA, cA, sB, cB, lane);
+    MOR_TRACE(16);
+    // ---- light pairs: one thread each
+    int lo, hi;
+    cta_slice(s_lpre[G], cta, G, &lo, &hi);
+    for (int base = lo; base < hi; base += kT) {
+        const int w = base + threadIdx.x;
+        bool hit = false;
+        int sA = 0, sB = 0;
+        if (w < hi) {
+            const int seg = segment_of(s_lpre, G, w);
+            const int2 lp = __ldcg(a.light + (size_t)seg * a.light_seg + (w - s_lpre[seg]));
+            sA = lp.x & 0x1FFFFFF; sB = lp.y & 0x1FFFFFF;
+            const int cA = (int)((unsigned)lp.x >> 25) + 1, cB = (int)((unsigned)lp.y >> 25) + 1;
+            MOR_CHECK(sA + cA <= a.counts[MOR_CNT_NC] && sB + cB <= a.counts[MOR_CNT_NC], "light pair", sB);
+            // the smaller cell (at most 16 points: the product is bounded) is held in registers, 4 or 8 points at a time,
+            // and the larger one streams past it: one load per point of the larger cell and block instead of one per
+            // test (the loads of 32 lanes go to 32 different lines: the L1 tag stage was the limit); the distance is
+            // symmetric bit for bit, so the roles do not matter
+            const bool a_small = cA <= cB;
+            const float4* S = a.spts + (a_small ? sA : sB);
+            const float4* L = a.spts + (a_small ? sB : sA);
+            const int cS = a_small ? cA : cB, cL = a_small ? cB : cA;
+            if (cS <= 4) hit = light_pair_connected<4>(S, cS, L, cL, r2);
+            else hit = light_pair_connected<8>(S, cS, L, cL, r2);
+        }
+        if (hit) atomicMin(&a.hook[max(sA, sB)], min(sA, sB));
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (m) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&s_edges, __popc(m));
+            slot = __shfl_sync(kFull, slot, 0) + __popc(m & ((1u << lane) - 1u));
+            if (hit) { if (slot < a.edge_seg) eseg[slot] = make_int2(sA, sB); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
+        }
+    }
+    MOR_TRACE(17);
+    // ---- heavy pairs: one warp each; the CTA's share is dealt out from the last warp down (the first warps hold the
+    // light pairs). The few pairs that need the full scan are put aside and then taken on by the whole CTA, one chunk
+    // of B per warp: a single warp would keep the group waiting for tens of microseconds on a pair of crowded cells.
+    int hlo, hhi;
+    {
+        const int th = s_hpre[G];
+        hlo = (int)(((long long)th * cta) / G); hhi = (int)(((long long)th * (cta + 1)) / G);
+    }
+    for (int w = hlo + (kWarps - 1 - warp); w < hhi; w += kWarps) {
+        const int seg = segment_of(s_hpre, G, w);
+        const int4 hp = __ldcg(a.heavy + (size_t)seg * a.heavy_seg + (w - s_hpre[seg]));
+        MOR_CHECK(hp.x + hp.y <= a.counts[MOR_CNT_NC] && hp.z + hp.w <= a.counts[MOR_CNT_NC], "heavy pair", hp.z);
+        bool hit = heavy_probe(a, hp.x, hp.y, hp.z, hp.w, lane);
+        if (!hit) {
+            HeavyBoxes hb;
+            if (heavy_boxes_apart(a, hp.x, hp.y, hp.z, hp.w, &hb)) continue;
+            int slot = kHardCap;
+            if (lane == 0) slot = atomicAdd(&s_nhard, 1);
+            slot = __shfl_sync(kFull, slot, 0);
+            if (slot < kHardCap) { if (lane == 0) { s_hard[slot] = hp; s_hard_hit[slot] = 0; } continue; }
+            for (int b0 = 0; b0 < hp.w && !hit; b0 += 32) hit = heavy_scan_chunk(a, hb, hp.x, hp.y, hp.z, hp.w, b0, lane);  // (list full)
+        }
         if (hit && lane == 0) {
             const int slot = atomicAdd(&s_edges, 1);
-            if (slot < a.edge_seg) eseg[slot] = hp; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
-            atomicMin(&a.hook[max(hp.x, hp.y)], min(hp.x, hp.y));
+            if (slot < a.edge_seg) eseg[slot] = make_int2(hp.x, hp.z); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
+            atomicMin(&a.hook[max(hp.x, hp.z)], min(hp.x, hp.z));
+        }
+    }
+    __syncthreads();
+    MOR_TRACE(18);
+    const int nhard = min(s_nhard, kHardCap);
+    if (nhard) {
+        // work items (pair, chunk of B) in pair order, dealt out to the warps round-robin
+        int item = warp;
+        for (int p = 0, first = 0; p < nhard; p++) {
+            const int4 hp = s_hard[p];
+            const int chunks = (hp.w + 31) >> 5;
+            if (item < first + chunks) {
+                HeavyBoxes hb;
+                heavy_boxes_apart(a, hp.x, hp.y, hp.z, hp.w, &hb);
+                for (; item < first + chunks; item += kWarps) {
+                    if (*(volatile int*)&s_hard_hit[p]) continue;
+                    if (heavy_scan_chunk(a, hb, hp.x, hp.y, hp.z, hp.w, (item - first) * 32, lane) && lane == 0) s_hard_hit[p] = 1;
+                }
+            }
+            first += chunks;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < nhard; p += kT) {
+            if (!s_hard_hit[p]) continue;
+            const int4 hp = s_hard[p];
+            const int slot = atomicAdd(&s_edges, 1);
+            if (slot < a.edge_seg) eseg[slot] = make_int2(hp.x, hp.z); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
+            atomicMin(&a.hook[max(hp.x, hp.z)], min(hp.x, hp.z));
         }
     }
     __syncthreads();
@@ -840,12 +932,13 @@ __device__ __forceinline__ void phase_jump(const FramePtrs& a, int cta, int G) {
     int lo, hi;
     cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
     for (int i = lo + threadIdx.x; i < hi; i += kT) {
-        int p = ld_parent(a.hook + i);
-        MOR_CHECK(p >= 0 && p <= i, "jump p", p);
+        const int node = a.cstart[i];
+        int p = ld_parent(a.hook + node);
+        MOR_CHECK(p >= 0 && p <= node, "jump p", p);
         while (true) {  // every cell jumps at the same time, so the distance to the root halves per step
             const int g = ld_parent(a.hook + p);
             if (g == p) break;
-            st_parent(a.hook + i, g);
+            st_parent(a.hook + node, g);
             p = g;
         }
     }
@@ -856,9 +949,9 @@ __device__ __forceinline__ void phase_cross(const FramePtrs& a, int cta, int G) 
     const int2* seg = a.edges + (size_t)cta * a.edge_seg;
     for (int e = threadIdx.x; e < n; e += kT) {
         const int2 uv = __ldcg(seg + e);
-        MOR_CHECK(uv.x >= 0 && uv.x < a.scratch->n_cells && uv.y >= 0 && uv.y < a.scratch->n_cells, "cross uv", uv.y);
+        MOR_CHECK(uv.x >= 0 && uv.x < a.counts[MOR_CNT_NC] && uv.y >= 0 && uv.y < a.counts[MOR_CNT_NC], "cross uv", uv.y);
         const int lu = ld_parent(a.hook + uv.x), lv = ld_parent(a.hook + uv.y);
-        MOR_CHECK(lu >= 0 && lu < a.scratch->n_cells && lv >= 0 && lv < a.scratch->n_cells, "cross label", lu);
+        MOR_CHECK(lu >= 0 && lu < a.counts[MOR_CNT_NC] && lv >= 0 && lv < a.counts[MOR_CNT_NC], "cross label", lu);
         if (lu != lv) uf_union(a.hook, lu, lv);
     }
 }
@@ -875,9 +968,9 @@ __device__ __forceinline__ void phase_roots(const FramePtrs& a, int cta, int G) 
             const int s0 = a.cstart[i], s1 = a.cstart[i + 1];
             mn = __ldcg(&a.cmin[i]);
             cnt = s1 - s0;
-            r = uf_find_ro(a.hook, i);  // (no path halving here: nothing but the roots themselves may be stored in this phase)
-            st_parent(a.hook + i, r);   // flat for the per-point look-ups of the statistics phase
-            if (r == i) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = i;
+            r = uf_find_ro(a.hook, s0);  // (no path halving here: nothing but the roots themselves may be stored in this phase)
+            st_parent(a.hook + s0, r);   // flat for the per-point look-ups of the statistics phase
+            if (r == s0) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s0;
         }
         const unsigned grp = __match_any_sync(kFull, r);
         const int gsum = __reduce_add_sync(grp, cnt), gmin = __reduce_min_sync(grp, mn);
@@ -957,8 +1050,7 @@ __device__ __forceinline__ void phase_stats(const FramePtrs& a, int cta, int G) 
         if (s < hi) {
             p = a.spts[s];
             const int c = __float_as_int(p.w);
-            MOR_CHECK(a.scell[s] >= 0 && a.scell[s] < a.scratch->n_cells, "scell", a.scell[s]);
-            const int lab = a.rmin[a.hook[a.scell[s]]];  // hook is flat: the cell's root; consecutive points share all three words
+            const int lab = a.rmin[a.hook[a.slead[s]]];  // hook is flat: the cell's root; consecutive points share all three words
             MOR_CHECK(lab >= 0 && lab < nc, "label", lab);
             a.label[c] = lab;
             k = a.cid_of_root[lab];
@@ -1391,7 +1483,7 @@ __device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShar
     }
     int tot;
     const int in_block = block_exclusive_scan<int, kT>(keep ? 1 : 0, &tot);
-    const int before = (int)tile_exclusive_prefix(a.st_out, tile, (unsigned long long)tot);
+    const int before = (int)tile_prefix_wide<kT>(a.st_out, tile, (unsigned long long)tot);
     if (keep) {
         const int o = before + in_block;
         a.out[2 * o] = make_float4(p.x, p.y, p.z, 1.0f);
@@ -1429,7 +1521,7 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
 }
 
 // ===================================================================================== the frame kernel
-enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_LINK_HEAVY, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
+enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_TEST, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
 
 struct FrameShared {
     unsigned long long mbar;
@@ -1439,14 +1531,14 @@ struct FrameShared {
 template <int PH>
 __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
     if (PH == PH_INGEST) { if (a.skip_ingest) phase_bin_cloud(a, cta, G); else phase_ingest(a, cta, G); }
-    if (PH == PH_CELLS) phase_cells_and_transform(a, cta, G);
+    if (PH == PH_CELLS) phase_cells(a, cta, G);
     if (PH == PH_SCATTER) phase_scatter(a, cta, G);
-    if (PH == PH_LINK) phase_link(a, cta, G, reinterpret_cast<float4*>(dyn), reinterpret_cast<int*>(dyn) + kLinkTilePts * 4, &sh.mbar, parity);
-    if (PH == PH_LINK_HEAVY) phase_link_heavy(a, cta, G);
+    if (PH == PH_LINK) phase_link(a, cta, G);
+    if (PH == PH_TEST) phase_test(a, cta, G);
     if (PH == PH_JUMP) phase_jump(a, cta, G);
     if (PH == PH_CROSS) phase_cross(a, cta, G);
     if (PH == PH_ROOTS) phase_roots(a, cta, G);
-    if (PH == PH_SELECT) { if (cta == 0) phase_select(a, dyn); }
+    if (PH == PH_SELECT) { if (cta == 0) phase_select(a, dyn); phase_transform(a, cta, G); }
     if (PH == PH_STATS) phase_stats(a, cta, G);
     if (PH == PH_MATCH) { if (cta == 0) phase_match(a); }
     if (PH == PH_MOVING) { if (a.two_frames) { if (a.method == 2) phase_lattice_count(a, cta, G); else phase_pde_count(a, cta, G); } }
@@ -1454,11 +1546,6 @@ __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, Fr
     if (PH == PH_FILTER) phase_filter(a, cta, G, sh.filter);
 }
 
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 template <int PH>
 __device__ __forceinline__ void frame_step(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity, GroupBarrier& bar) {
@@ -1478,7 +1565,7 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
     frame_step<PH_CELLS>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_SCATTER>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_LINK>(a, cta, G, sh, dyn, parity, bar);
-    frame_step<PH_LINK_HEAVY>(a, cta, G, sh, dyn, parity, bar);
+    frame_step<PH_TEST>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_JUMP>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_CROSS>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_ROOTS>(a, cta, G, sh, dyn, parity, bar);
