@@ -150,7 +150,7 @@ namespace {
 
 enum KernelId { KID_PHASE0 = 0, KID_FRAME = PH__COUNT, KID_FILTER_AGAIN,
                 KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_CELLS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells", "ph_scatter", "ph_link", "ph_test", "ph_jump", "ph_cross", "ph_roots", "ph_select+transform", "ph_stats", "ph_match",
+const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells", "ph_scatter+link", "ph_test", "ph_jump", "ph_cross", "ph_roots", "ph_select+transform", "ph_stats", "ph_match",
                                               "ph_moving_test", "ph_chain+cleanup", "ph_filter", "k_frame", "k_filter_again",
                                               "k_ingest_raw", "k_ground_keys", "k_scan_cells", "k_scan_voxels", "k_ground_scatter",
                                               "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
@@ -246,18 +246,17 @@ int allocate(mor_handle* h) {
         h->slot[0].d_in = h->d_in; h->slot[1].d_in = carve<uint8_t>(p, h->d_in_bytes);
         b.scratch = carve<Scratch>(p, 1);
         b.st_ingest = carve<unsigned long long>(p, tiles_pts);
-        b.st_cscan = carve<unsigned long long>(p, tiles_pts);
         b.st_out = carve<unsigned long long>(p, tiles_pts);
         b.table = carve<Cell>(p, tab);
-        b.cell_list = carve<int>(p, N); b.ckey = carve<unsigned long long>(p, N + 1); b.cstart = carve<int>(p, N + 1);
+        b.cell_list = carve<int>(p, N); b.ckey = carve<unsigned long long>(p, N + 1); b.cstart = carve<int>(p, N + 1); b.ccnt = carve<int>(p, N + 1);
         b.pslot = carve<int2>(p, N); b.slead = carve<int>(p, N);
         b.edges = carve<int2>(p, h->edge_cap); b.light = carve<int2>(p, h->edge_cap); b.heavy = carve<int4>(p, h->heavy_cap);
-        b.edge_cnt = carve<int>(p, 256); b.light_cnt = carve<int>(p, 256); b.heavy_cnt = carve<int>(p, 256);
-        b.cmin = carve<int>(p, N); b.hook = carve<int>(p, N); b.rsize = carve<int>(p, N); b.rmin = carve<int>(p, N); b.root_list = carve<int>(p, N);
+        b.edge_cnt = carve<int>(p, 256);
+        b.hook = carve<int>(p, N); b.rsize = carve<int>(p, N); b.rmin = carve<int>(p, N); b.root_list = carve<int>(p, N);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
         b.label = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
-        b.scid = carve<int>(p, N); b.cell_box = carve<uint4>(p, 2 * N);
+        b.scid = carve<int>(p, N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
         b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
         b.recip_q = carve<int>(p, K); b.recip_m = carve<int>(p, K); b.match_q = carve<int>(p, K); b.match_m = carve<int>(p, K);
@@ -299,6 +298,7 @@ int allocate(mor_handle* h) {
     int P = 1;
     while (P < (int)K) P <<= 1;
     h->frame_smem = (size_t)P * sizeof(unsigned long long);
+    if (h->frame_smem < kLinkSmem) h->frame_smem = kLinkSmem;
     return MOR_OK;
 }
 
@@ -311,6 +311,7 @@ int configure_kernels(mor_handle* h) {
     MOR_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
     MOR_CUDA(cudaFuncSetAttribute(k_frame_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
     int st = set_phase_smem<PH_SELECT>(h);
+    if (st == MOR_OK) st = set_phase_smem<PH_LINK>(h);
     if (st != MOR_OK) return st;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->num_sms = sms;
@@ -366,8 +367,7 @@ int input_mode(const void* d_points, uint32_t step, uint32_t ox, uint32_t oy, ui
 // The link phases write their results into one segment per CTA of the group that runs the frame.
 void set_segments(mor_handle* h, FramePtrs& a, int group_ctas) {
     a.edge_seg = (int)(h->edge_cap / (size_t)group_ctas);
-    a.light_seg = a.edge_seg;
-    a.heavy_seg = (int)(h->heavy_cap / (size_t)group_ctas);
+    a.light_cap = (int)h->edge_cap; a.heavy_cap = (int)h->heavy_cap;
 }
 
 // Arguments of the current frame (everything the kernels read) from the handle's host-side state.
@@ -391,7 +391,7 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
 template <int PH>
 int launch_phase(mor_handle* h, const FramePtrs& a) {
     prof_begin(h, KID_PHASE0 + PH);
-    const size_t smem = PH == PH_SELECT ? h->frame_smem : 0;
+    const size_t smem = (PH == PH_SELECT || PH == PH_LINK) ? h->frame_smem : 0;
     cudaError_t e = launch_coop(k_phase<PH>, (unsigned)h->frame_ctas, smem, h->stream, a);
     prof_end(h);
     h->launches++;
@@ -421,7 +421,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     }
     if (h->profiling) {  // one launch per phase, each between a pair of events
         int s;
-        if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_SCATTER>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) || (s = launch_phase<PH_TEST>(h, a)) ||
+        if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) || (s = launch_phase<PH_TEST>(h, a)) ||
             (s = launch_phase<PH_JUMP>(h, a)) || (s = launch_phase<PH_CROSS>(h, a)) || (s = launch_phase<PH_ROOTS>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || (s = launch_phase<PH_MATCH>(h, a)) ||
             (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_CHAIN>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
             return s;

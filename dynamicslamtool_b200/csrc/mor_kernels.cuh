@@ -21,9 +21,10 @@ namespace mor {
 constexpr int kT = 1024;         // threads per CTA of the frame kernel: one CTA per SM, up to 64 registers per thread
 constexpr int kSingle = kT;      // single-CTA bookkeeping phases use the whole CTA
 constexpr int kWarps = kT / 32;
-constexpr int kBoxMinCount = 8;  // cells with more points than this carry a tight bounding box
 constexpr int kLightPair = 256;  // a cell pair with at most this many point pairs is tested by one thread, a larger one by a warp
-constexpr int kLightCnt = 128;   // ... and with at most this many points in either cell (7 bits in the packed record)
+constexpr int kLightCnt = 32;    // ... and with at most this many points in either cell (the thread's loop stays short; 7 bits in the packed record)
+constexpr int kStageLight = 3072, kStageHeavy = 512;  // pair records a CTA collects in shared memory before they go to the lists (24 + 8 KB)
+constexpr size_t kLinkSmem = (size_t)kStageLight * 8 + (size_t)kStageHeavy * 16;
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16, ERR_EDGE_CAP = 32 };
 // counts[] slots in which the filter phase parks its results until filterCloud commits the frame (mor_b200.cu, do_filter)
@@ -45,7 +46,8 @@ struct GridDesc {  // dense grid of the voxel ground modes' ball query (mor_grou
 struct Scratch {  // all zero between frames: every counter is put back by the frame that used it
     unsigned bar;            // group barrier of k_frame (monotonic within a launch)
     int blocks_done;         // CTAs that have finished the frame
-    int n_cells, n_roots, pad2, pad3;
+    int n_cells, n_roots, n_light, n_heavy;  // list lengths of the frame
+    int n_sorted, pad1;      // bump allocator of the sorted array (phase B)
     int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
     int err_early;           // error bits raised before the frame's counts exist
     int pad0;
@@ -77,25 +79,23 @@ struct FramePtrs {
     // ---- clustering grid (sparse)
     Cell* table; unsigned table_mask;
     int* cell_list;            // [n_cells] table slot of every occupied cell, in creation order
-    unsigned long long* ckey; int* cstart;  // [n_cells(+1)] compact copies: key, first sorted position
+    unsigned long long* ckey; int* cstart; int* ccnt;  // [n_cells] compact copies: key, first sorted position, points
     int2* pslot;               // [N_c] (table slot, rank inside the cell) of every cloud point
     int* slead;                // [N_c] leader position (cell start = the cell's node) of every sorted position
-    // link lists, one segment per CTA of the group (no shared counters): cell pairs to test (light: one thread, heavy: one
-    // warp) and the connected pairs found (node A, node B)
-    int2* light; int light_seg; int* light_cnt;
-    int4* heavy; int heavy_seg; int* heavy_cnt;
+    // link lists: cell pairs to test (light: one thread, heavy: one warp; compact lists, a CTA adds its records in one
+    // block) and the connected pairs found (node A, node B; one segment per CTA of the group, no shared counter)
+    int2* light; int light_cap;
+    int4* heavy; int heavy_cap;
     int2* edges; int edge_seg; int* edge_cnt;
-    int* cmin;                 // [n_cells] minimum cloud index of the cell's points
     int* hook;                 // [N_c, at leader positions] union-find over the nodes: parent word (pointers lead to smaller positions)
     int* rsize; int* rmin;     // [N_c, at root positions] per root: points and minimum cloud index (= canonical label) of its component
     int* root_list;            // [n_roots] the roots, in no particular order
     // ---- per-frame scratch
-    Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_cscan; unsigned long long* st_out;
+    Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_out;
     uint8_t* point_class; uint8_t* removed_mask;
     int* cloud_src; float4* gpts; int* gsrc;
     int* label; int* cid_of_root;
     int* scid;                 // cluster id per sorted position
-    uint4* cell_box;           // [2*N] per leader position: {min x,y,z keys, -}, {max x,y,z keys, -}
     unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
     unsigned* acc_box;            // [kmax*6] min xyz, max xyz keys
     unsigned* pacc_box;           // [kmax*6] transformed prev clusters
@@ -133,8 +133,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 #ifdef MOR_CTA_TRACE  // debug builds: when did this CTA get here? (rows 16.. of the trace are sub-steps of phases; tools/cta_trace.py)
 #define MOR_TRACE(row) do { __syncthreads(); if (threadIdx.x == 0 && cta < 256) a.cta_trace[(row) * 256 + cta] = global_ns(); } while (0)
+#define MOR_TRACE_NOSYNC(row) do { if (threadIdx.x == 0 && cta < 256) a.cta_trace[(row) * 256 + cta] = global_ns(); } while (0)
 #else
 #define MOR_TRACE(row)
+#define MOR_TRACE_NOSYNC(row)
 #endif
 
 // ------------------------------------------------------------------------------------------------ group barrier
@@ -150,10 +152,9 @@ struct GroupBarrier {
         __syncthreads();
         if (G > 1 && threadIdx.x == 0) {
             target += G;
-            __threadfence();
-            atomicAdd(ctr, 1u);
+            // release: the CTA's writes (ordered before this by the barrier above) are visible to whoever acquires the count
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
             while (ld_acquire_u32(ctr) < target) {}
-            __threadfence();
         }
         __syncthreads();
     }
@@ -399,29 +400,44 @@ __device__ __forceinline__ void phase_bin_cloud(const FramePtrs& a, int cta, int
     }
 }
 
-// ===================================================================================== phase B: cell scan
-// Exclusive scan of the cell populations in cell-list order -> first sorted position of every cell (= the cell's
-// union-find node); its compact descriptors are set up on the way.
-__device__ __forceinline__ void cell_scan_tile(const FramePtrs& a, int tile, int n_cells, int ntiles) {
-    const int i = tile * kT + threadIdx.x;
-    int slot = 0, cnt = 0;
-    unsigned long long key = 0ull;
-    if (i < n_cells) {
-        slot = a.cell_list[i];
-        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(a.table + slot));
-        key = ((unsigned long long)raw.y << 32) | raw.x;
-        cnt = (int)raw.w;
+// Work over [0, n) that needs no CTA-wide cooperation is cut into one contiguous slice per CTA (warp granular): a phase
+// is short, so what counts is that all SMs take part, not that a CTA's threads are all busy.
+__device__ __forceinline__ void cta_slice(int n, int cta, int G, int* lo, int* hi) {
+    const int per = ((n + G - 1) / G + 31) & ~31;
+    *lo = min(n, cta * per);
+    *hi = min(n, *lo + per);
+}
+
+// ===================================================================================== phase B: cell ranges
+// Every cell gets its range of the sorted array (its first position = the cell's union-find node) and its compact
+// descriptors. The order of the cells in the sorted array is free, so the ranges are handed out by bump allocation -
+// 32 cells per warp and atomic - instead of a scan: no tile waits for another, and all CTAs take part.
+__device__ __forceinline__ void phase_cells(const FramePtrs& a, int cta, int G) {
+    const int lane = threadIdx.x & 31;
+    int lo, hi;
+    cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
+    for (int base = lo + (threadIdx.x & ~31); base < hi; base += kT) {  // (warp-uniform)
+        const int i = base + lane;
+        int slot = 0, cnt = 0;
+        unsigned long long key = 0ull;
+        if (i < hi) {
+            slot = a.cell_list[i];
+            const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(a.table + slot));
+            key = ((unsigned long long)raw.y << 32) | raw.x;
+            cnt = (int)raw.w;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+        int wbase = 0;
+        if (lane == 31) wbase = atomicAdd(&a.scratch->n_sorted, incl);
+        const int start = __shfl_sync(kFull, wbase, 31) + incl - cnt;
+        if (i < hi) {
+            a.table[slot].start = start;
+            a.ckey[i] = key; a.cstart[i] = start; a.ccnt[i] = cnt;
+            a.hook[start] = start; a.rsize[start] = 0; a.rmin[start] = 0x7FFFFFFF;
+        }
     }
-    int total;
-    const int in_block = block_exclusive_scan<int, kT>(cnt, &total);
-    const int before = (int)tile_prefix_wide<kT>(a.st_cscan, tile, (unsigned long long)total);
-    const int start = before + in_block;
-    if (i < n_cells) {
-        a.table[slot].start = start;
-        a.ckey[i] = key; a.cstart[i] = start;
-        a.hook[start] = start; a.rsize[start] = 0; a.rmin[start] = 0x7FFFFFFF;
-    }
-    if (tile == ntiles - 1 && threadIdx.x == 0) a.cstart[n_cells] = before + total;
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -505,14 +521,6 @@ __device__ __forceinline__ void block_cluster_accumulate(unsigned long long* acc
     }
 }
 
-// Work over [0, n) that needs no CTA-wide cooperation is cut into one contiguous slice per CTA (warp granular): a phase
-// is short, so what counts is that all SMs take part, not that a CTA's threads are all busy.
-__device__ __forceinline__ void cta_slice(int n, int cta, int G, int* lo, int* hi) {
-    const int per = ((n + G - 1) / G + 31) & ~31;
-    *lo = min(n, cta * per);
-    *hi = min(n, *lo + per);
-}
-
 // pcl_ros::transformPointCloud of every previous-frame cluster (cpp:544-551, A12), the bounding box of the transformed
 // points (getMinMax3D runs after the transform, cpp:272) and, for method 2, their octree leaves (cpp:319-324). Depends
 // on the previous frame only: it runs beside the single-CTA cluster selection, on the CTAs that one does not need.
@@ -547,11 +555,6 @@ __device__ __forceinline__ void phase_transform(const FramePtrs& a, int cta, int
     transform_range(a, lo, hi);
 }
 
-__device__ __forceinline__ void phase_cells(const FramePtrs& a, int cta, int G) {
-    const int n_cells = __ldcg(&a.scratch->n_cells);
-    const int ctiles = n_cells ? (n_cells + kT - 1) / kT : 1;
-    for (int vb = cta; vb < ctiles; vb += G) cell_scan_tile(a, vb, n_cells, ctiles);
-}
 
 // ===================================================================================== phase C: scatter
 // Cloud points into cell order (float4 xyz + cloud index): slot = cell start + the rank taken at binning time.
@@ -565,6 +568,7 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
         p.w = __int_as_float(c);
         a.spts[start + sr.y] = p;
         a.slead[start + sr.y] = start;
+        atomicMin(&a.rmin[start], c);  // the cell's minimum cloud index: its component's canonical label is the minimum over its cells
     }
 }
 
@@ -590,10 +594,18 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
 #define MOR_CHECK(cond, tag, v)
 #endif
 struct BoxF { float lx, ly, lz, hx, hy, hz; };
-__device__ __forceinline__ BoxF load_box(const FramePtrs& a, int start) {
-    const uint4 lo = __ldcg(a.cell_box + 2 * start), hi = __ldcg(a.cell_box + 2 * start + 1);
+// Tight bounding box of the n points from sorted position `start`, by the whole warp (only the few heavy pairs whose
+// probe found nothing need boxes, so they are made on demand).
+__device__ __forceinline__ BoxF warp_box(const FramePtrs& a, int start, int n, int lane) {
+    unsigned mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0u, mxy = 0u, mxz = 0u;
+    for (int k = lane; k < n; k += 32) {
+        const float4 p = a.spts[start + k];
+        const unsigned kx = fkey(p.x), ky = fkey(p.y), kz = fkey(p.z);
+        mnx = min(mnx, kx); mny = min(mny, ky); mnz = min(mnz, kz); mxx = max(mxx, kx); mxy = max(mxy, ky); mxz = max(mxz, kz);
+    }
     BoxF b;
-    b.lx = fkey_inv(lo.x); b.ly = fkey_inv(lo.y); b.lz = fkey_inv(lo.z); b.hx = fkey_inv(hi.x); b.hy = fkey_inv(hi.y); b.hz = fkey_inv(hi.z);
+    b.lx = fkey_inv(__reduce_min_sync(kFull, mnx)); b.ly = fkey_inv(__reduce_min_sync(kFull, mny)); b.lz = fkey_inv(__reduce_min_sync(kFull, mnz));
+    b.hx = fkey_inv(__reduce_max_sync(kFull, mxx)); b.hy = fkey_inv(__reduce_max_sync(kFull, mxy)); b.hz = fkey_inv(__reduce_max_sync(kFull, mxz));
     return b;
 }
 // conservative squared distance from a point to a box: no point of the box can be closer
@@ -611,10 +623,7 @@ __device__ __forceinline__ float box_box_d2(const BoxF& p, const BoxF& q) {
 // (1) Probe: 32 samples of B (one per lane) against up to 32 samples of A, spread over the cells, a vote after every
 // sample of A. In LiDAR data a crowded cell is connected to every crowded cell around it, and the first or second
 // sample shows it (C2: 6400 of 6470 connected heavy pairs per frame).
-__device__ __forceinline__ bool heavy_probe(const FramePtrs& a, int sA, int cntA, int sB, int cB, int lane) {
-    const float r2 = a.r2;
-    const float4 qb = a.spts[sB + (int)(((long long)lane * cB) >> 5)];
-    const float4 qa = a.spts[sA + (int)(((long long)lane * cntA) >> 5)];
+__device__ __forceinline__ bool heavy_probe(const float4& qa, const float4& qb, float r2) {  // the lane's sample of A and of B
     for (int t = 0; t < 32; t++) {
         const int u = (int)(__brev((unsigned)t) >> 27);  // 0, 16, 8, 24, ...: far apart first
         const float ax = __shfl_sync(kFull, qa.x, u), ay = __shfl_sync(kFull, qa.y, u), az = __shfl_sync(kFull, qa.z, u);
@@ -622,14 +631,12 @@ __device__ __forceinline__ bool heavy_probe(const FramePtrs& a, int sA, int cntA
     }
     return false;
 }
-// (2) The cells' bounding boxes (complete since the enumerate phase): most unconnected pairs end here.
-struct HeavyBoxes { BoxF A, B; bool hasA, hasB; };
-__device__ __forceinline__ bool heavy_boxes_apart(const FramePtrs& a, int sA, int cntA, int sB, int cB, HeavyBoxes* hb) {
-    hb->hasA = cntA > kBoxMinCount; hb->hasB = cB > kBoxMinCount;
-    hb->A = BoxF{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; hb->B = hb->A;
-    if (hb->hasA) hb->A = load_box(a, sA);
-    if (hb->hasB) hb->B = load_box(a, sB);
-    return hb->hasA && hb->hasB && box_box_d2(hb->A, hb->B) > a.r2 * 1.00001f;
+// (2) The cells' bounding boxes: most unconnected pairs end here.
+struct HeavyBoxes { BoxF A, B; };
+__device__ __forceinline__ bool heavy_boxes_apart(const FramePtrs& a, int sA, int cntA, int sB, int cB, HeavyBoxes* hb, int lane) {
+    hb->A = warp_box(a, sA, cntA, lane);
+    hb->B = warp_box(a, sB, cB, lane);
+    return box_box_d2(hb->A, hb->B) > a.r2 * 1.00001f;
 }
 // (3) Full scan of one chunk of 32 points of B (from b0) against all of A, both pruned by the other cell's box: A in
 // blocks of 32 per coalesced load, four blocks in flight, every candidate point broadcast by shuffle to all lanes.
@@ -639,19 +646,21 @@ __device__ __forceinline__ bool heavy_scan_chunk(const FramePtrs& a, const Heavy
     const int b = b0 + lane;
     bool valid = b < cB;
     float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        pb = a.spts[sB + b];
-        if (hb.hasA) valid = box_point_d2(hb.A, pb.x, pb.y, pb.z) <= r2_prune;
-    }
+    if (valid) pb = a.spts[sB + b];
+    float4 pa[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) pa[q] = A[min(32 * q + lane, cntA - 1)];  // (in flight together with B's points)
+    if (valid) valid = box_point_d2(hb.A, pb.x, pb.y, pb.z) <= r2_prune;
     if (!__any_sync(kFull, valid)) return false;
     for (int a0 = 0; a0 < cntA; a0 += 128) {
-        float4 pa[4];
+        if (a0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) pa[q] = A[min(a0 + 32 * q + lane, cntA - 1)];
+            for (int q = 0; q < 4; q++) pa[q] = A[min(a0 + 32 * q + lane, cntA - 1)];
+        }
         bool h = false;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const bool av = a0 + 32 * q + lane < cntA && (!hb.hasB || box_point_d2(hb.B, pa[q].x, pa[q].y, pa[q].z) <= r2_prune);
+            const bool av = a0 + 32 * q + lane < cntA && box_point_d2(hb.B, pa[q].x, pa[q].y, pa[q].z) <= r2_prune;
             for (unsigned m = __ballot_sync(kFull, av); m; m &= m - 1) {
                 const int u = __ffs(m) - 1;
                 const float ax = __shfl_sync(kFull, pa[q].x, u), ay = __shfl_sync(kFull, pa[q].y, u), az = __shfl_sync(kFull, pa[q].z, u);
@@ -686,25 +695,34 @@ __device__ __forceinline__ void grid_lookup2(const FramePtrs& a, bool v0, unsign
     }
 }
 
-// The lanes with f0 / f1 append one record each to the CTA's segment (counter in shared memory).
+struct LinkShared { int n_light, n_heavy, g_light, g_heavy; };
+
+// The lanes with f0 / f1 add one record each: to the CTA's staging area in shared memory, or - once that is full -
+// straight to the list.
 template <typename T>
-__device__ __forceinline__ void warp_append2(const FramePtrs& a, T* seg, int seg_cap, int* counter, bool f0, bool f1, const T& v0, const T& v1, int lane) {
+__device__ __forceinline__ void stage_append2(const FramePtrs& a, T* stage, int stage_cap, int* s_count, T* list, int list_cap, int* g_count,
+                                              bool f0, bool f1, const T& v0, const T& v1, int lane) {
     const unsigned m0 = __ballot_sync(kFull, f0), m1 = __ballot_sync(kFull, f1);
     if (!(m0 | m1)) return;
     int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(m0) + __popc(m1));
+    if (lane == 0) base = atomicAdd(s_count, __popc(m0) + __popc(m1));
     base = __shfl_sync(kFull, base, 0);
     const int w0 = base + __popc(m0 & ((1u << lane) - 1u)), w1 = base + __popc(m0) + __popc(m1 & ((1u << lane) - 1u));
-    if (f0) { if (w0 < seg_cap) seg[w0] = v0; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
-    if (f1) { if (w1 < seg_cap) seg[w1] = v1; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const bool f = q ? f1 : f0;
+        const int w = q ? w1 : w0;
+        if (!f) continue;
+        if (w < stage_cap) { stage[w] = q ? v1 : v0; continue; }
+        const int g = atomicAdd(g_count, 1);
+        if (g < list_cap) list[g] = q ? v1 : v0; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
+    }
 }
 
-struct LinkShared { int n_light, n_heavy; };
-
 // light record: (start | (count - 1) << 25) of both cells; heavy record: (start A, count A, start B, count B)
-__device__ __forceinline__ void enumerate_cell(const FramePtrs& a, int i, LinkShared& ls, int2* lseg, int4* hseg, int lane) {
+__device__ __forceinline__ void enumerate_cell(const FramePtrs& a, int i, LinkShared& ls, int2* s_light, int4* s_heavy, int lane) {
     const unsigned long long key = a.ckey[i];
-    const int startA = a.cstart[i], cntA = a.cstart[i + 1] - startA;
+    const int startA = a.cstart[i], cntA = a.ccnt[i];
     MOR_CHECK(startA >= 0 && cntA > 0 && startA + cntA <= a.counts[MOR_CNT_NC], "cellA", cntA);
     int cx, cy, cz;
     cell_unpack(key, cx, cy, cz);
@@ -718,25 +736,6 @@ __device__ __forceinline__ void enumerate_cell(const FramePtrs& a, int i, LinkSh
         MOR_CHECK(nb[0].y >= 0 && nb[0].x >= 0 && nb[0].x + nb[0].y <= a.counts[MOR_CNT_NC], "nb0", nb[0].y);
         MOR_CHECK(nb[1].y >= 0 && nb[1].x >= 0 && nb[1].x + nb[1].y <= a.counts[MOR_CNT_NC], "nb1", nb[1].y);
     }
-    {   // the cell's minimum cloud index (its component's canonical label is the minimum over its cells) and, for a
-        // crowded cell, its tight bounding box (prunes the point tests of the heavy pairs)
-        const float4* A = a.spts + startA;
-        int mn = 0x7FFFFFFF;
-        unsigned mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0u, mxy = 0u, mxz = 0u;
-        for (int k = lane; k < cntA; k += 32) {
-            const float4 pa = A[k];
-            mn = min(mn, __float_as_int(pa.w));
-            const unsigned kx = fkey(pa.x), ky = fkey(pa.y), kz = fkey(pa.z);
-            mnx = min(mnx, kx); mny = min(mny, ky); mnz = min(mnz, kz); mxx = max(mxx, kx); mxy = max(mxy, ky); mxz = max(mxz, kz);
-        }
-        mn = __reduce_min_sync(kFull, mn);
-        if (cntA > kBoxMinCount) {
-            mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny); mnz = __reduce_min_sync(kFull, mnz);
-            mxx = __reduce_max_sync(kFull, mxx); mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
-            if (lane == 0) { a.cell_box[2 * startA] = make_uint4(mnx, mny, mnz, 0u); a.cell_box[2 * startA + 1] = make_uint4(mxx, mxy, mxz, 0u); }
-        }
-        if (lane == 0) a.cmin[i] = mn;
-    }
     bool light[2], heavy[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
@@ -745,52 +744,38 @@ __device__ __forceinline__ void enumerate_cell(const FramePtrs& a, int i, LinkSh
         heavy[q] = occ && !light[q];
     }
     const int wa = startA | ((cntA - 1) << 25);
-    warp_append2<int2>(a, lseg, a.light_seg, &ls.n_light, light[0], light[1], make_int2(wa, nb[0].x | ((nb[0].y - 1) << 25)), make_int2(wa, nb[1].x | ((nb[1].y - 1) << 25)), lane);
-    warp_append2<int4>(a, hseg, a.heavy_seg, &ls.n_heavy, heavy[0], heavy[1], make_int4(startA, cntA, nb[0].x, nb[0].y), make_int4(startA, cntA, nb[1].x, nb[1].y), lane);
+    stage_append2<int2>(a, s_light, kStageLight, &ls.n_light, a.light, a.light_cap, &a.scratch->n_light, light[0], light[1],
+                        make_int2(wa, nb[0].x | ((nb[0].y - 1) << 25)), make_int2(wa, nb[1].x | ((nb[1].y - 1) << 25)), lane);
+    stage_append2<int4>(a, s_heavy, kStageHeavy, &ls.n_heavy, a.heavy, a.heavy_cap, &a.scratch->n_heavy, heavy[0], heavy[1],
+                        make_int4(startA, cntA, nb[0].x, nb[0].y), make_int4(startA, cntA, nb[1].x, nb[1].y), lane);
 }
 
-__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G) {
+__device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, unsigned long long* dyn) {
     __shared__ LinkShared ls;
+    int2* s_light = reinterpret_cast<int2*>(dyn);
+    int4* s_heavy = reinterpret_cast<int4*>(dyn + kStageLight);
     const int n_cells = __ldcg(&a.scratch->n_cells);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int2* lseg = a.light + (size_t)cta * a.light_seg;
-    int4* hseg = a.heavy + (size_t)cta * a.heavy_seg;
-    if (threadIdx.x == 0) { ls.n_light = 0; ls.n_heavy = 0; }
+    if (threadIdx.x == 0) { ls.n_light = 0; ls.n_heavy = 0; a.edge_cnt[cta] = 0; }
     __syncthreads();
-    // an equal share of the cells for every CTA, a warp per cell
-    const int lo = (int)(((long long)n_cells * cta) / G), hi = (int)(((long long)n_cells * (cta + 1)) / G);
-    for (int i = lo + warp; i < hi; i += kWarps) enumerate_cell(a, i, ls, lseg, hseg, lane);
+    phase_scatter(a, cta, G);  // independent of the enumeration: both need the cell ranges only
+    // an equal share of the cells for every CTA, a warp per cell (from the last warp down: the first warps hold the scatter)
+    const int per = (n_cells + G - 1) / G, lo = min(n_cells, cta * per), hi = min(n_cells, lo + per);
+    for (int i = lo + (kWarps - 1 - warp); i < hi; i += kWarps) enumerate_cell(a, i, ls, s_light, s_heavy, lane);
     __syncthreads();
-    if (threadIdx.x == 0) { a.light_cnt[cta] = min(ls.n_light, a.light_seg); a.heavy_cnt[cta] = min(ls.n_heavy, a.heavy_seg); a.edge_cnt[cta] = 0; }
-}
-
-// Running totals of the per-CTA list lengths (G <= 256) into pre[0..G], by one warp.
-__device__ __forceinline__ void warp_prefix_counts(const int* cnt, int G, int* pre, int lane) {
-    const int per = (G + 31) / 32;  // <= 8
-    int v[8], sum = 0;
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int c = lane * per + q;
-        v[q] = (q < per && c < G) ? __ldcg(cnt + c) : 0;
-        sum += v[q];
+    // the CTA's records go to the lists in one block each: one atomic per CTA and list
+    const int nl = min(ls.n_light, kStageLight), nh = min(ls.n_heavy, kStageHeavy);
+    if (threadIdx.x == 0 && nl) ls.g_light = atomicAdd(&a.scratch->n_light, nl);
+    if (threadIdx.x == 32 && nh) ls.g_heavy = atomicAdd(&a.scratch->n_heavy, nh);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nl; t += kT) {
+        const int g = ls.g_light + t;
+        if (g < a.light_cap) a.light[g] = s_light[t]; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
     }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-    int run = incl - sum;
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int c = lane * per + q;
-        if (q < per && c < G) pre[c] = run;
-        run += v[q];
+    for (int t = threadIdx.x; t < nh; t += kT) {
+        const int g = ls.g_heavy + t;
+        if (g < a.heavy_cap) a.heavy[g] = s_heavy[t]; else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
     }
-    if (lane == 31) pre[G] = incl;
-}
-// largest s in [0, G) with pre[s] <= w (w < pre[G])
-__device__ __forceinline__ int segment_of(const int* pre, int G, int w) {
-    int lo = 0, hi = G;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= w) lo = mid; else hi = mid; }
-    return lo;
 }
 
 template <int BLK>
@@ -799,11 +784,21 @@ __device__ __forceinline__ bool light_pair_connected(const float4* S, int cS, co
         float sx[BLK], sy[BLK], sz[BLK];
 #pragma unroll
         for (int q = 0; q < BLK; q++) { const float4 p = S[min(k0 + q, cS - 1)]; sx[q] = p.x; sy[q] = p.y; sz[q] = p.z; }  // (the last block may repeat a point)
-        for (int j = 0; j < cL; j++) {
-            const float4 pl = L[j];
+        // the block's bounding box: a point of L farther than r from it needs no test against the block (two thirds of the
+        // tests belong to unconnected pairs, whose points mostly lie well apart)
+        BoxF bx = {sx[0], sy[0], sz[0], sx[0], sy[0], sz[0]};
+#pragma unroll
+        for (int q = 1; q < BLK; q++) {
+            bx.lx = fminf(bx.lx, sx[q]); bx.ly = fminf(bx.ly, sy[q]); bx.lz = fminf(bx.lz, sz[q]);
+            bx.hx = fmaxf(bx.hx, sx[q]); bx.hy = fmaxf(bx.hy, sy[q]); bx.hz = fmaxf(bx.hz, sz[q]);
+        }
+        const float r2_prune = r2 * 1.00001f;
+        for (int j = 0; j < cL; j += 2) {  // two independent loads in flight (the last may repeat a point)
+            const float4 p0 = L[j], p1 = L[min(j + 1, cL - 1)];
+            if (fminf(box_point_d2(bx, p0.x, p0.y, p0.z), box_point_d2(bx, p1.x, p1.y, p1.z)) > r2_prune) continue;
             bool h = false;
 #pragma unroll
-            for (int q = 0; q < BLK; q++) h |= sqdist3(sx[q], sy[q], sz[q], pl.x, pl.y, pl.z) < r2;
+            for (int q = 0; q < BLK; q++) h |= (sqdist3(sx[q], sy[q], sz[q], p0.x, p0.y, p0.z) < r2) | (sqdist3(sx[q], sy[q], sz[q], p1.x, p1.y, p1.z) < r2);
             if (h) return true;
         }
     }
@@ -812,26 +807,31 @@ __device__ __forceinline__ bool light_pair_connected(const float4* S, int cS, co
 
 __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
     constexpr int kHardCap = 96;
-    __shared__ int s_lpre[257], s_hpre[257], s_edges, s_nhard, s_hard_hit[kHardCap];
+    __shared__ int s_edges, s_nhard, s_hard_hit[kHardCap];
     __shared__ int4 s_hard[kHardCap];
+    __shared__ HeavyBoxes s_hard_box[kHardCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp == 0) warp_prefix_counts(a.light_cnt, G, s_lpre, lane);
-    if (warp == 1) warp_prefix_counts(a.heavy_cnt, G, s_hpre, lane);
-    if (threadIdx.x == 64) { s_edges = 0; s_nhard = 0; }
+    if (threadIdx.x == 0) { s_edges = 0; s_nhard = 0; }
     __syncthreads();
     const float r2 = a.r2;
+    const int TL = min(__ldcg(&a.scratch->n_light), a.light_cap), TH = min(__ldcg(&a.scratch->n_heavy), a.heavy_cap);
     int2* eseg = a.edges + (size_t)cta * a.edge_seg;
     MOR_TRACE(16);
+    const int lper = (TL + G - 1) / G, llo = min(TL, cta * lper), lhi = min(TL, llo + lper);
+    const int hper = (TH + G - 1) / G, hlo = min(TH, cta * hper), hhi = min(TH, hlo + hper);
+    // The light pairs are packed into the first warps (a warp issues the same instructions whether 12 or 32 of its
+    // lanes hold a pair: spreading the pairs over all warps was 2x slower); the heavy pairs go to the other warps -
+    // from the last warp down - and both run side by side.
+    const int light_warps = min(kWarps, (lhi - llo + 31) >> 5);
+    const int heavy_warps = max(kWarps - light_warps, 8);
     // ---- light pairs: one thread each
-    int lo, hi;
-    cta_slice(s_lpre[G], cta, G, &lo, &hi);
-    for (int base = lo; base < hi; base += kT) {
+    for (int base = llo; base < lhi; base += kT) {
         const int w = base + threadIdx.x;
+        if (base + warp * 32 >= lhi) break;  // (warp-uniform)
         bool hit = false;
         int sA = 0, sB = 0;
-        if (w < hi) {
-            const int seg = segment_of(s_lpre, G, w);
-            const int2 lp = __ldcg(a.light + (size_t)seg * a.light_seg + (w - s_lpre[seg]));
+        if (w < lhi) {
+            const int2 lp = __ldcg(a.light + w);
             sA = lp.x & 0x1FFFFFF; sB = lp.y & 0x1FFFFFF;
             const int cA = (int)((unsigned)lp.x >> 25) + 1, cB = (int)((unsigned)lp.y >> 25) + 1;
             MOR_CHECK(sA + cA <= a.counts[MOR_CNT_NC] && sB + cB <= a.counts[MOR_CNT_NC], "light pair", sB);
@@ -843,6 +843,9 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
             const float4* S = a.spts + (a_small ? sA : sB);
             const float4* L = a.spts + (a_small ? sB : sA);
             const int cS = a_small ? cA : cB, cL = a_small ? cB : cA;
+            // all lines of the larger cell are requested now: the loop then finds them in L1 instead of paying an L2 round
+            // trip every eight points
+            for (int off = 128; off < cL * 16; off += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(L) + off));
             if (cS <= 4) hit = light_pair_connected<4>(S, cS, L, cL, r2);
             else hit = light_pair_connected<8>(S, cS, L, cL, r2);
         }
@@ -855,33 +858,43 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
             if (hit) { if (slot < a.edge_seg) eseg[slot] = make_int2(sA, sB); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
         }
     }
-    MOR_TRACE(17);
-    // ---- heavy pairs: one warp each; the CTA's share is dealt out from the last warp down (the first warps hold the
-    // light pairs). The few pairs that need the full scan are put aside and then taken on by the whole CTA, one chunk
-    // of B per warp: a single warp would keep the group waiting for tens of microseconds on a pair of crowded cells.
-    int hlo, hhi;
-    {
-        const int th = s_hpre[G];
-        hlo = (int)(((long long)th * cta) / G); hhi = (int)(((long long)th * (cta + 1)) / G);
-    }
-    for (int w = hlo + (kWarps - 1 - warp); w < hhi; w += kWarps) {
-        const int seg = segment_of(s_hpre, G, w);
-        const int4 hp = __ldcg(a.heavy + (size_t)seg * a.heavy_seg + (w - s_hpre[seg]));
-        MOR_CHECK(hp.x + hp.y <= a.counts[MOR_CNT_NC] && hp.z + hp.w <= a.counts[MOR_CNT_NC], "heavy pair", hp.z);
-        bool hit = heavy_probe(a, hp.x, hp.y, hp.z, hp.w, lane);
-        if (!hit) {
-            HeavyBoxes hb;
-            if (heavy_boxes_apart(a, hp.x, hp.y, hp.z, hp.w, &hb)) continue;
-            int slot = kHardCap;
-            if (lane == 0) slot = atomicAdd(&s_nhard, 1);
-            slot = __shfl_sync(kFull, slot, 0);
-            if (slot < kHardCap) { if (lane == 0) { s_hard[slot] = hp; s_hard_hit[slot] = 0; } continue; }
-            for (int b0 = 0; b0 < hp.w && !hit; b0 += 32) hit = heavy_scan_chunk(a, hb, hp.x, hp.y, hp.z, hp.w, b0, lane);  // (list full)
-        }
-        if (hit && lane == 0) {
-            const int slot = atomicAdd(&s_edges, 1);
-            if (slot < a.edge_seg) eseg[slot] = make_int2(hp.x, hp.z); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
-            atomicMin(&a.hook[max(hp.x, hp.z)], min(hp.x, hp.z));
+    MOR_TRACE_NOSYNC(17);
+    // ---- heavy pairs: one warp each, two pairs of a warp in flight together (their loads are the cost). The few pairs
+    // that need the full scan are put aside and then taken on by the whole CTA, one chunk of B per warp: a single warp
+    // would keep the group waiting for tens of microseconds on a pair of crowded cells.
+    const int hwarp = kWarps - 1 - warp;
+    if (hwarp < heavy_warps) {
+        for (int w = hlo + hwarp; w < hhi; w += 2 * heavy_warps) {
+            const bool two = w + heavy_warps < hhi;
+            int4 hp[2];
+            hp[0] = __ldcg(a.heavy + w);
+            hp[1] = two ? __ldcg(a.heavy + w + heavy_warps) : hp[0];
+            float4 qa[2], qb[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                MOR_CHECK(hp[q].x + hp[q].y <= a.counts[MOR_CNT_NC] && hp[q].z + hp[q].w <= a.counts[MOR_CNT_NC], "heavy pair", hp[q].z);
+                qa[q] = a.spts[hp[q].x + (int)(((long long)lane * hp[q].y) >> 5)];
+                qb[q] = a.spts[hp[q].z + (int)(((long long)lane * hp[q].w) >> 5)];
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (q && !two) break;
+                bool hit = heavy_probe(qa[q], qb[q], r2);
+                if (!hit) {
+                    HeavyBoxes hb;
+                    if (heavy_boxes_apart(a, hp[q].x, hp[q].y, hp[q].z, hp[q].w, &hb, lane)) continue;
+                    int slot = kHardCap;
+                    if (lane == 0) slot = atomicAdd(&s_nhard, 1);
+                    slot = __shfl_sync(kFull, slot, 0);
+                    if (slot < kHardCap) { if (lane == 0) { s_hard[slot] = hp[q]; s_hard_box[slot] = hb; s_hard_hit[slot] = 0; } continue; }
+                    for (int b0 = 0; b0 < hp[q].w && !hit; b0 += 32) hit = heavy_scan_chunk(a, hb, hp[q].x, hp[q].y, hp[q].z, hp[q].w, b0, lane);  // (list full)
+                }
+                if (hit && lane == 0) {
+                    const int slot = atomicAdd(&s_edges, 1);
+                    if (slot < a.edge_seg) eseg[slot] = make_int2(hp[q].x, hp[q].z); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
+                    atomicMin(&a.hook[max(hp[q].x, hp[q].z)], min(hp[q].x, hp[q].z));
+                }
+            }
         }
     }
     __syncthreads();
@@ -894,8 +907,7 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
             const int4 hp = s_hard[p];
             const int chunks = (hp.w + 31) >> 5;
             if (item < first + chunks) {
-                HeavyBoxes hb;
-                heavy_boxes_apart(a, hp.x, hp.y, hp.z, hp.w, &hb);
+                const HeavyBoxes hb = s_hard_box[p];
                 for (; item < first + chunks; item += kWarps) {
                     if (*(volatile int*)&s_hard_hit[p]) continue;
                     if (heavy_scan_chunk(a, hb, hp.x, hp.y, hp.z, hp.w, (item - first) * 32, lane) && lane == 0) s_hard_hit[p] = 1;
@@ -965,9 +977,9 @@ __device__ __forceinline__ void phase_roots(const FramePtrs& a, int cta, int G) 
         const bool act = i < hi;
         int r = -1 - lane, cnt = 0, mn = 0x7FFFFFFF;
         if (act) {
-            const int s0 = a.cstart[i], s1 = a.cstart[i + 1];
-            mn = __ldcg(&a.cmin[i]);
-            cnt = s1 - s0;
+            const int s0 = a.cstart[i];
+            mn = __ldcg(&a.rmin[s0]);  // (the cell's own minimum, or already a smaller one of its component)
+            cnt = a.ccnt[i];
             r = uf_find_ro(a.hook, s0);  // (no path halving here: nothing but the roots themselves may be stored in this phase)
             st_parent(a.hook + s0, r);   // flat for the per-point look-ups of the statistics phase
             if (r == s0) a.root_list[atomicAdd(&a.scratch->n_roots, 1)] = s0;
@@ -1369,7 +1381,7 @@ __device__ __forceinline__ void phase_chain_and_cleanup(const FramePtrs& a, int 
         const int w = cta - first;
         for (int i = w * kT + threadIdx.x; i < n_cells; i += workers * kT)
             *reinterpret_cast<uint4*>(a.table + a.cell_list[i]) = make_uint4(0u, 0u, 0u, 0u);
-        for (int t = w * kT + threadIdx.x; t < a.tiles_pts; t += workers * kT) { a.st_ingest[t] = 0ull; a.st_cscan[t] = 0ull; }
+        for (int t = w * kT + threadIdx.x; t < a.tiles_pts; t += workers * kT) a.st_ingest[t] = 0ull;
     }
     if (cta == 0) {
         if (a.two_frames) phase_chain(a);
@@ -1514,14 +1526,14 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
     if (threadIdx.x == 0) {
         Scratch* sc = a.scratch;
-        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->err_early = 0;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_light = 0; sc->n_heavy = 0; sc->n_sorted = 0; sc->err_early = 0;
         sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
         for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
     }
 }
 
 // ===================================================================================== the frame kernel
-enum Phase { PH_INGEST = 0, PH_CELLS, PH_SCATTER, PH_LINK, PH_TEST, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
+enum Phase { PH_INGEST = 0, PH_CELLS, PH_LINK, PH_TEST, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
 
 struct FrameShared {
     unsigned long long mbar;
@@ -1532,8 +1544,7 @@ template <int PH>
 __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
     if (PH == PH_INGEST) { if (a.skip_ingest) phase_bin_cloud(a, cta, G); else phase_ingest(a, cta, G); }
     if (PH == PH_CELLS) phase_cells(a, cta, G);
-    if (PH == PH_SCATTER) phase_scatter(a, cta, G);
-    if (PH == PH_LINK) phase_link(a, cta, G);
+    if (PH == PH_LINK) phase_link(a, cta, G, dyn);
     if (PH == PH_TEST) phase_test(a, cta, G);
     if (PH == PH_JUMP) phase_jump(a, cta, G);
     if (PH == PH_CROSS) phase_cross(a, cta, G);
@@ -1563,7 +1574,6 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
     if (cta == 0 && threadIdx.x == 0) a.phase_ts[0] = global_ns();
     frame_step<PH_INGEST>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_CELLS>(a, cta, G, sh, dyn, parity, bar);
-    frame_step<PH_SCATTER>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_LINK>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_TEST>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_JUMP>(a, cta, G, sh, dyn, parity, bar);

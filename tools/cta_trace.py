@@ -30,8 +30,8 @@ for f in range(max(want) + 1):
         rel = (arr - prev_end) / 1e3
         order = np.argsort(rel)
         print(f"  {name:20s} first {rel.min():6.1f}  p50 {np.median(rel):6.1f}  p90 {np.percentile(rel, 90):6.1f}  last {rel.max():6.1f} us   slowest CTAs {order[-3:][::-1].tolist()}")
-        if name == "ph_test":  # sub-steps (rows 16..18): list prefix done, light pairs done, heavy probes done
-            for row, what in ((16, "prefix"), (17, "light"), (18, "heavy probes")):
+        if name == "ph_test":  # sub-steps (rows 16..18)
+            for row, what in ((16, "start"), (17, "warp 0: light done"), (18, "light + heavy")):
                 r2 = (t[row] - prev_end) / 1e3
                 print(f"      .. {what:14s} p50 {np.median(r2):6.1f}  p90 {np.percentile(r2, 90):6.1f}  last {r2.max():6.1f}")
         prev_end = arr.max()

@@ -3,7 +3,7 @@ usage: ncu_lines.py report.ncu-rep <launch index> <library.so> [top N]
 (ncu's CLI prints per-instruction samples for SASS only; nvdisasm -g gives SASS offset -> source line.)"""
 import collections, csv, io, re, subprocess, sys, tempfile, os
 rep, kid, lib = sys.argv[1], sys.argv[2], sys.argv[3]
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+top = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{kid}"], capture_output=True, text=True).stdout
 lines = out.splitlines()
 kname = next(csv.reader([lines[0]]))[1]
@@ -39,12 +39,15 @@ for l in sec.splitlines():
     if m and cur:
         line_of[int(m.group(1), 16)] = cur
 agg = collections.Counter()
+inst = collections.Counter()
 stall = collections.defaultdict(collections.Counter)
 tot = 0
 for r in rows:
     if not (r["# Samples"] or "").isdigit() or not r["Address"].startswith("0x"):
         continue
     s = int(r["# Samples"])
+    if (r.get("Instructions Executed") or "").isdigit():
+        inst[line_of.get(int(r["Address"], 16) - base, ("?", 0))] += int(r["Instructions Executed"])
     if not s:
         continue
     off = int(r["Address"], 16) - base
@@ -67,3 +70,8 @@ print(kname, "samples", tot)
 for (f, n), s in agg.most_common(top):
     st = ", ".join(f"{k}:{v}" for k, v in stall[(f, n)].most_common(3))
     print(f"{100*s/tot:5.1f}%  {f}:{n:<5} {src(f, n):105s} [{st}]")
+if "--inst" in sys.argv:
+    ti = sum(inst.values()) or 1
+    print("warp instructions executed", ti)
+    for (f, n), c in inst.most_common(top):
+        print(f"{100*c/ti:5.1f}%  {c:9d}  {f}:{n:<5} {src(f, n):105s}")
