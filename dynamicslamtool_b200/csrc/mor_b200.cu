@@ -150,8 +150,8 @@ namespace {
 
 enum KernelId { KID_PHASE0 = 0, KID_FRAME = PH__COUNT, KID_FILTER_AGAIN,
                 KID_G_INGEST, KID_G_KEYS, KID_G_SCAN_CELLS, KID_G_SCAN_VOX, KID_G_SCATTER, KID_G_EVAL, KID_G_MODE, KID_G_MARK, KID_G_PARTITION, KID__COUNT };
-const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells", "ph_scatter+link", "ph_test", "ph_jump", "ph_cross", "ph_roots", "ph_select+transform", "ph_stats", "ph_match",
-                                              "ph_moving_test", "ph_chain+cleanup", "ph_filter", "k_frame", "k_filter_again",
+const char* const kKernelNames[KID__COUNT] = {"ph_ingest", "ph_cells", "ph_scatter+link", "ph_test", "ph_jump", "ph_cross", "ph_roots", "ph_select+transform", "ph_stats+match",
+                                              "ph_moving_test+chain", "ph_filter+cleanup", "k_frame", "k_filter_again",
                                               "k_ingest_raw", "k_ground_keys", "k_scan_cells", "k_scan_voxels", "k_ground_scatter",
                                               "k_voxel_eval", "k_ground_mode", "k_ground_mark", "k_ground_partition"};
 static_assert(KID__COUNT <= 40, "profile table too small");
@@ -255,7 +255,7 @@ int allocate(mor_handle* h) {
         b.hook = carve<int>(p, N); b.rsize = carve<int>(p, N); b.rmin = carve<int>(p, N); b.root_list = carve<int>(p, N);
         b.point_class = carve<uint8_t>(p, N); b.removed_mask = carve<uint8_t>(p, N);
         b.cloud_src = carve<int>(p, N); b.gpts = carve<float4>(p, N); b.gsrc = carve<int>(p, N);
-        b.label = carve<int>(p, N); b.cid_of_root = carve<int>(p, N);
+        b.label = carve<int>(p, N); b.cid_of_root = carve<int>(p, N); b.cid_of_pos = carve<int>(p, N);
         b.scid = carve<int>(p, N);
         b.acc_sum = carve<unsigned long long>(p, K * 6); b.acc_box = carve<unsigned>(p, K * 6); b.pacc_box = carve<unsigned>(p, K * 6);
         b.tpts = carve<float4>(p, N); b.pct = carve<float>(p, K * 3); b.pbbox = carve<float>(p, K * 6);
@@ -312,6 +312,7 @@ int configure_kernels(mor_handle* h) {
     MOR_CUDA(cudaFuncSetAttribute(k_frame_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
     int st = set_phase_smem<PH_SELECT>(h);
     if (st == MOR_OK) st = set_phase_smem<PH_LINK>(h);
+    if (st == MOR_OK) st = set_phase_smem<PH_STATS>(h);
     if (st != MOR_OK) return st;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->num_sms = sms;
@@ -339,6 +340,7 @@ void fill_static(mor_handle* h) {
     b.pde_ring = h->pde_ring;
     b.lattice_words16 = (unsigned)(h->lattice_cap / 2);
     b.tiles_pts = (int)(h->nmax / kBlock + 2);
+    b.frame_smem = (int)h->frame_smem;
     b.max_cells = h->max_cells;
     b.tiles_cells = (int)((size_t)h->max_cells / kScanTile + 2);
     if (c.ground_mode != MOR_GROUND_CROP) {
@@ -391,7 +393,7 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
 template <int PH>
 int launch_phase(mor_handle* h, const FramePtrs& a) {
     prof_begin(h, KID_PHASE0 + PH);
-    const size_t smem = (PH == PH_SELECT || PH == PH_LINK) ? h->frame_smem : 0;
+    const size_t smem = (PH == PH_SELECT || PH == PH_LINK || PH == PH_STATS) ? h->frame_smem : 0;
     cudaError_t e = launch_coop(k_phase<PH>, (unsigned)h->frame_ctas, smem, h->stream, a);
     prof_end(h);
     h->launches++;
@@ -422,8 +424,8 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
     if (h->profiling) {  // one launch per phase, each between a pair of events
         int s;
         if ((s = launch_phase<PH_INGEST>(h, a)) || (s = launch_phase<PH_CELLS>(h, a)) || (s = launch_phase<PH_LINK>(h, a)) || (s = launch_phase<PH_TEST>(h, a)) ||
-            (s = launch_phase<PH_JUMP>(h, a)) || (s = launch_phase<PH_CROSS>(h, a)) || (s = launch_phase<PH_ROOTS>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || (s = launch_phase<PH_MATCH>(h, a)) ||
-            (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_CHAIN>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
+            (s = launch_phase<PH_JUMP>(h, a)) || (s = launch_phase<PH_CROSS>(h, a)) || (s = launch_phase<PH_ROOTS>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || 
+            (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
             return s;
     } else {
         cudaError_t e = launch_coop(k_frame, (unsigned)h->frame_ctas, h->frame_smem, st, a);

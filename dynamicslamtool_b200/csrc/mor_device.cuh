@@ -119,6 +119,18 @@ __device__ __forceinline__ int uf_union(int* parent, int a, int b) {
     }
 }
 
+// The same union with both climbs in flight together: one round trip per level instead of two, and - the usual case
+// when the forest has just been flattened - one round trip to see that both nodes are roots, one for the hook.
+__device__ __forceinline__ void uf_union_pair(int* parent, int a, int b) {
+    while (true) {
+        const int pa = ld_parent(parent + a), pb = ld_parent(parent + b);
+        if (pa != a || pb != b) { a = pa; b = pb; continue; }
+        if (a == b) return;
+        const int hi = max(a, b), lo = min(a, b);
+        if (atomicCAS(&parent[hi], hi, lo) == hi) return;
+    }
+}
+
 // ----------------------------------------------------------------------------- look-back tile prefix
 // status word: bits 63..62 = 0 invalid / 1 aggregate / 2 inclusive prefix; low 62 bits = value.
 constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62, kStMask = (1ull << 62) - 1;

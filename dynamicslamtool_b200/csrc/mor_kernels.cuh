@@ -48,6 +48,7 @@ struct Scratch {  // all zero between frames: every counter is put back by the f
     int blocks_done;         // CTAs that have finished the frame
     int n_cells, n_roots, n_light, n_heavy;  // list lengths of the frame
     int n_sorted, pad1;      // bump allocator of the sorted array (phase B)
+    unsigned tail_match, tail_chain;  // arrival counters of the phases that end with a single-CTA step
     int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
     int err_early;           // error bits raised before the frame's counts exist
     int pad0;
@@ -94,7 +95,7 @@ struct FramePtrs {
     Scratch* scratch; unsigned long long* st_ingest; unsigned long long* st_out;
     uint8_t* point_class; uint8_t* removed_mask;
     int* cloud_src; float4* gpts; int* gsrc;
-    int* label; int* cid_of_root;
+    int* label; int* cid_of_root; int* cid_of_pos;  // cluster id by canonical label / by root position (-1: not a size-valid cluster)
     int* scid;                 // cluster id per sorted position
     unsigned long long* acc_sum;  // [kmax*6] hi/lo per axis
     unsigned* acc_box;            // [kmax*6] min xyz, max xyz keys
@@ -121,6 +122,7 @@ struct FramePtrs {
     int mo_parity;  // which half of the mo_vec double buffer is current
     int pde_ring;   // method 1: search reach in cells, ceil(sqrt(pde_ub)/h)
     int tiles_pts;  // size of the scan status arrays
+    int frame_smem; // bytes of dynamic shared memory of the frame kernel
     unsigned lattice_words16;    // lattice size in 16-byte units
     // ---- voxel ground modes only (mor_ground.cuh): dense ball-query grid
     int* cell_count; int* cell_start; int* cell_key; int* skey; GridDesc* dgrid; unsigned long long* st_cells; int tiles_cells; int max_cells;
@@ -159,6 +161,38 @@ struct GroupBarrier {
         __syncthreads();
     }
 };
+
+// The sizes every later phase starts from are final once the ingest phase is over: each CTA reads them once and keeps
+// them in shared memory (a phase that fetched them itself would begin with a round trip to L2).
+struct FrameVars { int n_cells, nc, ng; };
+__device__ __forceinline__ FrameVars& frame_vars() {
+    __shared__ FrameVars v;
+    return v;
+}
+template <typename P>
+__device__ __forceinline__ void load_frame_vars(const P& a) {
+    if (threadIdx.x == 0) {
+        FrameVars& v = frame_vars();
+        v.n_cells = __ldcg(&a.scratch->n_cells); v.nc = __ldcg(&a.counts[MOR_CNT_NC]); v.ng = __ldcg(&a.counts[MOR_CNT_NG]);
+    }
+    __syncthreads();
+}
+
+// "Last one in does the rest": all CTAs of a group call this when they have finished a phase that a short single-CTA
+// step follows; it returns true in the CTA that arrived last, which sees everything the others wrote and runs that
+// step right away. The others go on to the next barrier. Against a barrier of its own in front of the single-CTA step
+// this saves the barrier's latency and the start-up of a phase. `ctr` counts from zero in every frame.
+__device__ __forceinline__ bool group_last_arrival(unsigned* ctr, unsigned G) {
+    __shared__ int s_last_in;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned old = 0u;
+        if (G > 1) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+        s_last_in = old == G - 1u;
+    }
+    __syncthreads();
+    return s_last_in != 0;
+}
 
 // ------------------------------------------------------------------------------------------------ 1-D bulk copy (TMA)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -415,7 +449,7 @@ __device__ __forceinline__ void cta_slice(int n, int cta, int G, int* lo, int* h
 __device__ __forceinline__ void phase_cells(const FramePtrs& a, int cta, int G) {
     const int lane = threadIdx.x & 31;
     int lo, hi;
-    cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
+    cta_slice(frame_vars().n_cells, cta, G, &lo, &hi);
     for (int base = lo + (threadIdx.x & ~31); base < hi; base += kT) {  // (warp-uniform)
         const int i = base + lane;
         int slot = 0, cnt = 0;
@@ -560,7 +594,7 @@ __device__ __forceinline__ void phase_transform(const FramePtrs& a, int cta, int
 // Cloud points into cell order (float4 xyz + cloud index): slot = cell start + the rank taken at binning time.
 __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G) {
     int lo, hi;
-    cta_slice(a.counts[MOR_CNT_NC], cta, G, &lo, &hi);
+    cta_slice(frame_vars().nc, cta, G, &lo, &hi);
     for (int c = lo + threadIdx.x; c < hi; c += kT) {
         const int2 sr = a.pslot[c];
         const int start = __ldcg(&a.table[sr.x].start);
@@ -588,6 +622,13 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
 // samples first (a heavy pair is nearly always connected and nearly any sample shows it), bounding-box pruning and the
 // full scan only when the probe finds nothing. Connected pairs are RECORDED (edges, per-CTA segments) and the larger
 // node of a pair is pointed at the smaller one (atomicMin on its own word): the forest phase E starts from.
+// The frame kernel is 220-290 KB of code, more than an SM's instruction cache holds. Keeping the large once-per-frame
+// steps out of line (-DMOR_OUTLINE_BIG) was measured and is slower (8.6k vs 9.0k frames/s on C2): inlined by default.
+#ifdef MOR_OUTLINE_BIG
+#define MOR_OUTLINE __device__ __noinline__
+#else
+#define MOR_OUTLINE __device__ __forceinline__
+#endif
 #ifdef MOR_DEBUG_BOUNDS
 #define MOR_CHECK(cond, tag, v) do { if (!(cond)) { printf("BOUNDS %s: %d (line %d, cta %d thread %d)\n", tag, (int)(v), __LINE__, (int)blockIdx.x, (int)threadIdx.x); } } while (0)
 #else
@@ -596,7 +637,7 @@ __device__ __forceinline__ void phase_scatter(const FramePtrs& a, int cta, int G
 struct BoxF { float lx, ly, lz, hx, hy, hz; };
 // Tight bounding box of the n points from sorted position `start`, by the whole warp (only the few heavy pairs whose
 // probe found nothing need boxes, so they are made on demand).
-__device__ __forceinline__ BoxF warp_box(const FramePtrs& a, int start, int n, int lane) {
+MOR_OUTLINE BoxF warp_box(const FramePtrs& a, int start, int n, int lane) {
     unsigned mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0u, mxy = 0u, mxz = 0u;
     for (int k = lane; k < n; k += 32) {
         const float4 p = a.spts[start + k];
@@ -640,7 +681,7 @@ __device__ __forceinline__ bool heavy_boxes_apart(const FramePtrs& a, int sA, in
 }
 // (3) Full scan of one chunk of 32 points of B (from b0) against all of A, both pruned by the other cell's box: A in
 // blocks of 32 per coalesced load, four blocks in flight, every candidate point broadcast by shuffle to all lanes.
-__device__ __forceinline__ bool heavy_scan_chunk(const FramePtrs& a, const HeavyBoxes& hb, int sA, int cntA, int sB, int cB, int b0, int lane) {
+MOR_OUTLINE bool heavy_scan_chunk(const FramePtrs& a, const HeavyBoxes& hb, int sA, int cntA, int sB, int cB, int b0, int lane) {
     const float r2 = a.r2, r2_prune = a.r2 * 1.00001f;
     const float4* A = a.spts + sA;
     const int b = b0 + lane;
@@ -754,7 +795,7 @@ __device__ __forceinline__ void phase_link(const FramePtrs& a, int cta, int G, u
     __shared__ LinkShared ls;
     int2* s_light = reinterpret_cast<int2*>(dyn);
     int4* s_heavy = reinterpret_cast<int4*>(dyn + kStageLight);
-    const int n_cells = __ldcg(&a.scratch->n_cells);
+    const int n_cells = frame_vars().n_cells;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { ls.n_light = 0; ls.n_heavy = 0; a.edge_cnt[cta] = 0; }
     __syncthreads();
@@ -942,7 +983,7 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
 //  E4  one CTA selects and sorts the clusters (bitonic sort of (~size, min index) keys in shared memory).
 __device__ __forceinline__ void phase_jump(const FramePtrs& a, int cta, int G) {
     int lo, hi;
-    cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
+    cta_slice(frame_vars().n_cells, cta, G, &lo, &hi);
     for (int i = lo + threadIdx.x; i < hi; i += kT) {
         const int node = a.cstart[i];
         int p = ld_parent(a.hook + node);
@@ -964,13 +1005,13 @@ __device__ __forceinline__ void phase_cross(const FramePtrs& a, int cta, int G) 
         MOR_CHECK(uv.x >= 0 && uv.x < a.counts[MOR_CNT_NC] && uv.y >= 0 && uv.y < a.counts[MOR_CNT_NC], "cross uv", uv.y);
         const int lu = ld_parent(a.hook + uv.x), lv = ld_parent(a.hook + uv.y);
         MOR_CHECK(lu >= 0 && lu < a.counts[MOR_CNT_NC] && lv >= 0 && lv < a.counts[MOR_CNT_NC], "cross label", lu);
-        if (lu != lv) uf_union(a.hook, lu, lv);
+        if (lu != lv) uf_union_pair(a.hook, lu, lv);
     }
 }
 
 __device__ __forceinline__ void phase_roots(const FramePtrs& a, int cta, int G) {
     int lo, hi;
-    cta_slice(__ldcg(&a.scratch->n_cells), cta, G, &lo, &hi);
+    cta_slice(frame_vars().n_cells, cta, G, &lo, &hi);
     const int lane = threadIdx.x & 31;
     for (int base = lo; base < hi; base += kT) {
         const int i = base + threadIdx.x;
@@ -990,7 +1031,7 @@ __device__ __forceinline__ void phase_roots(const FramePtrs& a, int cta, int G) 
     }
 }
 
-__device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long long* keys) {
+MOR_OUTLINE void phase_select(const FramePtrs& a, unsigned long long* keys) {
     __shared__ int s_k;
     const int n_roots = __ldcg(&a.scratch->n_roots);
     if (threadIdx.x == 0) s_k = 0;
@@ -1041,6 +1082,12 @@ __device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long l
         for (int q = 0; q < 3; q++) { a.acc_box[k * 6 + q] = 0xFFFFFFFFu; a.acc_box[k * 6 + 3 + q] = 0u; }
     }
     atomicAdd(&a.counts[MOR_CNT_NK], nk);
+    __syncthreads();
+    // the same map by root position: the statistics phase then needs one dependent look-up less per point
+    for (int t = threadIdx.x; t < n_roots; t += kT) {
+        const int i = a.root_list[t];
+        a.cid_of_pos[i] = __ldcg(&a.cid_of_root[__ldcg(&a.rmin[i])]);
+    }
     if (threadIdx.x == 0) {
         a.counts[MOR_CNT_K] = K;
         const int e = __ldcg(&a.scratch->err_early);
@@ -1052,7 +1099,7 @@ __device__ __forceinline__ void phase_select(const FramePtrs& a, unsigned long l
 // Per-cluster statistics (cpp:221-244): cluster id of every point, exact coordinate sums for
 // compute3DCentroid<double> (A10) and getMinMax3D bounding boxes (cpp:272-275).
 __device__ __forceinline__ void phase_stats(const FramePtrs& a, int cta, int G) {
-    const int nc = a.counts[MOR_CNT_NC];
+    const int nc = frame_vars().nc;
     int lo, hi;
     cta_slice(nc, cta, G, &lo, &hi);
     for (int base = lo; base < hi; base += kT) {
@@ -1062,10 +1109,11 @@ __device__ __forceinline__ void phase_stats(const FramePtrs& a, int cta, int G) 
         if (s < hi) {
             p = a.spts[s];
             const int c = __float_as_int(p.w);
-            const int lab = a.rmin[a.hook[a.slead[s]]];  // hook is flat: the cell's root; consecutive points share all three words
+            const int root = a.hook[a.slead[s]];  // hook is flat: the cell's root; consecutive points share these words
+            const int lab = a.rmin[root];
             MOR_CHECK(lab >= 0 && lab < nc, "label", lab);
             a.label[c] = lab;
-            k = a.cid_of_root[lab];
+            k = a.cid_of_pos[root];
             a.cid[c] = k;
             a.scid[s] = k;
         }
@@ -1113,53 +1161,121 @@ __device__ __forceinline__ int nn_brute(const float* pts, int n, float qx, float
     return best;
 }
 
-__device__ __forceinline__ void phase_match(const FramePtrs& a) {
+// The working set (centroids, boxes, the reciprocal list) lives in shared memory when the frame has few enough clusters
+// for it (a few hundred: every LiDAR frame) - the step is a chain of small dependent passes, and each pass through
+// global memory would cost a round trip; every result is written to its global array as well.
+constexpr int kMatchBytesPerCluster = (3 + 6 + 3 + 6 + 3) * 4;
+// The same search by a whole warp (lanes across the candidates): equal distances go to the lowest index, like the
+// sequential scan; -1 if no candidate compares below FLT_MAX. The result is valid in every lane.
+__device__ __forceinline__ int nn_warp(const float* pts, int n, float qx, float qy, float qz, float* out_d, int lane) {
+    int best = -1;
+    float bd = 3.402823466e+38f;
+    for (int i = lane; i < n; i += 32) {
+        const float d = sqdist3(qx, qy, qz, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]);
+        if (d < bd) { bd = d; best = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(kFull, bd, o);
+        const int ob = __shfl_xor_sync(kFull, best, o);
+        if (ob >= 0 && (best < 0 || od < bd || (od == bd && ob < best))) { bd = od; best = ob; }
+    }
+    *out_d = bd;
+    return best;
+}
+
+MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
     const int K = a.counts[MOR_CNT_K];
-    for (int c = threadIdx.x; c < K; c += kSingle) {
+    const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
+    constexpr int kNnBytes = kSingle * 12;  // (ok, match, distance) of one chunk of queries
+    const int cap = (a.frame_smem - kNnBytes) / kMatchBytesPerCluster;
+    const bool fast = K <= cap && Kp <= cap;
+    const int cta = 0; (void)cta;
+    MOR_TRACE(19);
+    float* const sm = reinterpret_cast<float*>(dyn);
+    float* const cc = fast ? sm : a.cl_centroid;                 // [K][3]
+    float* const cb = fast ? sm + 3 * cap : a.cl_bbox;           // [K][6]
+    float* const pc = fast ? sm + 9 * cap : a.pct;               // [Kp][3]
+    float* const pb = fast ? sm + 12 * cap : a.pbbox;            // [Kp][6]
+    int* const rq = fast ? reinterpret_cast<int*>(sm + 18 * cap) : a.recip_q;
+    int* const rm = fast ? reinterpret_cast<int*>(sm + 19 * cap) : a.recip_m;
+    float* const rd = fast ? sm + 20 * cap : a.match_dist;
+    int* const nn_j = reinterpret_cast<int*>(sm + 21 * cap);  // [kSingle] each: the chunk's nearest neighbour, its distance, reciprocal?
+    float* const nn_d = sm + 21 * cap + kSingle;
+    int* const nn_ok = reinterpret_cast<int*>(sm + 21 * cap + 2 * kSingle);
+    // the current clusters are finalised by the first half of the CTA while the second half brings the previous ones over
+    // (two chains of dependent loads side by side)
+    const int half = kSingle / 2;
+    for (int c = threadIdx.x; c < K && threadIdx.x < half; c += half) {
         const double n = (double)a.cl_size[c];
 #pragma unroll
-        for (int q = 0; q < 3; q++)
-            a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
+        for (int q = 0; q < 3; q++) {
+            const float v = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
+            a.cl_centroid[c * 3 + q] = v;
+            if (fast) cc[c * 3 + q] = v;
+        }
 #pragma unroll
-        for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
+        for (int q = 0; q < 6; q++) {
+            const float v = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
+            a.cl_bbox[c * 6 + q] = v;
+            if (fast) cb[c * 6 + q] = v;
+        }
     }
     if (!a.two_frames) return;
-    const int Kp = a.p_counts[MOR_CNT_K];
     // previous centroids and boxes into the current frame
-    for (int i = threadIdx.x; i < Kp; i += kSingle) {
+    for (int i = (int)threadIdx.x - half; i >= 0 && i < Kp; i += half) {
         const float3 t = xform(a.M, a.p_cl_centroid[i * 3], a.p_cl_centroid[i * 3 + 1], a.p_cl_centroid[i * 3 + 2]);
         a.pct[i * 3] = t.x; a.pct[i * 3 + 1] = t.y; a.pct[i * 3 + 2] = t.z;
+        if (fast) { pc[i * 3] = t.x; pc[i * 3 + 1] = t.y; pc[i * 3 + 2] = t.z; }
 #pragma unroll
-        for (int q = 0; q < 6; q++) a.pbbox[i * 6 + q] = fkey_inv(__ldcg(&a.pacc_box[i * 6 + q]));
+        for (int q = 0; q < 6; q++) {
+            const float v = fkey_inv(__ldcg(&a.pacc_box[i * 6 + q]));
+            a.pbbox[i * 6 + q] = v;
+            if (fast) pb[i * 6 + q] = v;
+        }
         a.match_of_prev[i] = -1; a.mid_of_prev[i] = -1;
     }
     for (int j = threadIdx.x; j < K; j += kSingle) a.mid_of_cur[j] = -1;
     __syncthreads();
+    MOR_TRACE(20);
     // reciprocal correspondences, ascending query index
     int n_recip = 0;
     for (int base = 0; base < Kp; base += kSingle) {
+        {   // a warp per query: nearest current cluster, then that cluster's nearest previous one
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int u = warp; u < kSingle && base + u < Kp; u += kWarps) {
+                const int q = base + u;
+                float dq = 0.f, dr;
+                int jq = -1, ir = -1;
+                if (K > 0) {
+                    jq = nn_warp(cc, K, pc[q * 3], pc[q * 3 + 1], pc[q * 3 + 2], &dq, lane);
+                    ir = nn_warp(pc, Kp, cc[jq * 3], cc[jq * 3 + 1], cc[jq * 3 + 2], &dr, lane);
+                }
+                if (lane == 0) { nn_j[u] = jq; nn_d[u] = dq; nn_ok[u] = (K > 0 && ir == q) ? 1 : 0; }
+            }
+        }
+        __syncthreads();
         const int i = base + threadIdx.x;
         bool ok = false; int j = -1; float d = 0.f;
-        if (i < Kp && K > 0) {
-            j = nn_brute(a.cl_centroid, K, a.pct[i * 3], a.pct[i * 3 + 1], a.pct[i * 3 + 2], &d);
-            float dr;
-            const int ir = nn_brute(a.pct, Kp, a.cl_centroid[j * 3], a.cl_centroid[j * 3 + 1], a.cl_centroid[j * 3 + 2], &dr);
-            ok = (ir == i);
-        }
+        if (i < Kp) { ok = nn_ok[threadIdx.x] != 0; j = nn_j[threadIdx.x]; d = nn_d[threadIdx.x]; }
         int tot;
         const int r = single_block_rank(ok, &tot);
-        if (ok) { a.recip_q[n_recip + r] = i; a.recip_m[n_recip + r] = j; a.match_dist[n_recip + r] = d; }
+        if (ok) {
+            rq[n_recip + r] = i; rm[n_recip + r] = j; rd[n_recip + r] = d;
+            if (fast) { a.recip_q[n_recip + r] = i; a.recip_m[n_recip + r] = j; }
+        }
         n_recip += tot;
     }
     __syncthreads();
-    // volume constraint; match_dist is rewritten in place (rank <= index, chunked with barriers)
+    MOR_TRACE(21);
+    // volume constraint (slow path: match_dist is rewritten in place - rank <= index, chunked with barriers)
     int n_match = 0;
     for (int base = 0; base < n_recip; base += kSingle) {
         const int u = base + threadIdx.x;
         bool ok = false; int i = -1, j = -1; float d = 0.f;
         if (u < n_recip) {
-            i = a.recip_q[u]; j = a.recip_m[u]; d = a.match_dist[u];
-            const float* bp = a.pbbox + i * 6; const float* bc = a.cl_bbox + j * 6;
+            i = rq[u]; j = rm[u]; d = rd[u];
+            const float* bp = pb + i * 6; const float* bc = cb + j * 6;
             const double volp = (double)__fmul_rn(__fmul_rn(__fsub_rn(bp[3], bp[0]), __fsub_rn(bp[4], bp[1])), __fsub_rn(bp[5], bp[2]));
             const double volc = (double)__fmul_rn(__fmul_rn(__fsub_rn(bc[3], bc[0]), __fsub_rn(bc[4], bc[1])), __fsub_rn(bc[5], bc[2]));
             ok = (fabs(volp - volc) / (volp + volc)) < (double)a.volume_constraint;  // NaN -> false
@@ -1176,6 +1292,7 @@ __device__ __forceinline__ void phase_match(const FramePtrs& a) {
         }
         n_match += tot;
     }
+    MOR_TRACE(22);
     if (threadIdx.x == 0) {
         a.counts[MOR_CNT_MU] = n_recip; a.counts[MOR_CNT_M] = n_match;
         a.counts[MOR_CNT_NKPREV] = a.p_counts[MOR_CNT_NK];
@@ -1187,7 +1304,7 @@ __device__ __forceinline__ void phase_match(const FramePtrs& a) {
 // holds no point of the transformed previous cluster (cpp:325-330).
 __device__ __forceinline__ void phase_lattice_count(const FramePtrs& a, int cta, int G) {
     int lo, hi;
-    cta_slice(a.counts[MOR_CNT_NC], cta, G, &lo, &hi);
+    cta_slice(frame_vars().nc, cta, G, &lo, &hi);
     const int lane = threadIdx.x & 31;
     for (int base = lo; base < hi; base += kT) {
         const int s = base + threadIdx.x;
@@ -1214,7 +1331,7 @@ __device__ __forceinline__ void phase_lattice_count(const FramePtrs& a, int cta,
 // count, so the search is bounded by sqrt(pde_ub) on the clustering grid. Shells of growing Chebyshev distance around
 // the query's cell: a point in shell r is at least (r-1)*h away, so the search stops as soon as that bound exceeds the
 // best distance (or pde_ub: farther neighbours never count), and a neighbour at d2 <= pde_lb settles the answer.
-__device__ __forceinline__ void phase_pde_count(const FramePtrs& a, int cta, int G) {
+MOR_OUTLINE void phase_pde_count(const FramePtrs& a, int cta, int G) {
     const int ncp = a.p_counts[MOR_CNT_NC];
     const int ring = a.pde_ring;
     const float h = (float)a.cell_h;
@@ -1259,7 +1376,7 @@ __device__ __forceinline__ void phase_pde_count(const FramePtrs& a, int cta, int
 // Detection flags (cpp:580-606) and the N-frame consistency chain: checkMovingClusterChain (cpp:478-514),
 // recurseFindClusterChain (cpp:415-453), pushCentroid (cpp:455-476). corrs_vec / res_vec are device-resident ring
 // buffers; a correspondence map is stored as match_of_prev[].
-__device__ __forceinline__ void phase_chain(const FramePtrs& a) {
+MOR_OUTLINE void phase_chain(const FramePtrs& a) {
     const int K = a.counts[MOR_CNT_K], Kp = a.p_counts[MOR_CNT_K], M = a.counts[MOR_CNT_M];
     const int D = a.ring_depth, kmax = a.kmax;
     TrackState* ts = a.track;
@@ -1372,22 +1489,19 @@ __device__ __forceinline__ void phase_chain(const FramePtrs& a) {
     }
 }
 
-// The clustering grid and the scan states go back to "all zero" for the next frame; CTA 0 meanwhile runs the chain.
-__device__ __forceinline__ void phase_chain_and_cleanup(const FramePtrs& a, int cta, int G) {
-    const int n_cells = __ldcg(&a.scratch->n_cells);
-    const int first = G > 1 ? 1 : 0;          // with more than one CTA, CTA 0 is busy with the chain
-    const int workers = G > 1 ? G - 1 : 1;
-    if (cta >= first) {
-        const int w = cta - first;
-        for (int i = w * kT + threadIdx.x; i < n_cells; i += workers * kT)
-            *reinterpret_cast<uint4*>(a.table + a.cell_list[i]) = make_uint4(0u, 0u, 0u, 0u);
-        for (int t = w * kT + threadIdx.x; t < a.tiles_pts; t += workers * kT) a.st_ingest[t] = 0ull;
-    }
-    if (cta == 0) {
-        if (a.two_frames) phase_chain(a);
-        __syncthreads();
-        if (threadIdx.x == 0) a.counts[MOR_CNT_NMO] = a.track->n_mo[a.mo_parity];
-    }
+// The clustering grid and the scan states go back to "all zero" for the next frame (in the last phase, beside the
+// compaction: nothing reads them any more).
+__device__ __forceinline__ void frame_cleanup(const FramePtrs& a, int cta, int G) {
+    const int n_cells = frame_vars().n_cells;
+    for (int i = cta * kT + threadIdx.x; i < n_cells; i += G * kT)
+        *reinterpret_cast<uint4*>(a.table + a.cell_list[i]) = make_uint4(0u, 0u, 0u, 0u);
+    for (int t = cta * kT + threadIdx.x; t < a.tiles_pts; t += G * kT) a.st_ingest[t] = 0ull;
+}
+// The single-CTA end of the moving-test phase.
+__device__ __forceinline__ void phase_chain_tail(const FramePtrs& a) {
+    if (a.two_frames) phase_chain(a);
+    __syncthreads();
+    if (threadIdx.x == 0) a.counts[MOR_CNT_NMO] = a.track->n_mo[a.mo_parity];
 }
 
 // ===================================================================================== phase K: filterCloud
@@ -1405,12 +1519,13 @@ constexpr int kRemovedBits = 16384;  // = max kmax
 struct FilterShared {
     unsigned removed[kRemovedBits / 32];
     int total, keep_base;
+    int nn_k[kT]; float nn_d[kT];  // nearest cluster of one chunk of mo_vec entries
 };
 
 __device__ __forceinline__ int filter_tracking(const FramePtrs& a, FilterShared& sh, bool writer) {
     const int mo_parity = a.mo_parity;
     const int K = a.counts[MOR_CNT_K];
-    const int nc = a.counts[MOR_CNT_NC];
+    const int nc = frame_vars().nc;
     TrackState* ts = a.track;
     const int n_mo = ts->n_mo[mo_parity];
     const float* mo_c_in = a.mo_centroid + (size_t)mo_parity * a.momax * 3;
@@ -1423,14 +1538,24 @@ __device__ __forceinline__ int filter_tracking(const FramePtrs& a, FilterShared&
     __syncthreads();
     // K == 0: un-built kd-tree in the reference (UB) -> entries untouched
     for (int base = 0; base < n_mo && K > 0; base += kT) {
+        {   // a warp per entry
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int u = warp; u < kT && base + u < n_mo; u += kWarps) {
+                const int e = base + u;
+                float d;
+                const int k = nn_warp(a.cl_centroid, K, mo_c_in[e * 3], mo_c_in[e * 3 + 1], mo_c_in[e * 3 + 2], &d, lane);
+                if (lane == 0) { sh.nn_k[u] = k; sh.nn_d[u] = d; }
+            }
+        }
+        __syncthreads();
         const int t = base + threadIdx.x;
         bool keep = false;
         float cx = 0, cy = 0, cz = 0; int conf = 0;
         if (t < n_mo) {
             cx = mo_c_in[t * 3]; cy = mo_c_in[t * 3 + 1]; cz = mo_c_in[t * 3 + 2];
             conf = mo_f_in[t];
-            float d;
-            const int k = nn_brute(a.cl_centroid, K, cx, cy, cz, &d);
+            const float d = sh.nn_d[threadIdx.x];
+            const int k = sh.nn_k[threadIdx.x];
             if (writer) a.marker_cluster[t] = k;
             atomicOr(&sh.removed[k >> 5], 1u << (k & 31));
             atomicAdd(&sh.total, a.cl_size[k]);
@@ -1478,19 +1603,27 @@ __device__ __forceinline__ int filter_tracking(const FramePtrs& a, FilterShared&
     return overflow;
 }
 
-__device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShared& sh, int overflow, int tile, int last_tile) {
-    const int nc = a.counts[MOR_CNT_NC], ng = a.counts[MOR_CNT_NG];
+struct FilterTileIn { float4 p; int c; };  // a thread's item of a tile: the point and, for a cloud point, its cluster
+__device__ __forceinline__ FilterTileIn filter_tile_load(const FramePtrs& a, int tile) {
+    const int nc = frame_vars().nc, ng = frame_vars().ng;
+    const int t = tile * kOutTile + threadIdx.x;
+    FilterTileIn in;
+    in.p = make_float4(0, 0, 0, 0); in.c = -1;
+    if (t < nc) { in.p = a.pts[t]; in.c = a.cid[t]; }
+    else if (t < nc + ng) in.p = a.gpts[t - nc];
+    return in;
+}
+__device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShared& sh, int overflow, int tile, int last_tile, const FilterTileIn& in) {
+    const int nc = frame_vars().nc, ng = frame_vars().ng;
     const int t = tile * kOutTile + threadIdx.x;
     bool keep = false;
-    float4 p = make_float4(0, 0, 0, 0);
+    const float4 p = in.p;
     if (t < nc) {
-        p = a.pts[t];
-        const int c = a.cid[t];
+        const int c = in.c;
         const bool removed = overflow || (c >= 0 && ((sh.removed[c >> 5] >> (c & 31)) & 1u));
         keep = !removed;
         if (removed) a.removed_mask[a.cloud_src[t]] = 2;
     } else if (t < nc + ng) {
-        p = a.gpts[t - nc];
         keep = true;
     }
     int tot;
@@ -1505,11 +1638,16 @@ __device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShar
 }
 
 __device__ __forceinline__ void phase_filter(const FramePtrs& a, int cta, int G, FilterShared& sh) {
-    const int total_items = a.counts[MOR_CNT_NC] + a.counts[MOR_CNT_NG];
+    const int total_items = frame_vars().nc + frame_vars().ng;
     const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
+    frame_cleanup(a, cta, G);
     if (cta > last_tile) return;  // nothing to compact here (CTA 0 always has tile 0: it owns the mo_vec update)
+    FilterTileIn in = filter_tile_load(a, cta);  // the first tile's loads are in flight while the tracking part runs
     const int overflow = filter_tracking(a, sh, cta == 0);
-    for (int tile = cta; tile <= last_tile; tile += G) filter_tile(a, sh, overflow, tile, last_tile);
+    for (int tile = cta; tile <= last_tile; tile += G) {
+        if (tile != cta) in = filter_tile_load(a, tile);
+        filter_tile(a, sh, overflow, tile, last_tile, in);
+    }
 }
 
 // Last CTA out: every counter of the frame back to zero.
@@ -1526,14 +1664,14 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
     if (threadIdx.x == 0) {
         Scratch* sc = a.scratch;
-        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_light = 0; sc->n_heavy = 0; sc->n_sorted = 0; sc->err_early = 0;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_light = 0; sc->n_heavy = 0; sc->n_sorted = 0; sc->tail_match = 0u; sc->tail_chain = 0u; sc->err_early = 0;
         sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
         for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
     }
 }
 
 // ===================================================================================== the frame kernel
-enum Phase { PH_INGEST = 0, PH_CELLS, PH_LINK, PH_TEST, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MATCH, PH_MOVING, PH_CHAIN, PH_FILTER, PH__COUNT };
+enum Phase { PH_INGEST = 0, PH_CELLS, PH_LINK, PH_TEST, PH_JUMP, PH_CROSS, PH_ROOTS, PH_SELECT, PH_STATS, PH_MOVING, PH_FILTER, PH__COUNT };
 
 struct FrameShared {
     unsigned long long mbar;
@@ -1550,10 +1688,11 @@ __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, Fr
     if (PH == PH_CROSS) phase_cross(a, cta, G);
     if (PH == PH_ROOTS) phase_roots(a, cta, G);
     if (PH == PH_SELECT) { if (cta == 0) phase_select(a, dyn); phase_transform(a, cta, G); }
-    if (PH == PH_STATS) phase_stats(a, cta, G);
-    if (PH == PH_MATCH) { if (cta == 0) phase_match(a); }
-    if (PH == PH_MOVING) { if (a.two_frames) { if (a.method == 2) phase_lattice_count(a, cta, G); else phase_pde_count(a, cta, G); } }
-    if (PH == PH_CHAIN) phase_chain_and_cleanup(a, cta, G);
+    if (PH == PH_STATS) { phase_stats(a, cta, G); if (group_last_arrival(&a.scratch->tail_match, (unsigned)G)) phase_match(a, dyn); }
+    if (PH == PH_MOVING) {
+        if (a.two_frames) { if (a.method == 2) phase_lattice_count(a, cta, G); else phase_pde_count(a, cta, G); }
+        if (group_last_arrival(&a.scratch->tail_chain, (unsigned)G)) phase_chain_tail(a);
+    }
     if (PH == PH_FILTER) phase_filter(a, cta, G, sh.filter);
 }
 
@@ -1573,6 +1712,7 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
     GroupBarrier bar{&a.scratch->bar, 0u, (unsigned)G};
     if (cta == 0 && threadIdx.x == 0) a.phase_ts[0] = global_ns();
     frame_step<PH_INGEST>(a, cta, G, sh, dyn, parity, bar);
+    load_frame_vars(a);
     frame_step<PH_CELLS>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_LINK>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_TEST>(a, cta, G, sh, dyn, parity, bar);
@@ -1581,9 +1721,7 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
     frame_step<PH_ROOTS>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_SELECT>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_STATS>(a, cta, G, sh, dyn, parity, bar);
-    frame_step<PH_MATCH>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_MOVING>(a, cta, G, sh, dyn, parity, bar);
-    frame_step<PH_CHAIN>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_FILTER>(a, cta, G, sh, dyn, parity, bar);
     frame_epilogue(a, G);
 }
@@ -1618,6 +1756,7 @@ __global__ void __launch_bounds__(kT, 1) k_phase(const __grid_constant__ FramePt
     if (threadIdx.x == 0) mbar_init(&sh.mbar, 1);
     __syncthreads();
     unsigned parity = 0;
+    if (PH != PH_INGEST) load_frame_vars(a);
     run_phase<PH>(a, blockIdx.x, gridDim.x, sh, dyn, parity);
     if (PH == PH_FILTER) frame_epilogue(a, gridDim.x);
 }
@@ -1628,13 +1767,14 @@ __global__ void __launch_bounds__(kT, 1) k_filter_again(const __grid_constant__ 
     __shared__ FilterShared sh;
     __shared__ int s_tile, s_last;
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.scratch->ticket_out, 1);
-    __syncthreads();
+    load_frame_vars(a);
     const int tile = s_tile;
-    const int total_items = a.counts[MOR_CNT_NC] + a.counts[MOR_CNT_NG];
+    const int total_items = frame_vars().nc + frame_vars().ng;
     const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
     if (tile <= last_tile) {
+        const FilterTileIn in = filter_tile_load(a, tile);
         const int overflow = filter_tracking(a, sh, tile == 0);
-        filter_tile(a, sh, overflow, tile, last_tile);
+        filter_tile(a, sh, overflow, tile, last_tile, in);
     }
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&a.scratch->out_blocks_done, 1) == (int)gridDim.x - 1;

@@ -34,4 +34,7 @@ for f in range(max(want) + 1):
             for row, what in ((16, "start"), (17, "warp 0: light done"), (18, "light + heavy")):
                 r2 = (t[row] - prev_end) / 1e3
                 print(f"      .. {what:14s} p50 {np.median(r2):6.1f}  p90 {np.percentile(r2, 90):6.1f}  last {r2.max():6.1f}")
+        if name.startswith("ph_stats"):  # the single-CTA tail (rows 19..22, slot 0): entry, centroids done, reciprocal NN done, end
+            tt = [(t[row][0] - prev_end) / 1e3 for row in (19, 20, 21, 22)]
+            print("      .. match: entry %.1f  centroids %.1f  nn %.1f  volume %.1f" % tuple(tt))
         prev_end = arr.max()
