@@ -524,6 +524,24 @@ def run_product(args, rank, local_rank, world):
         if nf == F:
             spot["timed_run_last_frame_equals_oracle"] = crcs_o[-1][0] == crc_dev_last
         mg.close()
+        # north_star: "any tie-breaking divergence at the exact clustering radius counted and reported": point pairs within
+        # 2 ulps of r^2 (the pairs a differently rounded distance or a pruned kd-tree search could classify the other way),
+        # counted by brute force on both sides for a few frames of the sequence
+        mt = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+        mo2 = MovingObjectRemoval(CFG, 4, 3, binding=orc)
+        tie_frames, ties_gpu, ties_orc, pairs_checked = 0, 0, 0, 0
+        for f in range(min(3, F)):
+            mt.push_raw_cloud_and_pose(pts[f, : npts[f]], poses[f]); mt.filter_cloud(out_host)
+            mo2.push_raw_cloud_and_pose(pts[f, : npts[f]], poses[f]); mo2.filter_cloud(out_o)
+            ties_gpu += mt.radius_ties(2); ties_orc += mo2.radius_ties(2)
+            nc_f = mt.counts()["NC"]
+            pairs_checked += nc_f * (nc_f - 1) // 2
+            tie_frames += 1
+        spot["radius_ties"] = {"frames": tie_frames, "ulps": 2, "pairs_within_band": ties_gpu, "oracle_pairs_within_band": ties_orc,
+                               "point_pairs_examined": pairs_checked,
+                               "note": "pairs of cloud points with |d2 - r2| <= 2 ulp(r2): the only pairs on which a real PCL/FLANN build could cluster differently "
+                                       "from the bit-exact strict `<` both sides evaluate; 0 means no such pair exists in these frames"}
+        mt.close()
 
     b.device_free(local_rank, d_frames)
     if world > 1:

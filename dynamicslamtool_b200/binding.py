@@ -107,6 +107,7 @@ class MorBinding:
         self.tap = f("tap", [vp, C.c_int, vp, sz, C.POINTER(sz)])
         self.get_cluster_collection = f("get_cluster_collection", [vp, vp, u32, C.POINTER(u32)])
         self.get_moving_markers = f("get_moving_markers", [vp, vp, u32, C.POINTER(u32)])
+        self.count_radius_ties = f("count_radius_ties", [vp, C.c_int, C.POINTER(C.c_uint64)])
         # product-only entry points (absent from the oracle)
         self.get_limits = f("get_limits", [vp, C.POINTER(MorLimits)], True)
         self.push_device = f("push_raw_cloud_and_pose_device", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)], True)
@@ -264,6 +265,12 @@ class MovingObjectRemoval:
         if n.value:
             self._check(self.b.get_moving_markers(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "get_moving_markers")
         return out
+
+    def radius_ties(self, ulps: int = 2) -> int:
+        """Point pairs of the current cloud within `ulps` units in the last place of the squared clustering radius."""
+        v = C.c_uint64(0)
+        self._check(self.b.count_radius_ties(self.h, ulps, C.byref(v)), "count_radius_ties")
+        return v.value
 
     def sync(self):
         self._check(self.b.sync(self.h), "sync")

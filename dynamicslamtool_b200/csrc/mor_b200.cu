@@ -313,6 +313,7 @@ int configure_kernels(mor_handle* h) {
     int st = set_phase_smem<PH_SELECT>(h);
     if (st == MOR_OK) st = set_phase_smem<PH_LINK>(h);
     if (st == MOR_OK) st = set_phase_smem<PH_STATS>(h);
+    if (st == MOR_OK) st = set_phase_smem<PH_INGEST>(h);
     if (st != MOR_OK) return st;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->num_sms = sms;
@@ -393,7 +394,7 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
 template <int PH>
 int launch_phase(mor_handle* h, const FramePtrs& a) {
     prof_begin(h, KID_PHASE0 + PH);
-    const size_t smem = (PH == PH_SELECT || PH == PH_LINK || PH == PH_STATS) ? h->frame_smem : 0;
+    const size_t smem = (PH == PH_INGEST || PH == PH_SELECT || PH == PH_LINK || PH == PH_STATS) ? h->frame_smem : 0;
     cudaError_t e = launch_coop(k_phase<PH>, (unsigned)h->frame_ctas, smem, h->stream, a);
     prof_end(h);
     h->launches++;
@@ -1062,6 +1063,26 @@ int mor_get_cluster_collection(mor_handle* h, void* out, uint32_t cap_points, ui
     if (!out) return MOR_OK;
     if (nk > cap_points) return MOR_ERR_CAPACITY;
     if (nk) MOR_CUDA(cudaMemcpy(out, c.out, (size_t)nk * 32, cudaMemcpyDeviceToHost));
+    return MOR_OK;
+}
+
+int mor_count_radius_ties(mor_handle* h, int ulps, uint64_t* pairs) {
+    if (!h || !pairs || ulps < 0) return MOR_ERR_ARG;
+    if (!h->have_cur) return MOR_ERR_STATE;
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    const float r2 = (float)((double)h->cfg.ec_distance_threshold * (double)h->cfg.ec_distance_threshold);
+    float lo = r2, hi = r2;
+    for (int u = 0; u < ulps; u++) { lo = std::nextafterf(lo, 0.f); hi = std::nextafterf(hi, 3.402823466e+38f); }
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->coll_cursor);  // (scratch of the on-request outputs, 8-byte aligned)
+    MOR_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), h->stream));
+    k_radius_ties<<<h->num_sms * 2, 1024, 0, h->stream>>>(h->frame.pts, h->frame.counts, lo, hi, d_cnt);
+    h->launches++;
+    MOR_CUDA(cudaGetLastError());
+    unsigned long long v = 0;
+    MOR_CUDA(cudaMemcpyAsync(&v, d_cnt, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    MOR_CUDA(cudaStreamSynchronize(h->stream));
+    *pairs = v;
     return MOR_OK;
 }
 

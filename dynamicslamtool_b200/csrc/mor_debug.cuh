@@ -110,4 +110,42 @@ __global__ void __launch_bounds__(kCollBlock) k_cluster_collection(CollectionPtr
     }
 }
 
+// ---------------------------------------------------------------------------------------------- radius ties
+// north_star: "any tie-breaking divergence at the exact clustering radius counted and reported". The predicate of the
+// hot path is evaluated bit for bit like FLANN's L2_Simple, so nothing diverges against the oracle; what CAN differ
+// against a real PCL build are point pairs whose squared distance sits within a few units in the last place of r^2
+// (another rounding of the distance, a pruned tree search). This diagnostic counts them: all pairs (i < j) of the
+// current frame's `cloud` with d2 in [lo, hi], brute force over tiles of 1024 points in shared memory.
+__global__ void __launch_bounds__(1024) k_radius_ties(const float4* __restrict__ pts, const int* __restrict__ counts, float lo, float hi,
+                                                      unsigned long long* __restrict__ out) {
+    __shared__ float sx[1024], sy[1024], sz[1024];
+    const int nc = counts[MOR_CNT_NC];
+    const int tiles = (nc + 1023) / 1024;
+    unsigned long long mine = 0;
+    // block b takes the tile pairs (ti <= tj) with index b, b + gridDim.x, ...
+    const long long npairs = (long long)tiles * (tiles + 1) / 2;
+    for (long long pidx = blockIdx.x; pidx < npairs; pidx += gridDim.x) {
+        int ti = 0;
+        long long rem = pidx;
+        while (rem >= tiles - ti) { rem -= tiles - ti; ti++; }
+        const int tj = ti + (int)rem;
+        __syncthreads();
+        const int j = tj * 1024 + threadIdx.x;
+        if (j < nc) { const float4 p = pts[j]; sx[threadIdx.x] = p.x; sy[threadIdx.x] = p.y; sz[threadIdx.x] = p.z; }
+        __syncthreads();
+        const int i = ti * 1024 + threadIdx.x;
+        if (i < nc) {
+            const float4 p = pts[i];
+            const int jn = min(1024, nc - tj * 1024);
+            for (int t = 0; t < jn; t++) {
+                if (ti == tj && t <= (int)threadIdx.x) continue;  // i < j
+                const float d = sqdist3(p.x, p.y, p.z, sx[t], sy[t], sz[t]);
+                mine += (d >= lo && d <= hi) ? 1ull : 0ull;
+            }
+        }
+    }
+    mine = warp_sum_u64(mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 }  // namespace mor

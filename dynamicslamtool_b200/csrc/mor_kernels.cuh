@@ -349,20 +349,49 @@ __device__ __forceinline__ unsigned long long bin_point(const FramePtrs& a, cons
     return cell_pack(cx, cy, cz);
 }
 
-__device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G) {
+// A float field of a record staged in shared memory (any alignment).
+__device__ __forceinline__ float smem_f32(const uint8_t* p) {
+    if ((smem_u32(p) & 3u) == 0u) return *reinterpret_cast<const float*>(p);
+    return __uint_as_float((unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24));
+}
+
+__device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G, unsigned long long* dyn, unsigned long long* mbar, unsigned& parity) {
     frame_housekeeping(a, cta, G);
     const int ntiles = a.n ? (int)((a.n + kIngestTile - 1) / kIngestTile) : 1;
     __shared__ int s_created, s_cbase;
+    // Records that are not plain float4 (PCLPointCloud2 layouts with padding or extra fields, e.g. the 22-byte velodyne
+    // XYZIRT record) are staged: the tile's bytes come into shared memory by ONE bulk copy (TMA, 1-D) and the fields are
+    // picked out there - instead of four strided word loads, or sixteen byte loads, per point from global memory.
+#ifdef MOR_NO_INGEST_STAGE  // (measurement variant)
+    const bool staged = false;
+#else
+    const bool staged = a.in_mode != 0 && (size_t)kIngestTile * a.step + 32 <= (size_t)a.frame_smem && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+#endif
+    uint8_t* const stage = reinterpret_cast<uint8_t*>(dyn);
     for (int tile = cta; tile < ntiles; tile += G) {
         const uint32_t i = (uint32_t)tile * kIngestTile + threadIdx.x;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int cls = 0;
         if (threadIdx.x == 0) s_created = 0;
-        __syncthreads();  // (also: the previous tile's readers of s_cbase are done)
+        __syncthreads();  // (also: the previous tile's readers of s_cbase and of the staged bytes are done)
+        size_t stage_skew = 0;
+        if (staged) {
+            const size_t b0 = (size_t)tile * kIngestTile * a.step, b1 = min((size_t)a.n * a.step, b0 + (size_t)kIngestTile * a.step);
+            const size_t c0 = b0 & ~(size_t)15, c1 = max(c0, b1 & ~(size_t)15);  // [c0, c1): 16-byte granules for the bulk copy; [c1, b1): the last bytes
+            stage_skew = b0 - c0;
+            if (threadIdx.x == 0 && c1 > c0) bulk_load(stage, a.in + c0, (unsigned)(c1 - c0), mbar);
+            if (threadIdx.x < b1 - c1) stage[c1 - c0 + threadIdx.x] = a.in[c1 + threadIdx.x];
+            if (c1 > c0) { mbar_wait(mbar, parity); parity ^= 1u; }
+            __syncthreads();
+        }
         if (i < a.n) {
             const uint8_t* p = a.in + (size_t)i * a.step;
             if (a.in_mode == 0) {
                 v = __ldg(reinterpret_cast<const float4*>(p));
+            } else if (staged) {
+                const uint8_t* q = stage + stage_skew + (size_t)threadIdx.x * a.step;
+                v.x = smem_f32(q + a.off_x); v.y = smem_f32(q + a.off_y); v.z = smem_f32(q + a.off_z);
+                v.w = a.off_i != 0xFFFFFFFFu ? smem_f32(q + a.off_i) : 0.f;
             } else {
                 v.x = load_f32(p + a.off_x, a.in_mode); v.y = load_f32(p + a.off_y, a.in_mode); v.z = load_f32(p + a.off_z, a.in_mode);
                 v.w = a.off_i != 0xFFFFFFFFu ? load_f32(p + a.off_i, a.in_mode) : 0.f;
@@ -1680,7 +1709,7 @@ struct FrameShared {
 
 template <int PH>
 __device__ __forceinline__ void run_phase(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
-    if (PH == PH_INGEST) { if (a.skip_ingest) phase_bin_cloud(a, cta, G); else phase_ingest(a, cta, G); }
+    if (PH == PH_INGEST) { if (a.skip_ingest) phase_bin_cloud(a, cta, G); else phase_ingest(a, cta, G, dyn, &sh.mbar, parity); }
     if (PH == PH_CELLS) phase_cells(a, cta, G);
     if (PH == PH_LINK) phase_link(a, cta, G, dyn);
     if (PH == PH_TEST) phase_test(a, cta, G);

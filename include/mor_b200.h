@@ -60,10 +60,10 @@ typedef struct mor_limits {
     uint32_t max_points;    /* largest frame accepted (default 300000) */
     uint32_t max_clusters;  /* largest number of size-valid clusters per frame (default 8192, at most 16384) */
     uint32_t max_moving;    /* capacity of the confirmed-moving list mo_vec (default 1024) */
-    uint32_t max_cells;     /* largest dense cell table (default 2^27 cells = 1 GB). A crop box that needs up to 2^22 cells
-                               gets a fixed grid; up to max_cells the tables cover the box and each frame's grid follows
-                               the bounding box of its cloud; a box that needs more gets bounding-box grids in tables of
-                               max_cells (default then 2^24) cells, and a frame that does not fit is MOR_ERR_CAPACITY */
+    uint32_t max_cells;     /* voxel ground modes only (ground_mode 1/2): largest dense voxel / ball-query table over the
+                               bounding box of a frame's raw cloud (default 2^24 cells; a frame that needs more is
+                               MOR_ERR_CAPACITY). The clustering grid is a sparse hash grid with no such limit: neither
+                               the crop box nor the radius enters its size */
     uint32_t reserved[4];
 } mor_limits;
 
@@ -129,7 +129,7 @@ int mor_get_output_device(mor_handle* h, const void** d_records);
 int mor_sync(mor_handle* h);
 
 /* Batched device-resident step (BASELINE config 5: many independent sequences per GPU): one pushRawCloudAndPose +
- * filterCloud for S sequences in ONE set of kernel launches (blockIdx.z selects the sequence). All handles must
+ * filterCloud for S sequences in ONE launch of the frame kernel (a group of CTAs per sequence). All handles must
  * live on the same device with the same config, limits and frame count, ground_mode 0. d_data[s] / d_out[s] are
  * device pointers (d_out[s] must hold n[s] records), poses7 = S x 7 doubles. Asynchronous on hs[0]'s stream;
  * mor_sync / mor_tap on any of the handles waits for it. */
@@ -209,6 +209,12 @@ typedef struct mor_marker {
     int32_t cluster; /* index into this frame's cluster list */
 } mor_marker;
 int mor_get_moving_markers(mor_handle* h, mor_marker* out, uint32_t cap, uint32_t* n_out);
+
+/* Diagnostic, on request: the number of point pairs of the current frame's `cloud` whose squared distance lies within
+ * `ulps` units in the last place of the squared clustering radius (float)((double)tol*tol) - the pairs on which an
+ * implementation that rounds the distance differently, or prunes its tree search (FLANN), could decide the
+ * other way than EuclideanClusterExtraction's strict `<` (cpp:213-218). Brute force over all pairs, ~1 ms. */
+int mor_count_radius_ties(mor_handle* h, int ulps, uint64_t* pairs);
 
 /* ---- parity taps ------------------------------------------------------------------------ */
 typedef enum mor_tap_id {

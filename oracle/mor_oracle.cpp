@@ -425,6 +425,10 @@ struct mor_handle {
     std::vector<PointXYZI> f_cloud;
     std::vector<mor_marker> markers;  // VISUALIZE: marker_pub.publish(mark_cluster(...)) calls of the last filterCloud
     std::string last_error;
+    // F3 literal probe (oracle_set_literal_ground_probe): voxels whose accept test (cpp:145) comes out differently under
+    // the reference's literal float arithmetic (A14/A15) than under the order-independent definition above
+    bool literal_probe = false;
+    long long literal_tested = 0, literal_differ = 0;
 
     // ---------------- mark_cluster, cpp:7-58: pcl::compute3DCentroid into a Vector4f (float sums in index order,
     // divided by n), getMinMax3D extents, zero extents widened to 0.1; `id` is filterCloud's running counter (cpp:622, :669)
@@ -501,6 +505,7 @@ struct mor_handle {
             }
             struct Vox { int64_t idx; double sx, sy, sz; int n; };
             std::vector<Vox> vox;
+            std::vector<std::vector<int>> vox_members;  // (literal probe only) the points of every voxel, ascending index
             {
                 std::vector<std::pair<int64_t, int>> keyed(n);
                 for (int i = 0; i < n; i++) {
@@ -516,6 +521,10 @@ struct mor_handle {
                     while (e < n && keyed[e].first == keyed[s].first) {
                         const PointXYZI& p = raw[keyed[e].second];
                         v.sx += p.x; v.sy += p.y; v.sz += p.z; v.n++; e++;
+                    }
+                    if (literal_probe) {
+                        vox_members.emplace_back();
+                        for (int t = s; t < e; t++) vox_members.back().push_back(keyed[t].second);
                     }
                     vox.push_back(v);
                     s = e;
@@ -549,6 +558,36 @@ struct mor_handle {
                 bool ok; long long key;
                 if (mode == MOR_GROUND_VOXEL_COV) {
                     ok = std::fabs(S[2]) < 0.001 && std::fabs(S[4]) < 0.001 && std::fabs(S[5]) < 0.001;  // cpp:145
+                    if (literal_probe) {
+                        // The same voxel the way the reference's own arithmetic would run: VoxelGrid centroid as
+                        // float sums in index order, radiusSearch results sorted by distance, pcl::compute3DCentroid into a
+                        // Vector4f (float sums / n) and pcl::computeCovarianceMatrix<float> (float products about that centroid,
+                        // un-normalised), both over the neighbours in that order (cpp:137-144).
+                        float fx = 0.f, fy = 0.f, fz = 0.f;
+                        for (int j : vox_members[v]) { fx += raw[j].x; fy += raw[j].y; fz += raw[j].z; }
+                        const float inv = (float)vox[v].n;
+                        const float lqx = fx / inv, lqy = fy / inv, lqz = fz / inv;
+                        std::vector<int> li;
+                        tree.radius(lqx, lqy, lqz, r2, li);
+                        bool lok = false;
+                        if (li.size() > 3) {
+                            std::vector<std::pair<float, int>> byd(li.size());
+                            for (size_t t = 0; t < li.size(); t++) byd[t] = {sqdist3(lqx, lqy, lqz, raw[li[t]].x, raw[li[t]].y, raw[li[t]].z), li[t]};
+                            std::sort(byd.begin(), byd.end());
+                            float cx = 0.f, cy = 0.f, cz = 0.f;
+                            for (const auto& e : byd) { cx += raw[e.second].x; cy += raw[e.second].y; cz += raw[e.second].z; }
+                            const float fn = (float)byd.size();
+                            cx /= fn; cy /= fn; cz /= fn;
+                            float c02 = 0.f, c12 = 0.f, c22 = 0.f;
+                            for (const auto& e : byd) {
+                                const float dx = raw[e.second].x - cx, dy = raw[e.second].y - cy, dz = raw[e.second].z - cz;
+                                c12 += dy * dz; c22 += dz * dz; c02 += dx * dz;
+                            }
+                            lok = std::fabs(c02) < 0.001 && std::fabs(c12) < 0.001 && std::fabs(c22) < 0.001;
+                        }
+                        literal_tested++;
+                        if (lok != ok) literal_differ++;
+                    }
                     key = (long long)(int)(qz * 10);  // cpp:166: (float)((int)(z*10))/bin_gap is monotone in this integer
                     gv[5] = 0; gv[6] = 0; gv[7] = 1;
                 } else {
@@ -1043,6 +1082,40 @@ int oracle_tap(mor_handle* h, int tap, void* dst, size_t cap_bytes, size_t* n_by
 }
 
 // Building blocks exposed for the oracle's own cross-checks (tests/test_oracle_*.py)
+// F3 literal probe (test infrastructure): count, over the frames pushed while it is on, the voxels whose accept flag
+// differs between the literal float arithmetic of cpp:137-145 and the order-independent definition both sides implement.
+int oracle_set_literal_ground_probe(mor_handle* h, int enabled) {
+    if (!h) return MOR_ERR_ARG;
+    h->literal_probe = enabled != 0; h->literal_tested = 0; h->literal_differ = 0;
+    return MOR_OK;
+}
+int oracle_get_literal_ground_stats(mor_handle* h, long long* tested, long long* differ) {
+    if (!h || !tested || !differ) return MOR_ERR_ARG;
+    *tested = h->literal_tested; *differ = h->literal_differ;
+    return MOR_OK;
+}
+
+// Point pairs of the current frame's `cloud` whose squared distance lies within `ulps` units in the last place of r^2
+// (the pairs a differently rounded distance or a pruned tree search could classify the other way; north_star: "any
+// tie-breaking divergence at the exact clustering radius counted and reported"). Brute force over all pairs.
+int oracle_count_radius_ties(mor_handle* h, int ulps, uint64_t* pairs) {
+    if (!h || !pairs || ulps < 0) return MOR_ERR_ARG;
+    if (!h->cb) return MOR_ERR_STATE;
+    const std::vector<PointXYZI>& c = h->cb->cloud;
+    const float r2 = (float)((double)h->cfg.ec_distance_threshold * (double)h->cfg.ec_distance_threshold);
+    float lo = r2, hi = r2;
+    for (int u = 0; u < ulps; u++) { lo = std::nextafterf(lo, 0.f); hi = std::nextafterf(hi, FLT_MAX); }
+    uint64_t cnt = 0;
+    const size_t n = c.size();
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 1; j < n; j++) {
+            const float d = sqdist3(c[i].x, c[i].y, c[i].z, c[j].x, c[j].y, c[j].z);
+            if (d >= lo && d <= hi) cnt++;
+        }
+    *pairs = cnt;
+    return MOR_OK;
+}
+
 int oracle_pose_delta(const double pose_prev7[7], const double pose_cur7[7], float m12[12]) {
     TfTransform t = tf_inverse_times(tf_from_pose(pose_cur7), tf_from_pose(pose_prev7));
     tf_to_affine3f(t, m12);

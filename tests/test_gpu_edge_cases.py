@@ -416,3 +416,20 @@ def test_fuzz_random_configs_and_scenes(product, oracle, tmp_path, seed):
         pts[rng.integers(0, len(pts), 3), 0] = np.inf
         pose = np.concatenate([pos, rot.as_quat()])
         step(gpu, orc, np.ascontiguousarray(pts), pose)
+
+
+def test_radius_tie_counter_equals_the_oracles(product, oracle, cfg_dir):
+    """mor_count_radius_ties (north_star: divergence at the exact radius counted): the same brute-force count on both sides,
+    on real frames (C1, 29k points; the first frames of C2) and for several band widths."""
+    from dynamicslamtool_b200 import Synth
+    for scenario, cfg, frames in ((1, "MOR_config.txt", 3), (2, "MOR_config_hdl64.txt", 2)):
+        s = Synth(scenario, scenario)
+        gpu = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
+        orc = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=oracle)
+        for f in range(frames):
+            pts, pose = s.frame(f)
+            gpu.push_raw_cloud_and_pose(pts, pose); orc.push_raw_cloud_and_pose(pts, pose)
+            for ulps in (0, 2, 64):
+                assert gpu.radius_ties(ulps) == orc.radius_ties(ulps), (scenario, f, ulps)
+            gpu.filter_cloud(); orc.filter_cloud()
+        assert orc.radius_ties(1 << 12) > 0  # a band wide enough to hold pairs: the counters do count

@@ -302,3 +302,44 @@ def test_partition_and_output_do_not_depend_on_point_order(oracle, tmp_path, see
         assert sorted(map(bytes, oa)) == sorted(map(bytes, ob))
         assert a.counts()["NMO"] == b.counts()["NMO"]
     assert a.counts()["NMO"] == 1
+
+
+def test_radius_tie_counter_counts_pairs_within_n_ulps_of_r2(oracle, tmp_path):
+    """north_star: divergence at the exact clustering radius is to be counted. Pairs are placed along x at squared
+    distances exactly r2, r2 -/+ 1 ulp, r2 -/+ 3 ulps (and far from each other): the counter must see exactly the ones
+    inside the requested band."""
+    cfg = write_cfg(tmp_path, ec_distance_threshold=0.25, min_cluster_size=1, **OPEN_CFG)
+    r2 = np.float32(np.float64(np.float32(0.25)) ** 2)
+    want = {0: r2}
+    v = r2
+    for u in range(1, 4):
+        v = np.nextafter(v, np.float32(0))
+        want[-u] = v
+    v = r2
+    for u in range(1, 4):
+        v = np.nextafter(v, np.float32(10))
+        want[u] = v
+    pts = []
+    found = {}
+    for k, (u, d2) in enumerate(sorted(want.items())):
+        base = np.float32(10.0 * k)  # pairs far apart from each other
+        # search a float dx whose float square (the kernel's arithmetic with dy = dz = 0) equals d2 exactly
+        dx = np.float32(np.sqrt(np.float64(d2)))
+        for cand in (dx, np.nextafter(dx, np.float32(0)), np.nextafter(dx, np.float32(10))):
+            if np.float32(cand * cand) == d2:
+                found[u] = True
+                pts += [[0.0, base, 0.0], [float(cand), base, 0.0]]
+                break
+    xyz = np.array(pts, np.float32)
+    d2s = f32_sqdist_matrix(xyz)
+    m = MovingObjectRemoval(cfg, 4, 3, binding=oracle)
+    m.push_raw_cloud_and_pose(with_intensity(xyz), IDENTITY_POSE)
+    r2f = np.float32(r2)
+    for ulps in (0, 1, 2, 3):
+        lo, hi = r2f, r2f
+        for _ in range(ulps):
+            lo, hi = np.nextafter(lo, np.float32(0)), np.nextafter(hi, np.float32(10))
+        iu = np.triu_indices(len(xyz), 1)
+        expect = int(np.sum((d2s[iu] >= lo) & (d2s[iu] <= hi)))
+        assert m.radius_ties(ulps) == expect
+    assert len(found) >= 3 and m.radius_ties(3) >= 3  # the construction did produce pairs inside the band
