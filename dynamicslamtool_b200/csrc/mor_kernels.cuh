@@ -49,6 +49,7 @@ struct Scratch {  // all zero between frames: every counter is put back by the f
     int n_cells, n_roots, n_light, n_heavy;  // list lengths of the frame
     int n_sorted, pad1;      // bump allocator of the sorted array (phase B)
     unsigned tail_match, tail_chain;  // arrival counters of the phases that end with a single-CTA step
+    int ticket_light, ticket_heavy;   // next unclaimed record of the pair lists (test phase)
     int ticket_out, out_blocks_done;  // stand-alone filter kernel (repeated filterCloud on one frame)
     int err_early;           // error bits raised before the frame's counts exist
     int pad0;
@@ -360,12 +361,15 @@ __device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G,
     const int ntiles = a.n ? (int)((a.n + kIngestTile - 1) / kIngestTile) : 1;
     __shared__ int s_created, s_cbase;
     // Records that are not plain float4 (PCLPointCloud2 layouts with padding or extra fields, e.g. the 22-byte velodyne
-    // XYZIRT record) are staged: the tile's bytes come into shared memory by ONE bulk copy (TMA, 1-D) and the fields are
-    // picked out there - instead of four strided word loads, or sixteen byte loads, per point from global memory.
-#ifdef MOR_NO_INGEST_STAGE  // (measurement variant)
-    const bool staged = false;
-#else
+    // XYZIRT record) can be staged: the tile's bytes come into shared memory by ONE bulk copy (TMA, 1-D) and the fields
+    // are picked out there - instead of four strided word loads, or sixteen byte loads, per point from global memory.
+    // Measured on C2 (profiles/README.md): the phase is a latency chain, not load-bound - 13.0 us staged vs 12.4 us direct
+    // for 22-byte records, 13.3 vs 12.1 us for 32-byte records (the copy's round trip and two CTA barriers sit in front
+    // of everything else). Off unless built with -DMOR_INGEST_STAGE.
+#ifdef MOR_INGEST_STAGE
     const bool staged = a.in_mode != 0 && (size_t)kIngestTile * a.step + 32 <= (size_t)a.frame_smem && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+#else
+    const bool staged = false;
 #endif
     uint8_t* const stage = reinterpret_cast<uint8_t*>(dyn);
     for (int tile = cta; tile < ntiles; tile += G) {
@@ -887,20 +891,12 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
     const int TL = min(__ldcg(&a.scratch->n_light), a.light_cap), TH = min(__ldcg(&a.scratch->n_heavy), a.heavy_cap);
     int2* eseg = a.edges + (size_t)cta * a.edge_seg;
     MOR_TRACE(16);
-    const int lper = (TL + G - 1) / G, llo = min(TL, cta * lper), lhi = min(TL, llo + lper);
-    const int hper = (TH + G - 1) / G, hlo = min(TH, cta * hper), hhi = min(TH, hlo + hper);
-    // The light pairs are packed into the first warps (a warp issues the same instructions whether 12 or 32 of its
-    // lanes hold a pair: spreading the pairs over all warps was 2x slower); the heavy pairs go to the other warps -
-    // from the last warp down - and both run side by side.
-    const int light_warps = min(kWarps, (lhi - llo + 31) >> 5);
-    const int heavy_warps = max(kWarps - light_warps, 8);
-    // ---- light pairs: one thread each
-    for (int base = llo; base < lhi; base += kT) {
-        const int w = base + threadIdx.x;
-        if (base + warp * 32 >= lhi) break;  // (warp-uniform)
+    // ---- light pairs: one thread each, 32 consecutive records per warp and step
+    auto light_chunk = [&](int w0, int wend) {
+        const int w = w0 + lane;
         bool hit = false;
         int sA = 0, sB = 0;
-        if (w < lhi) {
+        if (w < wend) {
             const int2 lp = __ldcg(a.light + w);
             sA = lp.x & 0x1FFFFFF; sB = lp.y & 0x1FFFFFF;
             const int cA = (int)((unsigned)lp.x >> 25) + 1, cB = (int)((unsigned)lp.y >> 25) + 1;
@@ -927,46 +923,78 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
             slot = __shfl_sync(kFull, slot, 0) + __popc(m & ((1u << lane) - 1u));
             if (hit) { if (slot < a.edge_seg) eseg[slot] = make_int2(sA, sB); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP); }
         }
-    }
-    MOR_TRACE_NOSYNC(17);
+    };
     // ---- heavy pairs: one warp each, two pairs of a warp in flight together (their loads are the cost). The few pairs
     // that need the full scan are put aside and then taken on by the whole CTA, one chunk of B per warp: a single warp
     // would keep the group waiting for tens of microseconds on a pair of crowded cells.
-    const int hwarp = kWarps - 1 - warp;
-    if (hwarp < heavy_warps) {
-        for (int w = hlo + hwarp; w < hhi; w += 2 * heavy_warps) {
-            const bool two = w + heavy_warps < hhi;
-            int4 hp[2];
-            hp[0] = __ldcg(a.heavy + w);
-            hp[1] = two ? __ldcg(a.heavy + w + heavy_warps) : hp[0];
-            float4 qa[2], qb[2];
+    auto heavy_pairs = [&](int w, int w2, bool two) {
+        int4 hp[2];
+        hp[0] = __ldcg(a.heavy + w);
+        hp[1] = two ? __ldcg(a.heavy + w2) : hp[0];
+        float4 qa[2], qb[2];
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                MOR_CHECK(hp[q].x + hp[q].y <= a.counts[MOR_CNT_NC] && hp[q].z + hp[q].w <= a.counts[MOR_CNT_NC], "heavy pair", hp[q].z);
-                qa[q] = a.spts[hp[q].x + (int)(((long long)lane * hp[q].y) >> 5)];
-                qb[q] = a.spts[hp[q].z + (int)(((long long)lane * hp[q].w) >> 5)];
+        for (int q = 0; q < 2; q++) {
+            MOR_CHECK(hp[q].x + hp[q].y <= a.counts[MOR_CNT_NC] && hp[q].z + hp[q].w <= a.counts[MOR_CNT_NC], "heavy pair", hp[q].z);
+            qa[q] = a.spts[hp[q].x + (int)(((long long)lane * hp[q].y) >> 5)];
+            qb[q] = a.spts[hp[q].z + (int)(((long long)lane * hp[q].w) >> 5)];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (q && !two) break;
+            bool hit = heavy_probe(qa[q], qb[q], r2);
+            if (!hit) {
+                HeavyBoxes hb;
+                if (heavy_boxes_apart(a, hp[q].x, hp[q].y, hp[q].z, hp[q].w, &hb, lane)) continue;
+                int slot = kHardCap;
+                if (lane == 0) slot = atomicAdd(&s_nhard, 1);
+                slot = __shfl_sync(kFull, slot, 0);
+                if (slot < kHardCap) { if (lane == 0) { s_hard[slot] = hp[q]; s_hard_box[slot] = hb; s_hard_hit[slot] = 0; } continue; }
+                for (int b0 = 0; b0 < hp[q].w && !hit; b0 += 32) hit = heavy_scan_chunk(a, hb, hp[q].x, hp[q].y, hp[q].z, hp[q].w, b0, lane);  // (list full)
             }
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                if (q && !two) break;
-                bool hit = heavy_probe(qa[q], qb[q], r2);
-                if (!hit) {
-                    HeavyBoxes hb;
-                    if (heavy_boxes_apart(a, hp[q].x, hp[q].y, hp[q].z, hp[q].w, &hb, lane)) continue;
-                    int slot = kHardCap;
-                    if (lane == 0) slot = atomicAdd(&s_nhard, 1);
-                    slot = __shfl_sync(kFull, slot, 0);
-                    if (slot < kHardCap) { if (lane == 0) { s_hard[slot] = hp[q]; s_hard_box[slot] = hb; s_hard_hit[slot] = 0; } continue; }
-                    for (int b0 = 0; b0 < hp[q].w && !hit; b0 += 32) hit = heavy_scan_chunk(a, hb, hp[q].x, hp[q].y, hp[q].z, hp[q].w, b0, lane);  // (list full)
-                }
-                if (hit && lane == 0) {
-                    const int slot = atomicAdd(&s_edges, 1);
-                    if (slot < a.edge_seg) eseg[slot] = make_int2(hp[q].x, hp[q].z); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
-                    atomicMin(&a.hook[max(hp[q].x, hp[q].z)], min(hp[q].x, hp[q].z));
-                }
+            if (hit && lane == 0) {
+                const int slot = atomicAdd(&s_edges, 1);
+                if (slot < a.edge_seg) eseg[slot] = make_int2(hp[q].x, hp[q].z); else atomicOr(&a.counts[MOR_CNT_ERRFLAGS], ERR_EDGE_CAP);
+                atomicMin(&a.hook[max(hp[q].x, hp[q].z)], min(hp[q].x, hp[q].z));
             }
         }
-    }
+    };
+#ifndef MOR_TEST_TICKETS
+    // Equal shares per CTA: the light pairs packed into the first warps (a warp issues the same instructions whether 12 or 32
+    // of its lanes hold a pair: spreading them over all warps was 2x slower), the heavy pairs on the others, side by side.
+    const int lper = (TL + G - 1) / G, llo = min(TL, cta * lper), lhi = min(TL, llo + lper);
+    const int hper = (TH + G - 1) / G, hlo = min(TH, cta * hper), hhi = min(TH, hlo + hper);
+    const int light_warps = min(kWarps, (lhi - llo + 31) >> 5);
+    const int heavy_warps = max(kWarps - light_warps, 8);
+    for (int base = llo + warp * 32; base < lhi; base += kT) light_chunk(base, lhi);
+    MOR_TRACE_NOSYNC(17);
+    const int hwarp = kWarps - 1 - warp;
+    if (hwarp < heavy_warps)
+        for (int w = hlo + hwarp; w < hhi; w += 2 * heavy_warps) heavy_pairs(w, w + heavy_warps, w + heavy_warps < hhi);
+#else
+    // Measurement variant (-DMOR_TEST_TICKETS): both lists dealt out by ticket over the whole group, a chunk per warp and
+    // step (32 light pairs or 2 heavy pairs), half of the warps starting on either list. It evens out the CTAs but puts a
+    // round trip - and 4,700 warps queueing on two words - in front of every chunk: 22.9 vs 16.1 us for the phase.
+    auto run_light = [&]() {
+        while (true) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&a.scratch->ticket_light, 32);
+            t = __shfl_sync(kFull, t, 0);
+            if (t >= TL) break;
+            light_chunk(t, TL);
+        }
+    };
+    auto run_heavy = [&]() {
+        while (true) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&a.scratch->ticket_heavy, 2);
+            t = __shfl_sync(kFull, t, 0);
+            if (t >= TH) break;
+            heavy_pairs(t, t + 1, t + 1 < TH);
+        }
+    };
+    if (warp < kWarps / 2) { run_light(); MOR_TRACE_NOSYNC(17); run_heavy(); }
+    else { run_heavy(); run_light(); }
+#endif
     __syncthreads();
     MOR_TRACE(18);
     const int nhard = min(s_nhard, kHardCap);
@@ -1693,7 +1721,7 @@ __device__ __forceinline__ void frame_epilogue(const FramePtrs& a, int G) {
     for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
     if (threadIdx.x == 0) {
         Scratch* sc = a.scratch;
-        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_light = 0; sc->n_heavy = 0; sc->n_sorted = 0; sc->tail_match = 0u; sc->tail_chain = 0u; sc->err_early = 0;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_light = 0; sc->n_heavy = 0; sc->n_sorted = 0; sc->tail_match = 0u; sc->tail_chain = 0u; sc->ticket_light = 0; sc->ticket_heavy = 0; sc->err_early = 0;
         sc->ticket_ingest = 0; sc->ticket_cells = 0;  // voxel ground modes (k_ground_partition leaves its tile tickets behind)
         for (int q = 0; q < 3; q++) { sc->box_inv_min[q] = 0u; sc->box_max[q] = 0u; }
     }
