@@ -1007,8 +1007,12 @@ __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
             if (item < first + chunks) {
                 const HeavyBoxes hb = s_hard_box[p];
                 for (; item < first + chunks; item += kWarps) {
-                    if (*(volatile int*)&s_hard_hit[p]) continue;
-                    if (heavy_scan_chunk(a, hb, hp.x, hp.y, hp.z, hp.w, (item - first) * 32, lane) && lane == 0) s_hard_hit[p] = 1;
+                    // (another warp may already have found the pair connected: the flag only ever goes from 0 to 1; atomics keep the
+                    // early exit free of a formal data race)
+                    int seen = 0;
+                    if (lane == 0) seen = atomicAdd(&s_hard_hit[p], 0);
+                    if (__shfl_sync(kFull, seen, 0)) continue;
+                    if (heavy_scan_chunk(a, hb, hp.x, hp.y, hp.z, hp.w, (item - first) * 32, lane) && lane == 0) atomicExch(&s_hard_hit[p], 1);
                 }
             }
             first += chunks;
@@ -1241,22 +1245,25 @@ __device__ __forceinline__ int nn_warp(const float* pts, int n, float qx, float 
     return best;
 }
 
-MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
+template <bool FAST>
+__device__ __forceinline__ void phase_match_impl(const FramePtrs& a, unsigned long long* dyn) {
     const int K = a.counts[MOR_CNT_K];
     const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
     constexpr int kNnBytes = kSingle * 12;  // (ok, match, distance) of one chunk of queries
     const int cap = (a.frame_smem - kNnBytes) / kMatchBytesPerCluster;
-    const bool fast = K <= cap && Kp <= cap;
+    constexpr bool fast = FAST;
     const int cta = 0; (void)cta;
     MOR_TRACE(19);
     float* const sm = reinterpret_cast<float*>(dyn);
-    float* const cc = fast ? sm : a.cl_centroid;                 // [K][3]
-    float* const cb = fast ? sm + 3 * cap : a.cl_bbox;           // [K][6]
-    float* const pc = fast ? sm + 9 * cap : a.pct;               // [Kp][3]
-    float* const pb = fast ? sm + 12 * cap : a.pbbox;            // [Kp][6]
-    int* const rq = fast ? reinterpret_cast<int*>(sm + 18 * cap) : a.recip_q;
-    int* const rm = fast ? reinterpret_cast<int*>(sm + 19 * cap) : a.recip_m;
-    float* const rd = fast ? sm + 20 * cap : a.match_dist;
+    // (no run-time choice between the two homes of an array: the compiler must see which address space a load goes to)
+    float *cc, *cb, *pc, *pb, *rd;
+    int *rq, *rm;
+    if (FAST) {
+        cc = sm; cb = sm + 3 * cap; pc = sm + 9 * cap; pb = sm + 12 * cap;       // [K][3], [K][6], [Kp][3], [Kp][6]
+        rq = reinterpret_cast<int*>(sm + 18 * cap); rm = reinterpret_cast<int*>(sm + 19 * cap); rd = sm + 20 * cap;
+    } else {
+        cc = a.cl_centroid; cb = a.cl_bbox; pc = a.pct; pb = a.pbbox; rq = a.recip_q; rm = a.recip_m; rd = a.match_dist;
+    }
     int* const nn_j = reinterpret_cast<int*>(sm + 21 * cap);  // [kSingle] each: the chunk's nearest neighbour, its distance, reciprocal?
     float* const nn_d = sm + 21 * cap + kSingle;
     int* const nn_ok = reinterpret_cast<int*>(sm + 21 * cap + 2 * kSingle);
@@ -1311,6 +1318,7 @@ MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
                 if (lane == 0) { nn_j[u] = jq; nn_d[u] = dq; nn_ok[u] = (K > 0 && ir == q) ? 1 : 0; }
             }
         }
+        MOR_TRACE(23);
         __syncthreads();
         const int i = base + threadIdx.x;
         bool ok = false; int j = -1; float d = 0.f;
@@ -1354,6 +1362,13 @@ MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
         a.counts[MOR_CNT_MU] = n_recip; a.counts[MOR_CNT_M] = n_match;
         a.counts[MOR_CNT_NKPREV] = a.p_counts[MOR_CNT_NK];
     }
+}
+
+MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
+    const int K = a.counts[MOR_CNT_K];
+    const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
+    const int cap = (a.frame_smem - kSingle * 12) / kMatchBytesPerCluster;
+    if (K <= cap && Kp <= cap) phase_match_impl<true>(a, dyn); else phase_match_impl<false>(a, dyn);
 }
 
 // ===================================================================================== phase I: moving test
@@ -1438,6 +1453,8 @@ MOR_OUTLINE void phase_chain(const FramePtrs& a) {
     const int D = a.ring_depth, kmax = a.kmax;
     TrackState* ts = a.track;
     __shared__ int s_flag_any;
+    const int cta = 0; (void)cta;
+    MOR_TRACE(24);
     for (int m = threadIdx.x; m < M; m += kSingle) {
         const unsigned long long n1 = (unsigned long long)a.p_cl_size[a.match_q[m]], n2 = (unsigned long long)a.cl_size[a.match_m[m]];
         double score, thr;
@@ -1473,6 +1490,7 @@ MOR_OUTLINE void phase_chain(const FramePtrs& a) {
     const int corr_count = ts->corr_count + 1;
     const int corr_head = ts->corr_head;
     __syncthreads();
+    MOR_TRACE(25);
     float* const mo_centroid = a.mo_centroid + (size_t)a.mo_parity * a.momax * 3;
     int* const mo_conf = a.mo_conf + (size_t)a.mo_parity * a.momax;
     int n_mo = ts->n_mo[a.mo_parity];
@@ -1505,6 +1523,7 @@ MOR_OUTLINE void phase_chain(const FramePtrs& a) {
             n_found += tot;
             __syncthreads();
         }
+        MOR_TRACE(26);
         // pushCentroid in that order; the scan over mo_vec is parallel, the append is serial
         for (int i = 0; i < n_found; i++) {
             const int f = a.found[i];
@@ -1535,6 +1554,7 @@ MOR_OUTLINE void phase_chain(const FramePtrs& a) {
             __syncthreads();
         }
     }
+    MOR_TRACE(27);
     if (threadIdx.x == 0) {
         if (res_count >= a.moving_confidence) {  // pop_front both deques, cpp:511-512
             ts->corr_head = (corr_head + 1) % D; ts->corr_count = corr_count - 1;

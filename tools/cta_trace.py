@@ -36,5 +36,7 @@ for f in range(max(want) + 1):
                 print(f"      .. {what:14s} p50 {np.median(r2):6.1f}  p90 {np.percentile(r2, 90):6.1f}  last {r2.max():6.1f}")
         if name.startswith("ph_stats"):  # the single-CTA tail (rows 19..22, slot 0): entry, centroids done, reciprocal NN done, end
             tt = [(t[row][0] - prev_end) / 1e3 for row in (19, 20, 21, 22)]
-            print("      .. match: entry %.1f  centroids %.1f  nn %.1f  volume %.1f" % tuple(tt))
+            print("      .. match: entry %.1f  centroids %.1f  nn %.1f  volume %.1f" % tuple(tt), " (nn searches done %.1f)" % ((t[23][0] - prev_end) / 1e3))
+        if name.startswith("ph_moving"):  # chain tail (rows 24..27, slot 0): entry, flags + ring pushes, chains followed, pushCentroid done
+            print("      .. chain: entry %.1f  flags+rings %.1f  follow %.1f  push %.1f" % tuple((t[row][0] - prev_end) / 1e3 for row in (24, 25, 26, 27)))
         prev_end = arr.max()
