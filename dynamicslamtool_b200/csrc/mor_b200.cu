@@ -112,7 +112,8 @@ struct mor_handle {
         uint8_t* d_in = nullptr; float4* d_out = nullptr; int32_t* h_counts = nullptr;
         cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
         void* out = nullptr; uint32_t cap = 0, spec = 0;
-    } slot[2];
+        bool used = false;
+    } slot[MOR_STREAM_DEPTH];
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_join = nullptr;
     int sf_head = 0, inflight = 0;
@@ -243,7 +244,8 @@ int allocate(mor_handle* h) {
         uint8_t* p = p0;
         FramePtrs& b = h->base;
         h->d_in = carve<uint8_t>(p, h->d_in_bytes);
-        h->slot[0].d_in = h->d_in; h->slot[1].d_in = carve<uint8_t>(p, h->d_in_bytes);
+        h->slot[0].d_in = h->d_in;
+        for (int q = 1; q < MOR_STREAM_DEPTH; q++) h->slot[q].d_in = carve<uint8_t>(p, h->d_in_bytes);
         b.scratch = carve<Scratch>(p, 1);
         b.st_ingest = carve<unsigned long long>(p, tiles_pts);
         b.st_out = carve<unsigned long long>(p, tiles_pts);
@@ -267,7 +269,8 @@ int allocate(mor_handle* h) {
         b.cluster_removed = carve<uint8_t>(p, K); b.found = carve<int>(p, K);
         b.marker_cluster = carve<int>(p, MO); b.phase_ts = carve<unsigned long long>(p, 32); b.cta_trace = carve<unsigned long long>(p, 32 * 256); h->coll_cursor = carve<int>(p, K); h->coll_turn = carve<int>(p, 2);
         b.out = carve<float4>(p, N * 2); h->coll_out = carve<float4>(p, N * 2);
-        h->slot[0].d_out = b.out; h->slot[1].d_out = carve<float4>(p, N * 2); h->out_cur = b.out;
+        h->slot[0].d_out = b.out; h->out_cur = b.out;
+        for (int q = 1; q < MOR_STREAM_DEPTH; q++) h->slot[q].d_out = carve<float4>(p, N * 2);
         for (int f = 0; f < 2; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
             h->cl_root[f] = carve<int>(p, K); h->cl_size[f] = carve<int>(p, K); h->cl_centroid[f] = carve<float>(p, K * 3);
@@ -755,10 +758,13 @@ int mor_sync(mor_handle* h) {
 }
 
 // ---- pipelined streaming ---------------------------------------------------------------------------
-// Frame f lives in slot f & 1. Three streams: copy_in (H2D of the raw records), the handle's stream (frame kernels, in
-// order: the tracker state is a chain through the frames) and copy_out (counts + filtered cloud). A slot is reused by
-// frame f + 2, which cannot be submitted before frame f has been collected, i.e. before its D2H copy - and with it the
-// kernel that read the slot's staging buffer and wrote its output buffer - has completed: no other ordering is needed.
+// Frame f lives in slot f mod MOR_STREAM_DEPTH. Three streams: copy_in (H2D of the raw records), the handle's stream
+// (frame kernels, in order: the tracker state is a chain through the frames) and copy_out (counts + filtered cloud). A
+// slot is reused by frame f + DEPTH, which cannot be submitted before frame f has been collected, i.e. before its D2H
+// copy - and with it the kernel that read the slot's staging buffer and wrote its output buffer - has completed. With
+// three frames in flight the H2D copy of frame f+1 is issued while the host still waits for frame f-1: the kernels then
+// run back to back (with two, every kernel waited ~14 us for its input). The per-frame counts are ping-pong (cur/prev):
+// the kernel of frame f overwrites the block frame f-2's D2H reads, so it waits for that copy (normally long done).
 static int ensure_streaming(mor_handle* h) {
     if (h->copy_in) return MOR_OK;
     MOR_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
@@ -785,8 +791,12 @@ int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step,
     MOR_CUDA(cudaSetDevice(h->device));
     { int st = ensure_streaming(h); if (st != MOR_OK) return st; }
     { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
-    const int si = (h->sf_head + h->inflight) & 1;
+    const int si = (h->sf_head + h->inflight) % MOR_STREAM_DEPTH;
     mor_handle::StreamSlot& sl = h->slot[si];
+    {   // the count block this frame's kernel writes was the one of the frame before last
+        mor_handle::StreamSlot& s2 = h->slot[(si + MOR_STREAM_DEPTH - 2) % MOR_STREAM_DEPTH];
+        if (s2.used) MOR_CUDA(cudaStreamWaitEvent(h->stream, s2.d2h, 0));
+    }
     if (!h->inflight) {  // the pipeline starts: earlier work of the synchronous calls may still use slot 0's buffers
         MOR_CUDA(cudaEventRecord(h->ev_join, h->stream));
         MOR_CUDA(cudaStreamWaitEvent(h->copy_in, h->ev_join, 0));
@@ -808,7 +818,7 @@ int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step,
     if (spec > cap_points) spec = cap_points;
     if (spec) MOR_CUDA(cudaMemcpyAsync(out, sl.d_out, (size_t)spec * 32, cudaMemcpyDeviceToHost, h->copy_out));
     MOR_CUDA(cudaEventRecord(sl.d2h, h->copy_out));
-    sl.out = out; sl.cap = cap_points; sl.spec = spec;
+    sl.out = out; sl.cap = cap_points; sl.spec = spec; sl.used = true;
     h->mo_parity ^= 1; h->frame.mo_parity = h->mo_parity; h->filtered = true;  // committed like push + one filterCloud
     h->inflight++;
     return MOR_OK;
@@ -820,7 +830,7 @@ int mor_collect_frame(mor_handle* h, uint32_t* n_out) {
     MOR_CUDA(cudaSetDevice(h->device));
     mor_handle::StreamSlot& sl = h->slot[h->sf_head];
     MOR_CUDA(cudaEventSynchronize(sl.d2h));
-    h->sf_head ^= 1; h->inflight--;
+    h->sf_head = (h->sf_head + 1) % MOR_STREAM_DEPTH; h->inflight--;
     const uint32_t no = (uint32_t)sl.h_counts[CNT_SPEC_NOUT];
     if (n_out) *n_out = no;
     h->spec_out = no;

@@ -33,19 +33,21 @@ def test_streamed_frames_equal_synchronous_frames_and_oracle(product, oracle, cf
         want_orc.append(crc(orc.filter_cloud()))
     assert want == want_orc
     m = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
+    DEPTH = 3  # MOR_STREAM_DEPTH
     ins, outs, keep = [], [], []
-    for _ in range(2):
+    for _ in range(DEPTH):
         a, pa = _pinned(product, (s.max_points, 4)); o, po = _pinned(product, (s.max_points, 8))
         ins.append(a); outs.append(o); keep += [pa, po]
     got = []
     for f, (pts, pose) in enumerate(seq):
-        slot = f & 1
+        slot = f % DEPTH
         ins[slot][: len(pts)] = pts
         m.submit_frame(ins[slot][: len(pts)], pose, outs[slot])
-        assert m.frames_in_flight() == (1 if f == 0 else 2)
-        if f >= 1:
+        assert m.frames_in_flight() == min(f + 1, DEPTH)
+        if f >= DEPTH - 1:
             got.append(crc(m.collect_frame()))
-    got.append(crc(m.collect_frame()))
+    while m.frames_in_flight():
+        got.append(crc(m.collect_frame()))
     assert m.frames_in_flight() == 0
     assert got == want
     # the tracker state at the end equals the synchronous handle's
@@ -60,29 +62,29 @@ def test_streaming_protocol_errors_and_mixing(product, cfg_dir):
     with pytest.raises(MorError) as e:
         m.collect_frame()
     assert e.value.status == 8  # nothing in flight
-    outs = [np.empty((s.max_points, 8), np.float32) for _ in range(3)]  # pageable memory works too (no overlap then)
-    frames = [s.frame(f) for f in range(6)]
-    m.submit_frame(frames[0][0], frames[0][1], outs[0])
-    m.submit_frame(frames[1][0], frames[1][1], outs[1])
+    outs = [np.empty((s.max_points, 8), np.float32) for _ in range(4)]  # pageable memory works too (no overlap then)
+    frames = [s.frame(f) for f in range(8)]
+    for q in range(3):
+        m.submit_frame(frames[q][0], frames[q][1], outs[q])
     with pytest.raises(MorError) as e:
-        m.submit_frame(frames[2][0], frames[2][1], outs[2])
-    assert e.value.status == 8  # depth 2
+        m.submit_frame(frames[3][0], frames[3][1], outs[3])
+    assert e.value.status == 8  # MOR_STREAM_DEPTH = 3
     with pytest.raises(MorError) as e:
-        m.push_raw_cloud_and_pose(*frames[2])
+        m.push_raw_cloud_and_pose(*frames[3])
     assert e.value.status == 8  # synchronous calls only while nothing is in flight
-    a = m.collect_frame().copy(); b = m.collect_frame().copy()
+    got = [m.collect_frame().copy() for _ in range(3)]
     # ... after which the synchronous calls continue the same sequence
-    m.push_raw_cloud_and_pose(*frames[2]); c = m.filter_cloud().copy()
-    m.submit_frame(frames[3][0], frames[3][1], outs[0]); d = m.collect_frame().copy()
+    m.push_raw_cloud_and_pose(*frames[3]); got.append(m.filter_cloud().copy())
+    m.submit_frame(frames[4][0], frames[4][1], outs[0]); got.append(m.collect_frame().copy())
     ref = MovingObjectRemoval(cfg_dir / "MOR_config.txt", 4, 3, binding=product, max_points=s.max_points)
     want = []
-    for pts, pose in frames[:4]:
+    for pts, pose in frames[:5]:
         ref.push_raw_cloud_and_pose(pts, pose); want.append(ref.filter_cloud().copy())
-    for x, y in zip((a, b, c, d), want):
+    for x, y in zip(got, want):
         assert np.array_equal(x, y)
     # an output buffer that is too small is reported at collection, with the needed count
     small = np.empty((16, 8), np.float32)
-    m.submit_frame(frames[4][0], frames[4][1], small)
+    m.submit_frame(frames[5][0], frames[5][1], small)
     with pytest.raises(MorError) as e:
         m.collect_frame()
     assert e.value.status == 6
