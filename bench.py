@@ -389,7 +389,7 @@ def run_product(args, rank, local_rank, world):
     # ------------------------------------------------------------------ C5: 128 sequences per GPU (1024 on 8 GPUs), 32 frames each, seeds 1000 + s
     c5 = None
     if args.c5_sequences > 0:
-        c5 = run_c5(b, local_rank, rank, world, args.c5_sequences, 32, args.sequences if args.sequences > 1 else 16, maxp, max_over_ranks, sum_over_ranks, barrier)
+        c5 = run_c5(b, local_rank, rank, world, args.c5_sequences, 32, args.sequences if args.sequences > 1 else 37, maxp, max_over_ranks, sum_over_ranks, barrier)
 
     # ------------------------------------------------------------------ multi-sequence, end to end: one host thread per sequence through
     # the host C ABI (pinned input, H2D, kernels, D2H): copies of one sequence overlap the kernels of the others
@@ -682,7 +682,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-sequences", type=int, default=8, help="sequences (= host threads) of the multi-sequence end-to-end figure (1 = skip)")
-    ap.add_argument("--sequences", type=int, default=16, help="independent sequences per GPU for the extra multi_sequence figure (1 = skip)")
+    ap.add_argument("--sequences", type=int, default=37, help="independent sequences per launch for the multi_sequence figure and the batches of the C5 leg (37 = a group of 4 CTAs per sequence on 148 SMs; 1 = skip)")
     ap.add_argument("--c5-sequences", type=int, default=128, help="BASELINE config 5: sequences per GPU (128 x 8 GPUs = the full 1024), 32 frames each (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

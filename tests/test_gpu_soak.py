@@ -36,13 +36,14 @@ def test_soak_every_tap_every_frame(product, oracle, cfg_dir, scenario, cfg, fra
     assert st.centroid_not_bitexact <= st.centroid_values // 1000
 
 
-def test_batched_step_at_the_benchmarked_configuration(product, oracle, cfg_dir):
-    """S = 16 sequences per launch on the C2 workload (bench.py multi_sequence, tools/c5_run.py). 8 distinct streams
-    (seed, first frame), each run twice inside the batch: the copies must agree with each other bit for bit and with
-    the oracle tap by tap. Streams 0-3 cross the dense stretch of seed 2 (frames 101-107)."""
+@pytest.mark.parametrize("S,frames", [(37, 34), (17, 10)])
+def test_batched_step_at_the_benchmarked_configuration(product, oracle, cfg_dir, S, frames):
+    """S = 37 sequences per launch (a group of 4 CTAs each: all 148 SMs) on the C2 workload - bench.py's multi_sequence and
+    the batches of its C5 leg, whose last batch of a GPU's 128 sequences holds 17. 8 distinct streams (seed, first frame),
+    each run several times inside the batch: the copies must agree with each other bit for bit and with the oracle tap by
+    tap. Streams 0-3 cross the dense stretch of seed 2 (frames 101-107) in the long run."""
     cfg = cfg_dir / "MOR_config_hdl64.txt"
     streams = [(2, 76), (2, 80), (2, 90), (2, 100), (1000, 0), (1001, 0), (1002, 3), (1003, 7)]
-    frames, S = 34, 16
     syn = [Synth(2, seed) for seed, _ in streams]
     maxp = syn[0].max_points
     gpus = [MovingObjectRemoval(cfg, 4, 3, binding=product, max_points=maxp) for _ in range(S)]
@@ -75,11 +76,12 @@ def test_batched_step_at_the_benchmarked_configuration(product, oracle, cfg_dir)
             oo = orcs[t].filter_cloud().copy()
             bad = compare_frame(gpus[t], orcs[t], outs[t], oo, stats)
             assert not bad, f"stream {t} frame {f}: {bad}"
-            assert outs[t].tobytes() == outs[t + 8].tobytes(), f"copies of stream {t} differ at frame {f}"
-            for tap in ("labels", "cluster_id", "centroids", "match_score", "flags", "mo_conf", "removed_mask"):
-                assert gpus[t].tap(tap).tobytes() == gpus[t + 8].tap(tap).tobytes(), f"{tap}: copies of stream {t} differ at frame {f}"
+            for c in range(t + 8, S, 8):
+                assert outs[t].tobytes() == outs[c].tobytes(), f"copy {c} of stream {t} differs at frame {f}"
+                for tap in ("labels", "cluster_id", "centroids", "match_score", "flags", "mo_conf", "removed_mask"):
+                    assert gpus[t].tap(tap).tobytes() == gpus[c].tap(tap).tobytes(), f"{tap}: copy {c} of stream {t} differs at frame {f}"
             dense = max(dense, int(gpus[t].tap("cluster_size").max(initial=0)))
     print("batched parity", stats.as_dict(), "largest cluster", dense)
-    assert stats.matches > 0 and dense > 20000
+    assert stats.matches > 0 and (frames < 30 or dense > 20000)
     for p in d_in + d_out:
         product.device_free(0, p)

@@ -33,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sequences", type=int, default=256)
     ap.add_argument("--frames", type=int, default=32)
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=37)
     ap.add_argument("--base-seed", type=int, default=1000)
     ap.add_argument("--threads", type=int, default=0)
     args = ap.parse_args()
