@@ -23,7 +23,12 @@ constexpr int kSingle = kT;      // single-CTA bookkeeping phases use the whole 
 constexpr int kWarps = kT / 32;
 constexpr int kLightPair = 256;  // a cell pair with at most this many point pairs is tested by one thread, a larger one by a warp
 constexpr int kLightCnt = 32;    // ... and with at most this many points in either cell (the thread's loop stays short; 7 bits in the packed record)
-constexpr int kStageLight = 3072, kStageHeavy = 512;  // pair records a CTA collects in shared memory before they go to the lists (24 + 8 KB)
+#ifndef MOR_STAGE_LIGHT  // (a stress build shrinks these to force the overflow paths: -DMOR_STAGE_LIGHT=64 -DMOR_STAGE_HEAVY=16 -DMOR_HARD_CAP=2)
+#define MOR_STAGE_LIGHT 3072
+#define MOR_STAGE_HEAVY 512
+#define MOR_HARD_CAP 96
+#endif
+constexpr int kStageLight = MOR_STAGE_LIGHT, kStageHeavy = MOR_STAGE_HEAVY;  // pair records a CTA collects in shared memory before they go to the lists (24 + 8 KB)
 constexpr size_t kLinkSmem = (size_t)kStageLight * 8 + (size_t)kStageHeavy * 16;
 
 enum ErrBits { ERR_CLUSTER_CAP = 1, ERR_MOVING_CAP = 2, ERR_LATTICE_RANGE = 4, ERR_GROUND_CAP = 8, ERR_GRID_RANGE = 16, ERR_EDGE_CAP = 32 };
@@ -880,7 +885,7 @@ __device__ __forceinline__ bool light_pair_connected(const float4* S, int cS, co
 }
 
 __device__ __forceinline__ void phase_test(const FramePtrs& a, int cta, int G) {
-    constexpr int kHardCap = 96;
+    constexpr int kHardCap = MOR_HARD_CAP;
     __shared__ int s_edges, s_nhard, s_hard_hit[kHardCap];
     __shared__ int4 s_hard[kHardCap];
     __shared__ HeavyBoxes s_hard_box[kHardCap];
