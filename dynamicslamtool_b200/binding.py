@@ -134,6 +134,7 @@ class MorBinding:
         self.submit_frame = f("submit_frame", [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double), vp, u32], True)
         self.collect_frame = f("collect_frame", [vp, C.POINTER(u32)], True)
         self.frames_in_flight = f("frames_in_flight", [vp, C.POINTER(u32)], True)
+        self.set_pipelining = f("set_pipelining", [vp, C.c_int], True)
 
     def _fn(self, name, argtypes, optional=False, restype=C.c_int):
         try:
@@ -337,6 +338,10 @@ class MovingObjectRemoval:
         out = q.pop(0)[1] if q else None
         self._check(st, "collect_frame")
         return out[: n_out.value]
+
+    def set_pipelining(self, enabled: bool):
+        """Throughput mode: the back half of a frame runs beside the front half of the next one (see mor_set_pipelining)."""
+        self._check(self.b.set_pipelining(self.h, 1 if enabled else 0), "set_pipelining")
 
     def frames_in_flight(self) -> int:
         v = C.c_uint32(0)

@@ -111,8 +111,9 @@ struct mor_handle {
     struct StreamSlot {
         uint8_t* d_in = nullptr; float4* d_out = nullptr; int32_t* h_counts = nullptr;
         cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
-        void* out = nullptr; uint32_t cap = 0, spec = 0;
-        bool used = false;
+        void* out = nullptr; uint32_t cap = 0, spec = 0, n = 0;
+        const int* d_counts = nullptr;
+        bool used = false, d2h_enqueued = false;
     } slot[MOR_STREAM_DEPTH];
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_join = nullptr;
@@ -123,8 +124,15 @@ struct mor_handle {
     int* coll_cursor = nullptr; int* coll_turn = nullptr; float4* coll_out = nullptr;  // mor_get_cluster_collection scratch
     GroundPtrs ground;  // voxel-covariance ground removal state (ground_mode 1/2 only)
     // ping-pong
-    float4* pts[2]; float4* spts[2]; int* cid[2]; int* cl_root[2]; int* cl_size[2]; float* cl_centroid[2]; uint8_t* cl_flags[2]; float* cl_bbox[2]; int* counts[2];
-    int cur = 0;
+    // frame products: three in rotation (cur, prev and - in a pipelined launch - the frame whose front half is running)
+    float4* pts[3]; float4* spts[3]; int* cid[3]; int* cl_root[3]; int* cl_size[3]; float* cl_centroid[3]; uint8_t* cl_flags[3]; float* cl_bbox[3]; int* counts[3];
+    // products of the front half that only the back half of the SAME frame reads: two, by frame parity
+    int* scid2[2]; float4* gpts2[2]; int* gsrc2[2]; int* cloud_src2[2]; uint8_t* removed_mask2[2];
+    int cur = 0, fpar = 0;
+    // pipelining (mor_set_pipelining): the back half of the last filtered frame waits to be launched beside the front half
+    // of the next frame
+    bool pipelining = false, back_pending = false;
+    FramePtrs back_frame;
     bool have_cur = false, have_prev = false, filtered = false;
     int mo_parity = 0;
     double cur_pose[7], prev_pose[7];
@@ -272,6 +280,10 @@ int allocate(mor_handle* h) {
         h->slot[0].d_out = b.out; h->out_cur = b.out;
         for (int q = 1; q < MOR_STREAM_DEPTH; q++) h->slot[q].d_out = carve<float4>(p, N * 2);
         for (int f = 0; f < 2; f++) {
+            h->scid2[f] = f ? carve<int>(p, N) : b.scid; h->gpts2[f] = f ? carve<float4>(p, N) : b.gpts; h->gsrc2[f] = f ? carve<int>(p, N) : b.gsrc;
+            h->cloud_src2[f] = f ? carve<int>(p, N) : b.cloud_src; h->removed_mask2[f] = f ? carve<uint8_t>(p, N) : b.removed_mask;
+        }
+        for (int f = 0; f < 3; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
             h->cl_root[f] = carve<int>(p, K); h->cl_size[f] = carve<int>(p, K); h->cl_centroid[f] = carve<float>(p, K * 3);
             h->cl_flags[f] = carve<uint8_t>(p, K); h->cl_bbox[f] = carve<float>(p, K * 6); h->counts[f] = carve<int>(p, MOR_NCOUNTS);
@@ -313,6 +325,7 @@ int set_phase_smem(mor_handle* h) {
 int configure_kernels(mor_handle* h) {
     MOR_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
     MOR_CUDA(cudaFuncSetAttribute(k_frame_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
+    MOR_CUDA(cudaFuncSetAttribute(k_frame_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->frame_smem));
     int st = set_phase_smem<PH_SELECT>(h);
     if (st == MOR_OK) st = set_phase_smem<PH_LINK>(h);
     if (st == MOR_OK) st = set_phase_smem<PH_STATS>(h);
@@ -380,7 +393,8 @@ void set_segments(mor_handle* h, FramePtrs& a, int group_ctas) {
 void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
     FramePtrs& a = h->frame;
     a = h->base;
-    const int cur = h->cur, prev = cur ^ 1;
+    const int cur = h->cur, prev = (cur + 2) % 3;
+    a.scid = h->scid2[h->fpar]; a.gpts = h->gpts2[h->fpar]; a.gsrc = h->gsrc2[h->fpar]; a.cloud_src = h->cloud_src2[h->fpar]; a.removed_mask = h->removed_mask2[h->fpar];
     a.in = d_points; a.n = n; a.step = step; a.off_x = ox; a.off_y = oy; a.off_z = oz; a.off_i = oi;
     a.in_mode = input_mode(d_points, step, ox, oy, oz, oi);
     a.pts = h->pts[cur]; a.spts = h->spts[cur]; a.cid = h->cid[cur]; a.cl_root = h->cl_root[cur]; a.cl_size = h->cl_size[cur];
@@ -405,7 +419,36 @@ int launch_phase(mor_handle* h, const FramePtrs& a) {
     return MOR_OK;
 }
 
-int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
+// Pipelined launches (k_frame_pipe): the front half of `front` on most CTAs beside the pending back half, or either alone.
+int launch_pipe(mor_handle* h, const FramePtrs* front, const FramePtrs* back) {
+    const int G = h->frame_ctas;
+    // the front half is tile-granular in its first phase (1024 input points per CTA): it gets at least one CTA per tile, at most
+    // 7/8 of the GPU; the back half scales with what is left
+    int Gf = G, Gb = 0;
+    if (front && back) {
+        const int tiles = (int)((front->n + kT - 1) / kT);
+        Gf = tiles + 1;
+        if (Gf < (G * 3) / 4) Gf = (G * 3) / 4;
+        if (Gf > (G * 7) / 8) Gf = (G * 7) / 8;
+        if (const char* env = std::getenv("MOR_PIPE_GF")) { const int v = std::atoi(env); if (v > 0 && v < G) Gf = v; }  // (tuning)
+        Gb = G - Gf;
+    } else if (back) { Gf = 0; Gb = G; }
+    FramePtrs f = front ? *front : *back, b = back ? *back : *front;
+    set_segments(h, f, Gf > 0 ? Gf : G);
+    (void)Gb;
+    cudaError_t e = launch_coop(k_frame_pipe, (unsigned)G, h->frame_smem, h->stream, f, b, Gf);
+    h->launches++;
+    if (e != cudaSuccess) { h->last_error = std::string("k_frame_pipe: ") + cudaGetErrorString(e); return MOR_ERR_CUDA; }
+    return MOR_OK;
+}
+// The back half of the last filtered frame, if it is still waiting for a partner: alone.
+int flush_back(mor_handle* h) {
+    if (!h->back_pending) return MOR_OK;
+    h->back_pending = false;
+    return launch_pipe(h, nullptr, &h->back_frame);
+}
+
+int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi, bool allow_pipe) {
     cudaStream_t st = h->stream;
     fill_frame(h, d_points, n, step, ox, oy, oz, oi);
     FramePtrs& a = h->frame;
@@ -431,6 +474,14 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
             (s = launch_phase<PH_JUMP>(h, a)) || (s = launch_phase<PH_CROSS>(h, a)) || (s = launch_phase<PH_ROOTS>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || 
             (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
             return s;
+    } else if (allow_pipe && h->pipelining && h->cfg.method_choice == 2) {
+        // front half of this frame, beside the back half of the frame before if that one has been filtered already
+        const bool fused = h->back_pending;
+        h->back_pending = false;
+        int s = launch_pipe(h, &a, fused ? &h->back_frame : nullptr);
+        if (s != MOR_OK) return s;
+        h->back_frame = a;  // this frame's back half: beside the next frame's front half, or alone as soon as somebody needs its results
+        h->back_pending = true;
     } else {
         cudaError_t e = launch_coop(k_frame, (unsigned)h->frame_ctas, h->frame_smem, st, a);
         h->launches++;
@@ -441,7 +492,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
 
 // ca = cb; cb = new frame (cpp:520-521), pose delta cb.ps^-1 * ca.ps (cpp:536)
 void advance_frame(mor_handle* h, uint32_t n, const double pose7[7]) {
-    if (h->have_cur) { h->cur ^= 1; std::memcpy(h->prev_pose, h->cur_pose, sizeof(h->cur_pose)); h->have_prev = true; h->n_prev_input = h->n_input; }
+    if (h->have_cur) { h->cur = (h->cur + 1) % 3; h->fpar ^= 1; std::memcpy(h->prev_pose, h->cur_pose, sizeof(h->cur_pose)); h->have_prev = true; h->n_prev_input = h->n_input; }
     std::memcpy(h->cur_pose, pose7, sizeof(h->cur_pose));
     h->n_input = n;
     h->two_frames = h->have_prev;  // ca->init && cb->init (cpp:534)
@@ -452,7 +503,8 @@ void advance_frame(mor_handle* h, uint32_t n, const double pose7[7]) {
 }
 
 // Work of a handle may have been enqueued on another handle's stream by mor_batch_step_device.
-int join_foreign_stream(mor_handle* h) {
+int join_foreign_stream(mor_handle* h, bool keep_pending_back = false) {
+    if (!keep_pending_back) { int fs = flush_back(h); if (fs != MOR_OK) return fs; }
     if (h->last_stream && h->last_stream != h->stream) {
         MOR_CUDA(cudaStreamSynchronize(h->last_stream));
         h->last_stream = h->stream;
@@ -467,7 +519,7 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
     if (h->inflight) { h->last_error = "submitted frames are in flight: collect them first"; return MOR_ERR_STATE; }
     h->out_cur = h->slot[0].d_out;
     MOR_CUDA(cudaSetDevice(h->device));
-    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    { int js = join_foreign_stream(h, on_device && h->pipelining && h->cfg.ground_mode == MOR_GROUND_CROP && !h->profiling); if (js != MOR_OK) return js; }
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (h->profiling && !h->prof_ids.empty()) { MOR_CUDA(cudaStreamSynchronize(h->stream)); prof_harvest(h); }
     const uint8_t* d_points = (const uint8_t*)data;
@@ -478,7 +530,7 @@ int do_push(mor_handle* h, const void* data, bool on_device, uint32_t n, uint32_
         d_points = h->d_in;
     }
     advance_frame(h, n, pose7);
-    int st = enqueue_push(h, d_points, n, step, ox, oy, oz, oi);
+    int st = enqueue_push(h, d_points, n, step, ox, oy, oz, oi, /*allow_pipe=*/on_device);
     if (st != MOR_OK) return st;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[1], h->stream));
     return MOR_OK;
@@ -494,7 +546,9 @@ int do_filter(mor_handle* h, void* out, bool on_device, uint32_t cap_points, uin
     if (!h->have_cur) return MOR_ERR_STATE;
     if (h->inflight) { h->last_error = "submitted frames are in flight: collect them first"; return MOR_ERR_STATE; }
     MOR_CUDA(cudaSetDevice(h->device));
-    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    // (pipelining: a filter call that asks for nothing now leaves the frame's back half waiting for the next frame's front half)
+    const bool stays_pending = h->back_pending && on_device && !n_out && !out && !h->profiling && !h->filtered;
+    { int js = join_foreign_stream(h, stays_pending); if (js != MOR_OK) return js; }
     cudaStream_t st = h->stream;
     if (h->timing) MOR_CUDA(cudaEventRecord(h->ev[2], st));
     FramePtrs& a = h->frame;
@@ -556,7 +610,7 @@ int reset_state(mor_handle* h) {
     h->inflight = 0; h->sf_head = 0; h->out_cur = h->slot[0].d_out;
     MOR_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     MOR_CUDA(cudaStreamSynchronize(h->stream));
-    h->cur = 0; h->have_cur = h->have_prev = h->filtered = h->two_frames = false;
+    h->cur = 0; h->fpar = 0; h->back_pending = false; h->have_cur = h->have_prev = h->filtered = h->two_frames = false;
     h->mo_parity = 0; h->n_input = h->n_prev_input = 0; h->spec_out = 0;
     h->last_stream = h->stream;
     return MOR_OK;
@@ -690,6 +744,7 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
             return MOR_ERR_ARG;
         }
         if (g->cfg.ground_mode != MOR_GROUND_CROP) { h->last_error = "batched stepping supports ground_mode 0 only"; return MOR_ERR_ARG; }
+        { int fs = flush_back(g); if (fs != MOR_OK) return fs; }
         if (n[s] > g->nmax || (!d_data[s] && n[s]) || !d_out[s]) return n[s] > g->nmax ? MOR_ERR_CAPACITY : MOR_ERR_ARG;
         for (uint32_t t = 0; t < s; t++) if (hs[t] == g) return MOR_ERR_ARG;
     }
@@ -779,6 +834,22 @@ static int ensure_streaming(mor_handle* h) {
     return MOR_OK;
 }
 
+// The frame of a slot is complete on the handle's stream: its counts and its cloud go to the host on copy_out.
+static int enqueue_slot_d2h(mor_handle* h, mor_handle::StreamSlot& sl) {
+    MOR_CUDA(cudaEventRecord(sl.done, h->stream));
+    MOR_CUDA(cudaStreamWaitEvent(h->copy_out, sl.done, 0));
+    MOR_CUDA(cudaMemcpyAsync(sl.h_counts, sl.d_counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, h->copy_out));
+    // the size of the output is known on the device only: the copy is sized from the last collected frame plus a margin
+    // and topped up at collection in the rare case the frame turned out larger
+    uint32_t spec = h->spec_out ? h->spec_out + h->spec_out / 32 + 1024 : sl.n;
+    if (spec > sl.n) spec = sl.n;
+    if (spec > sl.cap) spec = sl.cap;
+    if (spec) MOR_CUDA(cudaMemcpyAsync(sl.out, sl.d_out, (size_t)spec * 32, cudaMemcpyDeviceToHost, h->copy_out));
+    MOR_CUDA(cudaEventRecord(sl.d2h, h->copy_out));
+    sl.spec = spec; sl.d2h_enqueued = true;
+    return MOR_OK;
+}
+
 int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi,
                      const double pose7[7], void* out, uint32_t cap_points) {
     if (!h || (!data && n) || !pose7 || (!out && cap_points)) return MOR_ERR_ARG;
@@ -790,7 +861,7 @@ int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step,
     if (h->inflight >= MOR_STREAM_DEPTH) { h->last_error = "MOR_STREAM_DEPTH frames are in flight: collect one first"; return MOR_ERR_STATE; }
     MOR_CUDA(cudaSetDevice(h->device));
     { int st = ensure_streaming(h); if (st != MOR_OK) return st; }
-    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    { int js = join_foreign_stream(h, /*keep_pending_back=*/h->inflight > 0); if (js != MOR_OK) return js; }
     const int si = (h->sf_head + h->inflight) % MOR_STREAM_DEPTH;
     mor_handle::StreamSlot& sl = h->slot[si];
     {   // the count block this frame's kernel writes was the one of the frame before last
@@ -806,19 +877,20 @@ int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step,
     MOR_CUDA(cudaStreamWaitEvent(h->stream, sl.h2d, 0));
     advance_frame(h, n, pose7);
     h->out_cur = sl.d_out;
-    int st = enqueue_push(h, sl.d_in, n, step, ox, oy, oz, oi);
+    const bool piped = h->pipelining && h->cfg.method_choice == 2 && h->cfg.ground_mode == MOR_GROUND_CROP;
+    int st = enqueue_push(h, sl.d_in, n, step, ox, oy, oz, oi, /*allow_pipe=*/true);
     if (st != MOR_OK) return st;
-    MOR_CUDA(cudaEventRecord(sl.done, h->stream));
-    MOR_CUDA(cudaStreamWaitEvent(h->copy_out, sl.done, 0));
-    MOR_CUDA(cudaMemcpyAsync(sl.h_counts, h->frame.counts, sizeof(int32_t) * MOR_NCOUNTS, cudaMemcpyDeviceToHost, h->copy_out));
-    // the size of the output is known on the device only: the copy is sized from the last collected frame plus a margin
-    // and topped up at collection in the rare case the frame turned out larger
-    uint32_t spec = h->spec_out ? h->spec_out + h->spec_out / 32 + 1024 : n;
-    if (spec > n) spec = n;
-    if (spec > cap_points) spec = cap_points;
-    if (spec) MOR_CUDA(cudaMemcpyAsync(out, sl.d_out, (size_t)spec * 32, cudaMemcpyDeviceToHost, h->copy_out));
-    MOR_CUDA(cudaEventRecord(sl.d2h, h->copy_out));
-    sl.out = out; sl.cap = cap_points; sl.spec = spec; sl.used = true;
+    sl.out = out; sl.cap = cap_points; sl.n = n; sl.d_counts = h->frame.counts; sl.used = true; sl.d2h_enqueued = false;
+    if (piped) {
+        // the launch just enqueued carried the back half of the frame before (if one was waiting): that frame is complete now
+        if (h->inflight) {
+            mor_handle::StreamSlot& sp = h->slot[(si + MOR_STREAM_DEPTH - 1) % MOR_STREAM_DEPTH];
+            if (!sp.d2h_enqueued) { int es = enqueue_slot_d2h(h, sp); if (es != MOR_OK) return es; }
+        }
+    } else {
+        int es = enqueue_slot_d2h(h, sl);
+        if (es != MOR_OK) return es;
+    }
     h->mo_parity ^= 1; h->frame.mo_parity = h->mo_parity; h->filtered = true;  // committed like push + one filterCloud
     h->inflight++;
     return MOR_OK;
@@ -829,6 +901,10 @@ int mor_collect_frame(mor_handle* h, uint32_t* n_out) {
     if (!h->inflight) { h->last_error = "no frame in flight"; return MOR_ERR_STATE; }
     MOR_CUDA(cudaSetDevice(h->device));
     mor_handle::StreamSlot& sl = h->slot[h->sf_head];
+    if (!sl.d2h_enqueued) {  // pipelining: its back half is still waiting for a next frame that has not come
+        { int fs = flush_back(h); if (fs != MOR_OK) return fs; }
+        { int es = enqueue_slot_d2h(h, sl); if (es != MOR_OK) return es; }
+    }
     MOR_CUDA(cudaEventSynchronize(sl.d2h));
     h->sf_head = (h->sf_head + 1) % MOR_STREAM_DEPTH; h->inflight--;
     const uint32_t no = (uint32_t)sl.h_counts[CNT_SPEC_NOUT];
@@ -847,6 +923,15 @@ int mor_collect_frame(mor_handle* h, uint32_t* n_out) {
                                  cudaMemcpyDeviceToHost, h->copy_out));
         MOR_CUDA(cudaStreamSynchronize(h->copy_out));
     }
+    return MOR_OK;
+}
+
+int mor_set_pipelining(mor_handle* h, int enabled) {
+    if (!h) return MOR_ERR_ARG;
+    MOR_CUDA(cudaSetDevice(h->device));
+    { int js = join_foreign_stream(h); if (js != MOR_OK) return js; }
+    if (h->inflight) { h->last_error = "submitted frames are in flight: collect them first"; return MOR_ERR_STATE; }
+    h->pipelining = enabled != 0;
     return MOR_OK;
 }
 

@@ -51,6 +51,8 @@ struct GridDesc {  // dense grid of the voxel ground modes' ball query (mor_grou
 struct Scratch {  // all zero between frames: every counter is put back by the frame that used it
     unsigned bar;            // group barrier of k_frame (monotonic within a launch)
     int blocks_done;         // CTAs that have finished the frame
+    unsigned bar_back; int blocks_done_back;  // the same for the back group of a pipelined launch (k_frame_pipe)
+    unsigned tail_centroids, tail_match_back;
     int n_cells, n_roots, n_light, n_heavy;  // list lengths of the frame
     int n_sorted, pad1;      // bump allocator of the sorted array (phase B)
     unsigned tail_match, tail_chain;  // arrival counters of the phases that end with a single-CTA step
@@ -361,8 +363,8 @@ __device__ __forceinline__ float smem_f32(const uint8_t* p) {
     return __uint_as_float((unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24));
 }
 
-__device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G, unsigned long long* dyn, unsigned long long* mbar, unsigned& parity) {
-    frame_housekeeping(a, cta, G);
+__device__ __forceinline__ void phase_ingest(const FramePtrs& a, int cta, int G, unsigned long long* dyn, unsigned long long* mbar, unsigned& parity, bool housekeep = true) {
+    if (housekeep) frame_housekeeping(a, cta, G);
     const int ntiles = a.n ? (int)((a.n + kIngestTile - 1) / kIngestTile) : 1;
     __shared__ int s_created, s_cbase;
     // Records that are not plain float4 (PCLPointCloud2 layouts with padding or extra fields, e.g. the 22-byte velodyne
@@ -1250,7 +1252,22 @@ __device__ __forceinline__ int nn_warp(const float* pts, int n, float qx, float 
     return best;
 }
 
-template <bool FAST>
+// Centroids and boxes of the current clusters from the exact sums (the first step of the match step; in a pipelined
+// launch it is the last step of the FRONT half, so that the back half never reads the accumulators of a frame whose
+// successor is already being clustered).
+__device__ __forceinline__ void phase_centroids(const FramePtrs& a) {
+    const int K = a.counts[MOR_CNT_K];
+    for (int c = threadIdx.x; c < K; c += kSingle) {
+        const double n = (double)a.cl_size[c];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
+    }
+}
+
+template <bool FAST, bool FINALIZE = true>
 __device__ __forceinline__ void phase_match_impl(const FramePtrs& a, unsigned long long* dyn) {
     const int K = a.counts[MOR_CNT_K];
     const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
@@ -1279,14 +1296,15 @@ __device__ __forceinline__ void phase_match_impl(const FramePtrs& a, unsigned lo
         const double n = (double)a.cl_size[c];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-            const float v = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
-            a.cl_centroid[c * 3 + q] = v;
+            const float v = FINALIZE ? (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n)
+                                     : __ldcg(&a.cl_centroid[c * 3 + q]);
+            if (FINALIZE) a.cl_centroid[c * 3 + q] = v;
             if (fast) cc[c * 3 + q] = v;
         }
 #pragma unroll
         for (int q = 0; q < 6; q++) {
-            const float v = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
-            a.cl_bbox[c * 6 + q] = v;
+            const float v = FINALIZE ? fkey_inv(__ldcg(&a.acc_box[c * 6 + q])) : __ldcg(&a.cl_bbox[c * 6 + q]);
+            if (FINALIZE) a.cl_bbox[c * 6 + q] = v;
             if (fast) cb[c * 6 + q] = v;
         }
     }
@@ -1374,6 +1392,13 @@ MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
     const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
     const int cap = (a.frame_smem - kSingle * 12) / kMatchBytesPerCluster;
     if (K <= cap && Kp <= cap) phase_match_impl<true>(a, dyn); else phase_match_impl<false>(a, dyn);
+}
+// (pipelined launch, back half: the centroids and boxes are final already)
+MOR_OUTLINE void phase_match_back(const FramePtrs& a, unsigned long long* dyn) {
+    const int K = a.counts[MOR_CNT_K];
+    const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
+    const int cap = (a.frame_smem - kSingle * 12) / kMatchBytesPerCluster;
+    if (K <= cap && Kp <= cap) phase_match_impl<true, false>(a, dyn); else phase_match_impl<false, false>(a, dyn);
 }
 
 // ===================================================================================== phase I: moving test
@@ -1719,10 +1744,10 @@ __device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShar
     if (tile == last_tile && threadIdx.x == 0) a.counts[CNT_SPEC_NOUT] = before + tot;
 }
 
-__device__ __forceinline__ void phase_filter(const FramePtrs& a, int cta, int G, FilterShared& sh) {
+__device__ __forceinline__ void phase_filter(const FramePtrs& a, int cta, int G, FilterShared& sh, bool cleanup = true) {
     const int total_items = frame_vars().nc + frame_vars().ng;
     const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
-    frame_cleanup(a, cta, G);
+    if (cleanup) frame_cleanup(a, cta, G);
     if (cta > last_tile) return;  // nothing to compact here (CTA 0 always has tile 0: it owns the mo_vec update)
     FilterTileIn in = filter_tile_load(a, cta);  // the first tile's loads are in flight while the tracking part runs
     const int overflow = filter_tracking(a, sh, cta == 0);
@@ -1806,6 +1831,93 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
     frame_step<PH_MOVING>(a, cta, G, sh, dyn, parity, bar);
     frame_step<PH_FILTER>(a, cta, G, sh, dyn, parity, bar);
     frame_epilogue(a, G);
+}
+
+// ===================================================================================== pipelined launch
+// Throughput mode (mor_set_pipelining; frames are known one ahead - replay, the streaming calls): clustering a frame needs
+// nothing of the frame before it, so ONE launch runs the front half of frame f+1 (ingest ... cluster statistics) on the
+// first Gf CTAs beside the back half of frame f (transform, match, moving test, chain, filter) on the others. The two
+// groups have their own barriers and counters and touch disjoint state: what the back half reads of frame f and f-1 is
+// triple-buffered (points, cluster ids, cluster tables, counts) or double-buffered (ground points, source indices, masks)
+// on the host side (mor_b200.cu, fill_frame). Method 2 and the crop ground mode only (method 1 searches the clustering
+// grid of frame f in the back half, which the front half of f+1 rebuilds).
+__device__ __forceinline__ void front_body(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
+    GroupBarrier bar{&a.scratch->bar, 0u, (unsigned)G};
+    phase_ingest(a, cta, G, dyn, &sh.mbar, parity, /*housekeep=*/false);
+    bar.sync();
+    load_frame_vars(a);
+    phase_cells(a, cta, G); bar.sync();
+    phase_link(a, cta, G, dyn); bar.sync();
+    phase_test(a, cta, G); bar.sync();
+    phase_jump(a, cta, G); bar.sync();
+    phase_cross(a, cta, G); bar.sync();
+    phase_roots(a, cta, G); bar.sync();
+    if (cta == 0) phase_select(a, dyn);
+    bar.sync();
+    phase_stats(a, cta, G);
+    if (group_last_arrival(&a.scratch->tail_centroids, (unsigned)G)) phase_centroids(a);
+    frame_cleanup(a, cta, G);
+    // last CTA of the group out: the front half's counters back to zero
+    __shared__ int s_last_front;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last_front = atomicAdd(&a.scratch->blocks_done, 1) == G - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last_front && threadIdx.x == 0) {
+        Scratch* sc = a.scratch;
+        sc->bar = 0u; sc->blocks_done = 0; sc->n_cells = 0; sc->n_roots = 0; sc->n_light = 0; sc->n_heavy = 0; sc->n_sorted = 0; sc->tail_centroids = 0u;
+        sc->ticket_light = 0; sc->ticket_heavy = 0; sc->err_early = 0;
+    }
+}
+
+__device__ __forceinline__ void back_body(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn) {
+    GroupBarrier bar{&a.scratch->bar_back, 0u, (unsigned)G};
+    if (threadIdx.x == 0) {  // (the cell count belongs to the front half, which is busy with the next frame)
+        FrameVars& v = frame_vars();
+        v.n_cells = 0; v.nc = __ldcg(&a.counts[MOR_CNT_NC]); v.ng = __ldcg(&a.counts[MOR_CNT_NG]);
+    }
+    __syncthreads();
+    frame_housekeeping(a, cta, G);
+    bar.sync();
+    if (a.two_frames) {
+        int lo, hi;
+        cta_slice(a.p_counts[MOR_CNT_NC], cta, G, &lo, &hi);
+        transform_range(a, lo, hi);
+    }
+    if (group_last_arrival(&a.scratch->tail_match_back, (unsigned)G)) phase_match_back(a, dyn);
+    bar.sync();
+    if (a.two_frames) phase_lattice_count(a, cta, G);
+    if (group_last_arrival(&a.scratch->tail_chain, (unsigned)G)) phase_chain_tail(a);
+    bar.sync();
+    phase_filter(a, cta, G, sh.filter, /*cleanup=*/false);
+    __shared__ int s_last_back;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last_back = atomicAdd(&a.scratch->blocks_done_back, 1) == G - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_last_back) return;
+    for (int t = threadIdx.x; t < a.tiles_pts; t += kT) a.st_out[t] = 0ull;
+    if (threadIdx.x == 0) {
+        Scratch* sc = a.scratch;
+        sc->bar_back = 0u; sc->blocks_done_back = 0; sc->tail_match_back = 0u; sc->tail_chain = 0u;
+    }
+}
+
+// Front half of `f` on the CTAs [0, Gf), back half of `b` on the rest; Gf = gridDim.x: front only, Gf = 0: back only.
+__global__ void __launch_bounds__(kT, 1) k_frame_pipe(const __grid_constant__ FramePtrs f, const __grid_constant__ FramePtrs b, int Gf) {
+    extern __shared__ __align__(128) unsigned long long dyn[];
+    __shared__ FrameShared sh;
+    if (threadIdx.x == 0) mbar_init(&sh.mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    if ((int)blockIdx.x < Gf) front_body(f, blockIdx.x, Gf, sh, dyn, parity);
+    else back_body(b, (int)blockIdx.x - Gf, (int)gridDim.x - Gf, sh, dyn);
 }
 
 // One sequence, the whole grid is its group; the frame's arguments travel in the constant bank.

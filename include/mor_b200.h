@@ -155,6 +155,13 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
 int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y,
                      uint32_t off_z, uint32_t off_i, const double pose7[7], void* out, uint32_t cap_points);
 int mor_collect_frame(mor_handle* h, uint32_t* n_out);
+/* Throughput mode for callers that hand frames over ahead of needing their results (replay; the device-resident calls with
+ * n_out == NULL; the streaming calls above): clustering a frame needs nothing of the frame before it, so the back half of
+ * frame f (pose transform, correspondences, moving test, chain, filterCloud's part) is launched together with the front
+ * half of frame f+1 (ingest ... cluster statistics), in ONE kernel on disjoint groups of SMs, instead of one after the
+ * other. Results are identical; a call that needs a frame's results (count, taps, host output) runs its back half at
+ * once. Applies to method_choice 2 with the crop ground mode; ignored otherwise. Off by default. */
+int mor_set_pipelining(mor_handle* h, int enabled);
 /* Frames submitted and not yet collected (0..MOR_STREAM_DEPTH). */
 int mor_frames_in_flight(const mor_handle* h, uint32_t* out);
 

@@ -19,8 +19,9 @@ def _pinned(b, shape, dtype=np.float32):
     return np.frombuffer(buf, dtype=dtype).reshape(shape), p
 
 
-@pytest.mark.parametrize("scenario,cfg,frames", [(1, "MOR_config.txt", 24), (2, "MOR_config_hdl64.txt", 40)])
-def test_streamed_frames_equal_synchronous_frames_and_oracle(product, oracle, cfg_dir, scenario, cfg, frames):
+@pytest.mark.parametrize("scenario,cfg,frames,pipelining", [(1, "MOR_config.txt", 24, False), (2, "MOR_config_hdl64.txt", 40, False),
+                                                            (1, "MOR_config.txt", 24, True), (2, "MOR_config_hdl64.txt", 40, True)])
+def test_streamed_frames_equal_synchronous_frames_and_oracle(product, oracle, cfg_dir, scenario, cfg, frames, pipelining):
     s = Synth(scenario, scenario)
     seq = [s.frame(f) for f in range(frames)]
     ref = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
@@ -33,6 +34,7 @@ def test_streamed_frames_equal_synchronous_frames_and_oracle(product, oracle, cf
         want_orc.append(crc(orc.filter_cloud()))
     assert want == want_orc
     m = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
+    m.set_pipelining(pipelining)  # the back half of frame f in one launch with the front half of frame f+1
     DEPTH = 3  # MOR_STREAM_DEPTH
     ins, outs, keep = [], [], []
     for _ in range(DEPTH):
@@ -88,3 +90,38 @@ def test_streaming_protocol_errors_and_mixing(product, cfg_dir):
     with pytest.raises(MorError) as e:
         m.collect_frame()
     assert e.value.status == 6
+
+
+@pytest.mark.parametrize("scenario,cfg,frames", [(1, "MOR_config.txt", 30), (2, "MOR_config_hdl64.txt", 36)])
+def test_pipelined_device_resident_frames_equal_unpipelined(product, oracle, cfg_dir, scenario, cfg, frames):
+    """mor_set_pipelining with the device-resident calls: frames enqueued without asking for anything run back half (f) beside
+    front half (f+1) in one launch. Every few frames everything is compared with a handle that runs one kernel per frame and
+    with the oracle (the comparison itself makes the pending back half run alone, so both ways of launching it are covered);
+    the tracker state is a function of ALL frames so far, so agreement at the checkpoints covers the fused launches between."""
+    from parity import ParityStats, compare_frame
+    s = Synth(scenario, scenario)
+    seq = [s.frame(f) for f in range(frames)]
+    maxp = s.max_points
+    pipe = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=maxp)
+    pipe.set_pipelining(True)
+    orc = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=oracle, max_points=maxp)
+    d = C.c_void_p()
+    assert product.device_alloc(0, len(seq) * maxp * 16, C.byref(d)) == 0
+    for f, (pts, _) in enumerate(seq):
+        assert product.device_upload(0, C.c_void_p(d.value + f * maxp * 16), pts.ctypes.data_as(C.c_void_p), pts.nbytes) == 0
+    stats = ParityStats()
+    checkpoints = {0, 1, 2, 5, 6, 13, frames - 2, frames - 1}
+    for f, (pts, pose) in enumerate(seq):
+        pipe.push_device(d.value + f * maxp * 16, len(pts), pose)
+        pipe.filter_device(None, 0, want_count=False)
+        orc.push_raw_cloud_and_pose(pts, pose)
+        oo = orc.filter_cloud().copy()
+        if f in checkpoints:
+            c = pipe.counts()  # (flushes the pending back half)
+            og = np.empty((c["NOUT"], 8), np.float32)
+            if og.size:
+                assert product.device_download(0, og.ctypes.data_as(C.c_void_p), C.c_void_p(pipe.output_device()), og.nbytes) == 0
+            bad = compare_frame(pipe, orc, og, oo, stats)
+            assert not bad, f"frame {f}: {bad}"
+    assert stats.matches > 0
+    product.device_free(0, d)
