@@ -275,10 +275,11 @@ def run_product(args, rank, local_rank, world):
     # ------------------------------------------------------------------ e2e, pipelined: mor_submit_frame / mor_collect_frame. Same frames, same
     # pinned buffers, every frame's H2D and D2H inside the timed region; the copies of frames f+1 and f-1 run beside the kernel of frame f
     # (results are delivered one call later). Wall clock from the first submit to the last collect.
-    DEPTH = 3  # MOR_STREAM_DEPTH: frames in flight (results arrive DEPTH - 1 calls late)
+    DEPTH = 4  # MOR_STREAM_DEPTH: frames in flight (results arrive DEPTH - 1 calls late)
     out_bufs = [out_host] + [pinned_array(b, (maxp, 8), np.float32)[0] for _ in range(DEPTH - 1)]
     out_ptrs = [C.c_void_p(o.ctypes.data) for o in out_bufs]
     m = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+    m.set_pipelining(True)
     submit_fn, collect_fn, hh = b.submit_frame, b.collect_frame, m.h
     for f in range(W):
         if submit_fn(hh, in_ptrs[f], ns[f], 16, 0, 4, 8, 12, pose_arrs[f], out_ptrs[f % DEPTH], maxp) or collect_fn(hh, n_out_ref):
@@ -309,33 +310,43 @@ def run_product(args, rank, local_rank, world):
     frame_bytes = maxp * 16
     assert b.device_alloc(local_rank, F * frame_bytes, C.byref(d_frames)) == 0
     assert b.device_upload(local_rank, d_frames, pts.ctypes.data_as(C.c_void_p), F * frame_bytes) == 0
-    m = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
-    for f in range(W):
-        m.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-        m.filter_device(None, 0, want_count=False)
-    m.sync()
-    barrier()
-    l0 = m.launch_count()
-    m.event_record(0)
-    for i in range(K):
-        f = W + i
-        m.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
-        m.filter_device(None, 0, want_count=False)  # the filtered cloud stays in the handle's device buffer
-    m.event_record(1)
-    dev_ms = m.event_elapsed_ms(0, 1)
-    barrier()
-    launches = m.launch_count() - l0
-    dev_ms = max_over_ranks(dev_ms)
+    def device_resident(pipelining):
+        """K frames through the device-resident calls, nothing asked back per frame. pipelining: mor_set_pipelining - the back half
+        of frame f (transform, match, moving test, chain, filter) in ONE launch with the front half of frame f+1 (ingest ...
+        cluster statistics) on disjoint SMs; the region ends when the last frame's back half has completed."""
+        mm = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
+        mm.set_pipelining(pipelining)
+        for f in range(W):
+            mm.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
+            mm.filter_device(None, 0, want_count=False)
+        mm.sync()
+        barrier()
+        l0 = mm.launch_count()
+        mm.event_record(0)
+        for i in range(K):
+            f = W + i
+            mm.push_device(d_frames.value + f * frame_bytes, int(npts[f]), poses[f])
+            mm.filter_device(None, 0, want_count=False)  # the filtered cloud stays in the handle's device buffer
+        mm.sync()  # (pipelining: launches the back half of the last frame; the region covers K whole frames either way)
+        mm.event_record(1)
+        ms = mm.event_elapsed_ms(0, 1)
+        barrier()
+        n_launches = mm.launch_count() - l0
+        ms = max_over_ranks(ms)
+        cl = mm.counts()
+        if cl["ERRFLAGS"]:
+            raise RuntimeError(f"device capacity flags {cl['ERRFLAGS']}")
+        # the timed run did the work: its last output equals the last output of the (independent) end-to-end run, byte for byte
+        last = np.empty((cl["NOUT"], 8), np.float32)
+        if last.size:
+            assert b.device_download(local_rank, last.ctypes.data_as(C.c_void_p), C.c_void_p(mm.output_device()), last.nbytes) == 0
+        crc_last = zlib.crc32(last.tobytes())
+        mm.close()
+        return ms, n_launches, crc_last
+
+    one_ms, one_launches, crc_one_last = device_resident(False)   # one kernel per frame: k_frame
+    dev_ms, launches, crc_dev_last = device_resident(True)        # the headline: k_frame_pipe
     launches_all = sum_over_ranks(launches)
-    counts_last = m.counts()
-    if counts_last["ERRFLAGS"]:
-        raise RuntimeError(f"device capacity flags {counts_last['ERRFLAGS']}")
-    # the timed run did the work: its last output equals the last output of the (independent) end-to-end run, byte for byte
-    last = np.empty((counts_last["NOUT"], 8), np.float32)
-    if last.size:
-        assert b.device_download(local_rank, last.ctypes.data_as(C.c_void_p), C.c_void_p(m.output_device()), last.nbytes) == 0
-    crc_dev_last = zlib.crc32(last.tobytes())
-    m.close()
 
     # ------------------------------------------------------------------ multi-sequence (C5-style): S independent sequences per GPU
     from dynamicslamtool_b200 import SequenceBatch
@@ -459,16 +470,24 @@ def run_product(args, rank, local_rank, world):
         nprof = max(nprof, 1)
         frame_bytes_alg = alg_sum / nprof
         kern_us = 1e3 * kern_ms / nprof
-        traffic, traffic_note = None, None
+        traffic, traffic_note, traffic_pipe = None, None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             tj = json.loads(tp.read_text())
             traffic, traffic_note = tj.get("k_frame"), tj.get("note")
-        roofline = {"bound": "hbm", "kernel": "k_frame", "achieved": frame_bytes_alg / (kern_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": frame_bytes_alg / (kern_us * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": which,
+            traffic_pipe = tj.get("k_frame_pipe")
+        pipe_us = 1e3 * dev_ms / K
+        roofline = {"bound": "hbm", "kernel": "k_frame_pipe", "achieved": frame_bytes_alg / (pipe_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": frame_bytes_alg / (pipe_us * 1e-6) / 1e9 / peak, "traffic": traffic_pipe, "traffic_note": traffic_note, "peak_source": which,
                     "algorithmic_bytes_per_launch": frame_bytes_alg, "units_per_launch": 1, "bytes_per_unit": frame_bytes_alg,
-                    "unit_note": "one launch = one frame; SURVEY 8(d): 16N + 17Nt + 104Nc + 24Nk' + 32(P1+P2) + 20Nt + 16Nout from the frame's device-side counts",
-                    "kernel_avg_us": kern_us, "kernel_share_of_frame": kern_us / (1e3 * dev_ms / K), "mean_cloud_points": nc_sum / nprof}
+                    "unit_note": "one launch = the back half of frame f + the front half of frame f+1 = one frame's worth of work; SURVEY 8(d): 16N + 17Nt + 104Nc + "
+                                 "24Nk' + 32(P1+P2) + 20Nt + 16Nout from the frames' device-side counts",
+                    "kernel_avg_us": pipe_us, "kernel_share_of_frame": 1.0,
+                    "how": "the timed region is K back-to-back launches of this kernel on one stream (one launch per step): its average duration is the step time, CUDA events",
+                    "mean_cloud_points": nc_sum / nprof,
+                    "single_frame_kernel": {"kernel": "k_frame", "what": "the whole frame as ONE launch (the latency path: synchronous calls, no pipelining)",
+                                            "kernel_avg_us": kern_us, "achieved": frame_bytes_alg / (kern_us * 1e-6) / 1e9,
+                                            "frac": frame_bytes_alg / (kern_us * 1e-6) / 1e9 / peak, "traffic": traffic}}
         # pass 2: one launch per phase (the same device functions), each between events
         m2 = MovingObjectRemoval(CFG, 4, 3, device=local_rank, binding=b, max_points=maxp)
         for f in range(w0):
@@ -578,17 +597,22 @@ def run_product(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "value_how": "device-resident calls with mor_set_pipelining: one k_frame_pipe launch per step = back half of frame f beside the front half of frame f+1 on disjoint "
+                     "SM groups; K whole frames inside the timed region (the last back half included); `unpipelined` = one k_frame launch per frame",
         "config": cfg,
         "clocks": clocks,
         "e2e": {"value": world * K / (stream_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(np.mean(npts[W:]) * 16 + 56), "d2h_bytes_per_step": int(d2h_s / K),
                 "ms_per_step": stream_ms / K,
                 "how": "host C ABI, pinned host buffers, mor_submit_frame + mor_collect_frame: every frame's H2D, frame kernel and D2H inside the timed region (wall clock, "
-                       "first submit to last collect, max over ranks); up to three frames in flight: copies of neighbouring frames overlap the kernel, results arrive two calls later",
+                       "first submit to last collect, max over ranks); up to four frames in flight, pipelined launches (mor_set_pipelining): copies of neighbouring frames overlap the kernels, results arrive three calls later",
                 "last_frame_crc_equals_serial": crc_stream_last == crc_e2e_last,
                 "serial": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / K, "d2h_bytes_per_step": int(d2h / K),
                            "how": "mor_push_raw_cloud_and_pose + mor_filter_cloud per frame, nothing overlapped (the reference's callback protocol): per-frame latency",
                            "latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3), "max": float(lat.max() * 1e3)}}},
         "gpu_launches": int(launches_all),
+        "unpipelined": {"value": world * K / (one_ms * 1e-3), "unit": "frames/s", "ms_per_step": one_ms / K, "launches": int(one_launches),
+                        "what": "the same K frames with one k_frame launch per frame (no overlap of consecutive frames): the per-frame device latency",
+                        "last_frame_crc_equals_pipelined": crc_one_last == crc_dev_last},
         "roofline": roofline,
         "frame_roofline": {"algorithmic_bytes_per_frame": frame_bytes_alg, "achieved_gbs": frame_bytes_alg * (K / (dev_ms * 1e-3)) / 1e9,
                            "frac": frame_bytes_alg * (K / (dev_ms * 1e-3)) / 1e9 / peak, "peak": peak, "peak_source": which},

@@ -818,8 +818,10 @@ int mor_sync(mor_handle* h) {
 // slot is reused by frame f + DEPTH, which cannot be submitted before frame f has been collected, i.e. before its D2H
 // copy - and with it the kernel that read the slot's staging buffer and wrote its output buffer - has completed. With
 // three frames in flight the H2D copy of frame f+1 is issued while the host still waits for frame f-1: the kernels then
-// run back to back (with two, every kernel waited ~14 us for its input). The per-frame counts are ping-pong (cur/prev):
-// the kernel of frame f overwrites the block frame f-2's D2H reads, so it waits for that copy (normally long done).
+// run back to back (with two, every kernel waited ~14 us for its input); with pipelined launches a frame's results come
+// one launch later (its back half rides with the next frame's front half), which takes a fourth. The per-frame counts
+// rotate through three blocks: the kernel of frame f overwrites the block frame f-3's D2H reads, so it waits for that
+// copy (normally long done).
 static int ensure_streaming(mor_handle* h) {
     if (h->copy_in) return MOR_OK;
     MOR_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
@@ -864,9 +866,9 @@ int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t step,
     { int js = join_foreign_stream(h, /*keep_pending_back=*/h->inflight > 0); if (js != MOR_OK) return js; }
     const int si = (h->sf_head + h->inflight) % MOR_STREAM_DEPTH;
     mor_handle::StreamSlot& sl = h->slot[si];
-    {   // the count block this frame's kernel writes was the one of the frame before last
-        mor_handle::StreamSlot& s2 = h->slot[(si + MOR_STREAM_DEPTH - 2) % MOR_STREAM_DEPTH];
-        if (s2.used) MOR_CUDA(cudaStreamWaitEvent(h->stream, s2.d2h, 0));
+    {   // the count block this frame's kernel writes (three in rotation) was the one of the frame three back: its D2H must be over
+        mor_handle::StreamSlot& s3 = h->slot[(si + MOR_STREAM_DEPTH - 3) % MOR_STREAM_DEPTH];
+        if (s3.used && s3.d2h_enqueued) MOR_CUDA(cudaStreamWaitEvent(h->stream, s3.d2h, 0));
     }
     if (!h->inflight) {  // the pipeline starts: earlier work of the synchronous calls may still use slot 0's buffers
         MOR_CUDA(cudaEventRecord(h->ev_join, h->stream));

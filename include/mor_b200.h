@@ -144,14 +144,14 @@ int mor_batch_step_device(mor_handle* const* hs, uint32_t S, const void* const* 
  *                     stream of its own (copies of frame f+1 and f-1 overlap the kernel of frame f), and returns;
  *   mor_collect_frame waits for the OLDEST submitted frame and delivers its count: `out` of that frame then holds the
  *                     records mor_filter_cloud would have written.
- * At most MOR_STREAM_DEPTH (3) frames may be in flight; a fourth mor_submit_frame returns MOR_ERR_STATE. `data` must stay
+ * At most MOR_STREAM_DEPTH (4) frames may be in flight; a fifth mor_submit_frame returns MOR_ERR_STATE. `data` must stay
  * untouched until the frame is collected and `out` (capacity cap_points records, >= n to be safe) until it has been
  * read; both should be pinned (mor_alloc_pinned / mor_host_register), else the copies do not overlap anything.
  * Every submitted frame is committed like push + one filterCloud (the tracker update of cpp:630-671 is applied once).
  * The synchronous calls above may be mixed in only while no frame is in flight (MOR_ERR_STATE otherwise).
  * mor_collect_frame returns MOR_ERR_STATE if nothing is in flight, MOR_ERR_CAPACITY (count in *n_out) if cap_points was
  * too small or a device-side capacity was exceeded (mor_last_error tells which). */
-#define MOR_STREAM_DEPTH 3
+#define MOR_STREAM_DEPTH 4
 int mor_submit_frame(mor_handle* h, const void* data, uint32_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y,
                      uint32_t off_z, uint32_t off_i, const double pose7[7], void* out, uint32_t cap_points);
 int mor_collect_frame(mor_handle* h, uint32_t* n_out);

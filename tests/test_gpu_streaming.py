@@ -35,7 +35,7 @@ def test_streamed_frames_equal_synchronous_frames_and_oracle(product, oracle, cf
     assert want == want_orc
     m = MovingObjectRemoval(cfg_dir / cfg, 4, 3, binding=product, max_points=s.max_points)
     m.set_pipelining(pipelining)  # the back half of frame f in one launch with the front half of frame f+1
-    DEPTH = 3  # MOR_STREAM_DEPTH
+    DEPTH = 4  # MOR_STREAM_DEPTH
     ins, outs, keep = [], [], []
     for _ in range(DEPTH):
         a, pa = _pinned(product, (s.max_points, 4)); o, po = _pinned(product, (s.max_points, 8))
@@ -64,29 +64,29 @@ def test_streaming_protocol_errors_and_mixing(product, cfg_dir):
     with pytest.raises(MorError) as e:
         m.collect_frame()
     assert e.value.status == 8  # nothing in flight
-    outs = [np.empty((s.max_points, 8), np.float32) for _ in range(4)]  # pageable memory works too (no overlap then)
-    frames = [s.frame(f) for f in range(8)]
-    for q in range(3):
+    outs = [np.empty((s.max_points, 8), np.float32) for _ in range(5)]  # pageable memory works too (no overlap then)
+    frames = [s.frame(f) for f in range(9)]
+    for q in range(4):
         m.submit_frame(frames[q][0], frames[q][1], outs[q])
     with pytest.raises(MorError) as e:
-        m.submit_frame(frames[3][0], frames[3][1], outs[3])
-    assert e.value.status == 8  # MOR_STREAM_DEPTH = 3
+        m.submit_frame(frames[4][0], frames[4][1], outs[4])
+    assert e.value.status == 8  # MOR_STREAM_DEPTH = 4
     with pytest.raises(MorError) as e:
-        m.push_raw_cloud_and_pose(*frames[3])
+        m.push_raw_cloud_and_pose(*frames[4])
     assert e.value.status == 8  # synchronous calls only while nothing is in flight
-    got = [m.collect_frame().copy() for _ in range(3)]
+    got = [m.collect_frame().copy() for _ in range(4)]
     # ... after which the synchronous calls continue the same sequence
-    m.push_raw_cloud_and_pose(*frames[3]); got.append(m.filter_cloud().copy())
-    m.submit_frame(frames[4][0], frames[4][1], outs[0]); got.append(m.collect_frame().copy())
+    m.push_raw_cloud_and_pose(*frames[4]); got.append(m.filter_cloud().copy())
+    m.submit_frame(frames[5][0], frames[5][1], outs[0]); got.append(m.collect_frame().copy())
     ref = MovingObjectRemoval(cfg_dir / "MOR_config.txt", 4, 3, binding=product, max_points=s.max_points)
     want = []
-    for pts, pose in frames[:5]:
+    for pts, pose in frames[:6]:
         ref.push_raw_cloud_and_pose(pts, pose); want.append(ref.filter_cloud().copy())
     for x, y in zip(got, want):
         assert np.array_equal(x, y)
     # an output buffer that is too small is reported at collection, with the needed count
     small = np.empty((16, 8), np.float32)
-    m.submit_frame(frames[5][0], frames[5][1], small)
+    m.submit_frame(frames[6][0], frames[6][1], small)
     with pytest.raises(MorError) as e:
         m.collect_frame()
     assert e.value.status == 6
