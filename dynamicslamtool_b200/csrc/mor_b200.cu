@@ -425,6 +425,10 @@ int launch_pipe(mor_handle* h, const FramePtrs* front, const FramePtrs* back) {
     // the front half is tile-granular in its first phase (1024 input points per CTA): it gets at least one CTA per tile, at most
     // 7/8 of the GPU; the back half scales with what is left
     int Gf = G, Gb = 0;
+    if (front && back && G < 8) {  // too few SMs to share: one half after the other
+        int s0 = launch_pipe(h, nullptr, back);
+        return s0 != MOR_OK ? s0 : launch_pipe(h, front, nullptr);
+    }
     if (front && back) {
         const int tiles = (int)((front->n + kT - 1) / kT);
         Gf = tiles + 1;
@@ -474,7 +478,7 @@ int enqueue_push(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t st
             (s = launch_phase<PH_JUMP>(h, a)) || (s = launch_phase<PH_CROSS>(h, a)) || (s = launch_phase<PH_ROOTS>(h, a)) || (s = launch_phase<PH_SELECT>(h, a)) || (s = launch_phase<PH_STATS>(h, a)) || 
             (s = launch_phase<PH_MOVING>(h, a)) || (s = launch_phase<PH_FILTER>(h, a)))
             return s;
-    } else if (allow_pipe && h->pipelining && h->cfg.method_choice == 2) {
+    } else if (allow_pipe && h->pipelining && h->cfg.method_choice == 2 && h->cfg.ground_mode == MOR_GROUND_CROP) {
         // front half of this frame, beside the back half of the frame before if that one has been filtered already
         const bool fused = h->back_pending;
         h->back_pending = false;
