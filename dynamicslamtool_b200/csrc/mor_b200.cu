@@ -128,6 +128,7 @@ struct mor_handle {
     float4* pts[3]; float4* spts[3]; int* cid[3]; int* cl_root[3]; int* cl_size[3]; float* cl_centroid[3]; uint8_t* cl_flags[3]; float* cl_bbox[3]; int* counts[3];
     // products of the front half that only the back half of the SAME frame reads: two, by frame parity
     int* scid2[2]; float4* gpts2[2]; int* gsrc2[2]; int* cloud_src2[2]; uint8_t* removed_mask2[2];
+    unsigned long long* acc_sum2[2]; unsigned* acc_box2[2];
     int cur = 0, fpar = 0;
     // pipelining (mor_set_pipelining): the back half of the last filtered frame waits to be launched beside the front half
     // of the next frame
@@ -282,6 +283,7 @@ int allocate(mor_handle* h) {
         for (int f = 0; f < 2; f++) {
             h->scid2[f] = f ? carve<int>(p, N) : b.scid; h->gpts2[f] = f ? carve<float4>(p, N) : b.gpts; h->gsrc2[f] = f ? carve<int>(p, N) : b.gsrc;
             h->cloud_src2[f] = f ? carve<int>(p, N) : b.cloud_src; h->removed_mask2[f] = f ? carve<uint8_t>(p, N) : b.removed_mask;
+            h->acc_sum2[f] = f ? carve<unsigned long long>(p, K * 6) : b.acc_sum; h->acc_box2[f] = f ? carve<unsigned>(p, K * 6) : b.acc_box;
         }
         for (int f = 0; f < 3; f++) {
             h->pts[f] = carve<float4>(p, N); h->spts[f] = carve<float4>(p, N); h->cid[f] = carve<int>(p, N);
@@ -395,6 +397,7 @@ void fill_frame(mor_handle* h, const uint8_t* d_points, uint32_t n, uint32_t ste
     a = h->base;
     const int cur = h->cur, prev = (cur + 2) % 3;
     a.scid = h->scid2[h->fpar]; a.gpts = h->gpts2[h->fpar]; a.gsrc = h->gsrc2[h->fpar]; a.cloud_src = h->cloud_src2[h->fpar]; a.removed_mask = h->removed_mask2[h->fpar];
+    a.acc_sum = h->acc_sum2[h->fpar]; a.acc_box = h->acc_box2[h->fpar];
     a.in = d_points; a.n = n; a.step = step; a.off_x = ox; a.off_y = oy; a.off_z = oz; a.off_i = oi;
     a.in_mode = input_mode(d_points, step, ox, oy, oz, oi);
     a.pts = h->pts[cur]; a.spts = h->spts[cur]; a.cid = h->cid[cur]; a.cl_root = h->cl_root[cur]; a.cl_size = h->cl_size[cur];
@@ -422,18 +425,18 @@ int launch_phase(mor_handle* h, const FramePtrs& a) {
 // Pipelined launches (k_frame_pipe): the front half of `front` on most CTAs beside the pending back half, or either alone.
 int launch_pipe(mor_handle* h, const FramePtrs* front, const FramePtrs* back) {
     const int G = h->frame_ctas;
-    // the front half is tile-granular in its first phase (1024 input points per CTA): it gets at least one CTA per tile, at most
-    // 7/8 of the GPU; the back half scales with what is left
+    // the back half gets 5/32 of the CTAs (23 of 148): measured optimum on C2 (swept 100 ... 140: the front half holds two thirds
+    // of a frame's chain of phases and is tile-granular in its first one, the back half is three short phases over the
+    // points plus its single-CTA steps)
     int Gf = G, Gb = 0;
     if (front && back && G < 8) {  // too few SMs to share: one half after the other
         int s0 = launch_pipe(h, nullptr, back);
         return s0 != MOR_OK ? s0 : launch_pipe(h, front, nullptr);
     }
     if (front && back) {
-        const int tiles = (int)((front->n + kT - 1) / kT);
-        Gf = tiles + 1;
-        if (Gf < (G * 3) / 4) Gf = (G * 3) / 4;
-        if (Gf > (G * 7) / 8) Gf = (G * 7) / 8;
+        Gb = (G * 5) / 32;
+        if (Gb < 4) Gb = 4;
+        Gf = G - Gb;
         if (const char* env = std::getenv("MOR_PIPE_GF")) { const int v = std::atoi(env); if (v > 0 && v < G) Gf = v; }  // (tuning)
         Gb = G - Gf;
     } else if (back) { Gf = 0; Gb = G; }

@@ -1252,21 +1252,6 @@ __device__ __forceinline__ int nn_warp(const float* pts, int n, float qx, float 
     return best;
 }
 
-// Centroids and boxes of the current clusters from the exact sums (the first step of the match step; in a pipelined
-// launch it is the last step of the FRONT half, so that the back half never reads the accumulators of a frame whose
-// successor is already being clustered).
-__device__ __forceinline__ void phase_centroids(const FramePtrs& a) {
-    const int K = a.counts[MOR_CNT_K];
-    for (int c = threadIdx.x; c < K; c += kSingle) {
-        const double n = (double)a.cl_size[c];
-#pragma unroll
-        for (int q = 0; q < 3; q++)
-            a.cl_centroid[c * 3 + q] = (float)join_fixed_mean((long long)__ldcg(&a.acc_sum[c * 6 + q * 2]), (long long)__ldcg(&a.acc_sum[c * 6 + q * 2 + 1]), n);
-#pragma unroll
-        for (int q = 0; q < 6; q++) a.cl_bbox[c * 6 + q] = fkey_inv(__ldcg(&a.acc_box[c * 6 + q]));
-    }
-}
-
 template <bool FAST, bool FINALIZE = true>
 __device__ __forceinline__ void phase_match_impl(const FramePtrs& a, unsigned long long* dyn) {
     const int K = a.counts[MOR_CNT_K];
@@ -1393,14 +1378,6 @@ MOR_OUTLINE void phase_match(const FramePtrs& a, unsigned long long* dyn) {
     const int cap = (a.frame_smem - kSingle * 12) / kMatchBytesPerCluster;
     if (K <= cap && Kp <= cap) phase_match_impl<true>(a, dyn); else phase_match_impl<false>(a, dyn);
 }
-// (pipelined launch, back half: the centroids and boxes are final already)
-MOR_OUTLINE void phase_match_back(const FramePtrs& a, unsigned long long* dyn) {
-    const int K = a.counts[MOR_CNT_K];
-    const int Kp = a.two_frames ? a.p_counts[MOR_CNT_K] : 0;
-    const int cap = (a.frame_smem - kSingle * 12) / kMatchBytesPerCluster;
-    if (K <= cap && Kp <= cap) phase_match_impl<true, false>(a, dyn); else phase_match_impl<false, false>(a, dyn);
-}
-
 // ===================================================================================== phase I: moving test
 // Method 2 (default): the score of a matched pair is the number of points of the current cluster whose octree leaf
 // holds no point of the transformed previous cluster (cpp:325-330).
@@ -1838,7 +1815,8 @@ __device__ __forceinline__ void frame_body(const FramePtrs& a, int cta, int G, F
 // nothing of the frame before it, so ONE launch runs the front half of frame f+1 (ingest ... cluster statistics) on the
 // first Gf CTAs beside the back half of frame f (transform, match, moving test, chain, filter) on the others. The two
 // groups have their own barriers and counters and touch disjoint state: what the back half reads of frame f and f-1 is
-// triple-buffered (points, cluster ids, cluster tables, counts) or double-buffered (ground points, source indices, masks)
+// triple-buffered (points, cluster ids, cluster tables, counts) or double-buffered (ground points, source indices, masks,
+// the clusters' coordinate sums and boxes)
 // on the host side (mor_b200.cu, fill_frame). Method 2 and the crop ground mode only (method 1 searches the clustering
 // grid of frame f in the back half, which the front half of f+1 rebuilds).
 __device__ __forceinline__ void front_body(const FramePtrs& a, int cta, int G, FrameShared& sh, unsigned long long* dyn, unsigned& parity) {
@@ -1851,11 +1829,10 @@ __device__ __forceinline__ void front_body(const FramePtrs& a, int cta, int G, F
     phase_test(a, cta, G); bar.sync();
     phase_jump(a, cta, G); bar.sync();
     phase_cross(a, cta, G); bar.sync();
-    phase_roots(a, cta, G); bar.sync();
-    if (cta == 0) phase_select(a, dyn);
+    phase_roots(a, cta, G);
+    if (group_last_arrival(&a.scratch->tail_centroids, (unsigned)G)) phase_select(a, dyn);  // (the last CTA in selects the clusters: no barrier in front of it)
     bar.sync();
-    phase_stats(a, cta, G);
-    if (group_last_arrival(&a.scratch->tail_centroids, (unsigned)G)) phase_centroids(a);
+    phase_stats(a, cta, G);  // (the sums it accumulates are double-buffered by frame parity: the back half turns them into centroids)
     frame_cleanup(a, cta, G);
     // last CTA of the group out: the front half's counters back to zero
     __shared__ int s_last_front;
@@ -1887,7 +1864,7 @@ __device__ __forceinline__ void back_body(const FramePtrs& a, int cta, int G, Fr
         cta_slice(a.p_counts[MOR_CNT_NC], cta, G, &lo, &hi);
         transform_range(a, lo, hi);
     }
-    if (group_last_arrival(&a.scratch->tail_match_back, (unsigned)G)) phase_match_back(a, dyn);
+    if (group_last_arrival(&a.scratch->tail_match_back, (unsigned)G)) phase_match(a, dyn);
     bar.sync();
     if (a.two_frames) phase_lattice_count(a, cta, G);
     if (group_last_arrival(&a.scratch->tail_chain, (unsigned)G)) phase_chain_tail(a);
