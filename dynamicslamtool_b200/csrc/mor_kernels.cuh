@@ -10,7 +10,11 @@
 // points, cells or clusters, strided over the group: sized from the device-side counts, so no CTA is launched for work
 // that does not exist) and meets at a group barrier in between. One sequence takes the whole GPU (G = #SMs); S
 // sequences per launch (mor_batch_step_device) take G = #SMs / S CTAs each and run independently side by side.
-// The same phase functions can be launched one kernel per phase (k_phase<>, per-phase timing for bench.py).
+// The same phase functions can be launched one kernel per phase (k_phase<>, per-phase timing for bench.py), and as
+// k_frame_pipe: the front half of one frame (ingest ... cluster statistics) on most CTAs beside the back half of the
+// frame before it (transform, match, moving test, chain, filter) on the rest - the throughput mode, see the end of the
+// file. Clustering is done on pair lists: an enumerate phase (a warp per cell) and a test phase (a thread per light
+// pair, a warp per heavy pair).
 #pragma once
 #include <cstdio>
 #include "mor_device.cuh"
