@@ -1725,10 +1725,58 @@ __device__ __forceinline__ void filter_tile(const FramePtrs& a, const FilterShar
     if (tile == last_tile && threadIdx.x == 0) a.counts[CNT_SPEC_NOUT] = before + tot;
 }
 
+// The same tile with four consecutive items per thread (4096 per CTA and round): for groups that have several rounds of
+// tiles per CTA (the back half of a pipelined launch on 23 CTAs, a sequence of a batch on 4) - a quarter of the rounds, each
+// a chain of scan, prefix round trip and stores.
+constexpr int kOutWide = 4;
+__device__ __forceinline__ void filter_tile_wide(const FramePtrs& a, const FilterShared& sh, int overflow, int tile, int last_tile) {
+    const int nc = frame_vars().nc, ng = frame_vars().ng;
+    const int t0 = (tile * kOutTile + (int)threadIdx.x) * kOutWide;
+    float4 p[kOutWide];
+    bool keep[kOutWide];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kOutWide; q++) {
+        const int t = t0 + q;
+        keep[q] = false;
+        p[q] = make_float4(0, 0, 0, 0);
+        if (t < nc) {
+            p[q] = a.pts[t];
+            const int c = a.cid[t];
+            const bool removed = overflow || (c >= 0 && ((sh.removed[c >> 5] >> (c & 31)) & 1u));
+            keep[q] = !removed;
+            if (removed) a.removed_mask[a.cloud_src[t]] = 2;
+        } else if (t < nc + ng) {
+            p[q] = a.gpts[t - nc];
+            keep[q] = true;
+        }
+        cnt += keep[q] ? 1 : 0;
+    }
+    int tot;
+    const int in_block = block_exclusive_scan<int, kT>(cnt, &tot);
+    const int before = (int)tile_prefix_wide<kT>(a.st_out, tile, (unsigned long long)tot);
+    int o = before + in_block;
+#pragma unroll
+    for (int q = 0; q < kOutWide; q++) {
+        if (!keep[q]) continue;
+        a.out[2 * o] = make_float4(p[q].x, p[q].y, p[q].z, 1.0f);
+        a.out[2 * o + 1] = make_float4(p[q].w, 0.f, 0.f, 0.f);
+        o++;
+    }
+    if (tile == last_tile && threadIdx.x == 0) a.counts[CNT_SPEC_NOUT] = before + tot;
+}
+
 __device__ __forceinline__ void phase_filter(const FramePtrs& a, int cta, int G, FilterShared& sh, bool cleanup = true) {
     const int total_items = frame_vars().nc + frame_vars().ng;
-    const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
     if (cleanup) frame_cleanup(a, cta, G);
+    if ((long long)total_items > 2ll * G * kOutTile) {  // several rounds per CTA: four items per thread
+        const int last_wide = (total_items - 1) / (kOutTile * kOutWide);
+        if (cta > last_wide) return;
+        const int overflow = filter_tracking(a, sh, cta == 0);
+        for (int tile = cta; tile <= last_wide; tile += G) filter_tile_wide(a, sh, overflow, tile, last_wide);
+        return;
+    }
+    const int last_tile = total_items ? (total_items - 1) / kOutTile : 0;
     if (cta > last_tile) return;  // nothing to compact here (CTA 0 always has tile 0: it owns the mo_vec update)
     FilterTileIn in = filter_tile_load(a, cta);  // the first tile's loads are in flight while the tracking part runs
     const int overflow = filter_tracking(a, sh, cta == 0);
