@@ -1,10 +1,13 @@
 // mor_b200.cu — handle, launch sequence and C ABI (include/mor_b200.h) of the B200-native MOR hot path.
 //
-// One handle = one CUDA device + one stream + device-resident SoA frame state that persists across
-// frames (previous frame's clusters, mo_vec, the corrs_vec / res_vec ring buffers). A frame is
-// pushRawCloudAndPose (reference cpp:516-611) = one H2D copy + ONE cooperative kernel launch (k_frame, all phases
-// of the frame incl. the filter phase, no host synchronisation), then filterCloud (cpp:613-696) = commit of the
-// filter phase's result + the D2H copy of the output cloud.
+// One handle = one CUDA device + one compute stream (+ two copy streams for the streaming calls) + device-resident SoA
+// frame state that persists across frames (previous frame's clusters, mo_vec, the corrs_vec / res_vec ring buffers). A
+// frame is pushRawCloudAndPose (reference cpp:516-611) = one H2D copy + ONE cooperative kernel launch (k_frame: all phases
+// of the frame incl. the filter phase, no host synchronisation), then filterCloud (cpp:613-696) = commit of the filter
+// phase's result + the D2H copy of the output cloud.
+// Throughput paths on top of that: mor_submit_frame / mor_collect_frame (copies of neighbouring frames on their own
+// streams, up to four frames in flight) and mor_set_pipelining (k_frame_pipe: the back half of frame f in one launch with
+// the front half of frame f+1; the frame products are triple-buffered for it, see fill_frame / launch_pipe).
 // There is no CPU fallback: every entry point that computes needs the device.
 #include <cmath>
 #include <cstdio>
