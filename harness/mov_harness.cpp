@@ -7,6 +7,7 @@
 //
 //   mov_harness <MOR_config.txt> <scenario 1..4> <seed> <frames> [n_bad=4] [n_good=3] [--quiet]
 //   mov_harness <MOR_config.txt> --replay <dir> [frames] [n_bad=4] [n_good=3] [--quiet] [--out <dir>]
+//       (either form: --stream replays through mor_submit_frame / mor_collect_frame with pipelined launches: full rate, results three frames late)
 //       (either form: --debug also fetches the VISUALIZE debug cloud and bounding-box markers of every frame)
 //       recorded data: KITTI-style .bin clouds + poses.txt (+ calib.txt), see replay_io.h; --out writes the filtered clouds
 //       unsynchronised recording: <dir>/times.txt (one stamp in seconds per cloud) + <dir>/odometry.txt (t tx ty tz qx qy qz qw,
@@ -141,12 +142,13 @@ int main(int argc, char** argv) {
     if (argc < 4) { std::fprintf(stderr, "usage: %s <config> <scenario> <seed> <frames> [n_bad] [n_good] [--quiet]\n       %s <config> --replay <dir> [frames] [n_bad] [n_good] [--quiet] [--out <dir>]\n", argv[0], argv[0]); return 2; }
     const std::string cfg = argv[1];
     const bool replay_mode = !std::strcmp(argv[2], "--replay");
-    bool quiet = false, debug = false;  // --debug: also fetch the VISUALIZE outputs (debug cloud, markers) every frame
+    bool quiet = false, debug = false, stream = false;  // --debug: also fetch the VISUALIZE outputs (debug cloud, markers) every frame
     std::string out_dir;
     std::vector<std::string> pos;  // positional arguments after the source
     for (int i = replay_mode ? 4 : 2; i < argc; i++) {
         if (!std::strcmp(argv[i], "--quiet")) quiet = true;
         else if (!std::strcmp(argv[i], "--debug")) debug = true;
+        else if (!std::strcmp(argv[i], "--stream")) stream = true;  // replay through the pipelined calls (results arrive three frames late)
         else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out_dir = argv[++i];
         else pos.push_back(argv[i]);
     }
@@ -176,6 +178,51 @@ int main(int argc, char** argv) {
     lim.max_points = std::max<uint32_t>(src.max_points, 1);
     ros::NodeHandle nh;
     MovingObjectRemoval mor(nh, cfg, n_bad, n_good, 0, &lim);  // mor.reset(new MovingObjectRemoval(nh, "...MOR_config.txt", 4, 3))
+
+    if (stream) {
+        // Replay at full rate (mor_b200.h, "pipelined streaming"): the frames go through mor_submit_frame / mor_collect_frame on
+        // the class's handle with pipelined launches; four pinned input and output buffers; frame f is collected - and would
+        // be published - when frame f+3 has been submitted. Same per-frame lines as the callback loop below.
+        mor_handle* h = mor.handle();
+        if (mor_set_pipelining(h, 1) != MOR_OK) { std::fprintf(stderr, "mor_set_pipelining: %s\n", mor_last_error(h)); return 1; }
+        const size_t cap = lim.max_points;
+        void* in[MOR_STREAM_DEPTH]; void* out[MOR_STREAM_DEPTH]; uint32_t n_of[MOR_STREAM_DEPTH];
+        for (int q = 0; q < MOR_STREAM_DEPTH; q++)
+            if (mor_alloc_pinned(cap * 16, &in[q]) != MOR_OK || mor_alloc_pinned(cap * 32, &out[q]) != MOR_OK) { std::fprintf(stderr, "pinned allocation failed\n"); return 1; }
+        pcl::PCLPointCloud2 c16;
+        c16.height = 1; c16.point_step = 16; c16.is_dense = 1;
+        const auto t_begin = std::chrono::steady_clock::now();
+        int collected = 0;
+        auto collect_one = [&]() -> bool {
+            uint32_t n_out = 0;
+            const int st = mor_collect_frame(h, &n_out);
+            if (st != MOR_OK) { std::fprintf(stderr, "frame %d: %s %s\n", collected, mor_status_string(st), mor_last_error(h)); return false; }
+            const int q = collected % MOR_STREAM_DEPTH;
+            if (!out_dir.empty()) {
+                char name[32];
+                std::snprintf(name, sizeof name, "/%06d.bin", collected);
+                if (!replay::write_bin(out_dir + name, (const uint8_t*)out[q], n_out)) { std::fprintf(stderr, "cannot write %s%s\n", out_dir.c_str(), name); return false; }
+            }
+            if (!quiet) std::printf("frame %d in %u out %u crc %08x ms 0\n", collected, n_of[q], n_out, crc32_buf((const uint8_t*)out[q], (size_t)n_out * 32));
+            collected++;
+            return true;
+        };
+        for (int f = 0; f < frames; f++) {
+            double p7[7];
+            if (!src.frame((uint32_t)f, c16, p7)) { std::fprintf(stderr, "frame %d: cannot read the cloud\n", f); return 1; }
+            const int q = f % MOR_STREAM_DEPTH;
+            if (f - collected >= MOR_STREAM_DEPTH && !collect_one()) return 1;  // the slot's previous frame must be out first
+            n_of[q] = c16.width;
+            std::memcpy(in[q], c16.data.data(), (size_t)c16.width * 16);
+            const int st = mor_submit_frame(h, in[q], c16.width, 16, 0, 4, 8, 12, p7, out[q], (uint32_t)cap);
+            if (st != MOR_OK) { std::fprintf(stderr, "frame %d: %s %s\n", f, mor_status_string(st), mor_last_error(h)); return 1; }
+        }
+        while (collected < frames) if (!collect_one()) return 1;
+        const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        std::printf("summary frames %d mean_ms %.3f fps %.1f (streamed: wall clock incl. reading / generating the frames)\n", frames, total_ms / std::max(frames, 1), 1e3 * frames / total_ms);
+        for (int q = 0; q < MOR_STREAM_DEPTH; q++) { mor_free_pinned(in[q]); mor_free_pinned(out[q]); }
+        return 0;
+    }
 
     pcl::PCLPointCloud2 cloud;  // what pcl_conversions::toPCL(*input, cloud) would hand over: 16-byte x,y,z,intensity records
     cloud.height = 1; cloud.point_step = 16; cloud.is_dense = 1;

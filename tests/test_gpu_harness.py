@@ -149,3 +149,19 @@ def test_replay_with_kitti_matrices_and_calibration(built, tmp_path):
     want = [int(l.split()[5]) for l in ref.stdout.splitlines() if l.startswith("frame ")]
     got = [int(r[5]) for r in rows]
     assert all(abs(a - b) <= max(20, a // 50) for a, b in zip(got, want)), (got, want)
+
+
+def test_cpp_harness_stream_mode_equals_callback_mode(built):
+    """mov_harness --stream (replay through mor_submit_frame / mor_collect_frame with pipelined launches, results three
+    frames late) must print the same per-frame counts and CRCs as the callback loop (pushRawCloudAndPose + filterCloud)."""
+    exe = ROOT / "harness" / "mov_harness"
+    cfg = ROOT / "config" / "MOR_config.txt"
+    n = 14
+    runs = []
+    for extra in ([], ["--stream"]):
+        res = subprocess.run([str(exe), str(cfg), "1", "1", str(n)] + extra, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr
+        lines = [l.split()[:8] for l in res.stdout.splitlines() if l.startswith("frame ")]
+        assert len(lines) == n
+        runs.append(lines)
+    assert runs[0] == runs[1]
