@@ -108,3 +108,13 @@ def test_config_parser_differential_fuzz(seed, product, oracle, tmp_path):
     assert sa == sb, f"status product {sa} vs oracle {sb} for\n{p.read_text()}"
     if sa == 0:
         assert bytes(ca) == bytes(cb), p.read_text()
+
+
+def test_stream_depth_constant_is_what_bench_and_tests_assume():
+    """include/mor_b200.h: MOR_STREAM_DEPTH frames may be in flight; bench.py and the streaming test keep that many buffers."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    depth = int(re.search(r"#define MOR_STREAM_DEPTH (\d+)", (root / "include" / "mor_b200.h").read_text()).group(1))
+    assert depth == int(re.search(r"DEPTH = (\d+)  # MOR_STREAM_DEPTH", (root / "bench.py").read_text()).group(1))
+    assert depth == int(re.search(r"DEPTH = (\d+)  # MOR_STREAM_DEPTH", (root / "tests" / "test_gpu_streaming.py").read_text()).group(1))
